@@ -1,0 +1,287 @@
+"""ctypes bindings for the TEST-ONLY oracle libraries (never imported by the product package).
+
+  Oracle()   -> oracle/liboracle.so        (C restatement, oracle/hh_oracle.c; always buildable)
+  RefShim()  -> oracle/_ref/libhhref_shim.so (the compiled, unmodified reference; built in the
+                authoring container from /root/reference, shipped prebuilt to the GPU box)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int)
+c_u8p = C.POINTER(C.c_uint8)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-C", HERE, "-s"])
+
+
+class Oracle:
+    def __init__(self):
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        self.lib = L = C.CDLL(path)
+        L.hho_viterbi_align.restype = C.c_int
+        L.hho_viterbi_align.argtypes = [C.c_int, c_f32p, c_f32p, c_u8p, C.c_int, c_f32p, c_f32p, c_u8p,
+                                        c_f32p, C.c_float, c_u8p, C.c_int, C.c_float, C.c_float,
+                                        C.c_float, c_f32p, c_i32p, c_i32p, c_u8p]
+        L.hho_backtrace.restype = C.c_int
+        L.hho_backtrace.argtypes = [C.c_int, c_u8p, C.c_int, C.c_int, c_i32p, c_i32p, c_u8p, c_i32p]
+        L.hho_exclude_alignment.restype = None
+        L.hho_exclude_alignment.argtypes = [C.c_int, C.c_int, c_i32p, c_i32p, C.c_int, c_u8p]
+        L.hho_prefilter_query_profile.restype = None
+        L.hho_prefilter_query_profile.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_u8p]
+        L.hho_ungapped_score.restype = C.c_int
+        L.hho_ungapped_score.argtypes = [C.c_int, c_u8p, c_u8p, C.c_int, C.c_int]
+        L.hho_ungapped_corrected.restype = C.c_int
+        L.hho_ungapped_corrected.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hho_flog2.restype = C.c_float
+        L.hho_flog2.argtypes = [C.c_float]
+
+    def viterbi(self, q_p, q_tr, t_p, t_tr, q_ss=None, t_ss=None, S33=None, ssw=0.11, celloff=None,
+                local=True, egq=0.0, egt=0.0, shift=-0.03, want_bt=True):
+        Lq = q_p.shape[0] - 2
+        Lt = t_p.shape[0] - 2
+        q_p = np.ascontiguousarray(q_p, np.float32); q_tr = np.ascontiguousarray(q_tr, np.float32)
+        t_p = np.ascontiguousarray(t_p, np.float32); t_tr = np.ascontiguousarray(t_tr, np.float32)
+        bt = np.zeros((Lq + 1, Lt + 1), np.uint8) if want_bt else None
+        sc = C.c_float(); i2 = C.c_int(); j2 = C.c_int()
+        use_ss = S33 is not None
+        self.lib.hho_viterbi_align(Lq, _p(q_p, c_f32p), _p(q_tr, c_f32p), _p(q_ss, c_u8p) if use_ss else None,
+                                   Lt, _p(t_p, c_f32p), _p(t_tr, c_f32p), _p(t_ss, c_u8p) if use_ss else None,
+                                   _p(S33, c_f32p) if use_ss else None, ssw, _p(celloff, c_u8p),
+                                   1 if local else 0, egq, egt, shift, C.byref(sc), C.byref(i2),
+                                   C.byref(j2), _p(bt, c_u8p))
+        return sc.value, i2.value, j2.value, bt
+
+    def backtrace(self, bt, i2, j2):
+        Lt = bt.shape[1] - 1
+        n = i2 + j2 + 2
+        i_s = np.zeros(n, np.int32); j_s = np.zeros(n, np.int32); st = np.zeros(n, np.uint8)
+        mc = C.c_int()
+        k = self.lib.hho_backtrace(Lt, _p(bt, c_u8p), i2, j2, _p(i_s, c_i32p), _p(j_s, c_i32p),
+                                   _p(st, c_u8p), C.byref(mc))
+        return k, i_s[:k + 1], j_s[:k + 1], st[:k + 1], mc.value
+
+    def exclude_alignment(self, celloff, i_steps, j_steps, nsteps):
+        Lq, Lt = celloff.shape[0] - 1, celloff.shape[1] - 1
+        i_s = np.ascontiguousarray(i_steps, np.int32); j_s = np.ascontiguousarray(j_steps, np.int32)
+        self.lib.hho_exclude_alignment(Lq, Lt, _p(i_s, c_i32p), _p(j_s, c_i32p), nsteps, _p(celloff, c_u8p))
+
+    def prefilter_query_profile(self, q_p, q_pav, lib219, offset=50, bit_factor=4):
+        Lq = q_p.shape[0] - 2
+        prof = np.zeros((220, Lq), np.uint8)
+        q_p = np.ascontiguousarray(q_p, np.float32)
+        q_pav = np.ascontiguousarray(q_pav, np.float32)
+        lib219 = np.ascontiguousarray(lib219, np.float32)
+        self.lib.hho_prefilter_query_profile(Lq, _p(q_p, c_f32p), _p(q_pav, c_f32p), _p(lib219, c_f32p),
+                                             offset, bit_factor, _p(prof, c_u8p))
+        return prof
+
+    def ungapped(self, prof, seq, offset=50):
+        seq = np.ascontiguousarray(seq, np.uint8)
+        return self.lib.hho_ungapped_score(prof.shape[1], _p(prof, c_u8p), _p(seq, c_u8p), len(seq), offset)
+
+
+class RefShim:
+    """The compiled reference. Raises FileNotFoundError when oracle/_ref was not built/shipped."""
+
+    def __init__(self, nocontxt=True, maxres=4096):
+        path = os.path.join(HERE, "_ref", "libhhref_shim.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = L = C.CDLL(path)
+        L.hhref_init.argtypes = [C.c_int, C.c_int]
+        L.hhref_par_shift.restype = C.c_float
+        L.hhref_par_ssw.restype = C.c_float
+        L.hhref_par_corr.restype = C.c_float
+        L.hhref_load_query_hhm.argtypes = [C.c_char_p]
+        L.hhref_get_query.argtypes = [c_f32p, c_f32p, c_f32p, c_u8p, c_u8p, c_u8p, c_f32p]
+        L.hhref_set_query.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p]
+        L.hhref_prepare_template_hhm.argtypes = [C.c_char_p, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p, c_u8p,
+                                                 c_f32p, C.c_int]
+        L.hhref_viterbi_align.argtypes = [C.c_int, c_i32p, C.POINTER(c_f32p), C.POINTER(c_f32p),
+                                          C.POINTER(c_u8p), C.POINTER(c_u8p), C.POINTER(c_u8p), C.c_int,
+                                          C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                          c_f32p, c_i32p, c_i32p, C.POINTER(c_u8p)]
+        L.hhref_backtrace.argtypes = [C.c_int, c_i32p, c_i32p, C.c_char_p, c_i32p]
+        L.hhref_score_for_backtrace.argtypes = [C.c_int, c_f32p, c_f32p]
+        L.hhref_viterbi_bench.restype = C.c_double
+        L.hhref_viterbi_bench.argtypes = [C.c_int, c_i32p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                          c_f32p, c_f32p, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_double), c_f32p]
+        L.hhref_get_cs219.argtypes = [c_f32p]
+        L.hhref_get_S33.argtypes = [c_f32p]
+        L.hhref_get_pb.argtypes = [c_f32p]
+        L.hhref_stripe_query_profile.argtypes = [C.c_int, C.c_int, c_u8p]
+        L.hhref_ungapped_score.argtypes = [c_u8p, C.c_int, c_u8p, C.c_int, C.c_int]
+        L.hhref_sw_striped_byte.argtypes = [c_u8p, C.c_int, c_u8p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hhref_ungapped_bench.restype = C.c_double
+        L.hhref_ungapped_bench.argtypes = [c_u8p, C.c_int, C.c_int, c_u8p, C.POINTER(C.c_longlong), c_i32p,
+                                           C.c_int, C.c_int, c_i32p]
+        L.hhref_init(1 if nocontxt else 0, maxres)
+        self.maxres = maxres
+        self.V = L.hhref_vecsize()
+        self.Lq = 0
+
+    # -- parameters
+    def defaults(self):
+        return dict(shift=self.lib.hhref_par_shift(), ssw=self.lib.hhref_par_ssw(),
+                    corr=self.lib.hhref_par_corr())
+
+    def S33(self):
+        out = np.zeros(44 * 44, np.float32)
+        self.lib.hhref_get_S33(_p(out, c_f32p))
+        return out
+
+    # -- query
+    def load_query_hhm(self, path):
+        L = self.lib.hhref_load_query_hhm(path.encode())
+        if L < 0:
+            raise IOError(path)
+        self.Lq = L
+        return self.get_query()
+
+    def get_query(self):
+        L = self.Lq
+        p = np.zeros((L + 2, 20), np.float32); tr = np.zeros((L + 1, 7), np.float32)
+        pav = np.zeros(20, np.float32)
+        sp = np.zeros(L + 2, np.uint8); sc = np.zeros(L + 2, np.uint8); sd = np.zeros(L + 2, np.uint8)
+        neff = C.c_float()
+        self.lib.hhref_get_query(_p(p, c_f32p), _p(tr, c_f32p), _p(pav, c_f32p), _p(sp, c_u8p),
+                                 _p(sc, c_u8p), _p(sd, c_u8p), C.byref(neff))
+        return dict(L=L, p=p, tr=tr, pav=pav, ss_pred=sp, ss_conf=sc, ss=(sp * 11 + sc).astype(np.uint8),
+                    neff=neff.value)
+
+    def set_query(self, p, tr, pav=None, ss=None):
+        L = p.shape[0] - 2
+        p = np.ascontiguousarray(p, np.float32); tr = np.ascontiguousarray(tr, np.float32)
+        sp = sc = None
+        if ss is not None:
+            sp = np.ascontiguousarray(ss // 11, np.uint8); sc = np.ascontiguousarray(ss % 11, np.uint8)
+        if pav is not None:
+            pav = np.ascontiguousarray(pav, np.float32)
+        r = self.lib.hhref_set_query(L, _p(p, c_f32p), _p(tr, c_f32p), _p(pav, c_f32p), _p(sp, c_u8p),
+                                     _p(sc, c_u8p))
+        assert r == L
+        self.Lq = L
+
+    def prepare_template_hhm(self, path, maxL=4000):
+        p = np.zeros((maxL + 2, 20), np.float32); tr = np.zeros((maxL + 1, 7), np.float32)
+        pav = np.zeros(20, np.float32)
+        sp = np.zeros(maxL + 2, np.uint8); sc = np.zeros(maxL + 2, np.uint8); sd = np.zeros(maxL + 2, np.uint8)
+        neff = C.c_float()
+        L = self.lib.hhref_prepare_template_hhm(path.encode(), _p(p, c_f32p), _p(tr, c_f32p), _p(pav, c_f32p),
+                                                _p(sp, c_u8p), _p(sc, c_u8p), _p(sd, c_u8p),
+                                                C.byref(neff), maxL)
+        if L < 0:
+            raise IOError(path)
+        return dict(L=L, p=p[:L + 2].copy(), tr=tr[:L + 1].copy(), pav=pav,
+                    ss=(sp[:L + 2] * 11 + sc[:L + 2]).astype(np.uint8), neff=neff.value)
+
+    # -- the kernel
+    def viterbi(self, targets, use_ss=False, celloff=None, local=True, egq=0.0, egt=0.0, shift=-0.03,
+                ssw=0.11, corr=0.1):
+        """targets: list (<= V) of (p, tr, ss|None). Returns list of (score, i2, j2, bt)."""
+        n = len(targets)
+        assert 1 <= n <= self.V
+        Lq = self.Lq
+        Lt = np.array([t[0].shape[0] - 2 for t in targets], np.int32)
+        ps = [np.ascontiguousarray(t[0], np.float32) for t in targets]
+        trs = [np.ascontiguousarray(t[1], np.float32) for t in targets]
+        P = (c_f32p * n)(*[_p(a, c_f32p) for a in ps])
+        T = (c_f32p * n)(*[_p(a, c_f32p) for a in trs])
+        SP = SCF = None
+        keep = []
+        if use_ss:
+            sp = [np.ascontiguousarray(t[2] // 11, np.uint8) for t in targets]
+            sc = [np.ascontiguousarray(t[2] % 11, np.uint8) for t in targets]
+            keep += sp + sc
+            SP = (c_u8p * n)(*[_p(a, c_u8p) for a in sp])
+            SCF = (c_u8p * n)(*[_p(a, c_u8p) for a in sc])
+        CO = None
+        if celloff is not None:
+            co = [None if c is None else np.ascontiguousarray(c, np.uint8) for c in celloff]
+            keep += co
+            CO = (c_u8p * n)(*[_p(a, c_u8p) for a in co])
+        bts = [np.zeros((Lq + 1, int(l) + 1), np.uint8) for l in Lt]
+        BT = (c_u8p * n)(*[_p(a, c_u8p) for a in bts])
+        score = np.zeros(n, np.float32); i2 = np.zeros(n, np.int32); j2 = np.zeros(n, np.int32)
+        r = self.lib.hhref_viterbi_align(n, _p(Lt, c_i32p), P, T, SP, SCF, CO, 1 if use_ss else 0,
+                                         1 if local else 0, egq, egt, shift, ssw, corr,
+                                         _p(score, c_f32p), _p(i2, c_i32p), _p(j2, c_i32p), BT)
+        assert r == 0, r
+        self._last = (score, i2, j2)
+        return [(float(score[k]), int(i2[k]), int(j2[k]), bts[k]) for k in range(n)]
+
+    def backtrace(self, elem):
+        score, i2, j2 = self._last
+        n = int(i2[elem] + j2[elem] + 2)
+        i_s = np.zeros(n, np.int32); j_s = np.zeros(n, np.int32)
+        st = C.create_string_buffer(n)
+        mc = C.c_int()
+        k = self.lib.hhref_backtrace(elem, _p(i_s, c_i32p), _p(j_s, c_i32p), st, C.byref(mc))
+        states = np.frombuffer(st.raw, np.uint8)[:k + 1].copy()
+        return k, i_s[:k + 1], j_s[:k + 1], states, mc.value
+
+    def hit_score(self, elem):
+        s = C.c_float(); ss = C.c_float()
+        self.lib.hhref_score_for_backtrace(elem, C.byref(s), C.byref(ss))
+        return s.value, ss.value
+
+    def viterbi_bench(self, db, threads, with_backtrace=True, repeats=1, want_scores=False):
+        """db: dict from synth.prepared_db. Returns (seconds, cells, scores|None)."""
+        N = len(db["L"])
+        L = np.ascontiguousarray(db["L"], np.int32)
+        po = np.ascontiguousarray(db["p_off"] * 20, np.int64)
+        to = np.ascontiguousarray(db["tr_off"] * 7, np.int64)
+        cells = C.c_double()
+        sc = np.zeros(N, np.float32) if want_scores else None
+        sec = self.lib.hhref_viterbi_bench(N, _p(L, c_i32p), po.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                           to.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                           _p(db["p"], c_f32p), _p(db["tr"], c_f32p), threads,
+                                           1 if with_backtrace else 0, repeats, C.byref(cells),
+                                           _p(sc, c_f32p))
+        return sec, cells.value, sc
+
+    # -- prefilter
+    def cs219(self):
+        out = np.zeros((219, 20), np.float32)
+        k = self.lib.hhref_get_cs219(_p(out, c_f32p))
+        assert k == 219
+        return out
+
+    def stripe_query_profile(self, offset=50, bit_factor=4):
+        qc = np.zeros(220 * (self.Lq + 64), np.uint8)
+        W = self.lib.hhref_stripe_query_profile(offset, bit_factor, _p(qc, c_u8p))
+        return qc, W
+
+    def ungapped(self, qc, seq, offset=50):
+        seq = np.ascontiguousarray(seq, np.uint8)
+        return self.lib.hhref_ungapped_score(_p(qc, c_u8p), self.Lq, _p(seq, c_u8p), len(seq), offset)
+
+    def sw_byte(self, qc, seq, gap_open=24, gap_extend=4, offset=50):
+        seq = np.ascontiguousarray(seq, np.uint8)
+        return self.lib.hhref_sw_striped_byte(_p(qc, c_u8p), self.Lq, _p(seq, c_u8p), len(seq), gap_open,
+                                              gap_extend, offset)
+
+    def ungapped_bench(self, qc, db, threads, offset=50):
+        N = len(db["L"])
+        sc = np.zeros(N, np.int32)
+        L = np.ascontiguousarray(db["L"], np.int32)
+        off = np.ascontiguousarray(db["off"], np.int64)
+        sec = self.lib.hhref_ungapped_bench(_p(qc, c_u8p), self.Lq, N, _p(db["seq"], c_u8p),
+                                            off.ctypes.data_as(C.POINTER(C.c_longlong)), _p(L, c_i32p),
+                                            offset, threads, _p(sc, c_i32p))
+        return sec, sc

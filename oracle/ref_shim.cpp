@@ -1,0 +1,419 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// A thin C-ABI driver around the UNMODIFIED reference (soedinglab/hh-suite) compiled by
+// oracle/ref_build.mk into oracle/_ref/libhhref.a.  It lets tests / bench.py's cpu_baseline
+//   * run the reference's own HHM reader + PrepareQueryHMM / PrepareTemplateHMM
+//     (src/hhfunc.cpp:121-202) and export the prepared fp32 DP inputs,
+//   * feed arbitrary prepared profiles through the reference's own AVX2 kernel
+//     Viterbi::Align (src/hhviterbi.cpp:163, src/hhviterbialgorithm.cpp:29-497),
+//     Viterbi::Backtrace (src/hhviterbi.cpp:83) and ScoreForBacktrace (:195),
+//   * call Prefilter::stripe_query_profile / ungapped_sse_score / swStripedByte
+//     (src/hhprefilter.cpp:356,214,70),
+//   * time the reference kernel on all host cores the way ViterbiRunner::alignment does
+//     (src/hhviterbirunner.cpp:117-128: length-sorted batches of VECSIZE_FLOAT, OpenMP dynamic,1).
+// Nothing here is linked into the product library (hh-suite_b200/csrc).  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference may load the .so.
+//
+// This file contains no reference code: it only includes the reference headers at build time
+// (-I/root/reference/src) and calls their API.  Private members are reached with the usual
+// test-harness trick (#define private public) after the std headers are included.
+
+#include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+#define private public
+#define protected public
+#include "hhdecl.h"
+#include "hhhmm.h"
+#include "hhhmmsimd.h"
+#include "hhviterbi.h"
+#include "hhviterbimatrix.h"
+#include "hhmatrices.h"
+#include "hhfunc.h"
+#include "hhprefilter.h"
+#include "hhhit.h"
+#include "cs219.lib.h"
+#undef private
+#undef protected
+
+namespace {
+
+struct RefCtx {
+  Parameters* par = nullptr;
+  float pb[21] __attribute__((aligned(32)));
+  float P[20][20] __attribute__((aligned(32)));
+  float R[20][20] __attribute__((aligned(32)));
+  float S[20][20] __attribute__((aligned(32)));
+  float Sim[20][20] __attribute__((aligned(32)));
+  float S73[NDSSP][NSSPRED][MAXCF];
+  float S37[NSSPRED][MAXCF][NDSSP];
+  float S33[NSSPRED][MAXCF][NSSPRED][MAXCF];
+  cs::ContextLibrary<cs::AA>* context_lib = nullptr;
+  cs::Crf<cs::AA>* crf = nullptr;
+  cs::Pseudocounts<cs::AA>* pc_hhm_context_engine = nullptr;
+  cs::Admix* pc_hhm_context_mode = nullptr;
+  cs::Pseudocounts<cs::AA>* pc_prefilter_context_engine = nullptr;
+  cs::Admix* pc_prefilter_context_mode = nullptr;
+  int maxres = 0;
+  HMM* q = nullptr;
+  HMMSimd* q_simd = nullptr;
+  // last batch state (for backtrace / scoring)
+  std::vector<HMM*> t_hmm;
+  HMMSimd* t_simd = nullptr;
+  ViterbiMatrix* matrix = nullptr;
+  Viterbi* viterbi = nullptr;
+  Viterbi::ViterbiResult last;
+  int last_ss_mode = 0;
+  Prefilter* prefilter = nullptr;  // raw storage, ctor never run (needs an ffindex DB)
+};
+
+RefCtx* g = nullptr;
+const char* kArgv[] = {"hhalign"};
+
+// tr index map: caller uses the reference's HMM enum order M2M,M2I,M2D,I2M,I2I,D2M,D2D (src/hhdecl.h:68)
+void fill_hmm(HMM* h, int L, const float* p, const float* tr, const unsigned char* ss_pred,
+              const unsigned char* ss_conf, const unsigned char* ss_dssp) {
+  h->L = L;
+  for (int i = 0; i <= L + 1 && i < h->maxres; ++i) {
+    for (int a = 0; a < 20; ++a) h->p[i][a] = p[(size_t)i * 20 + a];
+  }
+  for (int i = 0; i <= L; ++i)
+    for (int k = 0; k < 7; ++k) h->tr[i][k] = tr[(size_t)i * 7 + k];
+  h->nss_pred = h->nss_conf = h->nss_dssp = -1;
+  for (int i = 0; i <= L + 1 && i < h->maxres; ++i) {
+    h->ss_pred[i] = ss_pred ? (char)ss_pred[i] : 0;
+    h->ss_conf[i] = ss_conf ? (char)ss_conf[i] : 0;
+    h->ss_dssp[i] = ss_dssp ? (char)ss_dssp[i] : 0;
+  }
+  if (ss_pred) { h->nss_pred = 0; h->nss_conf = 0; }
+  if (ss_dssp) h->nss_dssp = 0;
+  h->mu = 0; h->lamda = 0;
+}
+
+void export_hmm(HMM* h, float* p, float* tr, float* pav, unsigned char* ss_pred,
+                unsigned char* ss_conf, unsigned char* ss_dssp, float* neff) {
+  const int L = h->L;
+  if (p) for (int i = 0; i <= L + 1; ++i) for (int a = 0; a < 20; ++a) p[(size_t)i * 20 + a] = h->p[i][a];
+  if (tr) for (int i = 0; i <= L; ++i) for (int k = 0; k < 7; ++k) tr[(size_t)i * 7 + k] = h->tr[i][k];
+  if (pav) for (int a = 0; a < 20; ++a) pav[a] = h->pav[a];
+  for (int i = 0; i <= L + 1; ++i) {
+    if (ss_pred) ss_pred[i] = (h->nss_pred >= 0) ? (unsigned char)h->ss_pred[i] : 0;
+    if (ss_conf) ss_conf[i] = (h->nss_conf >= 0) ? (unsigned char)h->ss_conf[i] : 0;
+    if (ss_dssp) ss_dssp[i] = (h->nss_dssp >= 0) ? (unsigned char)h->ss_dssp[i] : 0;
+  }
+  if (neff) *neff = h->Neff_HMM;
+}
+
+}  // namespace
+
+extern "C" {
+
+// flags: bit0 = nocontxt (substitution-matrix pseudocounts for the query instead of the CRF)
+int hhref_init(int nocontxt, int maxres) {
+  if (g) return 0;
+  Log::reporting_level() = WARNING;
+  g = new RefCtx();
+  g->par = new Parameters(1, kArgv);
+  g->par->nocontxt = nocontxt ? 1 : 0;
+  g->par->maxres = maxres;
+  g->par->threads = 1;
+  g->maxres = maxres;
+  SetSubstitutionMatrix(g->par->matrix, g->pb, g->P, g->R, g->S, g->Sim);
+  SetSecStrucSubstitutionMatrix(g->par->ssa, g->S73, g->S37, g->S33);
+  if (!nocontxt)
+    InitializePseudocountsEngine(*g->par, g->context_lib, g->crf, g->pc_hhm_context_engine,
+                                 g->pc_hhm_context_mode, g->pc_prefilter_context_engine,
+                                 g->pc_prefilter_context_mode);
+  g->q = new HMM(MAXSEQDIS, maxres);
+  g->q_simd = new HMMSimd(maxres);
+  g->t_simd = new HMMSimd(maxres);
+  g->matrix = new ViterbiMatrix();
+  for (int i = 0; i < VECSIZE_FLOAT; ++i) g->t_hmm.push_back(new HMM(64, maxres));
+  return 0;
+}
+
+int hhref_vecsize() { return VECSIZE_FLOAT; }
+
+// Parameter getters so tests use the reference's own defaults (src/hhdecl.cpp:82-127)
+float hhref_par_shift() { return g->par->shift; }
+float hhref_par_ssw() { return g->par->ssw; }
+float hhref_par_corr() { return g->par->corr; }
+int hhref_par_ssm() { return g->par->ssm; }
+
+// S33 table (for the SS variant): out[NSSPRED*MAXCF*NSSPRED*MAXCF]
+void hhref_get_S33(float* out) { memcpy(out, g->S33, sizeof(g->S33)); }
+void hhref_get_pb(float* out) { memcpy(out, g->pb, 20 * sizeof(float)); }
+
+// Read query HHM, add pseudocounts exactly like HHalign::run (src/hhalign.cpp:615-626), map to SIMD.
+int hhref_load_query_hhm(const char* path) {
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  char pathbuf[NAMELEN];
+  Pathname(pathbuf, const_cast<char*>(path));
+  g->q->Read(f, g->par->maxcol, g->par->nseqdis, g->pb, pathbuf);
+  fclose(f);
+  char input_format = 0;
+  PrepareQueryHMM(*g->par, input_format, g->q, g->pc_hhm_context_engine, g->pc_hhm_context_mode,
+                  g->pb, g->R);
+  g->q_simd->MapOneHMM(g->q);
+  return g->q->L;
+}
+
+int hhref_get_query(float* p, float* tr, float* pav, unsigned char* ss_pred, unsigned char* ss_conf,
+                    unsigned char* ss_dssp, float* neff) {
+  export_hmm(g->q, p, tr, pav, ss_pred, ss_conf, ss_dssp, neff);
+  return g->q->L;
+}
+
+// Install a synthetic, already prepared query.
+int hhref_set_query(int L, const float* p, const float* tr, const float* pav,
+                    const unsigned char* ss_pred, const unsigned char* ss_conf) {
+  if (L + 2 > g->maxres) return -1;
+  fill_hmm(g->q, L, p, tr, ss_pred, ss_conf, nullptr);
+  if (pav) for (int a = 0; a < 20; ++a) g->q->pav[a] = pav[a];
+  g->q_simd->MapOneHMM(g->q);
+  return L;
+}
+
+// Read a template HHM and run PrepareTemplateHMM against the current query
+// (src/hhviterbirunner.cpp:144-147); export the DP inputs.
+int hhref_prepare_template_hhm(const char* path, float* p, float* tr, float* pav,
+                               unsigned char* ss_pred, unsigned char* ss_conf,
+                               unsigned char* ss_dssp, float* neff, int maxL) {
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  HMM* t = new HMM(MAXSEQDIS, g->maxres);
+  char pathbuf[NAMELEN];
+  Pathname(pathbuf, const_cast<char*>(path));
+  t->Read(f, g->par->maxcol, g->par->nseqdis, g->pb, pathbuf);
+  fclose(f);
+  PrepareTemplateHMM(*g->par, g->q, t, 0, false, g->pb, g->R);
+  int L = t->L;
+  if (L > maxL) { delete t; return -2; }
+  export_hmm(t, p, tr, pav, ss_pred, ss_conf, ss_dssp, neff);
+  delete t;
+  return L;
+}
+
+// Run the reference AVX2 kernel on one batch of n<=VECSIZE_FLOAT prepared targets.
+//  t_p[k]: (Lt+2)*20, t_tr[k]: (Lt+1)*7 in HMM enum order, t_ss_pred/conf[k]: Lt+2 bytes or NULL
+//  celloff[k]: (Lq+1)*(Lt_k+1) bytes (non-zero = cell off) or NULL
+//  bt_out[k]:  (Lq+1)*(Lt_k+1) bytes, row-major [i][j], filled for 1<=i<=Lq,1<=j<=Lt_k
+int hhref_viterbi_align(int n, const int* Lt, const float* const* t_p, const float* const* t_tr,
+                        const unsigned char* const* t_ss_pred, const unsigned char* const* t_ss_conf,
+                        const unsigned char* const* celloff, int use_ss, int local, float egq,
+                        float egt, float shift, float ssw, float corr, float* score, int* i2,
+                        int* j2, unsigned char* const* bt_out) {
+  if (n < 1 || n > VECSIZE_FLOAT) return -1;
+  const int Lq = g->q->L;
+  int maxLt = 0;
+  std::vector<HMM*> v;
+  for (int k = 0; k < n; ++k) {
+    if (Lt[k] + 2 > g->maxres) return -2;
+    fill_hmm(g->t_hmm[k], Lt[k], t_p[k], t_tr[k], t_ss_pred ? t_ss_pred[k] : nullptr,
+             t_ss_conf ? t_ss_conf[k] : nullptr, nullptr);
+    v.push_back(g->t_hmm[k]);
+    maxLt = std::max(maxLt, Lt[k]);
+  }
+  g->t_simd->MapHMMVector(v);
+  g->matrix->AllocateBacktraceMatrix(Lq, maxLt);
+  // clear all bytes (a fresh reference matrix is not zeroed; cell-off bits must be defined)
+  for (int i = 0; i <= Lq; ++i) memset(g->matrix->getRow(i), 0, (size_t)(maxLt + 1) * VECSIZE_FLOAT);
+  g->matrix->setCellOff(false);
+  bool any_co = false;
+  if (celloff)
+    for (int k = 0; k < n; ++k)
+      if (celloff[k])
+        for (int i = 1; i <= Lq; ++i)
+          for (int j = 1; j <= Lt[k]; ++j)
+            if (celloff[k][(size_t)i * (Lt[k] + 1) + j]) { g->matrix->setCellOff(i, j, k, true); any_co = true; }
+  (void)any_co;
+  delete g->viterbi;
+  g->viterbi = new Viterbi(g->maxres, local != 0, egq, egt, corr, g->par->min_overlap, shift,
+                           g->par->ssm, ssw, g->S73, g->S33, g->S37);
+  const int ss_hmm_mode = use_ss ? HMM::PRED_PRED : HMM::NO_SS_INFORMATION;
+  g->last_ss_mode = ss_hmm_mode;
+  Viterbi::ViterbiResult* r = g->viterbi->Align(g->q_simd, g->t_simd, g->matrix, n, ss_hmm_mode);
+  g->last = *r;
+  for (int k = 0; k < n; ++k) {
+    score[k] = r->score[k]; i2[k] = r->i[k]; j2[k] = r->j[k];
+    if (bt_out && bt_out[k])
+      for (int i = 1; i <= Lq; ++i) {
+        const unsigned char* row = g->matrix->getRow(i);
+        for (int j = 1; j <= Lt[k]; ++j)
+          bt_out[k][(size_t)i * (Lt[k] + 1) + j] = row[j * VECSIZE_FLOAT + k];
+      }
+  }
+  delete r;
+  return 0;
+}
+
+// Viterbi::Backtrace on lane `elem` of the last batch. Arrays sized >= i2+j2+2. Returns nsteps.
+int hhref_backtrace(int elem, int* i_steps, int* j_steps, char* states, int* matched_cols) {
+  Viterbi::BacktraceResult b = Viterbi::Backtrace(g->matrix, elem, g->last.i, g->last.j);
+  for (int s = 0; s <= b.count; ++s) { i_steps[s] = s ? b.i_steps[s] : 0; j_steps[s] = s ? b.j_steps[s] : 0; states[s] = s ? b.states[s] : 0; }
+  *matched_cols = b.matched_cols;
+  int n = b.count;
+  delete[] b.i_steps; delete[] b.j_steps; delete[] b.states;
+  return n;
+}
+
+// Hit.score as the runner computes it (src/hhviterbirunner.cpp:29-42 -> hhviterbi.cpp:195-281)
+int hhref_score_for_backtrace(int elem, float* score, float* score_ss) {
+  Viterbi::BacktraceResult b = Viterbi::Backtrace(g->matrix, elem, g->last.i, g->last.j);
+  Viterbi::BacktraceScore s = g->viterbi->ScoreForBacktrace(g->q_simd, g->t_simd, elem, &b,
+                                                            g->last.score, g->last_ss_mode);
+  *score = s.score; *score_ss = s.score_ss;
+  delete[] s.S; delete[] s.S_ss;
+  delete[] b.i_steps; delete[] b.j_steps; delete[] b.states;
+  return b.count;
+}
+
+// CPU baseline: the reference AVX2 kernel over N prepared targets, batched/sorted like the runner
+// (src/hhviterbirunner.cpp:117-128).  db_p: concatenated per-target (L+2)*20, db_tr: (L+1)*7.
+// Returns seconds spent in Align(+Backtrace); *cells = Lq * sum(Lt).
+double hhref_viterbi_bench(int N, const int* Lt, const long long* p_off, const long long* tr_off,
+                           const float* db_p, const float* db_tr, int threads, int with_backtrace,
+                           int repeats, double* cells, float* scores_out) {
+  const int V = VECSIZE_FLOAT;
+  const int Lq = g->q->L;
+  std::vector<int> order(N);
+  for (int i = 0; i < N; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return Lt[a] > Lt[b]; });
+  const int nb = (N + V - 1) / V;
+  int maxL = 0;
+  for (int i = 0; i < N; ++i) maxL = std::max(maxL, Lt[i]);
+  // Pre-map every batch to its lane-interleaved form (time only Align+Backtrace)
+  std::vector<HMMSimd*> simd(nb);
+  std::vector<std::vector<HMM*>> hmms(nb);
+  for (int b = 0; b < nb; ++b) {
+    int n = std::min(V, N - b * V);
+    int bl = 0;
+    for (int k = 0; k < n; ++k) bl = std::max(bl, Lt[order[b * V + k]]);
+    simd[b] = new HMMSimd(bl + 2);
+    for (int k = 0; k < n; ++k) {
+      int t = order[b * V + k];
+      HMM* h = new HMM(2, Lt[t] + 2);
+      fill_hmm(h, Lt[t], db_p + p_off[t], db_tr + tr_off[t], nullptr, nullptr, nullptr);
+      hmms[b].push_back(h);
+    }
+    simd[b]->MapHMMVector(hmms[b]);
+  }
+  std::vector<Viterbi*> vit(threads);
+  std::vector<ViterbiMatrix*> mat(threads);
+  for (int t = 0; t < threads; ++t) {
+    vit[t] = new Viterbi(maxL + 2, g->par->loc, g->par->egq, g->par->egt, g->par->corr,
+                         g->par->min_overlap, g->par->shift, g->par->ssm, g->par->ssw, g->S73,
+                         g->S33, g->S37);
+    mat[t] = new ViterbiMatrix();
+    mat[t]->AllocateBacktraceMatrix(Lq, maxL);
+  }
+  double c = 0;
+  for (int i = 0; i < N; ++i) c += (double)Lq * Lt[i];
+  *cells = c * repeats;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int rep = 0; rep < repeats; ++rep) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+    for (int b = 0; b < nb; ++b) {
+      int tid = omp_get_thread_num();
+      int n = std::min(V, N - b * V);
+      Viterbi::ViterbiResult* r = vit[tid]->Align(g->q_simd, simd[b], mat[tid], n, HMM::NO_SS_INFORMATION);
+      if (with_backtrace)
+        for (int k = 0; k < n; ++k) {
+          Viterbi::BacktraceResult bt = Viterbi::Backtrace(mat[tid], k, r->i, r->j);
+          delete[] bt.i_steps; delete[] bt.j_steps; delete[] bt.states;
+        }
+      if (scores_out)
+        for (int k = 0; k < n; ++k) scores_out[order[b * V + k]] = r->score[k];
+      delete r;
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  for (int b = 0; b < nb; ++b) { for (HMM* h : hmms[b]) delete h; delete simd[b]; }
+  for (int t = 0; t < threads; ++t) { delete vit[t]; delete mat[t]; }
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---------------------------------------------------------------- prefilter pieces
+static void ensure_prefilter() {
+  if (g->prefilter) return;
+  // Prefilter's ctor needs an ffindex DB; the three routines we call only use cs_lib.
+  g->prefilter = (Prefilter*)calloc(1, sizeof(Prefilter));
+  FILE* fin = fmemopen((void*)_binary_cs219_lib_start,
+                       (size_t)(_binary_cs219_lib_end - _binary_cs219_lib_start), "r");
+  g->prefilter->cs_lib = new cs::ContextLibrary<cs::AA>(fin);
+  fclose(fin);
+  cs::TransformToLin(*g->prefilter->cs_lib);
+}
+
+// 219 x 20 linear column-state probabilities (cs219.lib after TransformToLin, src/hhprefilter.cpp:41-44)
+int hhref_get_cs219(float* out) {
+  ensure_prefilter();
+  const cs::ContextLibrary<cs::AA>& lib = *g->prefilter->cs_lib;
+  for (int k = 0; k < (int)cs::AS219::kSize; ++k)
+    for (int a = 0; a < 20; ++a) out[k * 20 + a] = lib[k].probs[0][a];
+  return (int)cs::AS219::kSize;
+}
+
+// striped query profile from the CURRENT query HMM; qc must hold 220*(Lq+32) bytes. Returns W.
+int hhref_stripe_query_profile(int score_offset, int bit_factor, unsigned char* qc) {
+  ensure_prefilter();
+  const int ec = VECSIZE_INT * 4;
+  const int W = (g->q->L + ec - 1) / ec;
+  g->prefilter->stripe_query_profile(g->q, score_offset, bit_factor, W, qc);
+  return W;
+}
+
+int hhref_ungapped_score(const unsigned char* qc, int Lq, const unsigned char* dbseq, int L, int offset) {
+  ensure_prefilter();
+  const int ec = VECSIZE_INT * 4;
+  simd_int* ws = (simd_int*)malloc_simd_int(3 * (Lq + ec) * sizeof(char));
+  int s = g->prefilter->ungapped_sse_score(qc, Lq, dbseq, L, (unsigned char)offset, ws);
+  free(ws);
+  return s;
+}
+
+int hhref_sw_striped_byte(unsigned char* qc, int Lq, unsigned char* dbseq, int L, int gap_open,
+                          int gap_extend, int offset) {
+  ensure_prefilter();
+  const int ec = VECSIZE_INT * 4;
+  const int W = (Lq + ec - 1) / ec;
+  simd_int* ws = (simd_int*)malloc_simd_int(3 * (Lq + ec) * sizeof(char));
+  int s = g->prefilter->swStripedByte(qc, Lq, dbseq, L, (unsigned short)gap_open,
+                                      (unsigned short)gap_extend, ws, ws + W, ws + 2 * W,
+                                      (unsigned short)offset);
+  free(ws);
+  return s;
+}
+
+// Reference ungapped prefilter over a whole cs219 DB on `threads` cores (src/hhprefilter.cpp:466-482).
+double hhref_ungapped_bench(const unsigned char* qc, int Lq, int N, const unsigned char* db,
+                            const long long* off, const int* len, int offset, int threads,
+                            int* scores) {
+  ensure_prefilter();
+  const int ec = VECSIZE_INT * 4;
+  std::vector<simd_int*> ws(threads);
+  for (int t = 0; t < threads; ++t) ws[t] = (simd_int*)malloc_simd_int(3 * (Lq + ec) * sizeof(char));
+  auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(static) num_threads(threads)
+  for (int n = 0; n < N; ++n)
+    scores[n] = g->prefilter->ungapped_sse_score(qc, Lq, db + off[n], len[n], (unsigned char)offset,
+                                                 ws[omp_get_thread_num()]);
+  auto t1 = std::chrono::steady_clock::now();
+  for (int t = 0; t < threads; ++t) free(ws[t]);
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
