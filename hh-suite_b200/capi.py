@@ -1,0 +1,281 @@
+"""ctypes binding of the C-ABI in include/hhg.h (the only way Python reaches the kernels).
+
+The classes mirror the reference's objects on this path:
+  Context  ~ one ViterbiRunner worker (stream + scratch)        src/hhviterbirunner.h:52
+  TargetDB ~ the HMMSimd batches of the whole shard, resident   src/hhhmmsimd.h:8
+  Plan     ~ one ViterbiRunner::alignment call over a target list
+There is no CPU fallback: loading fails loudly when the library or a GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+
+
+class Params(C.Structure):
+    _fields_ = [("local", C.c_int), ("egq", C.c_float), ("egt", C.c_float), ("shift", C.c_float),
+                ("ssw", C.c_float), ("use_ss", C.c_int)]
+
+
+HIT_DTYPE = np.dtype([("score", np.float32), ("i2", np.int32), ("j2", np.int32), ("i1", np.int32),
+                      ("j1", np.int32), ("nsteps", np.int32), ("matched_cols", np.int32),
+                      ("path_off", np.int32)])
+
+SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync", "hhg_ctx_launch_count",
+           "hhg_db_create", "hhg_db_destroy", "hhg_db_size", "hhg_db_columns", "hhg_query_set",
+           "hhg_viterbi_search", "hhg_plan_create", "hhg_plan_destroy", "hhg_plan_run", "hhg_plan_fetch",
+           "hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes", "hhg_plan_debug_bt",
+           "hhg_csdb_create", "hhg_csdb_destroy", "hhg_prefilter_ungapped", "hhg_prefilter_ungapped_run",
+           "hhg_prefilter_fetch"]
+
+
+class HhgError(RuntimeError):
+    pass
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return os.path.join(HERE, "libhhg.so")
+
+
+def load():
+    """Load libhhg.so (building it first if a toolchain is present). Never falls back to CPU code."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    from . import build as _build
+    path = _build.build()
+    L = C.CDLL(path)
+    L.hhg_last_error.restype = C.c_char_p
+    L.hhg_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.hhg_ctx_destroy.argtypes = [C.c_void_p]
+    L.hhg_ctx_sync.argtypes = [C.c_void_p]
+    L.hhg_ctx_launch_count.argtypes = [C.c_void_p]
+    L.hhg_ctx_launch_count.restype = C.c_longlong
+    L.hhg_db_create.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i64p, c_i64p, c_i64p, c_f32p, c_f32p, c_u8p,
+                                C.POINTER(C.c_void_p)]
+    L.hhg_db_destroy.argtypes = [C.c_void_p]
+    L.hhg_db_size.argtypes = [C.c_void_p]
+    L.hhg_db_columns.argtypes = [C.c_void_p]
+    L.hhg_db_columns.restype = C.c_longlong
+    L.hhg_query_set.argtypes = [C.c_void_p, C.c_int, c_f32p, c_f32p, c_u8p, c_f32p, C.POINTER(Params)]
+    L.hhg_viterbi_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, C.c_void_p, c_u8p, C.c_size_t,
+                                     c_i64p, c_i32p, c_i32p]
+    L.hhg_plan_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, C.POINTER(C.c_void_p)]
+    L.hhg_plan_destroy.argtypes = [C.c_void_p]
+    L.hhg_plan_run.argtypes = [C.c_void_p, C.c_void_p]
+    L.hhg_plan_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, c_u8p, C.c_size_t]
+    for f in ("hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes"):
+        getattr(L, f).argtypes = [C.c_void_p]
+        getattr(L, f).restype = C.c_double
+    L.hhg_plan_debug_bt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p]
+    L.hhg_csdb_create.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i64p, c_u8p, C.POINTER(C.c_void_p)]
+    L.hhg_csdb_destroy.argtypes = [C.c_void_p]
+    L.hhg_prefilter_ungapped.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p, C.c_int, c_i32p]
+    L.hhg_prefilter_ungapped_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p, C.c_int, C.c_int]
+    L.hhg_prefilter_fetch.argtypes = [C.c_void_p, C.c_void_p, c_i32p]
+    _lib = L
+    return L
+
+
+def _ck(rc):
+    if rc != 0:
+        raise HhgError(f"hhg error {rc}: {load().hhg_last_error().decode()}")
+
+
+class Context:
+    def __init__(self, device: int = -1, stream: int | None = None):
+        self.L = load()
+        h = C.c_void_p()
+        _ck(self.L.hhg_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.Lq = 0
+
+    def close(self):
+        if self.h:
+            self.L.hhg_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        _ck(self.L.hhg_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.hhg_ctx_launch_count(self.h))
+
+    def set_query(self, p, tr, ss=None, S33=None, local=True, egq=0.0, egt=0.0, shift=-0.03, ssw=0.11,
+                  use_ss=False):
+        p = np.ascontiguousarray(p, np.float32); tr = np.ascontiguousarray(tr, np.float32)
+        Lq = p.shape[0] - 2
+        assert tr.shape[0] == Lq + 1
+        ss = None if ss is None else np.ascontiguousarray(ss, np.uint8)
+        S33 = None if S33 is None else np.ascontiguousarray(S33, np.float32)
+        par = Params(1 if local else 0, egq, egt, shift, ssw, 1 if use_ss else 0)
+        _ck(self.L.hhg_query_set(self.h, Lq, _p(p, c_f32p), _p(tr, c_f32p), _p(ss, c_u8p), _p(S33, c_f32p),
+                                 C.byref(par)))
+        self.Lq = Lq
+
+
+class TargetDB:
+    """Device-resident shard of prepared target profiles (see synth.prepared_db for the host layout)."""
+
+    def __init__(self, ctx: Context, L, p, tr, p_off, tr_off, ss=None):
+        self.ctx = ctx
+        self.Lh = np.ascontiguousarray(L, np.int32)
+        n = len(self.Lh)
+        p = np.ascontiguousarray(p, np.float32); tr = np.ascontiguousarray(tr, np.float32)
+        po = np.ascontiguousarray(np.asarray(p_off, np.int64) * 20)
+        to = np.ascontiguousarray(np.asarray(tr_off, np.int64) * 7)
+        so = np.ascontiguousarray(np.asarray(p_off, np.int64))
+        ss = None if ss is None else np.ascontiguousarray(ss, np.uint8)
+        h = C.c_void_p()
+        _ck(ctx.L.hhg_db_create(ctx.h, n, _p(self.Lh, c_i32p), _p(po, c_i64p), _p(to, c_i64p), _p(so, c_i64p),
+                                _p(p, c_f32p), _p(tr, c_f32p), _p(ss, c_u8p), C.byref(h)))
+        self.h = h
+        self.n = n
+
+    @classmethod
+    def from_profiles(cls, ctx, profiles):
+        """profiles: list of (p[(L+2),20], tr[(L+1),7], ss[L+2]|None)."""
+        L = np.array([q[0].shape[0] - 2 for q in profiles], np.int32)
+        p_off = np.concatenate([[0], np.cumsum(L.astype(np.int64) + 2)[:-1]])
+        tr_off = np.concatenate([[0], np.cumsum(L.astype(np.int64) + 1)[:-1]])
+        P = np.concatenate([q[0] for q in profiles]).astype(np.float32)
+        T = np.concatenate([q[1] for q in profiles]).astype(np.float32)
+        has_ss = all(q[2] is not None for q in profiles)
+        S = np.concatenate([q[2] for q in profiles]).astype(np.uint8) if has_ss else None
+        return cls(ctx, L, P, T, p_off, tr_off, S)
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hhg_db_destroy(self.h)
+            self.h = None
+
+
+class Plan:
+    def __init__(self, ctx: Context, db: TargetDB, ids=None):
+        self.ctx, self.db = ctx, db
+        self.ids = np.arange(db.n, dtype=np.int32) if ids is None else np.ascontiguousarray(ids, np.int32)
+        self.n = len(self.ids)
+        h = C.c_void_p()
+        _ck(ctx.L.hhg_plan_create(ctx.h, db.h, self.n, _p(self.ids, c_i32p), C.byref(h)))
+        self.h = h
+        self.cells = ctx.L.hhg_plan_cells(h)
+        self.padded_cells = ctx.L.hhg_plan_padded_cells(h)
+        self.alg_bytes = ctx.L.hhg_plan_algorithmic_bytes(h)
+        self.path_cap = int(np.sum(self.ctx.Lq + db.Lh[self.ids].astype(np.int64) + 2))
+
+    def run(self):
+        _ck(self.ctx.L.hhg_plan_run(self.ctx.h, self.h))
+
+    def fetch(self, want_paths=True):
+        hits = np.zeros(self.n, HIT_DTYPE)
+        paths = np.zeros(self.path_cap, np.uint8) if want_paths else None
+        _ck(self.ctx.L.hhg_plan_fetch(self.ctx.h, self.h, hits.ctypes.data_as(C.c_void_p), _p(paths, c_u8p),
+                                      self.path_cap if want_paths else 0))
+        return hits, paths
+
+    def debug_bt(self, k):
+        Lt = int(self.db.Lh[self.ids[k]])
+        bt = np.zeros((self.ctx.Lq + 1, Lt + 1), np.uint8)
+        _ck(self.ctx.L.hhg_plan_debug_bt(self.ctx.h, self.h, k, _p(bt, c_u8p)))
+        return bt
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hhg_plan_destroy(self.h)
+            self.h = None
+
+
+def viterbi_search(ctx: Context, db: TargetDB, ids=None, exclusions=None, want_paths=True):
+    """One ViterbiRunner::alignment-style call with host buffers in and out.
+    exclusions: optional list (per request) of (i_steps, j_steps) int arrays to mask (alt. alignments)."""
+    ids = np.arange(db.n, dtype=np.int32) if ids is None else np.ascontiguousarray(ids, np.int32)
+    n = len(ids)
+    hits = np.zeros(n, HIT_DTYPE)
+    cap = int(np.sum(ctx.Lq + db.Lh[ids].astype(np.int64) + 2))
+    paths = np.zeros(cap, np.uint8) if want_paths else None
+    eo = ei = ej = None
+    if exclusions is not None:
+        cnt = np.array([0 if e is None else len(e[0]) for e in exclusions], np.int64)
+        eo = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        ei = np.concatenate([np.asarray(e[0], np.int32) for e in exclusions if e is not None] or
+                            [np.zeros(0, np.int32)]).astype(np.int32)
+        ej = np.concatenate([np.asarray(e[1], np.int32) for e in exclusions if e is not None] or
+                            [np.zeros(0, np.int32)]).astype(np.int32)
+        if len(ei) == 0:
+            ei = np.zeros(1, np.int32); ej = np.zeros(1, np.int32)
+    _ck(ctx.L.hhg_viterbi_search(ctx.h, db.h, n, _p(ids, c_i32p), hits.ctypes.data_as(C.c_void_p),
+                                 _p(paths, c_u8p), cap if want_paths else 0, _p(eo, c_i64p), _p(ei, c_i32p),
+                                 _p(ej, c_i32p)))
+    return hits, paths
+
+
+def expand_path(hit, paths):
+    """(i_steps, j_steps, states) arrays indexed 1..nsteps like Viterbi::BacktraceResult."""
+    n = int(hit["nsteps"])
+    st = paths[int(hit["path_off"]):int(hit["path_off"]) + n]
+    i_s = np.zeros(n + 1, np.int32); j_s = np.zeros(n + 1, np.int32); s_s = np.zeros(n + 1, np.uint8)
+    i, j = int(hit["i2"]), int(hit["j2"])
+    # replay the walk: the recorded state at each step decides which index moved (src/hhviterbi.cpp:106-140);
+    # the last recorded state was overwritten with MM, but positions do not depend on it.
+    for k in range(n):
+        i_s[k + 1], j_s[k + 1], s_s[k + 1] = i, j, st[k]
+        s = st[k] if k < n - 1 else None
+        if s == 2:
+            i -= 1; j -= 1
+        elif s in (3, 4):
+            j -= 1
+        elif s in (5, 6):
+            i -= 1
+    return i_s, j_s, s_s
+
+
+class CsDB:
+    def __init__(self, ctx: Context, L, off, seq):
+        self.ctx = ctx
+        self.Lh = np.ascontiguousarray(L, np.int32)
+        off = np.ascontiguousarray(off, np.int64); seq = np.ascontiguousarray(seq, np.uint8)
+        h = C.c_void_p()
+        _ck(ctx.L.hhg_csdb_create(ctx.h, len(self.Lh), _p(self.Lh, c_i32p), _p(off, c_i64p), _p(seq, c_u8p),
+                                  C.byref(h)))
+        self.h = h
+        self.n = len(self.Lh)
+
+    def ungapped(self, prof, offset=50):
+        prof = np.ascontiguousarray(prof, np.uint8)
+        assert prof.shape[0] == 220
+        sc = np.zeros(self.n, np.int32)
+        _ck(self.ctx.L.hhg_prefilter_ungapped(self.ctx.h, self.h, prof.shape[1], _p(prof, c_u8p), offset,
+                                              _p(sc, c_i32p)))
+        return sc
+
+    def run(self, prof, offset=50, upload=True):
+        prof = np.ascontiguousarray(prof, np.uint8)
+        _ck(self.ctx.L.hhg_prefilter_ungapped_run(self.ctx.h, self.h, prof.shape[1], _p(prof, c_u8p), offset,
+                                                  1 if upload else 0))
+
+    def fetch(self):
+        sc = np.zeros(self.n, np.int32)
+        _ck(self.ctx.L.hhg_prefilter_fetch(self.ctx.h, self.h, _p(sc, c_i32p)))
+        return sc
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hhg_csdb_destroy(self.h)
+            self.h = None

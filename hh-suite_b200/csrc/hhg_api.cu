@@ -1,0 +1,693 @@
+// hh-suite_b200/csrc/hhg_api.cu -- the C-ABI (include/hhg.h) over the sm_100a kernels.
+// Host side: planning (length-sorted 32-target warp jobs, strip work items, memory waves),
+// device memory, launches.  There is no CPU fallback: without a CUDA device every entry point fails.
+#include "../../include/hhg.h"
+#include "hhg_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace hhg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(expr)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(e__ == cudaErrorMemoryAllocation ? HHG_ENOMEM : HHG_ECUDA, "%s: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                   \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc((void**)&p, count * sizeof(T));
+  }
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    return alloc(count);
+  }
+};
+
+int strip_rows() {
+  const char* e = getenv("HHG_STRIP_ROWS");
+  if (e) {
+    int r = atoi(e);
+    if (r == 8 || r == 16) return r;
+  }
+  return 16;
+}
+
+}  // namespace
+
+struct hhg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  long long launches = 0;
+  // query
+  int Lq = 0, R = 16, nstrips = 0;
+  DevBuf<float4> qrec;
+  DevBuf<float> S33;
+  bool has_ss = false, has_S33 = false;
+  hhg_params par{1, 0.f, 0.f, -0.03f, 0.11f, 0};
+  // prefilter
+  DevBuf<uint8_t> pf_prof;
+  DevBuf<unsigned> pf_counter;
+  size_t max_bt_bytes = 0;   // memory-wave budget for backtrace words
+};
+
+struct hhg_db {
+  int device = 0;
+  int n = 0;
+  long long total_cols = 0;
+  bool has_ss = false;
+  std::vector<int> L;
+  std::vector<long long> col_off;
+  DevBuf<int> dL;
+  DevBuf<long long> dcol_off;
+  DevBuf<float4> cols;
+};
+
+struct hhg_csdb {
+  int n = 0;
+  long long total = 0;
+  DevBuf<int> dL;
+  DevBuf<long long> doff;
+  DevBuf<uint8_t> seq;
+  DevBuf<int> scores;
+};
+
+struct Wave {
+  int job_begin = 0, job_end = 0;
+  int req_begin = 0, req_end = 0;   // requests (in sorted order) covered by the wave
+};
+
+struct hhg_plan {
+  const hhg_db* db = nullptr;
+  int n = 0;            // requests
+  int Lq = 0, R = 16, nstrips = 0;
+  int njobs = 0;
+  double cells = 0, padded_cells = 0, alg_bytes = 0;
+  std::vector<int> ids;          // request -> target id
+  std::vector<int> order;        // sorted position -> request index
+  std::vector<int> req_job, req_lane;   // per request
+  std::vector<int> job_Lmax;
+  std::vector<long long> job_bt_off, job_bnd_off, job_co_off, path_off;
+  std::vector<Wave> waves;
+  long long path_total = 0;
+  // device
+  DevBuf<int> d_job_target, d_job_Lmax, d_req_job, d_req_lane, d_req_Lt;
+  DevBuf<long long> d_job_bt_off, d_job_bnd_off, d_job_co_off, d_path_off;
+  DevBuf<uint32_t> d_bt, d_co;
+  DevBuf<float4> d_bnd4;
+  DevBuf<float> d_bnd1, d_strip_score;
+  DevBuf<int> d_strip_ij;
+  DevBuf<unsigned> d_progress, d_counter;
+  DevBuf<HitRec> d_hits;
+  DevBuf<uint8_t> d_paths;
+  // cell-off input (optional)
+  bool celloff = false;
+  int n_excl_steps = 0;
+  DevBuf<int> d_step_req, d_step_i, d_step_j;
+};
+
+extern "C" {
+
+const char* hhg_last_error(void) { return g_err.c_str(); }
+
+int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
+  if (!out) return fail(HHG_EINVAL, "out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(HHG_ENODEV, "no CUDA device available (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0) CK(cudaGetDevice(&device));
+  if (device >= ndev) return fail(HHG_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(HHG_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  hhg_ctx* c = new hhg_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  c->R = strip_rows();
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const char* env = getenv("HHG_MAX_BT_GB");
+  double cap = env ? atof(env) * 1e9 : 48e9;
+  c->max_bt_bytes = (size_t)std::min(cap, 0.45 * (double)free_b);
+  *out = c;
+  return HHG_OK;
+}
+
+int hhg_ctx_destroy(hhg_ctx* ctx) {
+  if (!ctx) return HHG_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return HHG_OK;
+}
+
+int hhg_ctx_sync(hhg_ctx* ctx) {
+  if (!ctx) return fail(HHG_EINVAL, "ctx is NULL");
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HHG_OK;
+}
+
+long long hhg_ctx_launch_count(hhg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------ DB
+static int pack_profiles(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_off,
+                         const int64_t* tr_off, const int64_t* ss_off, const float* p, const float* tr,
+                         const uint8_t* ss, const std::vector<long long>& col_off, long long total_cols,
+                         float4* d_out) {
+  // upload the raw profiles in bounded chunks of targets, pack on the device
+  const size_t kChunkBytes = (size_t)1 << 30;
+  DevBuf<float> dp, dtr;
+  DevBuf<uint8_t> dss;
+  DevBuf<int> dL;
+  DevBuf<long long> dcol, dpo, dto, dso;
+  int t0 = 0;
+  while (t0 < n) {
+    // the profiles of consecutive targets need not be contiguous in the caller's arrays; upload per
+    // target range [lo, hi) covering min..max offsets when contiguous, else target by target.
+    int t1 = t0;
+    size_t bytes = 0;
+    while (t1 < n && (bytes == 0 || bytes + (size_t)(L[t1] + 2) * 80 < kChunkBytes)) {
+      bytes += (size_t)(L[t1] + 2) * 80;
+      ++t1;
+    }
+    const int m = t1 - t0;
+    std::vector<long long> po(m), to(m), so(m), co(m);
+    std::vector<int> LL(m);
+    size_t np = 0, ntr = 0, nss = 0;
+    for (int k = 0; k < m; ++k) {
+      LL[k] = L[t0 + k];
+      po[k] = (long long)np; to[k] = (long long)ntr; so[k] = (long long)nss;
+      co[k] = col_off[t0 + k] - col_off[t0];
+      np += (size_t)(LL[k] + 2) * 20; ntr += (size_t)(LL[k] + 1) * 7; nss += (size_t)(LL[k] + 2);
+    }
+    std::vector<float> hp(np), htr(ntr);
+    std::vector<uint8_t> hss(ss ? nss : 0);
+    for (int k = 0; k < m; ++k) {
+      memcpy(hp.data() + po[k], p + p_off[t0 + k], (size_t)(LL[k] + 2) * 20 * sizeof(float));
+      memcpy(htr.data() + to[k], tr + tr_off[t0 + k], (size_t)(LL[k] + 1) * 7 * sizeof(float));
+      if (ss) memcpy(hss.data() + so[k], ss + ss_off[t0 + k], (size_t)(LL[k] + 2));
+    }
+    const long long cols = (t1 < n ? col_off[t1] : total_cols) - col_off[t0];
+    CK(dp.ensure(np)); CK(dtr.ensure(ntr)); CK(dL.ensure(m)); CK(dcol.ensure(m)); CK(dpo.ensure(m));
+    CK(dto.ensure(m)); CK(dso.ensure(m));
+    if (ss) CK(dss.ensure(nss));
+    CK(cudaMemcpyAsync(dp.p, hp.data(), np * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dtr.p, htr.data(), ntr * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ss) CK(cudaMemcpyAsync(dss.p, hss.data(), nss, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dL.p, LL.data(), m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dcol.p, co.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dpo.p, po.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dto.p, to.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dso.p, so.data(), m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 128;
+    const long long blocks = (cols + threads - 1) / threads;
+    k_pack_cols<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
+        m, dL.p, dcol.p, dpo.p, dto.p, dso.p, dp.p, dtr.p, ss ? dss.p : nullptr,
+        reinterpret_cast<ColRec*>(d_out) + col_off[t0], cols);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));   // host staging vectors die at scope end
+    t0 = t1;
+  }
+  return HHG_OK;
+}
+
+int hhg_db_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_off, const int64_t* tr_off,
+                  const int64_t* ss_off, const float* p, const float* tr, const uint8_t* ss,
+                  hhg_db** out) {
+  if (!ctx || !out || n <= 0 || !L || !p_off || !tr_off || !p || !tr)
+    return fail(HHG_EINVAL, "hhg_db_create: bad argument");
+  if (ss && !ss_off) return fail(HHG_EINVAL, "hhg_db_create: ss given without ss_off");
+  CK(cudaSetDevice(ctx->device));
+  hhg_db* db = new hhg_db();
+  db->device = ctx->device;
+  db->n = n;
+  db->has_ss = ss != nullptr;
+  db->L.assign(L, L + n);
+  db->col_off.resize(n);
+  long long tot = 0;
+  for (int k = 0; k < n; ++k) {
+    if (L[k] < 1 || L[k] > 32767) { delete db; return fail(HHG_EINVAL, "target %d: length %d out of [1,32767]", k, L[k]); }
+    db->col_off[k] = tot;
+    tot += L[k];
+  }
+  db->total_cols = tot;
+  cudaError_t e;
+  if ((e = db->cols.alloc((size_t)tot * 7)) != cudaSuccess || (e = db->dL.alloc(n)) != cudaSuccess ||
+      (e = db->dcol_off.alloc(n)) != cudaSuccess) {
+    delete db;
+    return fail(HHG_ENOMEM, "hhg_db_create: %s", cudaGetErrorString(e));
+  }
+  CK(cudaMemcpyAsync(db->dL.p, db->L.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->dcol_off.p, db->col_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pack_profiles(ctx, n, L, p_off, tr_off, ss_off, p, tr, ss, db->col_off, tot, db->cols.p);
+  if (rc != HHG_OK) { delete db; return rc; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = db;
+  return HHG_OK;
+}
+
+int hhg_db_destroy(hhg_db* db) {
+  if (db) { cudaSetDevice(db->device); delete db; }
+  return HHG_OK;
+}
+int hhg_db_size(const hhg_db* db) { return db ? db->n : 0; }
+long long hhg_db_columns(const hhg_db* db) { return db ? db->total_cols : 0; }
+
+// --------------------------------------------------------------------------------------- query
+int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const uint8_t* ss,
+                  const float* S33, const hhg_params* par) {
+  if (!ctx || Lq < 1 || Lq > 32767 || !p || !tr || !par) return fail(HHG_EINVAL, "hhg_query_set: bad argument");
+  if (par->use_ss && (!ss || !S33)) return fail(HHG_EINVAL, "hhg_query_set: use_ss needs ss and S33");
+  CK(cudaSetDevice(ctx->device));
+  ctx->par = *par;
+  ctx->Lq = Lq;
+  ctx->nstrips = (Lq + ctx->R - 1) / ctx->R;
+  const int rows = ctx->nstrips * ctx->R;
+  CK(ctx->qrec.ensure((size_t)rows * 7));
+  CK(cudaMemsetAsync(ctx->qrec.p, 0, (size_t)rows * 112, ctx->stream));
+  // pack with the same kernel as the DB (a one-profile shard)
+  std::vector<long long> col_off(1, 0);
+  const int32_t L1 = Lq;
+  const int64_t zero = 0;
+  int rc = pack_profiles(ctx, 1, &L1, &zero, &zero, &zero, p, tr, ss, col_off, Lq, ctx->qrec.p);
+  if (rc != HHG_OK) return rc;
+  ctx->has_ss = ss != nullptr;
+  ctx->has_S33 = false;
+  if (S33) {
+    CK(ctx->S33.ensure(44 * 44));
+    CK(cudaMemcpyAsync(ctx->S33.p, S33, 44 * 44 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->has_S33 = true;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HHG_OK;
+}
+
+// ---------------------------------------------------------------------------------------- plan
+int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_plan** out) {
+  if (!ctx || !db || !out || n <= 0) return fail(HHG_EINVAL, "hhg_plan_create: bad argument");
+  if (ctx->Lq <= 0) return fail(HHG_EINVAL, "hhg_plan_create: no query set");
+  if (db->device != ctx->device) return fail(HHG_EINVAL, "db lives on device %d, ctx on %d", db->device, ctx->device);
+  CK(cudaSetDevice(ctx->device));
+  hhg_plan* pl = new hhg_plan();
+  pl->db = db;
+  pl->n = n;
+  pl->Lq = ctx->Lq; pl->R = ctx->R; pl->nstrips = ctx->nstrips;
+  pl->ids.resize(n);
+  for (int k = 0; k < n; ++k) {
+    const int id = ids ? ids[k] : k;
+    if (id < 0 || id >= db->n) { delete pl; return fail(HHG_EINVAL, "request %d: target id %d out of range", k, id); }
+    pl->ids[k] = id;
+  }
+  // sort requests by target length, longest first (as ViterbiRunner does per chunk,
+  // src/hhviterbirunner.cpp:117-119; here it also makes LPT scheduling of the work queue)
+  pl->order.resize(n);
+  std::iota(pl->order.begin(), pl->order.end(), 0);
+  std::stable_sort(pl->order.begin(), pl->order.end(),
+                   [&](int a, int b) { return db->L[pl->ids[a]] > db->L[pl->ids[b]]; });
+  pl->njobs = (n + 31) / 32;
+  pl->req_job.resize(n); pl->req_lane.resize(n);
+  pl->job_Lmax.resize(pl->njobs);
+  pl->job_bt_off.resize(pl->njobs); pl->job_bnd_off.resize(pl->njobs); pl->job_co_off.resize(pl->njobs);
+  std::vector<int> job_target((size_t)pl->njobs * 32);
+  std::vector<int> req_Lt(n);
+  const int rowgroups = pl->nstrips * pl->R / 4;
+  long long bnd = 0, co = 0;
+  size_t wave_bt = 0;   // words in the current wave
+  Wave w;
+  for (int jb = 0; jb < pl->njobs; ++jb) {
+    const int first = jb * 32;
+    const int cnt = std::min(32, n - first);
+    const int Lmax = db->L[pl->ids[pl->order[first]]];
+    pl->job_Lmax[jb] = Lmax;
+    for (int l = 0; l < 32; ++l) {
+      const int rq = pl->order[first + std::min(l, cnt - 1)];   // padded lanes repeat the last target
+      job_target[(size_t)jb * 32 + l] = pl->ids[rq];
+      if (l < cnt) { pl->req_job[rq] = jb; pl->req_lane[rq] = l; }
+    }
+    const size_t words = (size_t)rowgroups * (Lmax + 1) * 32;
+    if (wave_bt > 0 && (wave_bt + words) * 4 > ctx->max_bt_bytes) {
+      w.job_end = jb; w.req_end = first;
+      pl->waves.push_back(w);
+      w.job_begin = jb; w.req_begin = first;
+      wave_bt = 0;
+    }
+    pl->job_bt_off[jb] = (long long)wave_bt;
+    wave_bt += words;
+    pl->job_bnd_off[jb] = bnd;
+    bnd += (long long)(Lmax + 1) * 32;
+    pl->job_co_off[jb] = co;
+    co += (long long)pl->nstrips * (Lmax + 1) * 32;
+    pl->padded_cells += (double)pl->nstrips * pl->R * (double)Lmax * 32.0;
+  }
+  w.job_end = pl->njobs; w.req_end = n;
+  pl->waves.push_back(w);
+  size_t max_wave_words = 0;
+  for (const Wave& wv : pl->waves) {
+    size_t words = 0;
+    for (int jb = wv.job_begin; jb < wv.job_end; ++jb) words += (size_t)rowgroups * (pl->job_Lmax[jb] + 1) * 32;
+    max_wave_words = std::max(max_wave_words, words);
+  }
+  pl->path_off.resize(n);
+  long long po = 0;
+  double cols_sum = 0;
+  for (int k = 0; k < n; ++k) {
+    const int Lt = db->L[pl->ids[k]];
+    req_Lt[k] = Lt;
+    pl->path_off[k] = po;
+    po += pl->Lq + Lt + 2;
+    pl->cells += (double)pl->Lq * Lt;
+    cols_sum += Lt;
+  }
+  if (po > 0x7fffffffLL) { delete pl; return fail(HHG_EINVAL, "plan too large: %lld path bytes (> 2^31-1); split the request", po); }
+  pl->path_total = po;
+  pl->alg_bytes = cols_sum * 112.0 + pl->cells * 1.0 + 32.0 * n;
+
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(pl->d_job_target.alloc(job_target.size())); A(pl->d_job_Lmax.alloc(pl->njobs));
+  A(pl->d_job_bt_off.alloc(pl->njobs)); A(pl->d_job_bnd_off.alloc(pl->njobs)); A(pl->d_job_co_off.alloc(pl->njobs));
+  A(pl->d_req_job.alloc(n)); A(pl->d_req_lane.alloc(n)); A(pl->d_req_Lt.alloc(n)); A(pl->d_path_off.alloc(n));
+  A(pl->d_bt.alloc(max_wave_words));
+  A(pl->d_bnd4.alloc((size_t)bnd)); A(pl->d_bnd1.alloc((size_t)bnd));
+  A(pl->d_strip_score.alloc((size_t)pl->njobs * pl->nstrips * 32));
+  A(pl->d_strip_ij.alloc((size_t)pl->njobs * pl->nstrips * 32));
+  A(pl->d_progress.alloc((size_t)pl->njobs * pl->nstrips));
+  A(pl->d_counter.alloc(pl->waves.size()));
+  A(pl->d_hits.alloc(n));
+  A(pl->d_paths.alloc((size_t)po));
+  if (e != cudaSuccess) { delete pl; return fail(HHG_ENOMEM, "hhg_plan_create: %s", cudaGetErrorString(e)); }
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(pl->d_job_target.p, job_target.data(), job_target.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_job_Lmax.p, pl->job_Lmax.data(), (size_t)pl->njobs * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_job_bt_off.p, pl->job_bt_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_job_bnd_off.p, pl->job_bnd_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_job_co_off.p, pl->job_co_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_req_job.p, pl->req_job.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_req_lane.p, pl->req_lane.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_req_Lt.p, req_Lt.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_path_off.p, pl->path_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  *out = pl;
+  return HHG_OK;
+}
+
+int hhg_plan_destroy(hhg_plan* plan) {
+  if (plan) { if (plan->db) cudaSetDevice(plan->db->device); delete plan; }
+  return HHG_OK;
+}
+double hhg_plan_cells(const hhg_plan* plan) { return plan ? plan->cells : 0; }
+double hhg_plan_padded_cells(const hhg_plan* plan) { return plan ? plan->padded_cells : 0; }
+double hhg_plan_algorithmic_bytes(const hhg_plan* plan) { return plan ? plan->alg_bytes : 0; }
+
+static int set_exclusions(hhg_ctx* ctx, hhg_plan* pl, const int64_t* excl_off, const int32_t* excl_i,
+                          const int32_t* excl_j) {
+  pl->celloff = false;
+  pl->n_excl_steps = 0;
+  if (!excl_off) return HHG_OK;
+  const long long total = excl_off[pl->n];
+  if (total <= 0) return HHG_OK;
+  std::vector<int> sreq((size_t)total);
+  for (int k = 0; k < pl->n; ++k)
+    for (long long s = excl_off[k]; s < excl_off[k + 1]; ++s) sreq[(size_t)s] = k;
+  size_t co_words = 0;
+  for (int jb = 0; jb < pl->njobs; ++jb) co_words += (size_t)pl->nstrips * (pl->job_Lmax[jb] + 1) * 32;
+  CK(pl->d_co.ensure(co_words));
+  CK(pl->d_step_req.ensure((size_t)total)); CK(pl->d_step_i.ensure((size_t)total)); CK(pl->d_step_j.ensure((size_t)total));
+  CK(cudaMemcpyAsync(pl->d_step_req.p, sreq.data(), (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(pl->d_step_i.p, excl_i, (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(pl->d_step_j.p, excl_j, (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(pl->d_co.p, 0, co_words * 4, ctx->stream));
+  const int threads = 128;
+  k_celloff_raster<<<(unsigned)((total + threads - 1) / threads), threads, 0, ctx->stream>>>(
+      (int)total, pl->d_step_req.p, pl->d_step_i.p, pl->d_step_j.p, pl->d_req_job.p, pl->d_req_lane.p,
+      pl->d_req_Lt.p, pl->d_job_Lmax.p, pl->d_job_co_off.p, pl->Lq, pl->R, pl->d_co.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));   // sreq is a host temporary
+  pl->celloff = true;
+  pl->n_excl_steps = (int)total;
+  return HHG_OK;
+}
+
+}  // extern "C"
+
+template <int R>
+static int launch_viterbi(hhg_ctx* ctx, const VitParams& P, bool local, bool ss, bool co, int items) {
+  const size_t smem = (size_t)kWarpsPerCta * R * 112 + 64 + (ss ? 44 * 44 * 4 : 0);
+  void (*kern)(const VitParams) = nullptr;
+#define PICK(L_, S_, C_) kern = k_viterbi<R, L_, S_, C_>
+  if (local) { if (ss) { if (co) PICK(true, true, true); else PICK(true, true, false); }
+               else    { if (co) PICK(true, false, true); else PICK(true, false, false); } }
+  else       { if (ss) { if (co) PICK(false, true, true); else PICK(false, true, false); }
+               else    { if (co) PICK(false, false, true); else PICK(false, false, false); } }
+#undef PICK
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem));
+  if (per_sm < 1) return fail(HHG_ECUDA, "viterbi kernel does not fit on an SM");
+  // persistent grid: every CTA must be resident (strip items wait on their predecessor strip)
+  int grid = ctx->sm_count * per_sm;
+  const int need = (items + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (grid > need) grid = need;
+  kern<<<grid, kWarpsPerCta * 32, smem, ctx->stream>>>(P);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HHG_OK;
+}
+
+extern "C" {
+
+int hhg_plan_run(hhg_ctx* ctx, hhg_plan* pl) {
+  if (!ctx || !pl) return fail(HHG_EINVAL, "hhg_plan_run: bad argument");
+  if (pl->Lq != ctx->Lq || pl->R != ctx->R) return fail(HHG_EINVAL, "plan was made for another query length");
+  const hhg_db* db = pl->db;
+  if (ctx->par.use_ss && (!db->has_ss || !ctx->has_ss || !ctx->has_S33))
+    return fail(HHG_EINVAL, "use_ss requested but query/db/S33 carry no ss information");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(pl->d_progress.p, 0, pl->d_progress.n * 4, st));
+  CK(cudaMemsetAsync(pl->d_counter.p, 0, pl->d_counter.n * 4, st));
+  for (size_t wi = 0; wi < pl->waves.size(); ++wi) {
+    const Wave& w = pl->waves[wi];
+    const int nj = w.job_end - w.job_begin;
+    VitParams P{};
+    P.qrec = ctx->qrec.p; P.Lq = pl->Lq; P.nstrips = pl->nstrips;
+    P.cols = db->cols.p; P.col_off = db->dcol_off.p; P.Lt = db->dL.p;
+    P.njobs = nj;
+    P.job_target = pl->d_job_target.p + (size_t)w.job_begin * 32;
+    P.job_Lmax = pl->d_job_Lmax.p + w.job_begin;
+    P.job_bt_off = pl->d_job_bt_off.p + w.job_begin;
+    P.job_bnd_off = pl->d_job_bnd_off.p + w.job_begin;
+    P.job_co_off = pl->d_job_co_off.p + w.job_begin;
+    P.bt = pl->d_bt.p; P.bnd4 = pl->d_bnd4.p; P.bnd1 = pl->d_bnd1.p;
+    P.progress = pl->d_progress.p + (size_t)w.job_begin * pl->nstrips;
+    P.counter = pl->d_counter.p + wi;
+    P.strip_score = pl->d_strip_score.p + (size_t)w.job_begin * pl->nstrips * 32;
+    P.strip_ij = pl->d_strip_ij.p + (size_t)w.job_begin * pl->nstrips * 32;
+    P.celloff = pl->celloff ? pl->d_co.p : nullptr;
+    P.S33 = ctx->has_S33 ? ctx->S33.p : nullptr;
+    P.egq = ctx->par.egq; P.egt = ctx->par.egt; P.shift = ctx->par.shift; P.ssw = ctx->par.ssw;
+    P.one2 = 0x3F8000003F800000ull;
+    const int items = nj * pl->nstrips;
+    int rc;
+    if (pl->R == 8) rc = launch_viterbi<8>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
+    else rc = launch_viterbi<16>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
+    if (rc != HHG_OK) return rc;
+    // backtrace of this wave's requests.  Requests are addressed through the sorted order: the
+    // wave covers sorted positions [req_begin, req_end); req_job/req_lane are per original request.
+    BtParams B{};
+    B.n_req = pl->n;   // filtered by job range inside: simpler to launch per wave over all requests
+    B.nstrips = pl->nstrips;
+    B.req_job = pl->d_req_job.p; B.req_lane = pl->d_req_lane.p;
+    B.job_Lmax = pl->d_job_Lmax.p; B.job_bt_off = pl->d_job_bt_off.p;
+    B.bt = pl->d_bt.p; B.strip_score = pl->d_strip_score.p; B.strip_ij = pl->d_strip_ij.p;
+    B.path_off = pl->d_path_off.p; B.hits = pl->d_hits.p; B.paths = pl->d_paths.p;
+    B.job_begin = w.job_begin; B.job_end = w.job_end;
+    const int threads = 128;
+    k_backtrace<<<(pl->n + threads - 1) / threads, threads, 0, st>>>(B);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  return HHG_OK;
+}
+
+int hhg_plan_fetch(hhg_ctx* ctx, hhg_plan* pl, hhg_hit* hits, uint8_t* paths, size_t paths_cap) {
+  if (!ctx || !pl || !hits) return fail(HHG_EINVAL, "hhg_plan_fetch: bad argument");
+  static_assert(sizeof(hhg_hit) == sizeof(HitRec), "hhg_hit / HitRec layout");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(hits, pl->d_hits.p, (size_t)pl->n * sizeof(HitRec), cudaMemcpyDeviceToHost, ctx->stream));
+  if (paths) {
+    if (paths_cap < (size_t)pl->path_total)
+      return fail(HHG_EINVAL, "paths buffer too small: need %lld bytes", pl->path_total);
+    CK(cudaMemcpyAsync(paths, pl->d_paths.p, (size_t)pl->path_total, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HHG_OK;
+}
+
+int hhg_plan_debug_bt(hhg_ctx* ctx, hhg_plan* pl, int k, uint8_t* bt) {
+  if (!ctx || !pl || !bt || k < 0 || k >= pl->n) return fail(HHG_EINVAL, "hhg_plan_debug_bt: bad argument");
+  if (pl->waves.size() != 1) return fail(HHG_EINVAL, "debug_bt needs a single-wave plan");
+  CK(cudaSetDevice(ctx->device));
+  const int job = pl->req_job[k], lane = pl->req_lane[k];
+  const int Lt = pl->db->L[pl->ids[k]];
+  const int total = (pl->Lq + 1) * (Lt + 1);
+  DevBuf<uint8_t> tmp;
+  CK(tmp.alloc(total));
+  k_debug_bt<<<(total + 255) / 256, 256, 0, ctx->stream>>>(pl->d_bt.p, pl->job_bt_off[job], lane,
+                                                            pl->job_Lmax[job], pl->Lq, Lt, tmp.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(bt, tmp.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HHG_OK;
+}
+
+int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_hit* hits,
+                       uint8_t* paths, size_t paths_cap, const int64_t* excl_off,
+                       const int32_t* excl_i, const int32_t* excl_j) {
+  hhg_plan* pl = nullptr;
+  int rc = hhg_plan_create(ctx, db, n, ids, &pl);
+  if (rc != HHG_OK) return rc;
+  rc = set_exclusions(ctx, pl, excl_off, excl_i, excl_j);
+  if (rc == HHG_OK) rc = hhg_plan_run(ctx, pl);
+  if (rc == HHG_OK) rc = hhg_plan_fetch(ctx, pl, hits, paths, paths_cap);
+  hhg_plan_destroy(pl);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------ prefilter
+int hhg_csdb_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* off, const uint8_t* seq,
+                    hhg_csdb** out) {
+  if (!ctx || !out || n <= 0 || !L || !off || !seq) return fail(HHG_EINVAL, "hhg_csdb_create: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  hhg_csdb* db = new hhg_csdb();
+  db->n = n;
+  long long tot = 0;
+  for (int k = 0; k < n; ++k) tot = std::max<long long>(tot, off[k] + L[k]);
+  db->total = tot;
+  cudaError_t e;
+  if ((e = db->dL.alloc(n)) != cudaSuccess || (e = db->doff.alloc(n)) != cudaSuccess ||
+      (e = db->seq.alloc((size_t)tot)) != cudaSuccess || (e = db->scores.alloc(n)) != cudaSuccess) {
+    delete db;
+    return fail(HHG_ENOMEM, "hhg_csdb_create: %s", cudaGetErrorString(e));
+  }
+  CK(cudaMemcpyAsync(db->dL.p, L, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->doff.p, off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->seq.p, seq, (size_t)tot, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = db;
+  return HHG_OK;
+}
+
+int hhg_csdb_destroy(hhg_csdb* db) { delete db; return HHG_OK; }
+
+}  // extern "C"
+
+template <int WPL>
+static int launch_prefilter(hhg_ctx* ctx, const PfParams& P) {
+  const size_t smem = (size_t)220 * 32 * WPL * 4;
+  auto kern = k_prefilter_ungapped<WPL>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  if (per_sm < 1) return fail(HHG_ECUDA, "prefilter kernel does not fit on an SM");
+  kern<<<ctx->sm_count * per_sm, 256, smem, ctx->stream>>>(P);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HHG_OK;
+}
+
+extern "C" {
+
+int hhg_prefilter_ungapped_run(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const uint8_t* prof_host,
+                               int offset, int upload_profile) {
+  if (!ctx || !db || Lq < 1) return fail(HHG_EINVAL, "hhg_prefilter_ungapped_run: bad argument");
+  if (Lq > 128 * 8) return fail(HHG_EINVAL, "prefilter: query length %d > 1024 not supported yet", Lq);
+  CK(cudaSetDevice(ctx->device));
+  const int W4 = (Lq + 3) / 4;
+  if (upload_profile) {
+    if (!prof_host) return fail(HHG_EINVAL, "profile is NULL");
+    // repack [220][Lq] bytes into [220][W4] words (4 consecutive positions per word, zero padded)
+    std::vector<uint8_t> packed((size_t)220 * W4 * 4, 0);
+    for (int k = 0; k < 220; ++k) memcpy(packed.data() + (size_t)k * W4 * 4, prof_host + (size_t)k * Lq, Lq);
+    CK(ctx->pf_prof.ensure(packed.size()));
+    CK(cudaMemcpyAsync(ctx->pf_prof.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  CK(ctx->pf_counter.ensure(1));
+  CK(cudaMemsetAsync(ctx->pf_counter.p, 0, 4, ctx->stream));
+  PfParams P{};
+  P.n = db->n; P.L = db->dL.p; P.off = db->doff.p; P.seq = db->seq.p; P.prof = ctx->pf_prof.p;
+  P.Lq = Lq; P.W4 = W4; P.offset = offset; P.scores = db->scores.p; P.counter = ctx->pf_counter.p;
+  const int wpl = (W4 + 31) / 32;
+  if (wpl <= 1) return launch_prefilter<1>(ctx, P);
+  if (wpl <= 2) return launch_prefilter<2>(ctx, P);
+  if (wpl <= 4) return launch_prefilter<4>(ctx, P);
+  return launch_prefilter<8>(ctx, P);
+}
+
+int hhg_prefilter_fetch(hhg_ctx* ctx, const hhg_csdb* db, int32_t* scores) {
+  if (!ctx || !db || !scores) return fail(HHG_EINVAL, "hhg_prefilter_fetch: bad argument");
+  CK(cudaMemcpyAsync(scores, db->scores.p, (size_t)db->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HHG_OK;
+}
+
+int hhg_prefilter_ungapped(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const uint8_t* prof, int offset,
+                           int32_t* scores) {
+  int rc = hhg_prefilter_ungapped_run(ctx, db, Lq, prof, offset, 1);
+  if (rc != HHG_OK) return rc;
+  return hhg_prefilter_fetch(ctx, db, scores);
+}
+
+}  // extern "C"

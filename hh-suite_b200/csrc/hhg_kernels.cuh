@@ -1,0 +1,601 @@
+// hh-suite_b200/csrc/hhg_kernels.cuh -- sm_100a kernels of the HH-suite hot path.
+//
+// Viterbi HMM-HMM forward pass (replaces Viterbi::AlignWith[Out]CellOff[AndSS],
+// /root/reference/src/hhviterbialgorithm.cpp:29-497) and the byte backtrace
+// (Viterbi::Backtrace, src/hhviterbi.cpp:83-160).
+//
+// Mapping (B200-first, not the reference's 8-lane AVX2 row sweep):
+//   * one LANE = one target; one WARP-JOB = 32 length-sorted targets; the job's DP matrix is cut
+//     into STRIPS of R query rows.  A work item is (job, strip); persistent warps pull items from
+//     an atomic queue in (job, strip) order, so consecutive strips of a job run on different
+//     warps as a skewed wavefront: strip s+1 trails strip s by a few columns and receives the
+//     5-state boundary row through L2 (release/acquire progress flags).
+//   * inside a strip a lane sweeps target columns left to right and keeps the 5 pair-state
+//     values of its R rows in registers; the R query rows (20 emissions + 7 transitions each)
+//     are TMA-bulk-staged (cp.async.bulk + mbarrier) into the warp's shared-memory slice and
+//     read back as warp-uniform broadcast LDS.128.
+//   * target operands stream from HBM as 112-byte column records (7 x LDG.128 per lane per
+//     column, register-prefetched one column ahead).
+//   * 1 backtrace byte per cell, packed 4 rows per 32-bit word and stored lane-interleaved so
+//     every warp store writes one full 128-byte line.
+// Arithmetic is the reference's, operation for operation (unfused fp32 mul/add in the same order,
+// strict '>' tie rules), so scores and backtrace bytes are bit-identical to the AVX2 (no-FMA) build.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+namespace hhg {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kPublishEvery = 8;   // columns between progress-flag publications
+
+struct __align__(16) ColRec {      // one profile column = operands of DP cell (., j)   (112 B)
+  float p[20];
+  float m2m, m2d, d2m, d2d, i2m;   // tr[j-1][M2M,M2D,D2M,D2D,I2M]
+  float i2i, m2i;                  // tr[j][I2I,M2I]
+  uint32_t ss;                     // ss_pred*11+ss_conf of column j
+};
+static_assert(sizeof(ColRec) == 112, "ColRec must be 7 x 16 bytes");
+
+struct VitParams {
+  // query
+  const float4* qrec;        // [nstrips*R] records (rows 1..), zero padded
+  int Lq;
+  int nstrips;
+  // database shard
+  const float4* cols;        // column records of all targets
+  const long long* col_off;  // [n_targets] first column record of target t
+  const int* Lt;             // [n_targets]
+  // plan
+  int njobs;
+  const int* job_target;     // [njobs*32] target id (padded lanes repeat a valid id)
+  const int* job_Lmax;       // [njobs]
+  const long long* job_bt_off;   // [njobs] offset (in uint32 words) into bt
+  const long long* job_bnd_off;  // [njobs] offset (in columns*32) into bnd4/bnd1
+  uint32_t* bt;              // packed backtrace words
+  float4* bnd4;              // boundary row: MM,DG,MI,GD
+  float* bnd1;               // boundary row: IM
+  unsigned int* progress;    // [njobs*nstrips] columns published by (job, strip)
+  unsigned int* counter;     // work-item queue head
+  float* strip_score;        // [njobs*nstrips*32]
+  int* strip_ij;             // [njobs*nstrips*32]  (i<<16 | j)
+  const uint32_t* celloff;   // [sum over jobs nstrips*(Lmax+1)*32] bit r = row i0+1+r off, or null
+  const long long* job_co_off;
+  const float* S33;          // [44*44] or null
+  // scoring
+  float egq, egt, shift, ssw;
+  unsigned long long one2;   // bit pattern of (1.0f, 1.0f); see add2()
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// log2f4 (src/hhutil-inl.h:509-541), degree-4 minimax, unfused.  x >= 0.
+// The exponent int->float conversion uses the exact magic-number form (no I2F on the hot path):
+// bits(8388608.0f) + eb is the float 8388608+eb; subtracting 8388735 (=2^23+127) is exact.
+__device__ __forceinline__ float log2f4_dev(float x) {
+  const uint32_t u = __float_as_uint(x);
+  const float e = __fadd_rn(__uint_as_float((u >> 23) | 0x4B000000u), -8388735.0f);
+  const float m = __uint_as_float((u & 0x007FFFFFu) | 0x3F800000u);
+  float p = -0.107254423828329604454f;
+  p = __fadd_rn(__fmul_rn(p, m), 0.688243882994381274313f);
+  p = __fadd_rn(__fmul_rn(p, m), -1.75647175389045657003f);
+  p = __fadd_rn(__fmul_rn(p, m), 2.61761038894603480148f);
+  p = __fmul_rn(p, __fadd_rn(m, -1.0f));
+  return __fadd_rn(p, e);
+}
+
+// ScalarProd20Vec (src/hhviterbi.h:126-190) with packed f32x2 arithmetic: the four partial sums
+// r0..r3 live in two f32x2 registers (r0,r1) and (r2,r3); each half is an IEEE fp32 mul / add with
+// round-to-nearest, i.e. exactly the reference's unfused sequence.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// Packed add as fma(a, ONE, b) with ONE = (1.0f,1.0f) taken from a kernel parameter.  ptxas (12.9)
+// contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 even with -fmad=false, which would
+// change the rounding w.r.t. the reference; a*1+b rounds exactly like a+b and, because the value of
+// ONE is opaque to the compiler, cannot be folded back into an add and fused.
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b,
+                                                   unsigned long long one) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(one), "l"(b));
+  return r;
+}
+
+// t: 10 packed pairs of the target column, q: float4 x5 of the query row
+__device__ __forceinline__ float dot20_dev(const unsigned long long (&t)[10], const float4 (&q)[5],
+                                           const unsigned long long one) {
+  unsigned long long a01 = mul2(t[0], pack2(q[0].x, q[0].y));
+  unsigned long long a23 = mul2(t[1], pack2(q[0].z, q[0].w));
+#pragma unroll
+  for (int m = 1; m < 5; ++m) {
+    a01 = add2(mul2(t[2 * m], pack2(q[m].x, q[m].y)), a01, one);
+    a23 = add2(mul2(t[2 * m + 1], pack2(q[m].z, q[m].w)), a23, one);
+  }
+  float r0, r1, r2, r3;
+  unpack2(a01, r0, r1);
+  unpack2(a23, r2, r3);
+  return __fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3));
+}
+
+#define HHG_NEG (-FLT_MAX)
+
+// ---------------------------------------------------------------------------------------------
+// Forward pass.  R rows per strip (multiple of 4).  LOCAL: par.loc.  SS: PRED_PRED ss term.
+// CELLOFF: cell-off bit input (alternative alignments / excluded regions).
+// ---------------------------------------------------------------------------------------------
+template <int R, bool LOCAL, bool SS, bool CELLOFF>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 4 : 2)
+    k_viterbi(const VitParams P) {
+  static_assert(R % 4 == 0, "R must be a multiple of 4");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // smem carve-up: [warps][R] query records, then mbarriers, then (SS) the S33 table
+  float4* qs = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * R * 7;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarpsPerCta * R * 112);
+  float* s33 = reinterpret_cast<float*>(smem_raw + (size_t)kWarpsPerCta * R * 112 + 64);
+  uint64_t* bar = bars + warp;
+
+  if (lane == 0) mbar_init(bar, 1);
+  if (SS) {
+    for (int k = threadIdx.x; k < 44 * 44; k += blockDim.x) s33[k] = P.S33[k];
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const float smin = LOCAL ? 0.0f : HHG_NEG;
+  const int total_items = P.njobs * P.nstrips;
+  uint32_t parity = 0;
+
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = (int)atomicAdd(P.counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total_items) break;
+    const int job = item / P.nstrips;
+    const int s = item - job * P.nstrips;
+    const int i0 = s * R;
+
+    // ---- stage this strip's query rows with one TMA bulk copy
+    if (lane == 0) {
+      mbar_expect_tx(bar, R * 112);
+      tma_bulk_g2s(qs, P.qrec + (size_t)i0 * 7, R * 112, bar);
+    }
+
+    const int t = P.job_target[job * 32 + lane];
+    const int Lt = P.Lt[t];
+    const int Lmax = P.job_Lmax[job];
+    const float4* tc = P.cols + (size_t)P.col_off[t] * 7;
+    uint32_t* btj = P.bt + P.job_bt_off[job] + lane;
+    const size_t bt_row_stride = (size_t)(Lmax + 1) * 32;   // words per 4-row group
+    float4* b4 = P.bnd4 + P.job_bnd_off[job] + lane;
+    float* b1 = P.bnd1 + P.job_bnd_off[job] + lane;
+    const unsigned* prog_prev = P.progress + (size_t)job * P.nstrips + (s - 1);
+    unsigned* prog_mine = P.progress + (size_t)job * P.nstrips + s;
+    const bool last_strip = (s == P.nstrips - 1);
+    const uint32_t* co = nullptr;
+    if (CELLOFF) co = P.celloff + P.job_co_off[job] + (size_t)s * (Lmax + 1) * 32 + lane;
+
+    // ---- state of the R rows at the previous column (column 0 initially), :161-173
+    float MM[R], GD[R], IM[R], DG[R], MI[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      MM[r] = __fmul_rn((float)(-(i0 + 1 + r)), P.egq);
+      GD[r] = IM[r] = DG[r] = MI[r] = HHG_NEG;
+    }
+    // boundary row i0 at column j-1 (diagonal of the strip's first row)
+    float dtMM = __fmul_rn((float)(-i0), P.egq), dtDG = HHG_NEG, dtMI = HHG_NEG, dtGD = HHG_NEG,
+          dtIM = HHG_NEG;
+
+    float best = HHG_NEG;
+    int bi = 0, bj = 0;
+    unsigned avail = 0;   // columns of strip s-1 known to be published
+
+    // first column record (prefetch)
+    float4 nx[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) nx[k] = __ldg(tc + k);   // Lt >= 1
+
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+
+    for (int j = 1; j <= Lmax; ++j) {
+      // ---- current column operands (from the prefetch registers), prefetch the next column
+      unsigned long long tp[10];
+      tp[0] = pack2(nx[0].x, nx[0].y); tp[1] = pack2(nx[0].z, nx[0].w);
+      tp[2] = pack2(nx[1].x, nx[1].y); tp[3] = pack2(nx[1].z, nx[1].w);
+      tp[4] = pack2(nx[2].x, nx[2].y); tp[5] = pack2(nx[2].z, nx[2].w);
+      tp[6] = pack2(nx[3].x, nx[3].y); tp[7] = pack2(nx[3].z, nx[3].w);
+      tp[8] = pack2(nx[4].x, nx[4].y); tp[9] = pack2(nx[4].z, nx[4].w);
+      const float t_m2m = nx[5].x, t_m2d = nx[5].y, t_d2m = nx[5].z, t_d2d = nx[5].w;
+      const float t_i2m = nx[6].x, t_i2i = nx[6].y, t_m2i = nx[6].z;
+      const uint32_t t_ss = __float_as_uint(nx[6].w);
+      {
+        const int jn = min(j + 1, Lt);            // clamp: lanes shorter than the job keep re-reading
+        const float4* src = tc + (size_t)(jn - 1) * 7;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) nx[k] = __ldg(src + k);
+      }
+
+      // ---- boundary row i0 at column j
+      float tMM, tDG, tMI, tGD, tIM;
+      if (s == 0) {
+        tMM = __fmul_rn((float)(-j), P.egt);   // :148
+        tDG = tMI = tGD = tIM = HHG_NEG;
+      } else {
+        if ((unsigned)j > avail) {
+          unsigned v = 0;
+          if (lane == 0) {
+            v = ld_acquire(prog_prev);
+            while (v < (unsigned)j) { __nanosleep(64); v = ld_acquire(prog_prev); }
+          }
+          avail = __shfl_sync(0xffffffffu, v, 0);
+        }
+        const float4 v4 = __ldcg(b4 + (size_t)j * 32);
+        tIM = __ldcg(b1 + (size_t)j * 32);
+        tMM = v4.x; tDG = v4.y; tMI = v4.z; tGD = v4.w;
+      }
+      uint32_t cow = 0;
+      if (CELLOFF) cow = __ldg(co + (size_t)j * 32);
+
+      float dMM = dtMM, dGD = dtGD, dIM = dtIM, dDG = dtDG, dMI = dtMI;   // cell (i-1, j-1)
+      float uMM = tMM, uDG = tDG, uMI = tMI;                              // cell (i-1, j)
+      const float bcmp = (j <= Lt) ? best : INFINITY;   // padded columns never become the maximum
+      float bc = bcmp;
+
+      uint32_t word = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4* qr = qs + r * 7;
+        float4 q[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) q[k] = qr[k];
+        const float4 qa = qr[5], qb = qr[6];
+        const float q_m2m = qa.x, q_m2d = qa.y, q_d2m = qa.z, q_d2d = qa.w;
+        const float q_i2m = qb.x, q_i2i = qb.y, q_m2i = qb.z;
+
+        const float oMM = MM[r], oGD = GD[r], oIM = IM[r], oDG = DG[r], oMI = MI[r];   // (i, j-1)
+
+        // 5-way maximum with the reference's strict-'>' / first-wins rule, :241-273
+        uint32_t b;
+        float mm, c;
+        c = __fadd_rn(__fadd_rn(dMM, q_m2m), t_m2m);
+        b = (c > smin) ? 2u : 0u;
+        mm = fmaxf(smin, c);
+        c = __fadd_rn(__fadd_rn(dGD, q_m2m), t_d2m);
+        b = (c > mm) ? 3u : b;
+        mm = fmaxf(mm, c);
+        c = __fadd_rn(__fadd_rn(dIM, q_i2m), t_m2m);
+        b = (c > mm) ? 4u : b;
+        mm = fmaxf(mm, c);
+        c = __fadd_rn(__fadd_rn(dDG, q_d2m), t_m2m);
+        b = (c > mm) ? 5u : b;
+        mm = fmaxf(mm, c);
+        c = __fadd_rn(__fadd_rn(dMI, q_m2m), t_i2m);
+        b = (c > mm) ? 6u : b;
+        mm = fmaxf(mm, c);
+
+        float Si = log2f4_dev(dot20_dev(tp, q, P.one2));                       // :277
+        if (SS) {
+          const uint32_t q_ss = __float_as_uint(qb.w);
+          Si = __fadd_rn(__fmul_rn(P.ssw, s33[q_ss * 44 + t_ss]), Si);   // :210,279
+        }
+        Si = __fadd_rn(Si, P.shift);                                   // :281
+        mm = __fadd_rn(mm, Si);
+
+        float a1, a2, gd, im, dg, mi;
+        a1 = __fadd_rn(oMM, t_m2d); a2 = __fadd_rn(oGD, t_d2d);                                // :307
+        b |= (a1 > a2) ? 8u : 0u;  gd = fmaxf(a1, a2);
+        a1 = __fadd_rn(__fadd_rn(oMM, q_m2i), t_m2m); a2 = __fadd_rn(__fadd_rn(oIM, q_i2i), t_m2m);   // :324
+        b |= (a1 > a2) ? 16u : 0u; im = fmaxf(a1, a2);
+        a1 = __fadd_rn(uMM, q_m2d); a2 = __fadd_rn(uDG, q_d2d);                                // :340
+        b |= (a1 > a2) ? 32u : 0u; dg = fmaxf(a1, a2);
+        a1 = __fadd_rn(__fadd_rn(uMM, q_m2m), t_m2i); a2 = __fadd_rn(__fadd_rn(uMI, q_m2m), t_i2i);   // :358
+        b |= (a1 > a2) ? 64u : 0u; mi = fmaxf(a1, a2);
+
+        if (CELLOFF) {                                                 // :373-392
+          const float off = ((cow >> r) & 1u) ? HHG_NEG : 0.0f;
+          mm = __fadd_rn(mm, off); gd = __fadd_rn(gd, off); im = __fadd_rn(im, off);
+          dg = __fadd_rn(dg, off); mi = __fadd_rn(mi, off);
+        }
+
+        // running maximum, :423-455.  Strips are swept column-major, the reference row-major:
+        // on an exact tie the earlier ROW must win, hence the (rare) slow path.
+        if (mm >= bc) {
+          const int i = i0 + 1 + r;
+          const bool cand = (i <= P.Lq) && (LOCAL || i == P.Lq || j == Lt);
+          if (cand && (mm > best || i < bi)) { best = mm; bi = i; bj = j; bc = mm; }
+        }
+
+        word |= b << (8 * (r & 3));
+        if ((r & 3) == 3) {
+          __stcs(btj + (size_t)((i0 >> 2) + (r >> 2)) * bt_row_stride + (size_t)j * 32, word);
+          word = 0;
+        }
+        // rotate: this row's old values are the next row's diagonal, its new values the next row's up
+        dMM = oMM; dGD = oGD; dIM = oIM; dDG = oDG; dMI = oMI;
+        uMM = mm; uDG = dg; uMI = mi;
+        MM[r] = mm; GD[r] = gd; IM[r] = im; DG[r] = dg; MI[r] = mi;
+      }
+      dtMM = tMM; dtDG = tDG; dtMI = tMI; dtGD = tGD; dtIM = tIM;
+
+      if (!last_strip) {
+        __stcg(b4 + (size_t)j * 32, make_float4(MM[R - 1], DG[R - 1], MI[R - 1], GD[R - 1]));
+        __stcg(b1 + (size_t)j * 32, IM[R - 1]);
+        if ((j % kPublishEvery) == 0 || j == Lmax) {
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) st_release(prog_mine, (unsigned)j);
+        }
+      }
+    }
+    const size_t o = ((size_t)job * P.nstrips + s) * 32 + lane;
+    P.strip_score[o] = best;
+    P.strip_ij[o] = (bi << 16) | bj;
+    __syncwarp();   // all lanes done with the smem slice before the next TMA overwrites it
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backtrace: one thread per requested target.  Merges the per-strip maxima in row order (strict '>',
+// i.e. the reference's row-major first-occurrence rule) and walks the packed byte matrix.
+// ---------------------------------------------------------------------------------------------
+struct HitRec {
+  float score;
+  int i2, j2, i1, j1, nsteps, matched_cols, path_off;
+};
+
+struct BtParams {
+  int n_req;
+  int nstrips;
+  int job_begin, job_end;    // only requests whose job lies in [job_begin, job_end) are traced
+  const int* req_job;        // [n_req]
+  const int* req_lane;       // [n_req]
+  const int* job_Lmax;
+  const long long* job_bt_off;
+  const uint32_t* bt;
+  const float* strip_score;
+  const int* strip_ij;
+  const long long* path_off; // [n_req] offsets into paths
+  HitRec* hits;
+  uint8_t* paths;            // may be null
+};
+
+__device__ __forceinline__ uint32_t bt_byte(const uint32_t* btj, size_t row_stride, int i, int j) {
+  const uint32_t w = btj[(size_t)((i - 1) >> 2) * row_stride + (size_t)j * 32];
+  return (w >> (8 * ((i - 1) & 3))) & 0xFFu;
+}
+
+__global__ void k_backtrace(const BtParams P) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n_req) return;
+  const int job = P.req_job[k], lane = P.req_lane[k];
+  if (job < P.job_begin || job >= P.job_end) return;
+  float best = HHG_NEG;
+  int ij = 0;
+  for (int s = 0; s < P.nstrips; ++s) {
+    const size_t o = ((size_t)job * P.nstrips + s) * 32 + lane;
+    const float v = P.strip_score[o];
+    if (v > best) { best = v; ij = P.strip_ij[o]; }
+  }
+  const int i2 = ij >> 16, j2 = ij & 0xFFFF;
+  const int Lmax = P.job_Lmax[job];
+  const uint32_t* btj = P.bt + P.job_bt_off[job] + lane;
+  const size_t rs = (size_t)(Lmax + 1) * 32;
+  uint8_t* path = P.paths ? P.paths + P.path_off[k] : nullptr;
+
+  int step = 0, i = i2, j = j2, mc = 0, li = i2, lj = j2;
+  int state = 2;   // MM
+  while (state != 0) {
+    if (path) path[step] = (uint8_t)state;
+    ++step;
+    li = i; lj = j;
+    const uint32_t c = (i >= 1 && j >= 1) ? bt_byte(btj, rs, i, j) : 0u;
+    switch (state) {
+      case 2: ++mc; state = (i <= 1 || j <= 1) ? 0 : (int)(c & 7u); --i; --j; break;
+      case 3: if (j <= 1) state = 0; else { if (c & 8u) state = 2; --j; } break;
+      case 4: if (j <= 1) state = 0; else { if (c & 16u) state = 2; --j; } break;
+      case 5: if (i <= 1) state = 0; else { if (c & 32u) state = 2; --i; } break;
+      case 6: if (i <= 1) state = 0; else { if (c & 64u) state = 2; --i; } break;
+      default: state = 0; break;
+    }
+  }
+  if (path && step > 0) path[step - 1] = 2;   // states[nsteps] = MM, src/hhviterbi.cpp:147
+  HitRec h;
+  h.score = best; h.i2 = i2; h.j2 = j2; h.i1 = li; h.j1 = lj; h.nsteps = step;
+  h.matched_cols = mc; h.path_off = (int)P.path_off[k];
+  P.hits[k] = h;
+}
+
+// De-interleave one target's backtrace bytes into the reference's row-major cell matrix (parity tests).
+__global__ void k_debug_bt(const uint32_t* bt, long long bt_off, int lane, int Lmax, int Lq, int Lt,
+                           uint8_t* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = (Lq + 1) * (Lt + 1);
+  if (idx >= total) return;
+  const int i = idx / (Lt + 1), j = idx - i * (Lt + 1);
+  uint8_t v = 0;
+  if (i >= 1 && j >= 1) v = (uint8_t)bt_byte(bt + bt_off + lane, (size_t)(Lmax + 1) * 32, i, j);
+  out[idx] = v;
+}
+
+// Pack prepared profiles (include/hhg.h layout) into column records: thread per (target, column).
+__global__ void k_pack_cols(int n, const int* L, const long long* col_off, const long long* p_off,
+                            const long long* tr_off, const long long* ss_off, const float* p,
+                            const float* tr, const uint8_t* ss, ColRec* out, long long total_cols) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= total_cols) return;
+  // binary search the target owning column c
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (col_off[mid] <= c) lo = mid; else hi = mid - 1;
+  }
+  const int t = lo;
+  const int j = (int)(c - col_off[t]) + 1;   // 1-based column
+  const float* pp = p + p_off[t] + (size_t)j * 20;
+  const float* t1 = tr + tr_off[t] + (size_t)(j - 1) * 7;
+  const float* t0 = tr + tr_off[t] + (size_t)j * 7;
+  ColRec r;
+#pragma unroll
+  for (int a = 0; a < 20; ++a) r.p[a] = pp[a];
+  r.m2m = t1[0]; r.m2d = t1[2]; r.d2m = t1[5]; r.d2d = t1[6]; r.i2m = t1[3];
+  r.i2i = t0[4]; r.m2i = t0[1];
+  r.ss = ss ? (uint32_t)ss[ss_off[t] + j] : 0u;
+  out[c] = r;
+}
+
+// Rasterise excluded alignments into the cell-off bit words (Viterbi::ExcludeAlignment,
+// src/hhviterbi.cpp:61-77): one thread per excluded path step.
+__global__ void k_celloff_raster(int n_steps, const int* step_req, const int* step_i, const int* step_j,
+                                 const int* req_job, const int* req_lane, const int* req_Lt,
+                                 const int* job_Lmax, const long long* job_co_off, int Lq, int R,
+                                 uint32_t* co) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_steps) return;
+  const int rq = step_req[k];
+  const int job = req_job[rq], lane = req_lane[rq], Lt = req_Lt[rq];
+  const int Lmax = job_Lmax[job];
+  uint32_t* base = co + job_co_off[job] + lane;
+  const int i = step_i[k], j = step_j[k];
+  const int W = 40;   // VITERBI_PATH_WIDTH, src/hhdecl.h:50
+  for (int ii = max(i - W, 1); ii <= min(i + W, Lq); ++ii) {
+    const int s = (ii - 1) / R, r = (ii - 1) - s * R;
+    atomicOr(base + ((size_t)s * (Lmax + 1) + j) * 32, 1u << r);
+  }
+  for (int jj = max(j - W, 1); jj <= min(j + W, Lt); ++jj) {
+    const int s = (i - 1) / R, r = (i - 1) - s * R;
+    atomicOr(base + ((size_t)s * (Lmax + 1) + jj) * 32, 1u << r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cs219 ungapped prefilter (Prefilter::ungapped_sse_score, src/hhprefilter.cpp:214-275).
+//   S(i,j) = max(0, min(255, S(i-1,j-1) + prof[x_j][i]) - offset);  score = max over all cells.
+// One warp per database sequence; lane l owns query positions l, l+32, ... ; the diagonal
+// dependency S(i-1,j-1) comes from the lane below (shuffle) of the previous column.
+// The query profile (220 x Lq bytes) lives in shared memory, transposed to [pos][state] so the
+// lanes of a warp (consecutive positions, same state x_j) hit distinct banks.
+// Byte-SIMD: 4 query positions per 32-bit lane register (__vaddus4 / __vsubus4 / __vmaxu4).
+// ---------------------------------------------------------------------------------------------
+struct PfParams {
+  int n;
+  const int* L;
+  const long long* off;
+  const uint8_t* seq;
+  const uint8_t* prof;   // [220][Lq4] uint32-packed: prof4[k*W4 + w] = 4 consecutive positions
+  int Lq;
+  int W4;                // number of 4-position words = ceil(Lq/4)
+  int offset;
+  int* scores;
+  unsigned int* counter;
+};
+
+template <int WPL>   // 32-bit words (4 query positions each) per lane: covers Lq <= 128*WPL
+__global__ void __launch_bounds__(256) k_prefilter_ungapped(const PfParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* sprof = reinterpret_cast<uint32_t*>(smem_raw);   // [220][W4p] words, W4p = 32*WPL
+  const int W4p = 32 * WPL;
+  for (int idx = threadIdx.x; idx < 220 * W4p; idx += blockDim.x) {
+    const int k = idx / W4p, w = idx - k * W4p;
+    uint32_t v = 0;
+    if (w < P.W4) v = reinterpret_cast<const uint32_t*>(P.prof)[(size_t)k * P.W4 + w];
+    sprof[idx] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t off4 = 0x01010101u * (uint32_t)P.offset;
+  for (;;) {
+    int n = 0;
+    if (lane == 0) n = (int)atomicAdd(P.counter, 1u);
+    n = __shfl_sync(0xffffffffu, n, 0);
+    if (n >= P.n) break;
+    const uint8_t* x = P.seq + P.off[n];
+    const int L = P.L[n];
+    // lane l, word w holds query positions 4*(w*32 + l) .. +3   (word-interleaved across lanes)
+    uint32_t S[WPL];
+#pragma unroll
+    for (int w = 0; w < WPL; ++w) S[w] = 0;
+    uint32_t smax = 0;
+    for (int j0 = 0; j0 < L; j0 += 32) {
+      const int xl = (j0 + lane < L) ? (int)x[j0 + lane] : 0;
+      const int cnt = min(32, L - j0);
+      for (int jj = 0; jj < cnt; ++jj) {
+        const int xs = __shfl_sync(0xffffffffu, xl, jj);
+        const uint32_t* prow = sprof + xs * W4p + lane;
+        // shift the whole striped vector up by one query position: new S[pos] = old S[pos-1].
+        // Within a word: bytes shift left by 8 bits; the incoming low byte is the top byte of the
+        // previous word in position order = lane-1 of the same w (or lane 31 of w-1 for lane 0).
+        uint32_t carry_prev = 0;   // top byte of word (w-1, lane 31), for lane 0
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) {
+          const uint32_t top = S[w] >> 24;
+          uint32_t in = __shfl_up_sync(0xffffffffu, top, 1);
+          const uint32_t last = __shfl_sync(0xffffffffu, top, 31);
+          if (lane == 0) in = carry_prev;
+          carry_prev = last;
+          uint32_t v = (S[w] << 8) | in;
+          v = __vaddus4(v, prow[w * 32]);
+          v = __vsubus4(v, off4);
+          S[w] = v;
+          smax = __vmaxu4(smax, v);
+        }
+      }
+    }
+    // horizontal max over bytes and lanes
+    uint32_t m = max(max(smax & 0xFFu, (smax >> 8) & 0xFFu), max((smax >> 16) & 0xFFu, smax >> 24));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) P.scores[n] = (int)m;
+  }
+}
+
+}  // namespace hhg

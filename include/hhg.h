@@ -1,0 +1,147 @@
+/* include/hhg.h -- C-ABI of the B200-native HH-suite hot path (Viterbi HMM-HMM alignment +
+ * cs219 ungapped prefilter).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * This is the boundary a reference maintainer binds to.  The reference (soedinglab/hh-suite) has no
+ * FFI layer; the seam is two C++ member calls, and each entry point below names the reference
+ * interface it replaces (paths relative to the reference tree):
+ *
+ *   ViterbiRunner::alignment            src/hhviterbirunner.h:55   -> hhg_viterbi_search
+ *   Viterbi::Align                      src/hhviterbi.h:63         -> (inside hhg_viterbi_search)
+ *   Viterbi::Backtrace                  src/hhviterbi.h:99         -> (inside hhg_viterbi_search)
+ *   Viterbi::ExcludeAlignment           src/hhviterbi.h:112        -> hhg_viterbi_search(excl_*)
+ *   HMMSimd::MapHMMVector               src/hhhmmsimd.h:35         -> hhg_db_create (device layout)
+ *   HMMSimd::MapOneHMM                  src/hhhmmsimd.h:34         -> hhg_query_set
+ *   ViterbiMatrix (backtrace bytes)     src/hhviterbimatrix.h:29   -> hhg_viterbi_debug_bt
+ *   Prefilter::ungapped_sse_score       src/hhprefilter.h:108      -> hhg_prefilter_ungapped
+ *   Prefilter::prefilter_db (stage 1)   src/hhprefilter.h:80       -> hhg_prefilter_ungapped
+ *
+ * Error convention: every function returns 0 on success or a negative HHG_E* code;
+ * hhg_last_error() returns a thread-local message.  (The reference logs and exit()s,
+ * src/hhviterbimatrix.cpp:45; the host adapter maps a non-zero status to the same behaviour.)
+ * Threading: one hhg_ctx per (host thread, GPU); calls on different contexts are independent
+ * (hhblits_omp calls the path concurrently, src/hhblits_omp.cpp:119-138).
+ *
+ * Profile layout ("prepared profile" = what PrepareQueryHMM / PrepareTemplateHMM leave in HMM::p and
+ * HMM::tr, src/hhfunc.cpp:121-202):
+ *   p  : float[(L+2)*20]  p[i*20+a], i = 0..L+1                       (HMM::p,  src/hhhmm.h:153)
+ *   tr : float[(L+1)*7]   tr[i*7+k], k = M2M,M2I,M2D,I2M,I2I,D2M,D2D  (HMM::tr, src/hhdecl.h:68), log2
+ *   ss : uint8[L+2]       ss[i] = ss_pred[i]*11 + ss_conf[i]          (src/hhhmmsimd.cpp:133); may be NULL
+ */
+#ifndef HHG_H_
+#define HHG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HHG_OK 0
+#define HHG_EINVAL (-1)   /* bad argument */
+#define HHG_ECUDA (-2)    /* CUDA runtime error (message in hhg_last_error) */
+#define HHG_ENOMEM (-3)   /* device or host allocation failed */
+#define HHG_ENODEV (-4)   /* no usable sm_100 device: there is NO CPU fallback */
+
+typedef struct hhg_ctx hhg_ctx;   /* one GPU + one stream + scratch */
+typedef struct hhg_db hhg_db;     /* a device-resident shard of prepared target profiles */
+typedef struct hhg_csdb hhg_csdb; /* a device-resident shard of cs219 column-state sequences */
+
+/* Alignment parameters: the hot-path knobs of the reference's Parameters (src/hhdecl.cpp:82-127). */
+typedef struct hhg_params {
+  int local;        /* par.loc   (1)      : local (Smith-Waterman like) vs global            */
+  float egq;        /* par.egq   (0)      : end-gap penalty query                             */
+  float egt;        /* par.egt   (0)      : end-gap penalty template                          */
+  float shift;      /* par.shift (-0.03)  : score offset per match-match cell                 */
+  float ssw;        /* par.ssw   (0.11)   : secondary-structure weight                        */
+  int use_ss;       /* 1 = PRED_PRED ss term during alignment (Viterbi::Align dispatch,       */
+                    /*     src/hhviterbi.cpp:177; needs ss arrays on query and db + S33)      */
+} hhg_params;
+
+/* Per-target result: ViterbiResult (src/hhviterbi.h:21) + the scalar part of BacktraceResult (:34). */
+typedef struct hhg_hit {
+  float score;      /* raw Viterbi score (ViterbiResult::score)                               */
+  int32_t i2, j2;   /* end of alignment  (ViterbiResult::i/j)                                 */
+  int32_t i1, j1;   /* start of alignment (i_steps[nsteps], j_steps[nsteps])                  */
+  int32_t nsteps;   /* BacktraceResult::count                                                 */
+  int32_t matched_cols;
+  int32_t path_off; /* offset of this target's state string in the `paths` buffer             */
+} hhg_hit;
+
+const char* hhg_last_error(void);
+
+/* device < 0: use the current CUDA device.  stream: a cudaStream_t cast to void* or NULL for a
+ * private stream (bench.py passes torch's current stream so torch.cuda.Event brackets the work). */
+int hhg_ctx_create(int device, void* stream, hhg_ctx** out);
+int hhg_ctx_destroy(hhg_ctx* ctx);
+int hhg_ctx_sync(hhg_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long hhg_ctx_launch_count(hhg_ctx* ctx);
+
+/* Build the device-resident target shard from n prepared profiles held in HOST memory.
+ *   L[n]; p_off[n] = float offset of target k's p block inside `p`; tr_off[n] likewise inside `tr`;
+ *   ss_off[n] = byte offset inside `ss` (ignored when ss == NULL).
+ * Device layout: one 112-byte column record per target column j=1..L:
+ *   {p[j][0..19], tr[j-1][M2M,M2D,D2M,D2D,I2M], tr[j][I2I,M2I], ss[j]}  (the operands of cell (.,j),
+ *   src/hhviterbialgorithm.cpp:219-228,277). */
+int hhg_db_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_off, const int64_t* tr_off,
+                  const int64_t* ss_off, const float* p, const float* tr, const uint8_t* ss,
+                  hhg_db** out);
+int hhg_db_destroy(hhg_db* db);
+int hhg_db_size(const hhg_db* db);          /* number of targets */
+long long hhg_db_columns(const hhg_db* db); /* sum of target lengths */
+
+/* Set the query (replaces HMMSimd::MapOneHMM).  S33: float[44*44] or NULL (needed iff use_ss). */
+int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const uint8_t* ss,
+                  const float* S33, const hhg_params* par);
+
+/* Align the current query against `n` targets of `db` (ids == NULL: all targets in db order).
+ *   hits[n]      : one record per requested target, in request order.
+ *   paths        : caller buffer of `paths_cap` bytes receiving, per target, nsteps state bytes
+ *                  (ViterbiMatrix codes MM=2,GD=3,IM=4,DG=5,MI=6; byte 0 = step 1 = cell (i2,j2),
+ *                  last byte = step nsteps, forced to MM like src/hhviterbi.cpp:147); may be NULL.
+ *   excl_*       : optional cell-off input = previous alignments to exclude (alternative alignments,
+ *                  src/hhviterbirunner.cpp:277-288): for request k, the path steps
+ *                  excl_i/excl_j[excl_off[k] .. excl_off[k+1]) are masked with the +-40 cross of
+ *                  Viterbi::ExcludeAlignment.  NULL = no cell-off (AlignWithOutCellOff variants).
+ * All host buffers; copies in and out are part of the call. */
+int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_hit* hits,
+                       uint8_t* paths, size_t paths_cap, const int64_t* excl_off,
+                       const int32_t* excl_i, const int32_t* excl_j);
+
+/* Device-resident variant used for kernel-only timing: plan once, run many times, fetch at the end. */
+typedef struct hhg_plan hhg_plan;
+int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_plan** out);
+int hhg_plan_destroy(hhg_plan* plan);
+/* Enqueue forward pass + backtrace on the context stream; no host sync. */
+int hhg_plan_run(hhg_ctx* ctx, hhg_plan* plan);
+/* Copy results of the last run to the host (synchronises). paths may be NULL. */
+int hhg_plan_fetch(hhg_ctx* ctx, hhg_plan* plan, hhg_hit* hits, uint8_t* paths, size_t paths_cap);
+/* sum over planned targets of Lq*Lt (the unit of the GCUPS metric) and padded cells actually computed */
+double hhg_plan_cells(const hhg_plan* plan);
+double hhg_plan_padded_cells(const hhg_plan* plan);
+/* Algorithmic bytes of one run: 112 B per target column + 1 B per cell + 32 B per hit */
+double hhg_plan_algorithmic_bytes(const hhg_plan* plan);
+
+/* Debug / parity: raw backtrace bytes of request k of the last run of `plan` in the reference's
+ * ViterbiMatrix cell format, row-major bt[i*(Lt+1)+j] (host buffer of (Lq+1)*(Lt+1) bytes). */
+int hhg_plan_debug_bt(hhg_ctx* ctx, hhg_plan* plan, int k, uint8_t* bt);
+
+/* ---- cs219 ungapped prefilter (stage 1 of Prefilter::prefilter_db, src/hhprefilter.cpp:466-482) */
+int hhg_csdb_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* off, const uint8_t* seq,
+                    hhg_csdb** out);
+int hhg_csdb_destroy(hhg_csdb* db);
+/* prof: uint8[220*Lq] linear query profile prof[k*Lq+pos] (the un-striped content of
+ * Prefilter::stripe_query_profile, src/hhprefilter.cpp:356-424).  scores[n] receives the raw maximum
+ * ungapped score per sequence (0..255), before the length correction of :477. */
+int hhg_prefilter_ungapped(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const uint8_t* prof, int offset,
+                           int32_t* scores);
+/* device-resident timing variant: scores stay on the device until fetched */
+int hhg_prefilter_ungapped_run(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const uint8_t* prof_host,
+                               int offset, int upload_profile);
+int hhg_prefilter_fetch(hhg_ctx* ctx, const hhg_csdb* db, int32_t* scores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HHG_H_ */

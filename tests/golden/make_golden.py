@@ -1,0 +1,115 @@
+"""Generate tests/golden/golden_v1.npz from the UNMODIFIED compiled reference (oracle/_ref).
+
+Run in the authoring container only (needs /root/reference and `make -C oracle ref`):
+    python tests/golden/make_golden.py
+Every array below is produced by reference code paths:
+  * HMM::Read + PrepareQueryHMM / PrepareTemplateHMM   -> prepared fp32 profiles
+  * Viterbi::Align (AVX2, no FMA)                      -> score, i2, j2, backtrace bytes
+  * Viterbi::Backtrace / ScoreForBacktrace             -> path, Hit.score
+  * Prefilter::stripe_query_profile / ungapped_sse_score / swStripedByte
+The synthetic inputs come from hh-suite_b200/synth.py with fixed seeds.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.binding import RefShim  # noqa: E402
+import hhsuite_b200  # noqa: E402
+from hhsuite_b200 import synth  # noqa: E402
+
+REFDATA = "/root/reference/data"
+OUT = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def main():
+    R = RefShim(nocontxt=True, maxres=4096)
+    G = {}
+    # ---- config 1: data/query.hhm vs one synthetic HMM (L=150), plus self and reversed-self
+    q = R.load_query_hhm(os.path.join(REFDATA, "query.hhm"))
+    G["q_p"], G["q_tr"], G["q_pav"], G["q_ss"] = q["p"], q["tr"], q["pav"], q["ss"]
+    txt = synth.hhm_text(150, 7, "synth150")
+    open("/tmp/synth150.hhm", "w").write(txt)
+    G["synth150_hhm_sha"] = np.frombuffer(hashlib.sha256(txt.encode()).digest(), np.uint8)
+    t = R.prepare_template_hhm("/tmp/synth150.hhm")
+    ts = R.prepare_template_hhm(os.path.join(REFDATA, "query.hhm"))
+    rev = dict(p=np.ascontiguousarray(np.concatenate([ts["p"][:1], ts["p"][1:-1][::-1], ts["p"][-1:]])),
+               tr=ts["tr"], ss=ts["ss"])
+    for name, tt in (("t150", t), ("tself", ts), ("trev", rev)):
+        G[name + "_p"], G[name + "_tr"] = tt["p"], tt["tr"]
+    res = R.viterbi([(t["p"], t["tr"], None), (ts["p"], ts["tr"], None), (rev["p"], rev["tr"], None)])
+    for k, name in enumerate(("t150", "tself", "trev")):
+        sc, i2, j2, bt = res[k]
+        n, i_s, j_s, st, mc = R.backtrace(k)
+        hs, hss = R.hit_score(k)
+        G[name + "_res"] = np.array([i2, j2, n, mc, i_s[n], j_s[n]], np.int32)
+        G[name + "_score"] = np.array([sc, hs], np.float32)
+        G[name + "_states"] = st[1:]
+        G[name + "_bt_sha"] = sha(bt[1:, 1:])
+        if name == "t150":
+            G[name + "_bt"] = bt
+    # ---- variants on small synthetic prepared profiles: SS, cell-off, global, ragged 8-lane batch
+    qp, qtr, qss, qpav, _ = synth.query_profile(120, 5)
+    G["v_q_p"], G["v_q_tr"], G["v_q_ss"], G["v_q_pav"] = qp, qtr, qss, qpav
+    R.set_query(qp, qtr, qpav, qss)
+    G["S33"] = R.S33()
+    rng = np.random.default_rng(11)
+    lens = [100, 77, 64, 33, 150, 31, 8, 1]
+    tg = [synth.prepared_profile(L, rng) for L in lens]
+    for k, (p, tr, ss) in enumerate(tg):
+        G[f"v_t{k}_p"], G[f"v_t{k}_tr"], G[f"v_t{k}_ss"] = p, tr, ss
+    co = []
+    for (p, tr, ss) in tg:
+        m = np.zeros((121, p.shape[0] - 1), np.uint8)
+        m[40:60, :] = 1
+        m[:, 20:25] = 1
+        m[(np.add.outer(np.arange(121), np.arange(p.shape[0] - 1)) % 17) == 0] = 1
+        co.append(m)
+    G["v_celloff_rows"] = np.array([40, 60, 20, 25, 17], np.int32)
+    variants = dict(plain={}, ss=dict(use_ss=True), co=dict(celloff=co), co_ss=dict(celloff=co, use_ss=True),
+                    glob=dict(local=False, egq=0.1, egt=0.2))
+    for vn, kw in variants.items():
+        if vn == "glob":
+            # global mode is only well defined by the reference for equal-length lanes: one target per call
+            out = [R.viterbi([tg[k]], **kw)[0] for k in range(len(tg))]
+        else:
+            out = R.viterbi(tg, **kw)
+        for k, (sc, i2, j2, bt) in enumerate(out):
+            G[f"v_{vn}_{k}_res"] = np.array([i2, j2], np.int32)
+            G[f"v_{vn}_{k}_score"] = np.array([sc], np.float32)
+            G[f"v_{vn}_{k}_bt"] = bt
+    # ---- prefilter
+    q = R.load_query_hhm(os.path.join(REFDATA, "query.hhm"))
+    lib = R.cs219()
+    G["cs219_lin"] = lib
+    qc, W = R.stripe_query_profile(50, 4)
+    Lq = q["L"]
+    # un-stripe the reference profile: qc[k*W*32 + (pos % W)*32 + pos // W]  
+    prof = np.zeros((220, Lq), np.uint8)
+    pos = np.arange(Lq)
+    for k in range(220):
+        prof[k] = qc[k * W * 32 + (pos % W) * 32 + pos // W]
+    G["pf_prof"] = prof
+    rng = np.random.default_rng(3)
+    seqs = [rng.integers(0, 219, L, dtype=np.uint8) for L in (30, 64, 200, 431, 777, 1)]
+    # a planted near-match: the argmax state per query column
+    best = prof[:219].argmax(axis=0).astype(np.uint8)
+    seqs.append(best[50:250].copy())
+    seqs.append(best.copy())
+    G["pf_nseq"] = np.array([len(seqs)], np.int32)
+    for k, s in enumerate(seqs):
+        G[f"pf_seq{k}"] = s
+        G[f"pf_ref{k}"] = np.array([R.ungapped(qc, s, 50), R.sw_byte(qc, s, 24, 4, 50)], np.int32)
+    np.savez_compressed(OUT, **G)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(G), "arrays")
+
+
+if __name__ == "__main__":
+    main()
