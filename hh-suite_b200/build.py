@@ -23,6 +23,15 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
+def build_variant(tag: str, defines: list[str]) -> str:
+    """Developer helper: compile a kernel variant (-D switches) to hh-suite_b200/variants/libhhg_<tag>.so."""
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, f"libhhg_{tag}.so")
+    subprocess.check_call([NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-o", out, SRC])
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or stale():
         if not os.path.exists(NVCC):

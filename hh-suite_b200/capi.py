@@ -32,7 +32,7 @@ HIT_DTYPE = np.dtype([("score", np.float32), ("i2", np.int32), ("j2", np.int32),
 
 SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync", "hhg_ctx_launch_count",
            "hhg_db_create", "hhg_db_destroy", "hhg_db_size", "hhg_db_columns", "hhg_query_set",
-           "hhg_viterbi_search", "hhg_plan_create", "hhg_plan_destroy", "hhg_plan_run", "hhg_plan_fetch",
+           "hhg_viterbi_search", "hhg_plan_create", "hhg_plan_destroy", "hhg_plan_run", "hhg_plan_run_timed", "hhg_plan_fetch", "hhg_plan_hits_devptr",
            "hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes", "hhg_plan_debug_bt",
            "hhg_csdb_create", "hhg_csdb_destroy", "hhg_prefilter_ungapped", "hhg_prefilter_ungapped_run",
            "hhg_prefilter_fetch"]
@@ -59,7 +59,7 @@ def load():
     if _lib is not None:
         return _lib
     from . import build as _build
-    path = _build.build()
+    path = os.environ.get("HHG_LIB") or _build.build()   # HHG_LIB: developer override (kernel variants)
     L = C.CDLL(path)
     L.hhg_last_error.restype = C.c_char_p
     L.hhg_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -79,10 +79,13 @@ def load():
     L.hhg_plan_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, C.POINTER(C.c_void_p)]
     L.hhg_plan_destroy.argtypes = [C.c_void_p]
     L.hhg_plan_run.argtypes = [C.c_void_p, C.c_void_p]
+    L.hhg_plan_run_timed.argtypes = [C.c_void_p, C.c_void_p, c_f32p, c_f32p]
     L.hhg_plan_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, c_u8p, C.c_size_t]
     for f in ("hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes"):
         getattr(L, f).argtypes = [C.c_void_p]
         getattr(L, f).restype = C.c_double
+    L.hhg_plan_hits_devptr.argtypes = [C.c_void_p]
+    L.hhg_plan_hits_devptr.restype = C.c_void_p
     L.hhg_plan_debug_bt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p]
     L.hhg_csdb_create.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i64p, c_u8p, C.POINTER(C.c_void_p)]
     L.hhg_csdb_destroy.argtypes = [C.c_void_p]
@@ -183,9 +186,16 @@ class Plan:
     def run(self):
         _ck(self.ctx.L.hhg_plan_run(self.ctx.h, self.h))
 
-    def fetch(self, want_paths=True):
-        hits = np.zeros(self.n, HIT_DTYPE)
-        paths = np.zeros(self.path_cap, np.uint8) if want_paths else None
+    def run_timed(self):
+        """Returns (ms_viterbi_kernels, ms_backtrace_kernels) measured with CUDA events on the stream."""
+        a = C.c_float(); b = C.c_float()
+        _ck(self.ctx.L.hhg_plan_run_timed(self.ctx.h, self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fetch(self, want_paths=True, hits=None, paths=None):
+        hits = np.zeros(self.n, HIT_DTYPE) if hits is None else hits
+        if want_paths and paths is None:
+            paths = np.zeros(self.path_cap, np.uint8)
         _ck(self.ctx.L.hhg_plan_fetch(self.ctx.h, self.h, hits.ctypes.data_as(C.c_void_p), _p(paths, c_u8p),
                                       self.path_cap if want_paths else 0))
         return hits, paths
@@ -202,14 +212,19 @@ class Plan:
             self.h = None
 
 
-def viterbi_search(ctx: Context, db: TargetDB, ids=None, exclusions=None, want_paths=True):
+def viterbi_search(ctx: Context, db: TargetDB, ids=None, exclusions=None, want_paths=True, hits=None,
+                   paths=None):
     """One ViterbiRunner::alignment-style call with host buffers in and out.
-    exclusions: optional list (per request) of (i_steps, j_steps) int arrays to mask (alt. alignments)."""
+    exclusions: optional list (per request) of (i_steps, j_steps) int arrays to mask (alt. alignments).
+    hits/paths: optional caller-owned (e.g. pinned) output buffers."""
     ids = np.arange(db.n, dtype=np.int32) if ids is None else np.ascontiguousarray(ids, np.int32)
     n = len(ids)
-    hits = np.zeros(n, HIT_DTYPE)
+    hits = np.zeros(n, HIT_DTYPE) if hits is None else hits
     cap = int(np.sum(ctx.Lq + db.Lh[ids].astype(np.int64) + 2))
-    paths = np.zeros(cap, np.uint8) if want_paths else None
+    if want_paths and paths is None:
+        paths = np.zeros(cap, np.uint8)
+    if not want_paths:
+        paths = None
     eo = ei = ej = None
     if exclusions is not None:
         cnt = np.array([0 if e is None else len(e[0]) for e in exclusions], np.int64)

@@ -78,6 +78,8 @@ struct hhg_ctx {
   long long launches = 0;
   // query
   int Lq = 0, R = 16, nstrips = 0;
+  int group_jobs = 64;   // work-item interleave (see k_viterbi)
+  uint32_t epoch = 0;    // run counter feeding the boundary-slot tags
   DevBuf<float4> qrec;
   DevBuf<float> S33;
   bool has_ss = false, has_S33 = false;
@@ -86,6 +88,8 @@ struct hhg_ctx {
   DevBuf<uint8_t> pf_prof;
   DevBuf<unsigned> pf_counter;
   size_t max_bt_bytes = 0;   // memory-wave budget for backtrace words
+  struct hhg_plan* scratch_plan = nullptr;   // reused by hhg_viterbi_search
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct hhg_db {
@@ -131,10 +135,11 @@ struct hhg_plan {
   DevBuf<int> d_job_target, d_job_Lmax, d_req_job, d_req_lane, d_req_Lt;
   DevBuf<long long> d_job_bt_off, d_job_bnd_off, d_job_co_off, d_path_off;
   DevBuf<uint32_t> d_bt, d_co;
-  DevBuf<float4> d_bnd4;
-  DevBuf<float> d_bnd1, d_strip_score;
+  DevBuf<BndSlot> d_bnd;
+  DevBuf<float> d_strip_score;
   DevBuf<int> d_strip_ij;
-  DevBuf<unsigned> d_progress, d_counter;
+  DevBuf<unsigned> d_counter;
+  float ms_viterbi = 0, ms_backtrace = 0;   // filled by hhg_plan_run_timed
   DevBuf<HitRec> d_hits;
   DevBuf<uint8_t> d_paths;
   // cell-off input (optional)
@@ -144,6 +149,8 @@ struct hhg_plan {
 };
 
 extern "C" {
+
+int hhg_plan_destroy(hhg_plan* plan);
 
 const char* hhg_last_error(void) { return g_err.c_str(); }
 
@@ -172,6 +179,7 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
     c->own_stream = true;
   }
   c->R = strip_rows();
+  { const char* ge = getenv("HHG_GROUP_JOBS"); c->group_jobs = ge ? std::max(1, atoi(ge)) : 64; }
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const char* env = getenv("HHG_MAX_BT_GB");
@@ -184,6 +192,8 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
 int hhg_ctx_destroy(hhg_ctx* ctx) {
   if (!ctx) return HHG_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->scratch_plan) hhg_plan_destroy(ctx->scratch_plan);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return HHG_OK;
@@ -332,19 +342,23 @@ int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const u
 }
 
 // ---------------------------------------------------------------------------------------- plan
-int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_plan** out) {
-  if (!ctx || !db || !out || n <= 0) return fail(HHG_EINVAL, "hhg_plan_create: bad argument");
+// (Re)build a plan in place; device buffers only ever grow, so a plan object that is reused across
+// searches (hhg_viterbi_search keeps one per context) does not touch cudaMalloc in steady state.
+static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const int32_t* ids) {
+  if (!ctx || !db || n <= 0) return fail(HHG_EINVAL, "hhg_plan_create: bad argument");
   if (ctx->Lq <= 0) return fail(HHG_EINVAL, "hhg_plan_create: no query set");
   if (db->device != ctx->device) return fail(HHG_EINVAL, "db lives on device %d, ctx on %d", db->device, ctx->device);
   CK(cudaSetDevice(ctx->device));
-  hhg_plan* pl = new hhg_plan();
   pl->db = db;
+  pl->cells = pl->padded_cells = pl->alg_bytes = 0;
+  pl->waves.clear();
+  pl->celloff = false;
   pl->n = n;
   pl->Lq = ctx->Lq; pl->R = ctx->R; pl->nstrips = ctx->nstrips;
   pl->ids.resize(n);
   for (int k = 0; k < n; ++k) {
     const int id = ids ? ids[k] : k;
-    if (id < 0 || id >= db->n) { delete pl; return fail(HHG_EINVAL, "request %d: target id %d out of range", k, id); }
+    if (id < 0 || id >= db->n) return fail(HHG_EINVAL, "request %d: target id %d out of range", k, id);
     pl->ids[k] = id;
   }
   // sort requests by target length, longest first (as ViterbiRunner does per chunk,
@@ -407,24 +421,26 @@ int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, h
     pl->cells += (double)pl->Lq * Lt;
     cols_sum += Lt;
   }
-  if (po > 0x7fffffffLL) { delete pl; return fail(HHG_EINVAL, "plan too large: %lld path bytes (> 2^31-1); split the request", po); }
+  if (po > 0x7fffffffLL) return fail(HHG_EINVAL, "plan too large: %lld path bytes (> 2^31-1); split the request", po);
   pl->path_total = po;
   pl->alg_bytes = cols_sum * 112.0 + pl->cells * 1.0 + 32.0 * n;
 
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-  A(pl->d_job_target.alloc(job_target.size())); A(pl->d_job_Lmax.alloc(pl->njobs));
-  A(pl->d_job_bt_off.alloc(pl->njobs)); A(pl->d_job_bnd_off.alloc(pl->njobs)); A(pl->d_job_co_off.alloc(pl->njobs));
-  A(pl->d_req_job.alloc(n)); A(pl->d_req_lane.alloc(n)); A(pl->d_req_Lt.alloc(n)); A(pl->d_path_off.alloc(n));
-  A(pl->d_bt.alloc(max_wave_words));
-  A(pl->d_bnd4.alloc((size_t)bnd)); A(pl->d_bnd1.alloc((size_t)bnd));
-  A(pl->d_strip_score.alloc((size_t)pl->njobs * pl->nstrips * 32));
-  A(pl->d_strip_ij.alloc((size_t)pl->njobs * pl->nstrips * 32));
-  A(pl->d_progress.alloc((size_t)pl->njobs * pl->nstrips));
-  A(pl->d_counter.alloc(pl->waves.size()));
-  A(pl->d_hits.alloc(n));
-  A(pl->d_paths.alloc((size_t)po));
-  if (e != cudaSuccess) { delete pl; return fail(HHG_ENOMEM, "hhg_plan_create: %s", cudaGetErrorString(e)); }
+  A(pl->d_job_target.ensure(job_target.size())); A(pl->d_job_Lmax.ensure(pl->njobs));
+  A(pl->d_job_bt_off.ensure(pl->njobs)); A(pl->d_job_bnd_off.ensure(pl->njobs)); A(pl->d_job_co_off.ensure(pl->njobs));
+  A(pl->d_req_job.ensure(n)); A(pl->d_req_lane.ensure(n)); A(pl->d_req_Lt.ensure(n)); A(pl->d_path_off.ensure(n));
+  A(pl->d_bt.ensure(max_wave_words));
+  { BndSlot* before = pl->d_bnd.p; A(pl->d_bnd.ensure((size_t)bnd));
+    // fresh slots must not carry a bit pattern that looks like a valid tag (epochs start at 1)
+    if (e == cudaSuccess && pl->d_bnd.p != before) A(cudaMemsetAsync(pl->d_bnd.p, 0, pl->d_bnd.n * sizeof(BndSlot), ctx->stream)); }
+  A(pl->d_strip_score.ensure((size_t)pl->njobs * pl->nstrips * 32));
+  A(pl->d_strip_ij.ensure((size_t)pl->njobs * pl->nstrips * 32));
+  A(pl->d_counter.ensure(pl->waves.size()));
+  A(pl->d_hits.ensure(n));
+  A(pl->d_paths.ensure((size_t)po));
+  if (e != cudaSuccess) return fail(HHG_ENOMEM, "hhg_plan_create: %s", cudaGetErrorString(e));
+
   cudaStream_t st = ctx->stream;
   CK(cudaMemcpyAsync(pl->d_job_target.p, job_target.data(), job_target.size() * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_job_Lmax.p, pl->job_Lmax.data(), (size_t)pl->njobs * 4, cudaMemcpyHostToDevice, st));
@@ -436,6 +452,14 @@ int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, h
   CK(cudaMemcpyAsync(pl->d_req_Lt.p, req_Lt.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_path_off.p, pl->path_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));
+  return HHG_OK;
+}
+
+int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_plan** out) {
+  if (!out) return fail(HHG_EINVAL, "hhg_plan_create: out is NULL");
+  hhg_plan* pl = new hhg_plan();
+  int rc = plan_build(ctx, pl, db, n, ids);
+  if (rc != HHG_OK) { delete pl; return rc; }
   *out = pl;
   return HHG_OK;
 }
@@ -482,7 +506,9 @@ static int set_exclusions(hhg_ctx* ctx, hhg_plan* pl, const int64_t* excl_off, c
 
 template <int R>
 static int launch_viterbi(hhg_ctx* ctx, const VitParams& P, bool local, bool ss, bool co, int items) {
-  const size_t smem = (size_t)kWarpsPerCta * R * 112 + 64 + (ss ? 44 * 44 * 4 : 0);
+  const size_t smem = (size_t)kWarpsPerCta * R * 112 +
+                      (HHG_USE_CPASYNC ? (size_t)kWarpsPerCta * kStages * 32 * 112 : 0) + 64 +
+                      (ss ? 44 * 44 * 4 : 0);
   void (*kern)(const VitParams) = nullptr;
 #define PICK(L_, S_, C_) kern = k_viterbi<R, L_, S_, C_>
   if (local) { if (ss) { if (co) PICK(true, true, true); else PICK(true, true, false); }
@@ -506,7 +532,7 @@ static int launch_viterbi(hhg_ctx* ctx, const VitParams& P, bool local, bool ss,
 
 extern "C" {
 
-int hhg_plan_run(hhg_ctx* ctx, hhg_plan* pl) {
+static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
   if (!ctx || !pl) return fail(HHG_EINVAL, "hhg_plan_run: bad argument");
   if (pl->Lq != ctx->Lq || pl->R != ctx->R) return fail(HHG_EINVAL, "plan was made for another query length");
   const hhg_db* db = pl->db;
@@ -514,8 +540,9 @@ int hhg_plan_run(hhg_ctx* ctx, hhg_plan* pl) {
     return fail(HHG_EINVAL, "use_ss requested but query/db/S33 carry no ss information");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  CK(cudaMemsetAsync(pl->d_progress.p, 0, pl->d_progress.n * 4, st));
-  CK(cudaMemsetAsync(pl->d_counter.p, 0, pl->d_counter.n * 4, st));
+  ctx->epoch = (ctx->epoch + 1) & 0xFFFFFu;   // slot tags of earlier runs never match (20-bit epoch)
+  if (ctx->epoch == 0) ctx->epoch = 1;
+  CK(cudaMemsetAsync(pl->d_counter.p, 0, pl->waves.size() * 4, st));
   for (size_t wi = 0; wi < pl->waves.size(); ++wi) {
     const Wave& w = pl->waves[wi];
     const int nj = w.job_end - w.job_begin;
@@ -528,8 +555,8 @@ int hhg_plan_run(hhg_ctx* ctx, hhg_plan* pl) {
     P.job_bt_off = pl->d_job_bt_off.p + w.job_begin;
     P.job_bnd_off = pl->d_job_bnd_off.p + w.job_begin;
     P.job_co_off = pl->d_job_co_off.p + w.job_begin;
-    P.bt = pl->d_bt.p; P.bnd4 = pl->d_bnd4.p; P.bnd1 = pl->d_bnd1.p;
-    P.progress = pl->d_progress.p + (size_t)w.job_begin * pl->nstrips;
+    P.bt = pl->d_bt.p; P.bnd = pl->d_bnd.p;
+    P.tag_base = ctx->epoch << 12;
     P.counter = pl->d_counter.p + wi;
     P.strip_score = pl->d_strip_score.p + (size_t)w.job_begin * pl->nstrips * 32;
     P.strip_ij = pl->d_strip_ij.p + (size_t)w.job_begin * pl->nstrips * 32;
@@ -537,11 +564,14 @@ int hhg_plan_run(hhg_ctx* ctx, hhg_plan* pl) {
     P.S33 = ctx->has_S33 ? ctx->S33.p : nullptr;
     P.egq = ctx->par.egq; P.egt = ctx->par.egt; P.shift = ctx->par.shift; P.ssw = ctx->par.ssw;
     P.one2 = 0x3F8000003F800000ull;
+    P.group_jobs = ctx->group_jobs;
     const int items = nj * pl->nstrips;
     int rc;
+    if (timed) CK(cudaEventRecord(ctx->ev[0], st));
     if (pl->R == 8) rc = launch_viterbi<8>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
     else rc = launch_viterbi<16>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
     if (rc != HHG_OK) return rc;
+    if (timed) CK(cudaEventRecord(ctx->ev[1], st));
     // backtrace of this wave's requests.  Requests are addressed through the sorted order: the
     // wave covers sorted positions [req_begin, req_end); req_job/req_lane are per original request.
     BtParams B{};
@@ -556,7 +586,33 @@ int hhg_plan_run(hhg_ctx* ctx, hhg_plan* pl) {
     k_backtrace<<<(pl->n + threads - 1) / threads, threads, 0, st>>>(B);
     ctx->launches++;
     CK(cudaGetLastError());
+    if (timed) {
+      CK(cudaEventRecord(ctx->ev[2], st));
+      CK(cudaEventSynchronize(ctx->ev[2]));
+      float a = 0, b = 0;
+      CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+      CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+      pl->ms_viterbi += a;
+      pl->ms_backtrace += b;
+    }
   }
+  return HHG_OK;
+}
+
+int hhg_plan_run(hhg_ctx* ctx, hhg_plan* pl) { return plan_run_impl(ctx, pl, false); }
+
+// Same as hhg_plan_run but brackets every forward-pass and backtrace launch with CUDA events on the
+// context stream and returns their summed device times (ms).  Synchronises; used by bench.py for the
+// per-kernel roofline figure.
+int hhg_plan_run_timed(hhg_ctx* ctx, hhg_plan* pl, float* ms_viterbi, float* ms_backtrace) {
+  if (!ctx || !pl) return fail(HHG_EINVAL, "hhg_plan_run_timed: bad argument");
+  for (int k = 0; k < 3; ++k)
+    if (!ctx->ev[k]) CK(cudaEventCreate(&ctx->ev[k]));
+  pl->ms_viterbi = pl->ms_backtrace = 0;
+  int rc = plan_run_impl(ctx, pl, true);
+  if (rc != HHG_OK) return rc;
+  if (ms_viterbi) *ms_viterbi = pl->ms_viterbi;
+  if (ms_backtrace) *ms_backtrace = pl->ms_backtrace;
   return HHG_OK;
 }
 
@@ -573,6 +629,8 @@ int hhg_plan_fetch(hhg_ctx* ctx, hhg_plan* pl, hhg_hit* hits, uint8_t* paths, si
   CK(cudaStreamSynchronize(ctx->stream));
   return HHG_OK;
 }
+
+void* hhg_plan_hits_devptr(hhg_plan* plan) { return plan ? (void*)plan->d_hits.p : nullptr; }
 
 int hhg_plan_debug_bt(hhg_ctx* ctx, hhg_plan* pl, int k, uint8_t* bt) {
   if (!ctx || !pl || !bt || k < 0 || k >= pl->n) return fail(HHG_EINVAL, "hhg_plan_debug_bt: bad argument");
@@ -595,13 +653,14 @@ int hhg_plan_debug_bt(hhg_ctx* ctx, hhg_plan* pl, int k, uint8_t* bt) {
 int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_hit* hits,
                        uint8_t* paths, size_t paths_cap, const int64_t* excl_off,
                        const int32_t* excl_i, const int32_t* excl_j) {
-  hhg_plan* pl = nullptr;
-  int rc = hhg_plan_create(ctx, db, n, ids, &pl);
+  if (!ctx) return fail(HHG_EINVAL, "ctx is NULL");
+  if (!ctx->scratch_plan) ctx->scratch_plan = new hhg_plan();
+  hhg_plan* pl = ctx->scratch_plan;
+  int rc = plan_build(ctx, pl, db, n, ids);
   if (rc != HHG_OK) return rc;
   rc = set_exclusions(ctx, pl, excl_off, excl_i, excl_j);
   if (rc == HHG_OK) rc = hhg_plan_run(ctx, pl);
   if (rc == HHG_OK) rc = hhg_plan_fetch(ctx, pl, hits, paths, paths_cap);
-  hhg_plan_destroy(pl);
   return rc;
 }
 

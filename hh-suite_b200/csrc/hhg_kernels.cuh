@@ -9,7 +9,7 @@
 //     into STRIPS of R query rows.  A work item is (job, strip); persistent warps pull items from
 //     an atomic queue in (job, strip) order, so consecutive strips of a job run on different
 //     warps as a skewed wavefront: strip s+1 trails strip s by a few columns and receives the
-//     5-state boundary row through L2 (release/acquire progress flags).
+//     5-state boundary row through L2 as tagged 32-byte slots (one STG.256 / LDG.256 per column).
 //   * inside a strip a lane sweeps target columns left to right and keeps the 5 pair-state
 //     values of its R rows in registers; the R query rows (20 emissions + 7 transitions each)
 //     are TMA-bulk-staged (cp.async.bulk + mbarrier) into the warp's shared-memory slice and
@@ -25,10 +25,18 @@
 #include <float.h>
 #include <stdint.h>
 
+// Build-time experiment switches (defaults = the measured best; see DESIGN.md "kernel history").
+#ifndef HHG_USE_CPASYNC
+#define HHG_USE_CPASYNC 0   // 1: stage target columns in smem with cp.async; 0: register prefetch (__ldg)
+#endif
+#ifndef HHG_QDB
+#define HHG_QDB 0           // 1: double-buffer the query row registers
+#endif
+
 namespace hhg {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kPublishEvery = 8;   // columns between progress-flag publications
+constexpr int kStages = 3;         // cp.async ring depth for the target column records
 
 struct __align__(16) ColRec {      // one profile column = operands of DP cell (., j)   (112 B)
   float p[20];
@@ -37,6 +45,36 @@ struct __align__(16) ColRec {      // one profile column = operands of DP cell (
   uint32_t ss;                     // ss_pred*11+ss_conf of column j
 };
 static_assert(sizeof(ColRec) == 112, "ColRec must be 7 x 16 bytes");
+
+// Boundary hand-off between consecutive strips of a job: the 5 pair-state values of the strip's last
+// row at one column plus a tag, written with ONE 256-bit store (sm_100 STG.256 = one 32-byte sector)
+// and read with ONE 256-bit L2 load.  The consumer lane re-reads until the tag names the producing
+// strip of this run: per-lane dataflow synchronisation with no fences, flags or L1 invalidations.
+struct __align__(32) BndSlot {
+  float mm, dg, mi, gd, im;
+  uint32_t tag;
+  uint32_t pad0, pad1;
+};
+static_assert(sizeof(BndSlot) == 32, "BndSlot must be one 32-byte sector");
+
+__device__ __forceinline__ void st_slot(BndSlot* p, float mm, float dg, float mi, float gd, float im,
+                                        uint32_t tag) {
+  asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+               "r"(__float_as_uint(mm)), "r"(__float_as_uint(dg)), "r"(__float_as_uint(mi)),
+               "r"(__float_as_uint(gd)), "r"(__float_as_uint(im)), "r"(tag), "r"(0u), "r"(0u)
+               : "memory");
+}
+__device__ __forceinline__ void ld_slot(const BndSlot* p, float& mm, float& dg, float& mi, float& gd,
+                                        float& im, uint32_t& tag) {
+  uint32_t a, b, c, d, e, x, y;
+  asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(tag), "=r"(x), "=r"(y)
+               : "l"(p)
+               : "memory");
+  (void)x; (void)y;
+  mm = __uint_as_float(a); dg = __uint_as_float(b); mi = __uint_as_float(c);
+  gd = __uint_as_float(d); im = __uint_as_float(e);
+}
 
 struct VitParams {
   // query
@@ -52,11 +90,10 @@ struct VitParams {
   const int* job_target;     // [njobs*32] target id (padded lanes repeat a valid id)
   const int* job_Lmax;       // [njobs]
   const long long* job_bt_off;   // [njobs] offset (in uint32 words) into bt
-  const long long* job_bnd_off;  // [njobs] offset (in columns*32) into bnd4/bnd1
+  const long long* job_bnd_off;  // [njobs] offset (in slots) into bnd
   uint32_t* bt;              // packed backtrace words
-  float4* bnd4;              // boundary row: MM,DG,MI,GD
-  float* bnd1;               // boundary row: IM
-  unsigned int* progress;    // [njobs*nstrips] columns published by (job, strip)
+  struct BndSlot* bnd;       // boundary hand-off slots [job][col][lane], 32 B each (see BndSlot)
+  uint32_t tag_base;         // run epoch << 12; slot tag = tag_base + strip + 1
   unsigned int* counter;     // work-item queue head
   float* strip_score;        // [njobs*nstrips*32]
   int* strip_ij;             // [njobs*nstrips*32]  (i<<16 | j)
@@ -66,6 +103,7 @@ struct VitParams {
   // scoring
   float egq, egt, shift, ssw;
   unsigned long long one2;   // bit pattern of (1.0f, 1.0f); see add2()
+  int group_jobs;            // work-item interleave: jobs per group
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -98,9 +136,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+// Progress-flag poll.  Deliberately a RELAXED gpu-scope load: an acquire load makes ptxas emit
+// CCTL.IVALL (L1 invalidate) which drains every in-flight prefetch at each poll (ncu: 19% of all stall
+// samples).  Ordering is still guaranteed: the boundary values are read with ld.global.cg (L2, never
+// L1) and only after the poll loop's control dependency resolved; the producer orders its st.cg data
+// before the flag with __threadfence() + st.release.
+// 16-byte asynchronous global->shared copy (LDGSTS), L2-only (.cg): the staged target columns
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
@@ -172,16 +225,24 @@ __device__ __forceinline__ float dot20_dev(const unsigned long long (&t)[10], co
 // CELLOFF: cell-off bit input (alternative alignments / excluded regions).
 // ---------------------------------------------------------------------------------------------
 template <int R, bool LOCAL, bool SS, bool CELLOFF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 4 : 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 3 : 2)
     k_viterbi(const VitParams P) {
   static_assert(R % 4 == 0, "R must be a multiple of 4");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // smem carve-up: [warps][R] query records, then mbarriers, then (SS) the S33 table
+  // smem carve-up: [warps][R] query records | [warps][kStages][32 lanes] target column records |
+  // mbarriers | (SS) the S33 table
   float4* qs = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * R * 7;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarpsPerCta * R * 112);
-  float* s33 = reinterpret_cast<float*>(smem_raw + (size_t)kWarpsPerCta * R * 112 + 64);
+#if HHG_USE_CPASYNC
+  float4* tstage = reinterpret_cast<float4*>(smem_raw + (size_t)kWarpsPerCta * R * 112) +
+                   ((size_t)warp * kStages * 32 + lane) * 7;   // this lane's slot in stage 0
+  constexpr size_t kBarOff = (size_t)kWarpsPerCta * R * 112 + (size_t)kWarpsPerCta * kStages * 32 * 112;
+#else
+  constexpr size_t kBarOff = (size_t)kWarpsPerCta * R * 112;
+#endif
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kBarOff);
+  float* s33 = reinterpret_cast<float*>(smem_raw + kBarOff + 64);
   uint64_t* bar = bars + warp;
 
   if (lane == 0) mbar_init(bar, 1);
@@ -200,8 +261,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 4 : 2)
     if (lane == 0) item = (int)atomicAdd(P.counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= total_items) break;
-    const int job = item / P.nstrips;
-    const int s = item - job * P.nstrips;
+    // items are ordered group by group; inside a group of G jobs strip-major, so the strips s and s+1
+    // of one job are dispatched G items apart (natural skew) while the group's targets stay L2-resident
+    const int gsz = P.group_jobs * P.nstrips;
+    const int g = item / gsz;
+    const int rem = item - g * gsz;
+    const int gjobs = min(P.group_jobs, P.njobs - g * P.group_jobs);
+    const int s = rem / gjobs;
+    const int job = g * P.group_jobs + (rem - s * gjobs);
     const int i0 = s * R;
 
     // ---- stage this strip's query rows with one TMA bulk copy
@@ -216,10 +283,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 4 : 2)
     const float4* tc = P.cols + (size_t)P.col_off[t] * 7;
     uint32_t* btj = P.bt + P.job_bt_off[job] + lane;
     const size_t bt_row_stride = (size_t)(Lmax + 1) * 32;   // words per 4-row group
-    float4* b4 = P.bnd4 + P.job_bnd_off[job] + lane;
-    float* b1 = P.bnd1 + P.job_bnd_off[job] + lane;
-    const unsigned* prog_prev = P.progress + (size_t)job * P.nstrips + (s - 1);
-    unsigned* prog_mine = P.progress + (size_t)job * P.nstrips + s;
+    BndSlot* bnd = P.bnd + P.job_bnd_off[job] + lane;
+    const uint32_t tag_in = P.tag_base + (uint32_t)s;        // written by strip s-1
+    const uint32_t tag_out = P.tag_base + (uint32_t)s + 1u;  // what this strip writes
     const bool last_strip = (s == P.nstrips - 1);
     const uint32_t* co = nullptr;
     if (CELLOFF) co = P.celloff + P.job_co_off[job] + (size_t)s * (Lmax + 1) * 32 + lane;
@@ -237,17 +303,35 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 4 : 2)
 
     float best = HHG_NEG;
     int bi = 0, bj = 0;
-    unsigned avail = 0;   // columns of strip s-1 known to be published
 
-    // first column record (prefetch)
+#if !HHG_USE_CPASYNC
+    // first column record (register prefetch, one column ahead)
     float4 nx[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) nx[k] = __ldg(tc + k);   // Lt >= 1
+#else
+    // target column records: cp.async ring, kStages-1 columns in flight (columns clamp at Lt so
+    // lanes shorter than the job keep re-reading their last column)
+#pragma unroll
+    for (int c = 1; c < kStages; ++c) {
+      const float4* src = tc + (size_t)(min(c, Lt) - 1) * 7;
+      float4* dst = tstage + (size_t)(c % kStages) * 32 * 7;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) cp_async16(dst + k, src + k);
+      cp_async_commit();
+    }
+#endif
+
+    // boundary values of column 1 (strips > 0): issue the slot load now, validate the tag at use
+    float nMM = 0.f, nDG = 0.f, nMI = 0.f, nGD = 0.f, nIM = 0.f;
+    uint32_t ntag = 0;
+    if (s > 0) ld_slot(bnd + 32, nMM, nDG, nMI, nGD, nIM, ntag);
 
     mbar_wait(bar, parity);
     parity ^= 1u;
 
     for (int j = 1; j <= Lmax; ++j) {
+#if !HHG_USE_CPASYNC
       // ---- current column operands (from the prefetch registers), prefetch the next column
       unsigned long long tp[10];
       tp[0] = pack2(nx[0].x, nx[0].y); tp[1] = pack2(nx[0].z, nx[0].w);
@@ -264,24 +348,48 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 4 : 2)
 #pragma unroll
         for (int k = 0; k < 7; ++k) nx[k] = __ldg(src + k);
       }
+#else
+      // ---- current column operands from the staging ring; refill the slot freed by column j-1
+      cp_async_wait<kStages - 2>();
+      {
+        const float4* src = tc + (size_t)(min(j + kStages - 1, Lt) - 1) * 7;
+        float4* dst = tstage + (size_t)((j + kStages - 1) % kStages) * 32 * 7;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) cp_async16(dst + k, src + k);
+        cp_async_commit();
+      }
+      unsigned long long tp[10];
+      float t_m2m, t_m2d, t_d2m, t_d2d, t_i2m, t_i2i, t_m2i;
+      uint32_t t_ss;
+      {
+        const float4* cur = tstage + (size_t)(j % kStages) * 32 * 7;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const float4 v = cur[k];
+          tp[2 * k] = pack2(v.x, v.y);
+          tp[2 * k + 1] = pack2(v.z, v.w);
+        }
+        const float4 va = cur[5], vb = cur[6];
+        t_m2m = va.x; t_m2d = va.y; t_d2m = va.z; t_d2d = va.w;
+        t_i2m = vb.x; t_i2i = vb.y; t_m2i = vb.z;
+        t_ss = __float_as_uint(vb.w);
+      }
 
-      // ---- boundary row i0 at column j
+#endif
+
+      // ---- boundary row i0 at column j: slot prefetched during column j-1; spin (per lane) until the
+      // producer strip's tag is there, then prefetch column j+1
       float tMM, tDG, tMI, tGD, tIM;
       if (s == 0) {
         tMM = __fmul_rn((float)(-j), P.egt);   // :148
         tDG = tMI = tGD = tIM = HHG_NEG;
       } else {
-        if ((unsigned)j > avail) {
-          unsigned v = 0;
-          if (lane == 0) {
-            v = ld_acquire(prog_prev);
-            while (v < (unsigned)j) { __nanosleep(64); v = ld_acquire(prog_prev); }
-          }
-          avail = __shfl_sync(0xffffffffu, v, 0);
+        while (ntag != tag_in) {
+          __nanosleep(20);
+          ld_slot(bnd + (size_t)j * 32, nMM, nDG, nMI, nGD, nIM, ntag);
         }
-        const float4 v4 = __ldcg(b4 + (size_t)j * 32);
-        tIM = __ldcg(b1 + (size_t)j * 32);
-        tMM = v4.x; tDG = v4.y; tMI = v4.z; tGD = v4.w;
+        tMM = nMM; tDG = nDG; tMI = nMI; tGD = nGD; tIM = nIM;
+        if (j < Lmax) ld_slot(bnd + (size_t)(j + 1) * 32, nMM, nDG, nMI, nGD, nIM, ntag);
       }
       uint32_t cow = 0;
       if (CELLOFF) cow = __ldg(co + (size_t)j * 32);
@@ -292,13 +400,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 4 : 2)
       float bc = bcmp;
 
       uint32_t word = 0;
+      // query rows are double-buffered in registers: row r+1 is fetched (broadcast LDS.128) before
+      // row r is computed so the shared-memory latency overlaps the arithmetic
+#if HHG_QDB
+      float4 qn[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) qn[k] = qs[k];
+#endif
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float4* qr = qs + r * 7;
         float4 q[5];
+#if HHG_QDB
 #pragma unroll
-        for (int k = 0; k < 5; ++k) q[k] = qr[k];
-        const float4 qa = qr[5], qb = qr[6];
+        for (int k = 0; k < 5; ++k) q[k] = qn[k];
+        const float4 qa = qn[5], qb = qn[6];
+        if (r + 1 < R) {
+#pragma unroll
+          for (int k = 0; k < 7; ++k) qn[k] = qs[(r + 1) * 7 + k];
+        }
+#else
+#pragma unroll
+        for (int k = 0; k < 5; ++k) q[k] = qs[r * 7 + k];
+        const float4 qa = qs[r * 7 + 5], qb = qs[r * 7 + 6];
+#endif
         const float q_m2m = qa.x, q_m2d = qa.y, q_d2m = qa.z, q_d2d = qa.w;
         const float q_i2m = qb.x, q_i2i = qb.y, q_m2i = qb.z;
 
@@ -367,19 +491,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 4 : 2)
       }
       dtMM = tMM; dtDG = tDG; dtMI = tMI; dtGD = tGD; dtIM = tIM;
 
-      if (!last_strip) {
-        __stcg(b4 + (size_t)j * 32, make_float4(MM[R - 1], DG[R - 1], MI[R - 1], GD[R - 1]));
-        __stcg(b1 + (size_t)j * 32, IM[R - 1]);
-        if ((j % kPublishEvery) == 0 || j == Lmax) {
-          __threadfence();
-          __syncwarp();
-          if (lane == 0) st_release(prog_mine, (unsigned)j);
-        }
-      }
+      if (!last_strip)
+        st_slot(bnd + (size_t)j * 32, MM[R - 1], DG[R - 1], MI[R - 1], GD[R - 1], IM[R - 1], tag_out);
     }
     const size_t o = ((size_t)job * P.nstrips + s) * 32 + lane;
     P.strip_score[o] = best;
     P.strip_ij[o] = (bi << 16) | bj;
+#if HHG_USE_CPASYNC
+    cp_async_wait<0>();
+#endif
     __syncwarp();   // all lanes done with the smem slice before the next TMA overwrites it
   }
 }

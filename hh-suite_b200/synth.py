@@ -151,24 +151,26 @@ def prepared_db(n: int, seed: int, median: int = 200, sigma: float = 0.5, lo: in
     T = np.empty((int(t_rows.sum()), 7), dtype=np.float32)
     S = np.zeros(int(p_rows.sum()), dtype=np.uint8)
     if fast:
+        # columns and transition rows are drawn (with replacement) from pools of 65536 distinct
+        # Dirichlet columns / transition rows: i.i.d. columns as above at a fraction of the sampling cost
         tot = int(p_rows.sum())
-        alpha = rng.choice(np.array([0.3, 1.0, 3.0], dtype=np.float32), size=tot)[:, None] * \
-            (_PB[None, :].astype(np.float32) * 20.0)
-        f = rng.standard_gamma(alpha).astype(np.float32) + 1e-12
-        f /= f.sum(axis=1, keepdims=True)
-        P[:] = (0.85 * f + 0.15 * _PB[None, :].astype(np.float32)) / _PB[None, :].astype(np.float32)
-        S[:] = (rng.integers(1, 4, tot) * 11 + rng.integers(1, 11, tot)).astype(np.uint8)
+        NP = 65536
+        pool_f = _columns(NP, rng).astype(np.float32)
+        pool_p = ((0.85 * pool_f + 0.15 * _PB[None, :].astype(np.float32)) /
+                  _PB[None, :].astype(np.float32)).astype(np.float32)
+        idx = rng.integers(0, NP, tot, dtype=np.int32)
+        np.take(pool_p, idx, axis=0, out=P)
+        S[:] = (rng.integers(1, 4, tot, dtype=np.uint8) * 11 + rng.integers(1, 11, tot, dtype=np.uint8))
         tt = int(t_rows.sum())
-        tr = np.zeros((tt, 7), dtype=np.float64)
-        m2i = rng.uniform(0.005, 0.05, tt); m2d = rng.uniform(0.005, 0.05, tt)
-        i2i = rng.uniform(0.3, 0.7, tt); d2d = rng.uniform(0.3, 0.7, tt)
-        tr[:, 0] = 1 - m2i - m2d; tr[:, 1] = m2i; tr[:, 2] = m2d
-        tr[:, 3] = 1 - i2i; tr[:, 4] = i2i; tr[:, 5] = 1 - d2d; tr[:, 6] = d2d
+        pool_t = _log2_tr(_transitions(NP - 1, rng))
+        idx = rng.integers(1, NP - 1, tt, dtype=np.int32)
+        np.take(pool_t, idx, axis=0, out=T)
         first = tr_off
         last = tr_off + L
-        tr[first] = [1, 0, 0, 1, 0, 1, 0]
-        tr[last, 0] = 1 - tr[last, 1]; tr[last, 2] = 0; tr[last, 5] = 1; tr[last, 6] = 0
-        T[:] = _log2_tr(tr)
+        T[first] = _log2_tr(np.array([[1, 0, 0, 1, 0, 1, 0]], dtype=np.float64))[0]
+        lin = np.exp2(T[last].astype(np.float64))
+        lin[:, 0] = 1 - lin[:, 1]; lin[:, 2] = 0; lin[:, 5] = 1; lin[:, 6] = 0
+        T[last] = _log2_tr(lin)
         P[p_off] = 1.0
         P[p_off + L + 1] = 1.0
         S[p_off] = 0

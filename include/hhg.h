@@ -115,8 +115,14 @@ int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, h
 int hhg_plan_destroy(hhg_plan* plan);
 /* Enqueue forward pass + backtrace on the context stream; no host sync. */
 int hhg_plan_run(hhg_ctx* ctx, hhg_plan* plan);
+/* As hhg_plan_run, but brackets each forward-pass / backtrace launch with CUDA events on the context
+ * stream and returns the summed device times in ms (synchronises). */
+int hhg_plan_run_timed(hhg_ctx* ctx, hhg_plan* plan, float* ms_viterbi, float* ms_backtrace);
 /* Copy results of the last run to the host (synchronises). paths may be NULL. */
 int hhg_plan_fetch(hhg_ctx* ctx, hhg_plan* plan, hhg_hit* hits, uint8_t* paths, size_t paths_cap);
+/* Device pointer to the plan's hit records (n x hhg_hit on the context's device), valid until the plan
+ * is destroyed: lets the caller run the top-K selection / NCCL exchange without a host round trip. */
+void* hhg_plan_hits_devptr(hhg_plan* plan);
 /* sum over planned targets of Lq*Lt (the unit of the GCUPS metric) and padded cells actually computed */
 double hhg_plan_cells(const hhg_plan* plan);
 double hhg_plan_padded_cells(const hhg_plan* plan);
