@@ -64,14 +64,16 @@ __device__ __forceinline__ void st_slot(BndSlot* p, float mm, float dg, float mi
                "r"(__float_as_uint(gd)), "r"(__float_as_uint(im)), "r"(tag), "r"(0u), "r"(0u)
                : "memory");
 }
+// pad0/pad1 are returned so the caller can keep their registers live until the slot is consumed: a dead
+// destination register of an in-flight load gets reused by ptxas and the re-use then stalls on the load
+// (write-after-write on the long scoreboard; ncu showed 12% of all stall samples on one such FMUL).
 __device__ __forceinline__ void ld_slot(const BndSlot* p, float& mm, float& dg, float& mi, float& gd,
-                                        float& im, uint32_t& tag) {
-  uint32_t a, b, c, d, e, x, y;
+                                        float& im, uint32_t& tag, uint32_t& x, uint32_t& y) {
+  uint32_t a, b, c, d, e;
   asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(tag), "=r"(x), "=r"(y)
                : "l"(p)
                : "memory");
-  (void)x; (void)y;
   mm = __uint_as_float(a); dg = __uint_as_float(b); mi = __uint_as_float(c);
   gd = __uint_as_float(d); im = __uint_as_float(e);
 }
@@ -104,6 +106,7 @@ struct VitParams {
   float egq, egt, shift, ssw;
   unsigned long long one2;   // bit pattern of (1.0f, 1.0f); see add2()
   int group_jobs;            // work-item interleave: jobs per group
+  uint32_t zero;             // always 0, opaque to the compiler (register-liveness anchor)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -150,6 +153,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
+__device__ __forceinline__ void keep_alive(uint32_t v) { asm volatile("" ::"r"(v)); }
 
 __device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
   unsigned v;
@@ -324,8 +329,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 3 : 2)
 
     // boundary values of column 1 (strips > 0): issue the slot load now, validate the tag at use
     float nMM = 0.f, nDG = 0.f, nMI = 0.f, nGD = 0.f, nIM = 0.f;
-    uint32_t ntag = 0;
-    if (s > 0) ld_slot(bnd + 32, nMM, nDG, nMI, nGD, nIM, ntag);
+    uint32_t ntag = 0, npad0 = 0, npad1 = 0;
+    if (s > 0) ld_slot(bnd + 32, nMM, nDG, nMI, nGD, nIM, ntag, npad0, npad1);
 
     mbar_wait(bar, parity);
     parity ^= 1u;
@@ -384,12 +389,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 3 : 2)
         tMM = __fmul_rn((float)(-j), P.egt);   // :148
         tDG = tMI = tGD = tIM = HHG_NEG;
       } else {
-        while (ntag != tag_in) {
+        // pads are always 0 in a valid slot; testing them keeps their registers live (see ld_slot)
+        while (((ntag ^ tag_in) | npad0 | npad1) != 0u) {
           __nanosleep(20);
-          ld_slot(bnd + (size_t)j * 32, nMM, nDG, nMI, nGD, nIM, ntag);
+          ld_slot(bnd + (size_t)j * 32, nMM, nDG, nMI, nGD, nIM, ntag, npad0, npad1);
         }
         tMM = nMM; tDG = nDG; tMI = nMI; tGD = nGD; tIM = nIM;
-        if (j < Lmax) ld_slot(bnd + (size_t)(j + 1) * 32, nMM, nDG, nMI, nGD, nIM, ntag);
+        if (j < Lmax) ld_slot(bnd + (size_t)(j + 1) * 32, nMM, nDG, nMI, nGD, nIM, ntag, npad0, npad1);
       }
       uint32_t cow = 0;
       if (CELLOFF) cow = __ldg(co + (size_t)j * 32);
@@ -399,7 +405,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 3 : 2)
       const float bcmp = (j <= Lt) ? best : INFINITY;   // padded columns never become the maximum
       float bc = bcmp;
 
-      uint32_t word = 0;
+      // (t_ss & P.zero) is 0; it only keeps the 4th register of the prefetch LDG.128 live (see ld_slot)
+      uint32_t word = SS ? 0u : (t_ss & P.zero);
       // query rows are double-buffered in registers: row r+1 is fetched (broadcast LDS.128) before
       // row r is computed so the shared-memory latency overlaps the arithmetic
 #if HHG_QDB
