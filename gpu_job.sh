@@ -1,2 +1,3 @@
-python -m pytest tests/test_viterbi_gpu.py -x -q -m gpu 2>&1 | tail -2
-python tools/perf_probe.py HHG_GROUP_JOBS=64 HHG_GROUP_JOBS=64,HHG_STRIP_ROWS=8
+mkdir -p gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:k_viterbi -s 2 -c 1 -o gpurun_out/vit_r16_v4 python tools/perf_probe.py --targets 30000 HHG_GROUP_JOBS=64 > gpurun_out/ncu7.log 2>&1
+tail -n 2 gpurun_out/ncu7.log

@@ -63,7 +63,7 @@ int strip_rows() {
   const char* e = getenv("HHG_STRIP_ROWS");
   if (e) {
     int r = atoi(e);
-    if (r == 8 || r == 16) return r;
+    if (r == 8 || r == 12 || r == 16) return r;
   }
   return 16;
 }
@@ -570,6 +570,7 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
     int rc;
     if (timed) CK(cudaEventRecord(ctx->ev[0], st));
     if (pl->R == 8) rc = launch_viterbi<8>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
+    else if (pl->R == 12) rc = launch_viterbi<12>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
     else rc = launch_viterbi<16>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
     if (rc != HHG_OK) return rc;
     if (timed) CK(cudaEventRecord(ctx->ev[1], st));

@@ -230,7 +230,7 @@ __device__ __forceinline__ float dot20_dev(const unsigned long long (&t)[10], co
 // CELLOFF: cell-off bit input (alternative alignments / excluded regions).
 // ---------------------------------------------------------------------------------------------
 template <int R, bool LOCAL, bool SS, bool CELLOFF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 8) ? 3 : 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
     k_viterbi(const VitParams P) {
   static_assert(R % 4 == 0, "R must be a multiple of 4");
   extern __shared__ __align__(128) unsigned char smem_raw[];
