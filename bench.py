@@ -218,7 +218,7 @@ def main():
     n = plan.n
     base_id = rank * n
 
-    # device views for the top-K exchange: HitRec = 8 x 4 bytes, score first
+    # device views for the top-K exchange: HitRec = 10 x 4 bytes, score first
     def topk_exchange(hits_dev_i32):
         scores = hits_dev_i32[:, 0].view(torch.float32)
         k = min(TOPK, n)
@@ -233,7 +233,7 @@ def main():
         return rec
 
     hits_ptr = ctx.L.hhg_plan_hits_devptr(plan.h)
-    hits_dev = cuda_array(hits_ptr, n * 32).view(torch.int32).view(n, 8)
+    hits_dev = cuda_array(hits_ptr, n * 40).view(torch.int32).view(n, 10)
 
     def step():
         plan.run()
@@ -283,7 +283,7 @@ def main():
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
     qp_pin, qtr_pin = pin(qp), pin(qtr)
     ids_pin = pin(np.arange(n, dtype=np.int32))
-    hits_pin = torch.empty(n * 32, dtype=torch.uint8).pin_memory().numpy().view(hh.capi.HIT_DTYPE)
+    hits_pin = torch.empty(n * 40, dtype=torch.uint8).pin_memory().numpy().view(hh.capi.HIT_DTYPE)
     paths_pin = torch.empty(plan.path_cap, dtype=torch.uint8).pin_memory().numpy()
     h2d = qp_pin.nbytes + qtr_pin.nbytes + ids_pin.nbytes
     d2h = hits_pin.nbytes + paths_pin.nbytes
@@ -295,8 +295,8 @@ def main():
         top = np.argpartition(-hits["score"], k - 1)[:k]
         if world > 1:
             rec = torch.from_numpy(np.concatenate([(top + base_id).astype(np.int32)[:, None],
-                                                   hits[top].view(np.int32).reshape(k, 8)], axis=1)).to(dev)
-            out = torch.empty((world * k, 9), dtype=torch.int32, device=dev)
+                                                   hits[top].view(np.int32).reshape(k, 10)], axis=1)).to(dev)
+            out = torch.empty((world * k, 11), dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(out, rec)
             return out.cpu()
         return hits[top]

@@ -23,15 +23,15 @@ c_u8p = C.POINTER(C.c_uint8)
 
 class Params(C.Structure):
     _fields_ = [("local", C.c_int), ("egq", C.c_float), ("egt", C.c_float), ("shift", C.c_float),
-                ("ssw", C.c_float), ("use_ss", C.c_int)]
+                ("ssw", C.c_float), ("use_ss", C.c_int), ("corr", C.c_float), ("ssm", C.c_int)]
 
 
 HIT_DTYPE = np.dtype([("score", np.float32), ("i2", np.int32), ("j2", np.int32), ("i1", np.int32),
                       ("j1", np.int32), ("nsteps", np.int32), ("matched_cols", np.int32),
-                      ("path_off", np.int32)])
+                      ("path_off", np.int32), ("hit_score", np.float32), ("score_ss", np.float32)])
 
 SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync", "hhg_ctx_launch_count",
-           "hhg_db_create", "hhg_db_destroy", "hhg_db_size", "hhg_db_columns", "hhg_query_set",
+           "hhg_db_create", "hhg_db_create_raw", "hhg_db_apply_null_model", "hhg_debug_fastlog2_table", "hhg_db_destroy", "hhg_db_size", "hhg_db_columns", "hhg_query_set",
            "hhg_viterbi_search", "hhg_plan_create", "hhg_plan_destroy", "hhg_plan_run", "hhg_plan_run_timed", "hhg_plan_fetch", "hhg_plan_hits_devptr",
            "hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes", "hhg_plan_debug_bt",
            "hhg_csdb_create", "hhg_csdb_destroy", "hhg_prefilter_ungapped", "hhg_prefilter_ungapped_run",
@@ -69,6 +69,10 @@ def load():
     L.hhg_ctx_launch_count.restype = C.c_longlong
     L.hhg_db_create.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i64p, c_i64p, c_i64p, c_f32p, c_f32p, c_u8p,
                                 C.POINTER(C.c_void_p)]
+    L.hhg_db_create_raw.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i64p, c_i64p, c_i64p, c_f32p, c_f32p, c_u8p,
+                                    c_f32p, C.POINTER(C.c_void_p)]
+    L.hhg_db_apply_null_model.argtypes = [C.c_void_p, C.c_void_p, c_f32p, c_f32p, C.c_int]
+    L.hhg_debug_fastlog2_table.argtypes = [C.c_void_p, c_f32p]
     L.hhg_db_destroy.argtypes = [C.c_void_p]
     L.hhg_db_size.argtypes = [C.c_void_p]
     L.hhg_db_columns.argtypes = [C.c_void_p]
@@ -121,14 +125,19 @@ class Context:
     def launches(self) -> int:
         return int(self.L.hhg_ctx_launch_count(self.h))
 
+    def fastlog2_table(self):
+        out = np.zeros(1025, np.float32)
+        _ck(self.L.hhg_debug_fastlog2_table(self.h, _p(out, c_f32p)))
+        return out
+
     def set_query(self, p, tr, ss=None, S33=None, local=True, egq=0.0, egt=0.0, shift=-0.03, ssw=0.11,
-                  use_ss=False):
+                  use_ss=False, corr=0.1, ssm=2):
         p = np.ascontiguousarray(p, np.float32); tr = np.ascontiguousarray(tr, np.float32)
         Lq = p.shape[0] - 2
         assert tr.shape[0] == Lq + 1
         ss = None if ss is None else np.ascontiguousarray(ss, np.uint8)
         S33 = None if S33 is None else np.ascontiguousarray(S33, np.float32)
-        par = Params(1 if local else 0, egq, egt, shift, ssw, 1 if use_ss else 0)
+        par = Params(1 if local else 0, egq, egt, shift, ssw, 1 if use_ss else 0, corr, ssm)
         _ck(self.L.hhg_query_set(self.h, Lq, _p(p, c_f32p), _p(tr, c_f32p), _p(ss, c_u8p), _p(S33, c_f32p),
                                  C.byref(par)))
         self.Lq = Lq
@@ -137,7 +146,8 @@ class Context:
 class TargetDB:
     """Device-resident shard of prepared target profiles (see synth.prepared_db for the host layout)."""
 
-    def __init__(self, ctx: Context, L, p, tr, p_off, tr_off, ss=None):
+    def __init__(self, ctx: Context, L, p, tr, p_off, tr_off, ss=None, pav=None):
+        """pav given: p holds pre-null-model emissions; call apply_null_model(q_pav) per query."""
         self.ctx = ctx
         self.Lh = np.ascontiguousarray(L, np.int32)
         n = len(self.Lh)
@@ -147,10 +157,22 @@ class TargetDB:
         so = np.ascontiguousarray(np.asarray(p_off, np.int64))
         ss = None if ss is None else np.ascontiguousarray(ss, np.uint8)
         h = C.c_void_p()
-        _ck(ctx.L.hhg_db_create(ctx.h, n, _p(self.Lh, c_i32p), _p(po, c_i64p), _p(to, c_i64p), _p(so, c_i64p),
-                                _p(p, c_f32p), _p(tr, c_f32p), _p(ss, c_u8p), C.byref(h)))
+        if pav is None:
+            _ck(ctx.L.hhg_db_create(ctx.h, n, _p(self.Lh, c_i32p), _p(po, c_i64p), _p(to, c_i64p), _p(so, c_i64p),
+                                    _p(p, c_f32p), _p(tr, c_f32p), _p(ss, c_u8p), C.byref(h)))
+        else:
+            pav = np.ascontiguousarray(pav, np.float32)
+            assert pav.shape == (n, 20)
+            _ck(ctx.L.hhg_db_create_raw(ctx.h, n, _p(self.Lh, c_i32p), _p(po, c_i64p), _p(to, c_i64p),
+                                        _p(so, c_i64p), _p(p, c_f32p), _p(tr, c_f32p), _p(ss, c_u8p),
+                                        _p(pav, c_f32p), C.byref(h)))
         self.h = h
         self.n = n
+
+    def apply_null_model(self, q_pav=None, pb=None, columnscore=1):
+        q_pav = None if q_pav is None else np.ascontiguousarray(q_pav, np.float32)
+        pb = None if pb is None else np.ascontiguousarray(pb, np.float32)
+        _ck(self.ctx.L.hhg_db_apply_null_model(self.ctx.h, self.h, _p(q_pav, c_f32p), _p(pb, c_f32p), columnscore))
 
     @classmethod
     def from_profiles(cls, ctx, profiles):

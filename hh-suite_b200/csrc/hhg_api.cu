@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -82,8 +83,10 @@ struct hhg_ctx {
   uint32_t epoch = 0;    // run counter feeding the boundary-slot tags
   DevBuf<float4> qrec;
   DevBuf<float> S33;
+  DevBuf<float> lg2, diff;   // fast_log2 tables for Hit.score
+  std::vector<float> h_lg2;
   bool has_ss = false, has_S33 = false;
-  hhg_params par{1, 0.f, 0.f, -0.03f, 0.11f, 0};
+  hhg_params par{1, 0.f, 0.f, -0.03f, 0.11f, 0, 0.1f, 2};
   // prefilter
   DevBuf<uint8_t> pf_prof;
   DevBuf<unsigned> pf_counter;
@@ -101,7 +104,11 @@ struct hhg_db {
   std::vector<long long> col_off;
   DevBuf<int> dL;
   DevBuf<long long> dcol_off;
-  DevBuf<float4> cols;
+  DevBuf<float4> cols;       // prepared column records (what the DP reads)
+  bool raw = false;          // created by hhg_db_create_raw: cols is filled by hhg_db_apply_null_model
+  DevBuf<float4> cols_raw;   // pre-null-model records
+  DevBuf<float> pav;         // [n*20] template average aa frequencies
+  bool prepared = true;
 };
 
 struct hhg_csdb {
@@ -132,7 +139,8 @@ struct hhg_plan {
   std::vector<Wave> waves;
   long long path_total = 0;
   // device
-  DevBuf<int> d_job_target, d_job_Lmax, d_req_job, d_req_lane, d_req_Lt;
+  DevBuf<int> d_job_target, d_job_Lmax, d_req_job, d_req_lane, d_req_Lt, d_req_target;
+  DevBuf<float> d_S;
   DevBuf<long long> d_job_bt_off, d_job_bnd_off, d_job_co_off, d_path_off;
   DevBuf<uint32_t> d_bt, d_co;
   DevBuf<BndSlot> d_bnd;
@@ -179,6 +187,23 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
     c->own_stream = true;
   }
   c->R = strip_rows();
+  {
+    // fast_log2 tables exactly as the reference fills them on first use (src/util-inl.h:113-121):
+    // lg2[i] = log2(1 + i/1024) via the C library's double-precision log (that is the overload the
+    // reference's expression resolves to; verified against its table), diff[i] = slope / 8096
+    std::vector<float> lg2(1025, 0.f), diff(1025, 0.f);
+    float prev = 0.0f;
+    for (int i = 1; i <= 1024; ++i) {
+      lg2[i] = (float)(::log((double)(1024 + i)) * 1.442695041 - 10.0);
+      diff[i - 1] = (float)((double)(lg2[i] - prev) * 1.2352E-4);
+      prev = lg2[i];
+    }
+    c->h_lg2 = lg2;
+    cudaError_t e1 = c->lg2.alloc(1025), e2 = c->diff.alloc(1025);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { delete c; return fail(HHG_ENOMEM, "fast_log2 tables"); }
+    CK(cudaMemcpy(c->lg2.p, lg2.data(), 1025 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->diff.p, diff.data(), 1025 * 4, cudaMemcpyHostToDevice));
+  }
   { const char* ge = getenv("HHG_GROUP_JOBS"); c->group_jobs = ge ? std::max(1, atoi(ge)) : 64; }
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
@@ -305,6 +330,55 @@ int hhg_db_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_off, c
   return HHG_OK;
 }
 
+int hhg_db_create_raw(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_off, const int64_t* tr_off,
+                      const int64_t* ss_off, const float* p, const float* tr, const uint8_t* ss,
+                      const float* pav, hhg_db** out) {
+  if (!pav) return fail(HHG_EINVAL, "hhg_db_create_raw: pav is NULL");
+  int rc = hhg_db_create(ctx, n, L, p_off, tr_off, ss_off, p, tr, ss, out);
+  if (rc != HHG_OK) return rc;
+  hhg_db* db = *out;
+  cudaError_t e;
+  if ((e = db->cols_raw.alloc(db->cols.n)) != cudaSuccess || (e = db->pav.alloc((size_t)n * 20)) != cudaSuccess) {
+    delete db; *out = nullptr;
+    return fail(HHG_ENOMEM, "hhg_db_create_raw: %s", cudaGetErrorString(e));
+  }
+  CK(cudaMemcpyAsync(db->cols_raw.p, db->cols.p, db->cols.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->pav.p, pav, (size_t)n * 20 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  db->raw = true;
+  db->prepared = false;
+  return HHG_OK;
+}
+
+int hhg_db_apply_null_model(hhg_ctx* ctx, hhg_db* db, const float* q_pav, const float* pb, int columnscore) {
+  if (!ctx || !db || !db->raw) return fail(HHG_EINVAL, "hhg_db_apply_null_model: db was not created raw");
+  if (columnscore < 0 || columnscore > 3) return fail(HHG_EINVAL, "columnscore %d not supported (0..3)", columnscore);
+  if ((columnscore == 1 || columnscore == 3) && !q_pav) return fail(HHG_EINVAL, "q_pav is NULL");
+  if (columnscore == 0 && !pb) return fail(HHG_EINVAL, "pb is NULL");
+  CK(cudaSetDevice(ctx->device));
+  DevBuf<float> dq;
+  CK(dq.alloc(40));
+  float h[40] = {0};
+  if (q_pav) memcpy(h, q_pav, 80);
+  if (pb) memcpy(h + 20, pb, 80);
+  CK(cudaMemcpyAsync(dq.p, h, 160, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = 128;
+  k_null_model<<<(unsigned)((db->total_cols + threads - 1) / threads), threads, 0, ctx->stream>>>(
+      db->total_cols, db->n, db->dcol_off.p, db->cols_raw.p, db->pav.p, dq.p, dq.p + 20, columnscore,
+      db->cols.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  db->prepared = true;
+  return HHG_OK;
+}
+
+int hhg_debug_fastlog2_table(hhg_ctx* ctx, float* lg2_out) {
+  if (!ctx || !lg2_out) return fail(HHG_EINVAL, "bad argument");
+  memcpy(lg2_out, ctx->h_lg2.data(), 1025 * 4);
+  return HHG_OK;
+}
+
 int hhg_db_destroy(hhg_db* db) {
   if (db) { cudaSetDevice(db->device); delete db; }
   return HHG_OK;
@@ -423,13 +497,14 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   }
   if (po > 0x7fffffffLL) return fail(HHG_EINVAL, "plan too large: %lld path bytes (> 2^31-1); split the request", po);
   pl->path_total = po;
-  pl->alg_bytes = cols_sum * 112.0 + pl->cells * 1.0 + 32.0 * n;
+  pl->alg_bytes = cols_sum * 112.0 + pl->cells * 1.0 + (double)sizeof(HitRec) * n;
 
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   A(pl->d_job_target.ensure(job_target.size())); A(pl->d_job_Lmax.ensure(pl->njobs));
   A(pl->d_job_bt_off.ensure(pl->njobs)); A(pl->d_job_bnd_off.ensure(pl->njobs)); A(pl->d_job_co_off.ensure(pl->njobs));
   A(pl->d_req_job.ensure(n)); A(pl->d_req_lane.ensure(n)); A(pl->d_req_Lt.ensure(n)); A(pl->d_path_off.ensure(n));
+  A(pl->d_req_target.ensure(n)); A(pl->d_S.ensure((size_t)po));
   A(pl->d_bt.ensure(max_wave_words));
   { BndSlot* before = pl->d_bnd.p; A(pl->d_bnd.ensure((size_t)bnd));
     // fresh slots must not carry a bit pattern that looks like a valid tag (epochs start at 1)
@@ -450,6 +525,7 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   CK(cudaMemcpyAsync(pl->d_req_job.p, pl->req_job.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_req_lane.p, pl->req_lane.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_req_Lt.p, req_Lt.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_req_target.p, pl->ids.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_path_off.p, pl->path_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));
   return HHG_OK;
@@ -536,6 +612,7 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
   if (!ctx || !pl) return fail(HHG_EINVAL, "hhg_plan_run: bad argument");
   if (pl->Lq != ctx->Lq || pl->R != ctx->R) return fail(HHG_EINVAL, "plan was made for another query length");
   const hhg_db* db = pl->db;
+  if (!db->prepared) return fail(HHG_EINVAL, "raw db: call hhg_db_apply_null_model for the current query first");
   if (ctx->par.use_ss && (!db->has_ss || !ctx->has_ss || !ctx->has_S33))
     return fail(HHG_EINVAL, "use_ss requested but query/db/S33 carry no ss information");
   CK(cudaSetDevice(ctx->device));
@@ -584,6 +661,9 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
     B.bt = pl->d_bt.p; B.strip_score = pl->d_strip_score.p; B.strip_ij = pl->d_strip_ij.p;
     B.path_off = pl->d_path_off.p; B.hits = pl->d_hits.p; B.paths = pl->d_paths.p;
     B.job_begin = w.job_begin; B.job_end = w.job_end;
+    B.req_target = pl->d_req_target.p; B.qrec = ctx->qrec.p; B.cols = db->cols.p; B.col_off = db->dcol_off.p;
+    B.lg2 = ctx->lg2.p; B.diff = ctx->diff.p; B.S33 = ctx->has_S33 ? ctx->S33.p : nullptr; B.S = pl->d_S.p;
+    B.corr = ctx->par.corr; B.ssw = ctx->par.ssw; B.use_ss = ctx->par.use_ss; B.ss_score_mode = (ctx->par.ssm == 2);
     const int threads = 128;
     k_backtrace<<<(pl->n + threads - 1) / threads, threads, 0, st>>>(B);
     ctx->launches++;

@@ -518,6 +518,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
 struct HitRec {
   float score;
   int i2, j2, i1, j1, nsteps, matched_cols, path_off;
+  float hit_score;   // Hit.score: Viterbi score - ss score + correlation term (src/hhviterbi.cpp:215-256)
+  float score_ss;    // Hit.score_ss
 };
 
 struct BtParams {
@@ -534,7 +536,47 @@ struct BtParams {
   const long long* path_off; // [n_req] offsets into paths
   HitRec* hits;
   uint8_t* paths;            // may be null
+  // Hit.score (Viterbi::ScoreForBacktrace, src/hhviterbi.cpp:195-281)
+  const int* req_target;     // [n_req] target id in the shard
+  const float4* qrec;        // query row records (p in the first 5 float4)
+  const float4* cols;        // target column records
+  const long long* col_off;
+  const float* lg2;          // fast_log2 tables (src/util-inl.h:108-128): lg2[1025], diff[1025]
+  const float* diff;
+  const float* S33;          // may be null
+  float* S;                  // [path_total] per-step column scores (scratch)
+  float corr, ssw;
+  int use_ss;                // PRED_PRED ss term was part of the alignment score
+  int ss_score_mode;         // par.ssm == 2: subtract the ss score again (SCORE_ALIGNMENT)
 };
+
+// fast_log2 (src/util-inl.h:108-128): table lookup + linear interpolation, x > 0 else -100000
+__device__ __forceinline__ float fast_log2_dev(float x, const float* lg2, const float* diff) {
+  if (!(x > 0.0f)) return -100000.0f;
+  const uint32_t u = __float_as_uint(x);
+  const int a = (int)((u & 0x7F800000u) >> 23) - 0x7f;
+  const int b = (int)((u & 0x007FE000u) >> 13);
+  const int c = (int)(u & 0x00001FFFu);
+  return __fadd_rn(__fadd_rn((float)a, lg2[b]), __fmul_rn(diff[b], (float)c));
+}
+
+// Score(q.p[i], t.p[j]) = fast_log2(ScalarProd20(q, t)), src/hhhit-inl.h:61-134.  In the AVX2 build of the
+// reference (the pinned oracle) the macro SSE is not defined in that header, so ScalarProd20 is the
+// plain left-to-right sum  t0*q0 + t1*q1 + ... + t19*q19  (verified against the compiled reference:
+// 300/300 random vectors bit-identical; the SSE shuffle tree matches only ~70%).
+__device__ __forceinline__ float score_cols_dev(const float4* q, const float4* t, const float* lg2,
+                                                const float* diff) {
+  float sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float4 a = q[k], b = t[k];
+    if (k == 0) sum = __fmul_rn(b.x, a.x); else sum = __fadd_rn(sum, __fmul_rn(b.x, a.x));
+    sum = __fadd_rn(sum, __fmul_rn(b.y, a.y));
+    sum = __fadd_rn(sum, __fmul_rn(b.z, a.z));
+    sum = __fadd_rn(sum, __fmul_rn(b.w, a.w));
+  }
+  return fast_log2_dev(sum, lg2, diff);
+}
 
 __device__ __forceinline__ uint32_t bt_byte(const uint32_t* btj, size_t row_stride, int i, int j) {
   const uint32_t w = btj[(size_t)((i - 1) >> 2) * row_stride + (size_t)j * 32];
@@ -559,13 +601,30 @@ __global__ void k_backtrace(const BtParams P) {
   const size_t rs = (size_t)(Lmax + 1) * 32;
   uint8_t* path = P.paths ? P.paths + P.path_off[k] : nullptr;
 
+  const float4* tcol = P.cols + (size_t)P.col_off[P.req_target[k]] * 7;
+  float* S = P.S + P.path_off[k];
+  float score_ss = 0.0f;
+
   int step = 0, i = i2, j = j2, mc = 0, li = i2, lj = j2;
   int state = 2;   // MM
   while (state != 0) {
     if (path) path[step] = (uint8_t)state;
+    // per-step column score: only MM steps score (src/hhviterbi.cpp:219-235); the step that turns out to
+    // be the last one is re-scored below because the reference forces states[nsteps] = MM first
+    float Sv = 0.0f;
+    if (state == 2 && i >= 1 && j >= 1) {
+      Sv = score_cols_dev(P.qrec + (size_t)(i - 1) * 7, tcol + (size_t)(j - 1) * 7, P.lg2, P.diff);
+      if (P.use_ss) {
+        const uint32_t qs = __float_as_uint(P.qrec[(size_t)(i - 1) * 7 + 6].w);
+        const uint32_t ts = __float_as_uint(tcol[(size_t)(j - 1) * 7 + 6].w);
+        score_ss = __fadd_rn(score_ss, __fmul_rn(P.ssw, P.S33[qs * 44 + ts]));
+      }
+    }
+    S[step] = Sv;
     ++step;
     li = i; lj = j;
     const uint32_t c = (i >= 1 && j >= 1) ? bt_byte(btj, rs, i, j) : 0u;
+    const int prev_state = state;
     switch (state) {
       case 2: ++mc; state = (i <= 1 || j <= 1) ? 0 : (int)(c & 7u); --i; --j; break;
       case 3: if (j <= 1) state = 0; else { if (c & 8u) state = 2; --j; } break;
@@ -574,12 +633,68 @@ __global__ void k_backtrace(const BtParams P) {
       case 6: if (i <= 1) state = 0; else { if (c & 64u) state = 2; --i; } break;
       default: state = 0; break;
     }
+    if (state == 0 && prev_state != 2 && li >= 1 && lj >= 1) {
+      // last step ended in a gap state: the reference relabels it MM (src/hhviterbi.cpp:147) and scores it
+      S[step - 1] = score_cols_dev(P.qrec + (size_t)(li - 1) * 7, tcol + (size_t)(lj - 1) * 7, P.lg2, P.diff);
+      if (P.use_ss) {
+        const uint32_t qs = __float_as_uint(P.qrec[(size_t)(li - 1) * 7 + 6].w);
+        const uint32_t ts = __float_as_uint(tcol[(size_t)(lj - 1) * 7 + 6].w);
+        score_ss = __fadd_rn(score_ss, __fmul_rn(P.ssw, P.S33[qs * 44 + ts]));
+      }
+    }
   }
   if (path && step > 0) path[step - 1] = 2;   // states[nsteps] = MM, src/hhviterbi.cpp:147
+  // Hit.score, src/hhviterbi.cpp:237-256: four correlation passes in the reference's order
+  float hs = best;
+  if (P.ss_score_mode) hs = __fadd_rn(hs, -score_ss);
+  float scorr = 0.0f;
+  if (step > 0) {
+    for (int d = 1; d <= 4; ++d)
+      for (int st = d; st < step; ++st) scorr = __fadd_rn(scorr, __fmul_rn(S[st], S[st - d]));
+    hs = __fadd_rn(hs, __fmul_rn(P.corr, scorr));
+  }
   HitRec h;
   h.score = best; h.i2 = i2; h.j2 = j2; h.i1 = li; h.j1 = lj; h.nsteps = step;
   h.matched_cols = mc; h.path_off = (int)P.path_off[k];
+  h.hit_score = hs; h.score_ss = score_ss;
   P.hits[k] = h;
+}
+
+// Query-dependent part of PrepareTemplateHMM: factor the null model into the template emissions
+// (HMM::IncludeNullModelInHMM, src/hhhmm.cpp:2059-2088).  One thread per target column; exact fp32
+// division like the reference.  columnscore: 0 = pb, 1 = 0.5(q.pav + t.pav) (default), 2 = t.pav, 3 = q.pav.
+__global__ void k_null_model(long long total_cols, int n, const long long* col_off, const float4* raw,
+                             const float* t_pav, const float* q_pav, const float* pb, int columnscore,
+                             float4* out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= total_cols) return;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (col_off[mid] <= c) lo = mid; else hi = mid - 1;
+  }
+  const float* tp = t_pav + (size_t)lo * 20;
+  float pn[20];
+#pragma unroll
+  for (int a = 0; a < 20; ++a) {
+    switch (columnscore) {
+      case 0: pn[a] = pb[a]; break;
+      case 2: pn[a] = tp[a]; break;
+      case 3: pn[a] = q_pav[a]; break;
+      default: pn[a] = __fmul_rn(0.5f, __fadd_rn(q_pav[a], tp[a])); break;
+    }
+  }
+  const float4* src = raw + (size_t)c * 7;
+  float4* dst = out + (size_t)c * 7;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    float4 v = src[k];
+    v.x = __fdiv_rn(v.x, pn[4 * k + 0]); v.y = __fdiv_rn(v.y, pn[4 * k + 1]);
+    v.z = __fdiv_rn(v.z, pn[4 * k + 2]); v.w = __fdiv_rn(v.w, pn[4 * k + 3]);
+    dst[k] = v;
+  }
+  dst[5] = src[5];
+  dst[6] = src[6];
 }
 
 // De-interleave one target's backtrace bytes into the reference's row-major cell matrix (parity tests).

@@ -56,6 +56,9 @@ typedef struct hhg_params {
   float ssw;        /* par.ssw   (0.11)   : secondary-structure weight                        */
   int use_ss;       /* 1 = PRED_PRED ss term during alignment (Viterbi::Align dispatch,       */
                     /*     src/hhviterbi.cpp:177; needs ss arrays on query and db + S33)      */
+  float corr;       /* par.corr  (0.1)    : weight of the column-score correlation term       */
+  int ssm;          /* par.ssm   (2)      : 2 = ss score is part of the alignment and is      */
+                    /*     subtracted again from Hit.score (src/hhviterbi.cpp:236)             */
 } hhg_params;
 
 /* Per-target result: ViterbiResult (src/hhviterbi.h:21) + the scalar part of BacktraceResult (:34). */
@@ -66,6 +69,9 @@ typedef struct hhg_hit {
   int32_t nsteps;   /* BacktraceResult::count                                                 */
   int32_t matched_cols;
   int32_t path_off; /* offset of this target's state string in the `paths` buffer             */
+  float hit_score;  /* Hit.score = score - score_ss + corr * sum_{d=1..4} sum_k S[k]S[k-d]       */
+                    /*   (Viterbi::ScoreForBacktrace, src/hhviterbi.cpp:195-281)                 */
+  float score_ss;   /* Hit.score_ss                                                            */
 } hhg_hit;
 
 const char* hhg_last_error(void);
@@ -87,6 +93,17 @@ long long hhg_ctx_launch_count(hhg_ctx* ctx);
 int hhg_db_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_off, const int64_t* tr_off,
                   const int64_t* ss_off, const float* p, const float* tr, const uint8_t* ss,
                   hhg_db** out);
+/* Same, but the emissions are the pseudocount-added probabilities BEFORE the null model is factored in
+ * (what AddAminoAcidPseudocounts leaves in HMM::p, src/hhfunc.cpp:176-178) and pav[n*20] holds each
+ * target's average amino-acid frequencies (HMM::pav).  The query-dependent step of PrepareTemplateHMM
+ * -- HMM::IncludeNullModelInHMM, src/hhhmm.cpp:2059 -- then runs on the GPU for every new query:
+ * hhg_db_apply_null_model(columnscore = par.columnscore: 0 pb, 1 (q.pav+t.pav)/2, 2 t.pav, 3 q.pav). */
+int hhg_db_create_raw(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_off, const int64_t* tr_off,
+                      const int64_t* ss_off, const float* p, const float* tr, const uint8_t* ss,
+                      const float* pav, hhg_db** out);
+int hhg_db_apply_null_model(hhg_ctx* ctx, hhg_db* db, const float* q_pav, const float* pb, int columnscore);
+/* Debug / parity: the 1025-entry lg2 table of fast_log2 the library uses for Hit.score. */
+int hhg_debug_fastlog2_table(hhg_ctx* ctx, float* lg2_out);
 int hhg_db_destroy(hhg_db* db);
 int hhg_db_size(const hhg_db* db);          /* number of targets */
 long long hhg_db_columns(const hhg_db* db); /* sum of target lengths */

@@ -111,6 +111,11 @@ class RefShim:
         L.hhref_set_query.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p]
         L.hhref_prepare_template_hhm.argtypes = [C.c_char_p, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p, c_u8p,
                                                  c_f32p, C.c_int]
+        L.hhref_prepare_template_hhm_raw.argtypes = [C.c_char_p, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int]
+        L.hhref_fast_log2.restype = C.c_float
+        L.hhref_fast_log2.argtypes = [C.c_float]
+        L.hhref_score_cols.restype = C.c_float
+        L.hhref_score_cols.argtypes = [c_f32p, c_f32p]
         L.hhref_viterbi_align.argtypes = [C.c_int, c_i32p, C.POINTER(c_f32p), C.POINTER(c_f32p),
                                           C.POINTER(c_u8p), C.POINTER(c_u8p), C.POINTER(c_u8p), C.c_int,
                                           C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -134,6 +139,27 @@ class RefShim:
         self.maxres = maxres
         self.V = L.hhref_vecsize()
         self.Lq = 0
+        self._warm_fast_log2()
+
+    def _warm_fast_log2(self):
+        """Reference quirk: fast_log2's static table (src/util-inl.h:108-121) is filled by whichever
+        translation unit calls it first, and `log(float(..))` resolves to the double-precision C log in
+        hhhmm.cpp but to the float overload in hhviterbi.cpp -- two slightly different tables.  Every real
+        run of the reference reads the query HMM first (HMM::Read / PrepareQueryHMM), so the table that
+        matters is the hhhmm.cpp one; reproduce that order here before anything else touches fast_log2."""
+        import importlib.util
+        import tempfile
+        spec = importlib.util.spec_from_file_location(
+            "_hh_synth", os.path.join(os.path.dirname(HERE), "hh-suite_b200", "synth.py"))
+        synth = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(synth)
+        with tempfile.NamedTemporaryFile("w", suffix=".hhm", delete=False) as f:
+            f.write(synth.hhm_text(24, 0, "warm"))
+            path = f.name
+        try:
+            self.lib.hhref_load_query_hhm(path.encode())
+        finally:
+            os.unlink(path)
 
     # -- parameters
     def defaults(self):
@@ -189,6 +215,28 @@ class RefShim:
             raise IOError(path)
         return dict(L=L, p=p[:L + 2].copy(), tr=tr[:L + 1].copy(), pav=pav,
                     ss=(sp[:L + 2] * 11 + sc[:L + 2]).astype(np.uint8), neff=neff.value)
+
+    def prepare_template_hhm_raw(self, path, columnscore=1, maxL=4000):
+        p_raw = np.zeros((maxL + 2, 20), np.float32); p_prep = np.zeros((maxL + 2, 20), np.float32)
+        tr = np.zeros((maxL + 1, 7), np.float32); pav = np.zeros(20, np.float32)
+        L = self.lib.hhref_prepare_template_hhm_raw(path.encode(), columnscore, _p(p_raw, c_f32p),
+                                                    _p(p_prep, c_f32p), _p(tr, c_f32p), _p(pav, c_f32p), maxL)
+        if L < 0:
+            raise IOError(path)
+        return dict(L=L, p_raw=p_raw[:L + 2].copy(), p=p_prep[:L + 2].copy(), tr=tr[:L + 1].copy(), pav=pav)
+
+    def fast_log2_table(self):
+        """lg2[0..1024] of the reference's fast_log2 (x in [1,2): a=0, c=0 -> returns lg2[b] exactly)."""
+        x = ((np.arange(1024, dtype=np.uint32) << 13) | np.uint32(0x3F800000)).view(np.float32)
+        t = np.array([self.lib.hhref_fast_log2(float(v)) for v in x], np.float32)
+        return t
+
+    def fast_log2(self, x):
+        return self.lib.hhref_fast_log2(float(x))
+
+    def score_cols(self, qi, tj):
+        qi = np.ascontiguousarray(qi, np.float32); tj = np.ascontiguousarray(tj, np.float32)
+        return self.lib.hhref_score_cols(_p(qi, c_f32p), _p(tj, c_f32p))
 
     # -- the kernel
     def viterbi(self, targets, use_ss=False, celloff=None, local=True, egq=0.0, egt=0.0, shift=-0.03,

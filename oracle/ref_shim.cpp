@@ -207,6 +207,41 @@ int hhref_prepare_template_hhm(const char* path, float* p, float* tr, float* pav
   return L;
 }
 
+// Same as hhref_prepare_template_hhm but additionally exports the profile BEFORE the query-dependent
+// null-model division (IncludeNullModelInHMM, src/hhhmm.cpp:2059-2081): the steps of PrepareTemplateHMM
+// (src/hhfunc.cpp:165-202) are called one by one.  columnscore selects the null model (par.columnscore).
+int hhref_prepare_template_hhm_raw(const char* path, int columnscore, float* p_raw, float* p_prep,
+                                   float* tr, float* pav, int maxL) {
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  HMM* t = new HMM(MAXSEQDIS, g->maxres);
+  char pathbuf[NAMELEN];
+  Pathname(pathbuf, const_cast<char*>(path));
+  t->Read(f, g->par->maxcol, g->par->nseqdis, g->pb, pathbuf);
+  fclose(f);
+  Parameters& par = *g->par;
+  t->AddTransitionPseudocounts(par.gapd, par.gape, par.gapf, par.gapg, par.gaph, par.gapi, par.gapb, par.gapb);
+  t->PreparePseudocounts(g->R);
+  t->AddAminoAcidPseudocounts(par.pc_hhm_nocontext_mode, par.pc_hhm_nocontext_a, par.pc_hhm_nocontext_b,
+                              par.pc_hhm_nocontext_c);
+  t->CalculateAminoAcidBackground(g->pb);
+  int L = t->L;
+  if (L > maxL) { delete t; return -2; }
+  export_hmm(t, p_raw, tr, pav, nullptr, nullptr, nullptr, nullptr);
+  t->IncludeNullModelInHMM(g->q, t, columnscore, par.half_window_size_local_aa_bg_freqs, g->pb);
+  export_hmm(t, p_prep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  delete t;
+  return L;
+}
+
+// fast_log2 of the reference (table-based, src/util-inl.h:108-128) and Score() (src/hhhit-inl.h:132)
+float hhref_fast_log2(float x) { return fast_log2(x); }
+float hhref_score_cols(const float* qi, const float* tj) {
+  float q[20] __attribute__((aligned(32))), t[20] __attribute__((aligned(32)));
+  memcpy(q, qi, 80); memcpy(t, tj, 80);
+  return Score(q, t);
+}
+
 // Run the reference AVX2 kernel on one batch of n<=VECSIZE_FLOAT prepared targets.
 //  t_p[k]: (Lt+2)*20, t_tr[k]: (Lt+1)*7 in HMM enum order, t_ss_pred/conf[k]: Lt+2 bytes or NULL
 //  celloff[k]: (Lq+1)*(Lt_k+1) bytes (non-zero = cell off) or NULL

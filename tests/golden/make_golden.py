@@ -76,17 +76,33 @@ def main():
     variants = dict(plain={}, ss=dict(use_ss=True), co=dict(celloff=co), co_ss=dict(celloff=co, use_ss=True),
                     glob=dict(local=False, egq=0.1, egt=0.2))
     for vn, kw in variants.items():
+        hs = []
         if vn == "glob":
             # global mode is only well defined by the reference for equal-length lanes: one target per call
-            out = [R.viterbi([tg[k]], **kw)[0] for k in range(len(tg))]
+            out = []
+            for k in range(len(tg)):
+                out.append(R.viterbi([tg[k]], **kw)[0])
+                hs.append(R.hit_score(0))
         else:
             out = R.viterbi(tg, **kw)
+            hs = [R.hit_score(k) for k in range(len(tg))]
         for k, (sc, i2, j2, bt) in enumerate(out):
             G[f"v_{vn}_{k}_res"] = np.array([i2, j2], np.int32)
-            G[f"v_{vn}_{k}_score"] = np.array([sc], np.float32)
+            G[f"v_{vn}_{k}_score"] = np.array([sc, hs[k][0], hs[k][1]], np.float32)
             G[f"v_{vn}_{k}_bt"] = bt
-    # ---- prefilter
+    # ---- fast_log2 table and the query-dependent template preparation (null model)
+    G["fastlog2_lg2"] = R.fast_log2_table()
     q = R.load_query_hhm(os.path.join(REFDATA, "query.hhm"))
+    for cs in (0, 1, 2, 3):
+        for name, path in (("t150", "/tmp/synth150.hhm"), ("tself", os.path.join(REFDATA, "query.hhm"))):
+            t = R.prepare_template_hhm_raw(path, cs)
+            if cs == 1:
+                G[f"nm_{name}_praw"], G[f"nm_{name}_tr"], G[f"nm_{name}_pav"] = t["p_raw"], t["tr"], t["pav"]
+            G[f"nm_{name}_p_cs{cs}"] = t["p"]
+    pb = np.zeros(20, np.float32)
+    R.lib.hhref_get_pb(pb.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float)))
+    G["pb"] = pb
+    # ---- prefilter
     lib = R.cs219()
     G["cs219_lin"] = lib
     qc, W = R.stripe_query_profile(50, 4)

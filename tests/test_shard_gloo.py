@@ -25,7 +25,7 @@ def _worker(rank, world, port, n, k, ret):
         sc, i2, j2, bt = O.viterbi(qp, qtr, db["p"][db["p_off"][t]:db["p_off"][t] + L + 2],
                                    db["tr"][db["tr_off"][t]:db["tr_off"][t] + L + 1])
         ns, i_s, j_s, st, mc = O.backtrace(bt, i2, j2)
-        hits[x] = (sc, i2, j2, i_s[ns], j_s[ns], ns, mc, 0)
+        hits[x] = (sc, i2, j2, i_s[ns], j_s[ns], ns, mc, 0, sc, 0.0)
     merged = shard.allgather_topk(shard.local_topk(hits, ids, k), k)
     if rank == 0:
         ret["merged"] = merged
