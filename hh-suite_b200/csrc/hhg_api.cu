@@ -774,10 +774,10 @@ int hhg_csdb_destroy(hhg_csdb* db) { delete db; return HHG_OK; }
 
 }  // extern "C"
 
-template <int WPL>
+template <int WB>
 static int launch_prefilter(hhg_ctx* ctx, const PfParams& P) {
-  const size_t smem = (size_t)220 * 32 * WPL * 4;
-  auto kern = k_prefilter_ungapped<WPL>;
+  const size_t smem = (size_t)220 * WB * 32 * 2;
+  auto kern = k_prefilter_ungapped<WB>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
@@ -788,19 +788,31 @@ static int launch_prefilter(hhg_ctx* ctx, const PfParams& P) {
   return HHG_OK;
 }
 
+static int prefilter_wb(int Lq) {
+  static const int kWB[] = {2, 4, 6, 7, 8, 10, 12, 16};
+  for (int wb : kWB) if (Lq <= 64 * wb) return wb;
+  return 0;
+}
+
 extern "C" {
 
 int hhg_prefilter_ungapped_run(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const uint8_t* prof_host,
                                int offset, int upload_profile) {
   if (!ctx || !db || Lq < 1) return fail(HHG_EINVAL, "hhg_prefilter_ungapped_run: bad argument");
-  if (Lq > 128 * 8) return fail(HHG_EINVAL, "prefilter: query length %d > 1024 not supported yet", Lq);
+  const int WB = prefilter_wb(Lq);
+  if (!WB) return fail(HHG_EINVAL, "prefilter: query length %d > 1024 not supported yet (profile must fit in shared memory)", Lq);
   CK(cudaSetDevice(ctx->device));
-  const int W4 = (Lq + 3) / 4;
   if (upload_profile) {
     if (!prof_host) return fail(HHG_EINVAL, "profile is NULL");
-    // repack [220][Lq] bytes into [220][W4] words (4 consecutive positions per word, zero padded)
-    std::vector<uint8_t> packed((size_t)220 * W4 * 4, 0);
-    for (int k = 0; k < 220; ++k) memcpy(packed.data() + (size_t)k * W4 * 4, prof_host + (size_t)k * Lq, Lq);
+    // repack [220][Lq] bytes into [220][WB][32 lanes] halfwords: lane l owns positions l*2WB .. +2WB-1
+    std::vector<uint8_t> packed((size_t)220 * WB * 32 * 2, 0);
+    for (int k = 0; k < 220; ++k)
+      for (int l = 0; l < 32; ++l)
+        for (int w = 0; w < WB; ++w)
+          for (int h = 0; h < 2; ++h) {
+            const int pos = l * 2 * WB + 2 * w + h;
+            if (pos < Lq) packed[(((size_t)k * WB + w) * 32 + l) * 2 + h] = prof_host[(size_t)k * Lq + pos];
+          }
     CK(ctx->pf_prof.ensure(packed.size()));
     CK(cudaMemcpyAsync(ctx->pf_prof.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -808,13 +820,19 @@ int hhg_prefilter_ungapped_run(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const u
   CK(ctx->pf_counter.ensure(1));
   CK(cudaMemsetAsync(ctx->pf_counter.p, 0, 4, ctx->stream));
   PfParams P{};
-  P.n = db->n; P.L = db->dL.p; P.off = db->doff.p; P.seq = db->seq.p; P.prof = ctx->pf_prof.p;
-  P.Lq = Lq; P.W4 = W4; P.offset = offset; P.scores = db->scores.p; P.counter = ctx->pf_counter.p;
-  const int wpl = (W4 + 31) / 32;
-  if (wpl <= 1) return launch_prefilter<1>(ctx, P);
-  if (wpl <= 2) return launch_prefilter<2>(ctx, P);
-  if (wpl <= 4) return launch_prefilter<4>(ctx, P);
-  return launch_prefilter<8>(ctx, P);
+  P.n = db->n; P.L = db->dL.p; P.off = db->doff.p; P.seq = db->seq.p;
+  P.prof16 = reinterpret_cast<const uint16_t*>(ctx->pf_prof.p);
+  P.Lq = Lq; P.offset = offset; P.scores = db->scores.p; P.counter = ctx->pf_counter.p;
+  switch (WB) {
+    case 2: return launch_prefilter<2>(ctx, P);
+    case 4: return launch_prefilter<4>(ctx, P);
+    case 6: return launch_prefilter<6>(ctx, P);
+    case 7: return launch_prefilter<7>(ctx, P);
+    case 8: return launch_prefilter<8>(ctx, P);
+    case 10: return launch_prefilter<10>(ctx, P);
+    case 12: return launch_prefilter<12>(ctx, P);
+    default: return launch_prefilter<16>(ctx, P);
+  }
 }
 
 int hhg_prefilter_fetch(hhg_ctx* ctx, const hhg_csdb* db, int32_t* scores) {

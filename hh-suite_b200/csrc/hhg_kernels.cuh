@@ -762,39 +762,40 @@ __global__ void k_celloff_raster(int n_steps, const int* step_req, const int* st
 // ---------------------------------------------------------------------------------------------
 // cs219 ungapped prefilter (Prefilter::ungapped_sse_score, src/hhprefilter.cpp:214-275).
 //   S(i,j) = max(0, min(255, S(i-1,j-1) + prof[x_j][i]) - offset);  score = max over all cells.
-// One warp per database sequence; lane l owns query positions l, l+32, ... ; the diagonal
-// dependency S(i-1,j-1) comes from the lane below (shuffle) of the previous column.
-// The query profile (220 x Lq bytes) lives in shared memory, transposed to [pos][state] so the
-// lanes of a warp (consecutive positions, same state x_j) hit distinct banks.
-// Byte-SIMD: 4 query positions per 32-bit lane register (__vaddus4 / __vsubus4 / __vmaxu4).
+// One warp per database sequence; lane l owns the CONTIGUOUS query positions [l*2*WB, (l+1)*2*WB), two
+// positions per 32-bit register as s16x2.  The u8-saturating recurrence maps 1:1 onto the sm_90+/sm_100
+// DPX instructions: min(a+b, 255) = __viaddmin_s16x2, max(t-offset, 0) = __viaddmax_s16x2, running
+// maximum = __vimax3_s16x2 (3 instructions per 2 cells; the byte-SIMD __vaddus4 family is emulated on
+// this architecture, ~17 instructions per cell).  The diagonal dependency is a 16-bit funnel shift
+// between neighbouring registers plus ONE shuffle per column for the lane-boundary carry.
+// The query profile (220 x Lq bytes) sits in shared memory as [state][word][lane] halfwords, so the 32
+// lanes of a warp read 64 contiguous bytes (conflict-free).
 // ---------------------------------------------------------------------------------------------
 struct PfParams {
   int n;
   const int* L;
   const long long* off;
   const uint8_t* seq;
-  const uint8_t* prof;   // [220][Lq4] uint32-packed: prof4[k*W4 + w] = 4 consecutive positions
+  const uint16_t* prof16;   // [220][WB][32] halfwords: 2 consecutive query positions of one lane
   int Lq;
-  int W4;                // number of 4-position words = ceil(Lq/4)
   int offset;
   int* scores;
   unsigned int* counter;
 };
 
-template <int WPL>   // 32-bit words (4 query positions each) per lane: covers Lq <= 128*WPL
+template <int WB>   // 32-bit s16x2 registers per lane: covers Lq <= 64*WB
 __global__ void __launch_bounds__(256) k_prefilter_ungapped(const PfParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t* sprof = reinterpret_cast<uint32_t*>(smem_raw);   // [220][W4p] words, W4p = 32*WPL
-  const int W4p = 32 * WPL;
-  for (int idx = threadIdx.x; idx < 220 * W4p; idx += blockDim.x) {
-    const int k = idx / W4p, w = idx - k * W4p;
-    uint32_t v = 0;
-    if (w < P.W4) v = reinterpret_cast<const uint32_t*>(P.prof)[(size_t)k * P.W4 + w];
-    sprof[idx] = v;
+  uint16_t* sprof = reinterpret_cast<uint16_t*>(smem_raw);   // [220][WB][32]
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.prof16);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
+    for (int idx = threadIdx.x; idx < 220 * WB * 16; idx += blockDim.x) dst[idx] = src[idx];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const uint32_t off4 = 0x01010101u * (uint32_t)P.offset;
+  const uint32_t cap = 0x00FF00FFu;                                        // 255 | 255
+  const uint32_t noff = (uint32_t)((-P.offset) & 0xFFFF) * 0x00010001u;    // -offset | -offset
   for (;;) {
     int n = 0;
     if (lane == 0) n = (int)atomicAdd(P.counter, 1u);
@@ -802,38 +803,33 @@ __global__ void __launch_bounds__(256) k_prefilter_ungapped(const PfParams P) {
     if (n >= P.n) break;
     const uint8_t* x = P.seq + P.off[n];
     const int L = P.L[n];
-    // lane l, word w holds query positions 4*(w*32 + l) .. +3   (word-interleaved across lanes)
-    uint32_t S[WPL];
+    uint32_t S[WB];
 #pragma unroll
-    for (int w = 0; w < WPL; ++w) S[w] = 0;
+    for (int w = 0; w < WB; ++w) S[w] = 0;
     uint32_t smax = 0;
     for (int j0 = 0; j0 < L; j0 += 32) {
       const int xl = (j0 + lane < L) ? (int)x[j0 + lane] : 0;
       const int cnt = min(32, L - j0);
       for (int jj = 0; jj < cnt; ++jj) {
         const int xs = __shfl_sync(0xffffffffu, xl, jj);
-        const uint32_t* prow = sprof + xs * W4p + lane;
-        // shift the whole striped vector up by one query position: new S[pos] = old S[pos-1].
-        // Within a word: bytes shift left by 8 bits; the incoming low byte is the top byte of the
-        // previous word in position order = lane-1 of the same w (or lane 31 of w-1 for lane 0).
-        uint32_t carry_prev = 0;   // top byte of word (w-1, lane 31), for lane 0
+        const uint16_t* prow = sprof + (size_t)xs * (WB * 32) + lane;
+        // carry into this lane's first position: last position (high half of the last register) of
+        // lane-1 in the previous column; lane 0 starts every diagonal at 0
+        uint32_t carry = __shfl_up_sync(0xffffffffu, S[WB - 1], 1);
+        if (lane == 0) carry = 0;
 #pragma unroll
-        for (int w = 0; w < WPL; ++w) {
-          const uint32_t top = S[w] >> 24;
-          uint32_t in = __shfl_up_sync(0xffffffffu, top, 1);
-          const uint32_t last = __shfl_sync(0xffffffffu, top, 31);
-          if (lane == 0) in = carry_prev;
-          carry_prev = last;
-          uint32_t v = (S[w] << 8) | in;
-          v = __vaddus4(v, prow[w * 32]);
-          v = __vsubus4(v, off4);
+        for (int w = WB - 1; w >= 0; --w) {
+          const uint32_t below = (w > 0) ? S[w - 1] : carry;
+          const uint32_t diag = __funnelshift_l(below, S[w], 16);          // positions shifted up by one
+          const uint32_t pr = __byte_perm((uint32_t)prow[w * 32], 0u, 0x4140);   // u8,u8 -> s16x2
+          uint32_t v = __viaddmin_s16x2(diag, pr, cap);                     // min(S + prof, 255)
+          v = __viaddmax_s16x2(v, noff, 0u);                                // max(. - offset, 0)
           S[w] = v;
-          smax = __vmaxu4(smax, v);
+          smax = __vimax3_s16x2(smax, v, 0u);
         }
       }
     }
-    // horizontal max over bytes and lanes
-    uint32_t m = max(max(smax & 0xFFu, (smax >> 8) & 0xFFu), max((smax >> 16) & 0xFFu, smax >> 24));
+    uint32_t m = max(smax & 0xFFFFu, smax >> 16);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) P.scores[n] = (int)m;
