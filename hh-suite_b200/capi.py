@@ -35,7 +35,8 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_viterbi_search", "hhg_plan_create", "hhg_plan_destroy", "hhg_plan_run", "hhg_plan_run_timed", "hhg_plan_fetch", "hhg_plan_hits_devptr",
            "hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes", "hhg_plan_debug_bt",
            "hhg_csdb_create", "hhg_csdb_destroy", "hhg_prefilter_ungapped", "hhg_prefilter_ungapped_run",
-           "hhg_prefilter_fetch"]
+           "hhg_prefilter_fetch", "hhg_prefilter_build_profile", "hhg_prefilter_corrected_score",
+           "hhg_prefilter_sw", "hhg_prefilter_evalue"]
 
 
 class HhgError(RuntimeError):
@@ -96,6 +97,12 @@ def load():
     L.hhg_prefilter_ungapped.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p, C.c_int, c_i32p]
     L.hhg_prefilter_ungapped_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p, C.c_int, C.c_int]
     L.hhg_prefilter_fetch.argtypes = [C.c_void_p, C.c_void_p, c_i32p]
+    L.hhg_prefilter_build_profile.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_u8p]
+    L.hhg_prefilter_corrected_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.hhg_prefilter_evalue.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int]
+    L.hhg_prefilter_evalue.restype = C.c_double
+    L.hhg_prefilter_sw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, C.c_int, c_u8p, C.c_int, C.c_int, C.c_int,
+                                   c_i32p]
     _lib = L
     return L
 
@@ -283,6 +290,17 @@ def expand_path(hit, paths):
     return i_s, j_s, s_s
 
 
+def build_prefilter_profile(q_p, q_pav, lib219, offset=50, bit_factor=4):
+    """Host-side query profile (stripe_query_profile, linear layout [220][Lq])."""
+    q_p = np.ascontiguousarray(q_p, np.float32); q_pav = np.ascontiguousarray(q_pav, np.float32)
+    lib219 = np.ascontiguousarray(lib219, np.float32)
+    Lq = q_p.shape[0] - 2
+    prof = np.zeros((220, Lq), np.uint8)
+    _ck(load().hhg_prefilter_build_profile(Lq, _p(q_p, c_f32p), _p(q_pav, c_f32p), _p(lib219, c_f32p), offset,
+                                           bit_factor, _p(prof, c_u8p)))
+    return prof
+
+
 class CsDB:
     def __init__(self, ctx: Context, L, off, seq):
         self.ctx = ctx
@@ -300,6 +318,16 @@ class CsDB:
         sc = np.zeros(self.n, np.int32)
         _ck(self.ctx.L.hhg_prefilter_ungapped(self.ctx.h, self.h, prof.shape[1], _p(prof, c_u8p), offset,
                                               _p(sc, c_i32p)))
+        return sc
+
+    def sw(self, prof, ids=None, gap_open=24, gap_extend=4, bias=50):
+        """Stage-2 gapped scores (swStripedByte) for the selected sequences."""
+        prof = np.ascontiguousarray(prof, np.uint8)
+        ids = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        n = self.n if ids is None else len(ids)
+        sc = np.zeros(n, np.int32)
+        _ck(self.ctx.L.hhg_prefilter_sw(self.ctx.h, self.h, n, _p(ids, c_i32p), prof.shape[1], _p(prof, c_u8p),
+                                        gap_open, gap_extend, bias, _p(sc, c_i32p)))
         return sc
 
     def run(self, prof, offset=50, upload=True):

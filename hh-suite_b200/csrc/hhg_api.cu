@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <cfloat>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -88,7 +89,8 @@ struct hhg_ctx {
   bool has_ss = false, has_S33 = false;
   hhg_params par{1, 0.f, 0.f, -0.03f, 0.11f, 0, 0.1f, 2};
   // prefilter
-  DevBuf<uint8_t> pf_prof;
+  DevBuf<uint8_t> pf_prof, sw_prof;
+  DevBuf<int> sw_ids, sw_scores;
   DevBuf<unsigned> pf_counter;
   size_t max_bt_bytes = 0;   // memory-wave budget for backtrace words
   struct hhg_plan* scratch_plan = nullptr;   // reused by hhg_viterbi_search
@@ -833,6 +835,103 @@ int hhg_prefilter_ungapped_run(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const u
     case 12: return launch_prefilter<12>(ctx, P);
     default: return launch_prefilter<16>(ctx, P);
   }
+}
+
+// Host-side query profile of the prefilter (once per query; Prefilter::stripe_query_profile,
+// src/hhprefilter.cpp:356-424) in the LINEAR layout prof[k*Lq+pos]: 219 column states + the ANY state.
+// q_p is HMM::p of the (prefilter-pseudocount) query, i.e. float[(Lq+2)*20]; note the reference indexes
+// the 1-based p array with a 0-based position, reproduced here.  lib219: the 219x20
+// linear column-state probabilities of cs219.lib (cs::TransformToLin).
+static inline float flog2_host(float x) {       // flog2, src/util-inl.h:83-93 (double polynomial constants)
+  if (x <= 0) return -128;
+  uint32_t u; memcpy(&u, &x, 4);
+  float e = (float)((int)((u & 0x7F800000u) >> 23) - 0x7f);
+  u = (u & 0x007FFFFFu) | 0x3f800000u; memcpy(&x, &u, 4);
+  x -= 1.0;
+  x *= (1.441740 + x * (-0.7077702 + x * (0.4123442 + x * (-0.1903190 + x * 0.0440047))));
+  return x + e;
+}
+
+int hhg_prefilter_build_profile(int Lq, const float* q_p, const float* q_pav, const float* lib219,
+                                int score_offset, int bit_factor, uint8_t* prof) {
+  if (Lq < 1 || !q_p || !q_pav || !lib219 || !prof) return fail(HHG_EINVAL, "hhg_prefilter_build_profile: bad argument");
+  for (int k = 0; k < 219; ++k)
+    for (int pos = 0; pos < Lq; ++pos) {
+      float sum = 0;
+      for (int a = 0; a < 20; ++a) sum += ((q_p[(size_t)pos * 20 + a] * lib219[k * 20 + a]) / q_pav[a]);
+      float dummy = flog2_host(sum) * bit_factor + score_offset + 0.5;
+      prof[(size_t)k * Lq + pos] = dummy > 255.0 ? 255 : (dummy < 0 ? 0 : (uint8_t)dummy);
+    }
+  for (int pos = 0; pos < Lq; ++pos) prof[(size_t)219 * Lq + pos] = (uint8_t)(score_offset - 1);
+  return HHG_OK;
+}
+
+// Stage-1 length correction of Prefilter::prefilter_db (src/hhprefilter.cpp:477).
+int hhg_prefilter_corrected_score(int raw, int Lq, int Lt, int bit_factor) {
+  return raw - (int)(bit_factor * (flog2_host((float)Lq) + flog2_host((float)Lt)));
+}
+
+// Stage-2 E-value of Prefilter::prefilter_db (src/hhprefilter.cpp:529):
+//   evalue = (double)num_dbs * LQ * length * fpow2(-score / bit_factor)   with INTEGER division (App. D-6)
+// fpow2: src/util-inl.h:190-214.
+static inline float fpow2_host(float x) {
+  if (x >= FLT_MAX_EXP) return FLT_MAX;
+  if (x <= FLT_MIN_EXP) return 0.0f;
+  float tx = (x - 0.5f) + (3 << 22);
+  uint32_t ut; memcpy(&ut, &tx, 4);
+  int lx = (int)(ut - 0x4b400000u);
+  float dx = x - (float)lx;
+  x = 1.0f + dx * (0.693019f + dx * (0.241404f + dx * (0.0520749f + dx * 0.0134929f)));
+  uint32_t ux; memcpy(&ux, &x, 4);
+  ux += ((uint32_t)lx << 23);
+  memcpy(&x, &ux, 4);
+  return x;
+}
+
+double hhg_prefilter_evalue(int score, long long num_dbs, int Lq, int Lt, int bit_factor) {
+  const double factor = (double)num_dbs * Lq;
+  return factor * Lt * fpow2_host(-score / bit_factor);
+}
+
+// Gapped stage 2 on the GPU for `n` selected sequences (ids == NULL: the first n of the shard).
+// gap_open is the reference's gapOpen argument = prefilter_gap_open + prefilter_gap_extend (:456).
+int hhg_prefilter_sw(hhg_ctx* ctx, const hhg_csdb* db, int n, const int32_t* ids, int Lq,
+                     const uint8_t* prof, int gap_open, int gap_extend, int bias, int32_t* scores) {
+  if (!ctx || !db || n < 1 || Lq < 1 || !prof || !scores) return fail(HHG_EINVAL, "hhg_prefilter_sw: bad argument");
+  const int W = (Lq + 31) / 32;
+  const size_t prof_bytes = (size_t)220 * W * 32;
+  const size_t smem = prof_bytes + (size_t)8 * 3 * W * 32;
+  if (smem > 227 * 1024) return fail(HHG_EINVAL, "prefilter sw: query length %d too long for shared memory", Lq);
+  CK(cudaSetDevice(ctx->device));
+  for (int k = 0; ids && k < n; ++k)
+    if (ids[k] < 0 || ids[k] >= db->n) return fail(HHG_EINVAL, "prefilter sw: id %d out of range", ids[k]);
+  std::vector<uint8_t> striped(prof_bytes);
+  for (int k = 0; k < 220; ++k)
+    for (int j = 0; j < W; ++j)
+      for (int l = 0; l < 32; ++l) {
+        const int pos = l * W + j;
+        striped[((size_t)k * W + j) * 32 + l] = pos < Lq ? prof[(size_t)k * Lq + pos] : (uint8_t)bias;
+      }
+  CK(ctx->sw_prof.ensure(prof_bytes)); CK(ctx->sw_scores.ensure(n)); CK(ctx->pf_counter.ensure(1));
+  if (ids) CK(ctx->sw_ids.ensure(n));
+  CK(cudaMemcpyAsync(ctx->sw_prof.p, striped.data(), prof_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (ids) CK(cudaMemcpyAsync(ctx->sw_ids.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->pf_counter.p, 0, 4, ctx->stream));
+  SwParams P{};
+  P.n = n; P.ids = ids ? ctx->sw_ids.p : nullptr; P.L = db->dL.p; P.off = db->doff.p; P.seq = db->seq.p;
+  P.prof = ctx->sw_prof.p; P.W = W; P.gap_open = gap_open; P.gap_extend = gap_extend; P.bias = bias;
+  P.scores = ctx->sw_scores.p; P.counter = ctx->pf_counter.p;
+  CK(cudaFuncSetAttribute(k_prefilter_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prefilter_sw, 256, smem));
+  if (per_sm < 1) return fail(HHG_ECUDA, "prefilter sw kernel does not fit on an SM");
+  const int grid = std::min(ctx->sm_count * per_sm, (n + 7) / 8);
+  k_prefilter_sw<<<grid, 256, smem, ctx->stream>>>(P);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(scores, ctx->sw_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // `striped` is a host temporary
+  return HHG_OK;
 }
 
 int hhg_prefilter_fetch(hhg_ctx* ctx, const hhg_csdb* db, int32_t* scores) {

@@ -836,4 +836,97 @@ __global__ void __launch_bounds__(256) k_prefilter_ungapped(const PfParams P) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Gapped byte Smith-Waterman of prefilter stage 2 (Prefilter::swStripedByte, src/hhprefilter.cpp:70-212).
+// The reference's Farrar-striped AVX2 routine has 32 byte lanes and a lazy-F loop that does not update E,
+// so its score can depend on the striping.  To be bit-identical we execute exactly that
+// algorithm: one WARP = the 32 byte lanes of the AVX2 vector (lane k owns query positions k*W + j),
+// the full-width byte shift is __shfl_up, the movemask test is __all_sync.  Stage 2 only sees the
+// survivors of stage 1 (hundreds..thousands of sequences), so one byte per lane is plenty.
+// ---------------------------------------------------------------------------------------------
+struct SwParams {
+  int n;                    // number of requested sequences
+  const int* ids;           // [n] sequence ids (null = 0..n-1)
+  const int* L;
+  const long long* off;
+  const uint8_t* seq;
+  const uint8_t* prof;      // striped profile [220][W][32]: byte (k, j, lane) = position lane*W + j (bias pad)
+  int W;
+  int gap_open, gap_extend, bias;
+  int* scores;              // [n]
+  unsigned int* counter;
+};
+
+__global__ void __launch_bounds__(256) k_prefilter_sw(const SwParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int W = P.W;
+  uint8_t* sprof = smem_raw;                                   // [220][W][32]
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.prof);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
+    for (int idx = threadIdx.x; idx < 220 * W * 8; idx += blockDim.x) dst[idx] = src[idx];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* Hst = smem_raw + (size_t)220 * W * 32 + (size_t)warp * 3 * W * 32 + lane;   // + j*32
+  uint8_t* Hld = Hst + (size_t)W * 32;
+  uint8_t* E = Hld + (size_t)W * 32;
+  const int go = P.gap_open, ge = P.gap_extend, bias = P.bias;
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = (int)atomicAdd(P.counter, 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= P.n) break;
+    const int id = P.ids ? P.ids[it] : it;
+    const uint8_t* x = P.seq + P.off[id];
+    const int L = P.L[id];
+    for (int j = 0; j < W; ++j) { Hst[j * 32] = 0; Hld[j * 32] = 0; E[j * 32] = 0; }
+    int vmax = 0;
+    for (int i = 0; i < L; ++i) {
+      int vF = 0, vMaxCol = 0;
+      int vH = __shfl_up_sync(0xffffffffu, (int)Hst[(W - 1) * 32], 1);
+      if (lane == 0) vH = 0;
+      const uint8_t* row = sprof + (size_t)x[i] * W * 32 + lane;
+      { uint8_t* t = Hld; Hld = Hst; Hst = t; }
+      for (int j = 0; j < W; ++j) {
+        int h = min(vH + (int)row[j * 32], 255);
+        h = max(h - bias, 0);
+        int e = E[j * 32];
+        h = max(h, e);
+        h = max(h, vF);
+        vMaxCol = max(vMaxCol, h);
+        Hst[j * 32] = (uint8_t)h;
+        h = max(h - go, 0);
+        e = max(max(e - ge, 0), h);
+        E[j * 32] = (uint8_t)e;
+        vF = max(max(vF - ge, 0), h);
+        vH = Hld[j * 32];
+      }
+      // lazy F (:158-196)
+      int j = 0;
+      vF = __shfl_up_sync(0xffffffffu, vF, 1);
+      if (lane == 0) vF = 0;
+      for (;;) {
+        int h = Hst[j * 32];
+        const bool done = max(vF - max(h - go, 0), 0) == 0;
+        if (__all_sync(0xffffffffu, done)) break;
+        h = max(h, vF);
+        vMaxCol = max(vMaxCol, h);
+        Hst[j * 32] = (uint8_t)h;
+        vF = max(vF - ge, 0);
+        if (++j >= W) {
+          j = 0;
+          vF = __shfl_up_sync(0xffffffffu, vF, 1);
+          if (lane == 0) vF = 0;
+        }
+      }
+      vmax = max(vmax, vMaxCol);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0) P.scores[it] = vmax;
+    __syncwarp();
+  }
+}
+
 }  // namespace hhg

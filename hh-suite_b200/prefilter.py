@@ -1,0 +1,53 @@
+"""Host-side mirror of Prefilter::prefilter_db (src/hhprefilter.cpp:430-606) on top of the C-ABI: both
+scoring stages run on the GPU (ungapped DPX kernel over the whole cs219 shard, lane-exact gapped byte SW
+over the survivors); the selection logic between and after them is the reference's, restated:
+
+  stage 1: score = raw - (int)(bit_factor*(flog2(Lq)+flog2(Lt)))  (:477); sort descending by (score, n)
+           (comparePair + reverse, :489-490); keep entries while count < min_prefilter_hits or
+           score > smax_thresh (:494-506)
+  stage 2: evalue = N*Lq*Lt*fpow2(-score/bit_factor) (integer division, :529); keep evalue < coarse
+           threshold (:530); sort ascending by (evalue, n) (:545); keep while count < min_prefilter_hits or
+           evalue <= evalue_thresh (:547-558); cap at maxnumdb (:590)
+
+Returned: sequence ids in the reference's output order.  Name de-duplication and the old/new split by
+``previous_hits`` (:561-588) operate on ffindex entry names and stay in the reference host code."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+
+
+def prefilter_db(csdb: capi.CsDB, prof: np.ndarray, gap_open=20, gap_extend=4, score_offset=50, bit_factor=4,
+                 evalue_thresh=1000.0, evalue_coarse_thresh=100000.0, smax_thresh=10, min_prefilter_hits=100,
+                 maxnumdb=20000, return_details=False):
+    L = capi.load()
+    Lq = prof.shape[1]
+    n = csdb.n
+    raw = csdb.ungapped(prof, score_offset)
+    lens = csdb.Lh
+    corr = np.array([L.hhg_prefilter_corrected_score(int(raw[k]), Lq, int(lens[k]), bit_factor) for k in range(n)],
+                    np.int64)
+    order = np.lexsort((np.arange(n), corr))[::-1]          # descending (score, n)
+    keep = []
+    for idx in order:
+        if len(keep) >= min_prefilter_hits and corr[idx] <= smax_thresh:
+            break
+        keep.append(int(idx))
+    first = np.array(keep, np.int32)
+    sw = csdb.sw(prof, ids=first, gap_open=gap_open + gap_extend, gap_extend=gap_extend, bias=score_offset) \
+        if len(first) else np.zeros(0, np.int32)
+    ev = np.array([L.hhg_prefilter_evalue(int(sw[k]), n, Lq, int(lens[first[k]]), bit_factor)
+                   for k in range(len(first))], np.float64)
+    sel = [k for k in range(len(first)) if ev[k] < evalue_coarse_thresh]
+    sel.sort(key=lambda k: (ev[k], int(first[k])))
+    out = []
+    for k in sel:
+        if len(out) >= min_prefilter_hits and ev[k] > evalue_thresh:
+            break
+        out.append(k)
+    out = out[:maxnumdb]
+    ids = first[out] if len(out) else np.zeros(0, np.int32)
+    if return_details:
+        return ids, dict(raw=raw, corrected=corr, first=first, sw=sw, evalue=ev)
+    return ids

@@ -164,6 +164,21 @@ int hhg_prefilter_ungapped_run(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const u
                                int offset, int upload_profile);
 int hhg_prefilter_fetch(hhg_ctx* ctx, const hhg_csdb* db, int32_t* scores);
 
+/* Host-side, once per query: the 220 x Lq byte profile of Prefilter::stripe_query_profile
+ * (src/hhprefilter.cpp:356-424) in linear layout prof[k*Lq+pos].  q_p = HMM::p of the query
+ * (float[(Lq+2)*20]), lib219 = 219x20 linear column-state probabilities of cs219.lib. */
+int hhg_prefilter_build_profile(int Lq, const float* q_p, const float* q_pav, const float* lib219,
+                                int score_offset, int bit_factor, uint8_t* prof);
+/* Stage-1 length correction, src/hhprefilter.cpp:477. */
+int hhg_prefilter_corrected_score(int raw, int Lq, int Lt, int bit_factor);
+/* Stage-2 E-value, src/hhprefilter.cpp:529 (integer division of the score, fast fpow2). */
+double hhg_prefilter_evalue(int score, long long num_dbs, int Lq, int Lt, int bit_factor);
+/* Gapped stage 2 (Prefilter::swStripedByte, src/hhprefilter.cpp:70-212, AVX2 striping emulated lane for
+ * lane) for n selected sequences of the shard (ids == NULL: the first n). gap_open is the reference's
+ * gapOpen argument (= prefilter_gap_open + prefilter_gap_extend). scores[n]: host buffer. */
+int hhg_prefilter_sw(hhg_ctx* ctx, const hhg_csdb* db, int n, const int32_t* ids, int Lq,
+                     const uint8_t* prof, int gap_open, int gap_extend, int bias, int32_t* scores);
+
 #ifdef __cplusplus
 }
 #endif

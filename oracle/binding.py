@@ -48,6 +48,10 @@ class Oracle:
         L.hho_ungapped_corrected.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         L.hho_flog2.restype = C.c_float
         L.hho_flog2.argtypes = [C.c_float]
+        L.hho_fpow2.restype = C.c_float
+        L.hho_fpow2.argtypes = [C.c_float]
+        L.hho_sw_striped_byte.restype = C.c_int
+        L.hho_sw_striped_byte.argtypes = [C.c_int, c_u8p, c_u8p, C.c_int, C.c_int, C.c_int, C.c_int]
 
     def viterbi(self, q_p, q_tr, t_p, t_tr, q_ss=None, t_ss=None, S33=None, ssw=0.11, celloff=None,
                 local=True, egq=0.0, egt=0.0, shift=-0.03, want_bt=True):
@@ -92,6 +96,19 @@ class Oracle:
     def ungapped(self, prof, seq, offset=50):
         seq = np.ascontiguousarray(seq, np.uint8)
         return self.lib.hho_ungapped_score(prof.shape[1], _p(prof, c_u8p), _p(seq, c_u8p), len(seq), offset)
+
+
+    def sw_byte(self, prof, seq, gap_open=24, gap_extend=4, bias=50):
+        seq = np.ascontiguousarray(seq, np.uint8)
+        prof = np.ascontiguousarray(prof, np.uint8)
+        return self.lib.hho_sw_striped_byte(prof.shape[1], _p(prof, c_u8p), _p(seq, c_u8p), len(seq), gap_open,
+                                            gap_extend, bias)
+
+    def flog2(self, x):
+        return self.lib.hho_flog2(float(x))
+
+    def fpow2(self, x):
+        return self.lib.hho_fpow2(float(x))
 
 
 class RefShim:

@@ -249,3 +249,90 @@ int hho_ungapped_score(int Lq, const uint8_t* prof, const uint8_t* dbseq, int Lt
 int hho_ungapped_corrected(int raw, int Lq, int Lt, int bit_factor) {
   return raw - (int)(bit_factor * (flog2_scalar((float)Lq) + flog2_scalar((float)Lt)));
 }
+
+/* Follows Prefilter::swStripedByte, src/hhprefilter.cpp:70-212, for the AVX2 build (32 byte lanes,
+ * segLen = ceil(Lq/32), full-width byte shift _mm256_shift_left<1>, lib/simd/simd.h:184-187): gapped local
+ * SW on unsigned saturating bytes, Farrar striping with the SWPS3-style lazy-F loop that does NOT update E
+ * (so the result can depend on the striping, SURVEY App. D-5 -- hence this lane-exact emulation rather than
+ * a textbook SW).  prof: LINEAR profile [220][Lq]; padding positions behave as `bias` (:392-393).
+ * gap_open here is the reference's gapOpen argument (= prefilter_gap_open + prefilter_gap_extend, :456). */
+int hho_sw_striped_byte(int Lq, const uint8_t* prof, const uint8_t* dbseq, int Lt, int gap_open,
+                        int gap_extend, int bias) {
+  enum { V = 32 };
+  const int W = (Lq + V - 1) / V;
+  uint8_t* buf = (uint8_t*)calloc((size_t)3 * W * V, 1);
+  uint8_t *Hst = buf, *Hld = buf + (size_t)W * V, *E = buf + (size_t)2 * W * V;
+  int vmax[V];
+  for (int k = 0; k < V; ++k) vmax[k] = 0;
+#define SUBS(a, b) ((a) > (b) ? (a) - (b) : 0)
+  for (int i = 0; i < Lt; ++i) {
+    int vF[V], vH[V], vMaxCol[V];
+    const uint8_t* row = prof + (size_t)dbseq[i] * Lq;
+    for (int k = 0; k < V; ++k) { vF[k] = 0; vMaxCol[k] = 0; }
+    for (int k = V - 1; k > 0; --k) vH[k] = Hst[(size_t)(W - 1) * V + k - 1];   /* shiftl(pvHStore[segLen-1]) */
+    vH[0] = 0;
+    { uint8_t* t = Hld; Hld = Hst; Hst = t; }
+    for (int j = 0; j < W; ++j) {
+      for (int k = 0; k < V; ++k) {
+        const int pos = k * W + j;
+        const int p = pos < Lq ? row[pos] : bias;
+        int h = vH[k] + p; if (h > 255) h = 255;
+        h = SUBS(h, bias);
+        int e = E[(size_t)j * V + k];
+        if (e > h) h = e;
+        if (vF[k] > h) h = vF[k];
+        if (h > vMaxCol[k]) vMaxCol[k] = h;
+        Hst[(size_t)j * V + k] = (uint8_t)h;
+        h = SUBS(h, gap_open);
+        e = SUBS(e, gap_extend);
+        if (h > e) e = h;
+        E[(size_t)j * V + k] = (uint8_t)e;
+        int f = SUBS(vF[k], gap_extend);
+        if (h > f) f = h;
+        vF[k] = f;
+        vH[k] = Hld[(size_t)j * V + k];
+      }
+    }
+    /* lazy F */
+    int j = 0;
+    for (int k = V - 1; k > 0; --k) vF[k] = vF[k - 1];
+    vF[0] = 0;
+    for (;;) {
+      int all = 1;
+      for (int k = 0; k < V; ++k) {
+        const int h = Hst[(size_t)j * V + k];
+        if (SUBS(vF[k], SUBS(h, gap_open)) != 0) all = 0;
+      }
+      if (all) break;
+      for (int k = 0; k < V; ++k) {
+        int h = Hst[(size_t)j * V + k];
+        if (vF[k] > h) h = vF[k];
+        if (h > vMaxCol[k]) vMaxCol[k] = h;
+        Hst[(size_t)j * V + k] = (uint8_t)h;
+        vF[k] = SUBS(vF[k], gap_extend);
+      }
+      if (++j >= W) {
+        j = 0;
+        for (int k = V - 1; k > 0; --k) vF[k] = vF[k - 1];
+        vF[0] = 0;
+      }
+    }
+    for (int k = 0; k < V; ++k) if (vMaxCol[k] > vmax[k]) vmax[k] = vMaxCol[k];
+  }
+#undef SUBS
+  int score = 0;
+  for (int k = 0; k < V; ++k) if (vmax[k] > score) score = vmax[k];
+  free(buf);
+  return score;
+}
+
+/* Follows fpow2, src/util-inl.h:190-214. */
+float hho_fpow2(float x) {
+  if (x >= FLT_MAX_EXP) return FLT_MAX;
+  if (x <= FLT_MIN_EXP) return 0.0f;
+  float tx = (x - 0.5f) + (3 << 22);
+  int lx = (int)(f2u(tx) - 0x4b400000u);
+  float dx = x - (float)lx;
+  x = 1.0f + dx * (0.693019f + dx * (0.241404f + dx * (0.0520749f + dx * 0.0134929f)));
+  return u2f(f2u(x) + ((uint32_t)lx << 23));
+}

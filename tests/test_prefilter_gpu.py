@@ -75,3 +75,101 @@ def test_prefilter_rejects_overlong_query(hhg, gpu_ctx):
     with pytest.raises(hhg.HhgError):
         db.ungapped(np.zeros((220, 1025), np.uint8), 50)
     db.close()
+
+
+def test_host_profile_builder_matches_reference(hhg):
+    """hhg_prefilter_build_profile (host side, once per query) vs Prefilter::stripe_query_profile golden."""
+    G = golden()
+    prof = hhg.capi.build_prefilter_profile(G["q_p"], G["q_pav"], G["cs219_lin"], 50, 4)
+    assert np.array_equal(prof, G["pf_prof"])
+
+
+def _homologs(rng, best, n):
+    out = []
+    Lq = len(best)
+    for _ in range(n):
+        cut = int(rng.integers(1, Lq - 1))
+        ins = rng.integers(0, 219, int(rng.integers(1, 12)), dtype=np.uint8)
+        out.append(np.concatenate([best[:cut], ins, best[cut + int(rng.integers(0, 8)):]]))
+    return out
+
+
+@pytest.mark.parametrize("Lq", [20, 64, 130, 431])
+def test_gapped_sw_oracle_parity(hhg, gpu_ctx, oracle, Lq):
+    """Stage 2 (swStripedByte, lazy-F quirk and all) against the lane-exact oracle emulation."""
+    G = golden()
+    rng = np.random.default_rng(100 + Lq)
+    prof = G["pf_prof"][:, :Lq].copy() if Lq <= 431 else None
+    best = prof[:219].argmax(axis=0).astype(np.uint8)
+    seqs = [rng.integers(0, 219, L, dtype=np.uint8) for L in [1, 2, 33, 500] + list(rng.integers(5, 300, 60))]
+    seqs += _homologs(rng, best, 30) if Lq > 3 else []
+    db = _db(hhg, gpu_ctx, seqs)
+    got = db.sw(prof, gap_open=24, gap_extend=4, bias=50)
+    want = [oracle.sw_byte(prof, s, 24, 4, 50) for s in seqs]
+    assert got.tolist() == want
+    ids = rng.permutation(len(seqs))[:17].astype(np.int32)
+    assert db.sw(prof, ids=ids).tolist() == [want[i] for i in ids]
+    db.close()
+
+
+def test_gapped_sw_goldens_and_reference(hhg, gpu_ctx, refshim, tmp_path):
+    G = golden()
+    seqs = [G[f"pf_seq{k}"] for k in range(int(G["pf_nseq"][0]))]
+    db = _db(hhg, gpu_ctx, seqs)
+    assert db.sw(G["pf_prof"]).tolist() == [int(G[f"pf_ref{k}"][1]) for k in range(len(seqs))]
+    db.close()
+    from hhsuite_b200 import synth
+    f = tmp_path / "q.hhm"
+    f.write_text(synth.hhm_text(200, 33, "q200"))
+    q = refshim.load_query_hhm(str(f))
+    qc, W = refshim.stripe_query_profile(50, 4)
+    pos = np.arange(200)
+    prof = np.stack([qc[k * W * 32 + (pos % W) * 32 + pos // W] for k in range(220)])
+    rng = np.random.default_rng(9)
+    seqs = [rng.integers(0, 219, L, dtype=np.uint8) for L in rng.integers(1, 400, 50)]
+    seqs += _homologs(rng, prof[:219].argmax(axis=0).astype(np.uint8), 30)
+    db = _db(hhg, gpu_ctx, seqs)
+    assert db.sw(prof).tolist() == [refshim.sw_byte(qc, s, 24, 4, 50) for s in seqs]
+    db.close()
+
+
+def test_prefilter_db_selection(hhg, gpu_ctx, oracle):
+    """Two-stage prefilter_db mirror: GPU scores + reference selection logic vs the same logic fed with
+    oracle scores (flog2/fpow2 restated in oracle/hh_oracle.c)."""
+    G = golden()
+    prof = G["pf_prof"]
+    Lq = prof.shape[1]
+    rng = np.random.default_rng(31)
+    best = prof[:219].argmax(axis=0).astype(np.uint8)
+    seqs = [rng.integers(0, 219, L, dtype=np.uint8) for L in rng.integers(30, 400, 600)] + _homologs(rng, best, 25)
+    perm = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in perm]
+    db = _db(hhg, gpu_ctx, seqs)
+    kw = dict(min_prefilter_hits=20, smax_thresh=10, evalue_thresh=1000.0, evalue_coarse_thresh=100000.0, maxnumdb=40)
+    ids, det = hhg.prefilter.prefilter_db(db, prof, return_details=True, **kw)
+    n = len(seqs)
+    raw = np.array([oracle.ungapped(prof, s, 50) for s in seqs])
+    assert np.array_equal(det["raw"], raw)
+    corr = np.array([oracle.lib.hho_ungapped_corrected(int(raw[k]), Lq, len(seqs[k]), 4) for k in range(n)])
+    assert np.array_equal(det["corrected"], corr)
+    order = sorted(range(n), key=lambda k: (corr[k], k), reverse=True)
+    first = []
+    for k in order:
+        if len(first) >= 20 and corr[k] <= 10:
+            break
+        first.append(k)
+    assert det["first"].tolist() == first
+    sw = [oracle.sw_byte(prof, seqs[k], 24, 4, 50) for k in first]
+    assert det["sw"].tolist() == sw
+    ev = [float(n) * Lq * len(seqs[k]) * oracle.fpow2(float(int(-s / 4))) for k, s in zip(first, sw)]
+    assert np.allclose(det["evalue"], ev, rtol=0, atol=0)
+    sel = sorted([x for x in range(len(first)) if ev[x] < 100000.0], key=lambda x: (ev[x], first[x]))
+    out = []
+    for x in sel:
+        if len(out) >= 20 and ev[x] > 1000.0:
+            break
+        out.append(first[x])
+    assert ids.tolist() == out[:40]
+    planted = set(np.nonzero(perm >= 600)[0].tolist())
+    assert planted <= set(ids.tolist()[:40]) or len(planted & set(ids.tolist())) >= 20
+    db.close()
