@@ -1,1 +1,4 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -12
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python bench.py --steps 5 --warmup 3 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'], d['cpu_baseline']['value'], d['prefilter'], d['roofline']['frac'])"

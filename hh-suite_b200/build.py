@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "hhg_api.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "hhg_kernels.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "hhg_kernels.cuh"), os.path.join(HERE, "csrc", "hhg_viterbi2.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "hhg.h")]
 OUT = os.path.join(HERE, "libhhg.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

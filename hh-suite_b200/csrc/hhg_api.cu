@@ -3,6 +3,7 @@
 // device memory, launches.  There is no CPU fallback: without a CUDA device every entry point fails.
 #include "../../include/hhg.h"
 #include "hhg_kernels.cuh"
+#include "hhg_viterbi2.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -81,6 +82,7 @@ struct hhg_ctx {
   // query
   int Lq = 0, R = 16, nstrips = 0;
   int group_jobs = 64;   // work-item interleave (see k_viterbi)
+  int cols = 1;          // target columns per query-row visit: 1 = k_viterbi, 2 = k_viterbi2
   uint32_t epoch = 0;    // run counter feeding the boundary-slot tags
   DevBuf<float4> qrec;
   DevBuf<float> S33;
@@ -130,7 +132,7 @@ struct Wave {
 struct hhg_plan {
   const hhg_db* db = nullptr;
   int n = 0;            // requests
-  int Lq = 0, R = 16, nstrips = 0;
+  int Lq = 0, R = 16, nstrips = 0, cols = 1;
   int njobs = 0;
   double cells = 0, padded_cells = 0, alg_bytes = 0;
   std::vector<int> ids;          // request -> target id
@@ -150,6 +152,10 @@ struct hhg_plan {
   DevBuf<int> d_strip_ij;
   DevBuf<unsigned> d_counter;
   float ms_viterbi = 0, ms_backtrace = 0;   // filled by hhg_plan_run_timed
+  size_t max_bt_bytes = 0;
+  DevBuf<uint8_t> d_paths_compact;
+  DevBuf<long long> d_compact_off;
+  std::vector<long long> h_compact_off;
   DevBuf<HitRec> d_hits;
   DevBuf<uint8_t> d_paths;
   // cell-off input (optional)
@@ -189,6 +195,7 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
     c->own_stream = true;
   }
   c->R = strip_rows();
+  { const char* ce = getenv("HHG_COLS"); c->cols = (ce && atoi(ce) == 2) ? 2 : 1; }
   {
     // fast_log2 tables exactly as the reference fills them on first use (src/util-inl.h:113-121):
     // lg2[i] = log2(1 + i/1024) via the C library's double-precision log (that is the overload the
@@ -425,12 +432,22 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   if (ctx->Lq <= 0) return fail(HHG_EINVAL, "hhg_plan_create: no query set");
   if (db->device != ctx->device) return fail(HHG_EINVAL, "db lives on device %d, ctx on %d", db->device, ctx->device);
   CK(cudaSetDevice(ctx->device));
+  // the common case of a repeated request (same shard, same target list, same query geometry, e.g. every
+  // query of a batch against the whole shard) reuses the plan: no host sort, no uploads
+  if (pl->db == db && pl->n == n && pl->Lq == ctx->Lq && pl->R == ctx->R && pl->cols == ctx->cols &&
+      !pl->ids.empty() && pl->max_bt_bytes == ctx->max_bt_bytes) {
+    bool same = true;
+    if (ids) same = memcmp(ids, pl->ids.data(), (size_t)n * 4) == 0;
+    else for (int k = 0; k < n && same; ++k) same = pl->ids[k] == k;
+    if (same) { pl->celloff = false; return HHG_OK; }
+  }
   pl->db = db;
+  pl->max_bt_bytes = ctx->max_bt_bytes;
   pl->cells = pl->padded_cells = pl->alg_bytes = 0;
   pl->waves.clear();
   pl->celloff = false;
   pl->n = n;
-  pl->Lq = ctx->Lq; pl->R = ctx->R; pl->nstrips = ctx->nstrips;
+  pl->Lq = ctx->Lq; pl->R = ctx->R; pl->nstrips = ctx->nstrips; pl->cols = ctx->cols;
   pl->ids.resize(n);
   for (int k = 0; k < n; ++k) {
     const int id = ids ? ids[k] : k;
@@ -456,7 +473,8 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   for (int jb = 0; jb < pl->njobs; ++jb) {
     const int first = jb * 32;
     const int cnt = std::min(32, n - first);
-    const int Lmax = db->L[pl->ids[pl->order[first]]];
+    int Lmax = db->L[pl->ids[pl->order[first]]];
+    if (pl->cols == 2) Lmax += (Lmax & 1);   // the 2-column kernel sweeps column pairs
     pl->job_Lmax[jb] = Lmax;
     for (int l = 0; l < 32; ++l) {
       const int rq = pl->order[first + std::min(l, cnt - 1)];   // padded lanes repeat the last target
@@ -583,7 +601,7 @@ static int set_exclusions(hhg_ctx* ctx, hhg_plan* pl, const int64_t* excl_off, c
 }  // extern "C"
 
 template <int R>
-static int launch_viterbi(hhg_ctx* ctx, const VitParams& P, bool local, bool ss, bool co, int items) {
+static int launch_viterbi(hhg_ctx* ctx, const VitParams& P, bool local, bool ss, bool co, int items, int cols = 1) {
   const size_t smem = (size_t)kWarpsPerCta * R * 112 +
                       (HHG_USE_CPASYNC ? (size_t)kWarpsPerCta * kStages * 32 * 112 : 0) + 64 +
                       (ss ? 44 * 44 * 4 : 0);
@@ -594,6 +612,16 @@ static int launch_viterbi(hhg_ctx* ctx, const VitParams& P, bool local, bool ss,
   else       { if (ss) { if (co) PICK(false, true, true); else PICK(false, true, false); }
                else    { if (co) PICK(false, false, true); else PICK(false, false, false); } }
 #undef PICK
+  {
+    if (cols == 2) {
+#define PICK2(L_, S_, C_) kern = k_viterbi2<R, L_, S_, C_>
+      if (local) { if (ss) { if (co) PICK2(true, true, true); else PICK2(true, true, false); }
+                   else    { if (co) PICK2(true, false, true); else PICK2(true, false, false); } }
+      else       { if (ss) { if (co) PICK2(false, true, true); else PICK2(false, true, false); }
+                   else    { if (co) PICK2(false, false, true); else PICK2(false, false, false); } }
+#undef PICK2
+    }
+  }
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem));
@@ -612,7 +640,7 @@ extern "C" {
 
 static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
   if (!ctx || !pl) return fail(HHG_EINVAL, "hhg_plan_run: bad argument");
-  if (pl->Lq != ctx->Lq || pl->R != ctx->R) return fail(HHG_EINVAL, "plan was made for another query length");
+  if (pl->Lq != ctx->Lq || pl->R != ctx->R || pl->cols != ctx->cols) return fail(HHG_EINVAL, "plan was made for another query length");
   const hhg_db* db = pl->db;
   if (!db->prepared) return fail(HHG_EINVAL, "raw db: call hhg_db_apply_null_model for the current query first");
   if (ctx->par.use_ss && (!db->has_ss || !ctx->has_ss || !ctx->has_S33))
@@ -648,9 +676,9 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
     const int items = nj * pl->nstrips;
     int rc;
     if (timed) CK(cudaEventRecord(ctx->ev[0], st));
-    if (pl->R == 8) rc = launch_viterbi<8>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
-    else if (pl->R == 12) rc = launch_viterbi<12>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
-    else rc = launch_viterbi<16>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
+    if (pl->R == 8) rc = launch_viterbi<8>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items, pl->cols);
+    else if (pl->R == 12) rc = launch_viterbi<12>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items, pl->cols);
+    else rc = launch_viterbi<16>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items, pl->cols);
     if (rc != HHG_OK) return rc;
     if (timed) CK(cudaEventRecord(ctx->ev[1], st));
     // backtrace of this wave's requests.  Requests are addressed through the sorted order: the
@@ -705,12 +733,25 @@ int hhg_plan_fetch(hhg_ctx* ctx, hhg_plan* pl, hhg_hit* hits, uint8_t* paths, si
   static_assert(sizeof(hhg_hit) == sizeof(HitRec), "hhg_hit / HitRec layout");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(hits, pl->d_hits.p, (size_t)pl->n * sizeof(HitRec), cudaMemcpyDeviceToHost, ctx->stream));
-  if (paths) {
-    if (paths_cap < (size_t)pl->path_total)
-      return fail(HHG_EINVAL, "paths buffer too small: need %lld bytes", pl->path_total);
-    CK(cudaMemcpyAsync(paths, pl->d_paths.p, (size_t)pl->path_total, cudaMemcpyDeviceToHost, ctx->stream));
-  }
   CK(cudaStreamSynchronize(ctx->stream));
+  if (paths) {
+    // compact on the device: only nsteps bytes per request cross PCIe (capacity is Lq+Lt+2 each)
+    pl->h_compact_off.resize(pl->n);
+    long long tot = 0;
+    for (int k = 0; k < pl->n; ++k) { pl->h_compact_off[k] = tot; tot += hits[k].nsteps; }
+    if (paths_cap < (size_t)tot) return fail(HHG_EINVAL, "paths buffer too small: need %lld bytes", tot);
+    CK(pl->d_compact_off.ensure(pl->n));
+    CK(pl->d_paths_compact.ensure((size_t)std::max<long long>(tot, 1)));
+    CK(cudaMemcpyAsync(pl->d_compact_off.p, pl->h_compact_off.data(), (size_t)pl->n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 128;
+    k_gather_paths<<<(pl->n + threads - 1) / threads, threads, 0, ctx->stream>>>(
+        pl->n, pl->d_hits.p, pl->d_path_off.p, pl->d_compact_off.p, pl->d_paths.p, pl->d_paths_compact.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(paths, pl->d_paths_compact.p, (size_t)tot, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < pl->n; ++k) hits[k].path_off = (int32_t)pl->h_compact_off[k];
+  }
   return HHG_OK;
 }
 

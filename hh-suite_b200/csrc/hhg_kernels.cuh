@@ -478,14 +478,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
           dg = __fadd_rn(dg, off); mi = __fadd_rn(mi, off);
         }
 
-        // running maximum, :423-455.  Strips are swept column-major, the reference row-major:
-        // on an exact tie the earlier ROW must win, hence the (rare) slow path.
-        if (mm >= bc) {
-          const int i = i0 + 1 + r;
-          const bool cand = (i <= P.Lq) && (LOCAL || i == P.Lq || j == Lt);
-          if (cand && (mm > best || i < bi)) { best = mm; bi = i; bj = j; bc = mm; }
-        }
-
         word |= b << (8 * (r & 3));
         if ((r & 3) == 3) {
           __stcs(btj + (size_t)((i0 >> 2) + (r >> 2)) * bt_row_stride + (size_t)j * 32, word);
@@ -497,6 +489,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
         MM[r] = mm; GD[r] = gd; IM[r] = im; DG[r] = dg; MI[r] = mi;
       }
       dtMM = tMM; dtDG = tDG; dtMI = tMI; dtGD = tGD; dtIM = tIM;
+
+      // running maximum, :423-455: ONE test per column on the maximum of the R new MM values (a tree of
+      // FMNMX, 1 instruction per row instead of compare+branch per cell); only when it can matter the
+      // rows are examined in ascending order.  Strips are swept column-major, the reference row-major:
+      // on an exact tie the earlier ROW must win (mm == best && i < bi).
+      {
+        float cm[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) cm[r] = MM[r];
+#pragma unroll
+        for (int n = R; n > 1; n = (n + 1) / 2) {      // pairwise tree, any R
+#pragma unroll
+          for (int r = 0; r < n / 2; ++r) cm[r] = fmaxf(cm[r], cm[r + (n + 1) / 2]);
+        }
+        if (cm[0] >= bc) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float mm = MM[r];
+            if (mm >= bc) {
+              const int i = i0 + 1 + r;
+              const bool cand = (i <= P.Lq) && (LOCAL || i == P.Lq || j == Lt);
+              if (cand && (mm > best || i < bi)) { best = mm; bi = i; bj = j; bc = mm; }
+            }
+          }
+        }
+      }
 
       if (!last_strip)
         st_slot(bnd + (size_t)j * 32, MM[R - 1], DG[R - 1], MI[R - 1], GD[R - 1], IM[R - 1], tag_out);
@@ -695,6 +713,18 @@ __global__ void k_null_model(long long total_cols, int n, const long long* col_o
   }
   dst[5] = src[5];
   dst[6] = src[6];
+}
+
+// Compact the per-request path strings (capacity Lq+Lt+2 each) to their real lengths before the D2H copy:
+// one thread per request copies nsteps bytes to its compact offset.
+__global__ void k_gather_paths(int n, const HitRec* hits, const long long* src_off, const long long* dst_off,
+                               const uint8_t* src, uint8_t* dst) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int len = hits[k].nsteps;
+  const uint8_t* s = src + src_off[k];
+  uint8_t* d = dst + dst_off[k];
+  for (int b = 0; b < len; ++b) d[b] = s[b];
 }
 
 // De-interleave one target's backtrace bytes into the reference's row-major cell matrix (parity tests).

@@ -114,7 +114,8 @@ int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const u
 
 /* Align the current query against `n` targets of `db` (ids == NULL: all targets in db order).
  *   hits[n]      : one record per requested target, in request order.
- *   paths        : caller buffer of `paths_cap` bytes receiving, per target, nsteps state bytes
+ *   paths        : caller buffer of `paths_cap` bytes (>= sum of nsteps; sum(Lq+Lt+2) always suffices)
+ *                  receiving, per target and tightly packed at hits[k].path_off, nsteps state bytes
  *                  (ViterbiMatrix codes MM=2,GD=3,IM=4,DG=5,MI=6; byte 0 = step 1 = cell (i2,j2),
  *                  last byte = step nsteps, forced to MM like src/hhviterbi.cpp:147); may be NULL.
  *   excl_*       : optional cell-off input = previous alignments to exclude (alternative alignments,
