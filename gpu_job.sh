@@ -1,4 +1,3 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python bench.py --steps 5 --warmup 3 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'], d['cpu_baseline']['value'], d['prefilter'], d['roofline']['frac'])"
+V=hh-suite_b200/variants
+HHG_LIB=$V/libhhg_paramq.so python tools/perf_probe.py HHG_GROUP_JOBS=1 HHG_GROUP_JOBS=4 HHG_GROUP_JOBS=16 HHG_GROUP_JOBS=296 2>&1 | sed "s/^/paramq /"
+python tools/perf_probe.py HHG_GROUP_JOBS=1 HHG_GROUP_JOBS=4 HHG_GROUP_JOBS=16 2>&1 | sed "s/^/base /"

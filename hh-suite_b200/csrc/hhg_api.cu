@@ -673,6 +673,7 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
     P.one2 = 0x3F8000003F800000ull;
     P.group_jobs = ctx->group_jobs;
     P.zero = 0u;
+
     const int items = nj * pl->nstrips;
     int rc;
     if (timed) CK(cudaEventRecord(ctx->ev[0], st));
