@@ -249,7 +249,7 @@ def viterbi_search(ctx: Context, db: TargetDB, ids=None, exclusions=None, want_p
     ids = np.arange(db.n, dtype=np.int32) if ids is None else np.ascontiguousarray(ids, np.int32)
     n = len(ids)
     hits = np.zeros(n, HIT_DTYPE) if hits is None else hits
-    cap = int(np.sum(ctx.Lq + db.Lh[ids].astype(np.int64) + 2))
+    cap = int(np.sum(ctx.Lq + db.Lh[np.clip(ids, 0, db.n - 1)].astype(np.int64) + 2))   # ids validated in C
     if want_paths and paths is None:
         paths = np.zeros(cap, np.uint8)
     if not want_paths:
