@@ -36,7 +36,7 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes", "hhg_plan_debug_bt",
            "hhg_csdb_create", "hhg_csdb_destroy", "hhg_prefilter_ungapped", "hhg_prefilter_ungapped_run",
            "hhg_prefilter_fetch", "hhg_prefilter_build_profile", "hhg_prefilter_corrected_score",
-           "hhg_prefilter_sw", "hhg_prefilter_evalue"]
+           "hhg_prefilter_sw", "hhg_prefilter_evalue", "hhg_prefilter_corrected_scores", "hhg_prefilter_evalues"]
 
 
 class HhgError(RuntimeError):
@@ -101,6 +101,9 @@ def load():
     L.hhg_prefilter_corrected_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.hhg_prefilter_evalue.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int]
     L.hhg_prefilter_evalue.restype = C.c_double
+    L.hhg_prefilter_corrected_scores.argtypes = [C.c_int, c_i32p, c_i32p, C.c_int, C.c_int, c_i32p]
+    L.hhg_prefilter_evalues.argtypes = [C.c_int, c_i32p, c_i32p, C.c_longlong, C.c_int, C.c_int,
+                                        C.POINTER(C.c_double)]
     L.hhg_prefilter_sw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, C.c_int, c_u8p, C.c_int, C.c_int, C.c_int,
                                    c_i32p]
     _lib = L

@@ -935,6 +935,22 @@ double hhg_prefilter_evalue(int score, long long num_dbs, int Lq, int Lt, int bi
   return factor * Lt * fpow2_host(-score / bit_factor);
 }
 
+// Batch forms of the two host-side formulas (1M-sequence shards: no per-element FFI calls).
+int hhg_prefilter_corrected_scores(int n, const int32_t* raw, const int32_t* L, int Lq, int bit_factor,
+                                   int32_t* out) {
+  if (n < 0 || !raw || !L || !out) return fail(HHG_EINVAL, "hhg_prefilter_corrected_scores: bad argument");
+  const float lq = flog2_host((float)Lq);
+  for (int k = 0; k < n; ++k) out[k] = raw[k] - (int)(bit_factor * (lq + flog2_host((float)L[k])));
+  return HHG_OK;
+}
+
+int hhg_prefilter_evalues(int n, const int32_t* score, const int32_t* L, long long num_dbs, int Lq,
+                          int bit_factor, double* out) {
+  if (n < 0 || !score || !L || !out) return fail(HHG_EINVAL, "hhg_prefilter_evalues: bad argument");
+  for (int k = 0; k < n; ++k) out[k] = hhg_prefilter_evalue(score[k], num_dbs, Lq, L[k], bit_factor);
+  return HHG_OK;
+}
+
 // Gapped stage 2 on the GPU for `n` selected sequences (ids == NULL: the first n of the shard).
 // gap_open is the reference's gapOpen argument = prefilter_gap_open + prefilter_gap_extend (:456).
 int hhg_prefilter_sw(hhg_ctx* ctx, const hhg_csdb* db, int n, const int32_t* ids, int Lq,

@@ -26,19 +26,27 @@ def prefilter_db(csdb: capi.CsDB, prof: np.ndarray, gap_open=20, gap_extend=4, s
     n = csdb.n
     raw = csdb.ungapped(prof, score_offset)
     lens = csdb.Lh
-    corr = np.array([L.hhg_prefilter_corrected_score(int(raw[k]), Lq, int(lens[k]), bit_factor) for k in range(n)],
-                    np.int64)
+    import ctypes as C
+    corr32 = np.zeros(n, np.int32)
+    raw32 = np.ascontiguousarray(raw, np.int32)
+    lens32 = np.ascontiguousarray(lens, np.int32)
+    capi._ck(L.hhg_prefilter_corrected_scores(n, capi._p(raw32, capi.c_i32p), capi._p(lens32, capi.c_i32p), Lq,
+                                             bit_factor, capi._p(corr32, capi.c_i32p)))
+    corr = corr32.astype(np.int64)
     order = np.lexsort((np.arange(n), corr))[::-1]          # descending (score, n)
-    keep = []
-    for idx in order:
-        if len(keep) >= min_prefilter_hits and corr[idx] <= smax_thresh:
-            break
-        keep.append(int(idx))
-    first = np.array(keep, np.int32)
+    # keep while count < min_prefilter_hits or score > smax_thresh: first position (>= min hits) whose
+    # score is <= smax_thresh ends the list
+    stop = np.nonzero(corr[order[min_prefilter_hits:]] <= smax_thresh)[0]
+    ncut = min_prefilter_hits + int(stop[0]) if len(stop) else n
+    first = order[:min(ncut, n)].astype(np.int32)
     sw = csdb.sw(prof, ids=first, gap_open=gap_open + gap_extend, gap_extend=gap_extend, bias=score_offset) \
         if len(first) else np.zeros(0, np.int32)
-    ev = np.array([L.hhg_prefilter_evalue(int(sw[k]), n, Lq, int(lens[first[k]]), bit_factor)
-                   for k in range(len(first))], np.float64)
+    ev = np.zeros(len(first), np.float64)
+    if len(first):
+        sw32 = np.ascontiguousarray(sw, np.int32)
+        fl = np.ascontiguousarray(lens32[first])
+        capi._ck(L.hhg_prefilter_evalues(len(first), capi._p(sw32, capi.c_i32p), capi._p(fl, capi.c_i32p), n, Lq,
+                                        bit_factor, ev.ctypes.data_as(C.POINTER(C.c_double))))
     sel = [k for k in range(len(first)) if ev[k] < evalue_coarse_thresh]
     sel.sort(key=lambda k: (ev[k], int(first[k])))
     out = []

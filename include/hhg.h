@@ -174,6 +174,11 @@ int hhg_prefilter_build_profile(int Lq, const float* q_p, const float* q_pav, co
 int hhg_prefilter_corrected_score(int raw, int Lq, int Lt, int bit_factor);
 /* Stage-2 E-value, src/hhprefilter.cpp:529 (integer division of the score, fast fpow2). */
 double hhg_prefilter_evalue(int score, long long num_dbs, int Lq, int Lt, int bit_factor);
+/* Batch forms of the two formulas above (same arithmetic, element by element). */
+int hhg_prefilter_corrected_scores(int n, const int32_t* raw, const int32_t* L, int Lq, int bit_factor,
+                                   int32_t* out);
+int hhg_prefilter_evalues(int n, const int32_t* score, const int32_t* L, long long num_dbs, int Lq,
+                          int bit_factor, double* out);
 /* Gapped stage 2 (Prefilter::swStripedByte, src/hhprefilter.cpp:70-212, AVX2 striping emulated lane for
  * lane) for n selected sequences of the shard (ids == NULL: the first n). gap_open is the reference's
  * gapOpen argument (= prefilter_gap_open + prefilter_gap_extend). scores[n]: host buffer. */
