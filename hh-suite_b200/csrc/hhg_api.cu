@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <cmath>
 #include <cfloat>
 #include <numeric>
@@ -116,6 +117,7 @@ struct hhg_db {
 };
 
 struct hhg_csdb {
+  int device = 0;
   int n = 0;
   long long total = 0;
   DevBuf<int> dL;
@@ -185,7 +187,8 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
   if (prop.major < 10)
     return fail(HHG_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                 prop.major, prop.minor);
-  hhg_ctx* c = new hhg_ctx();
+  std::unique_ptr<hhg_ctx> holder(new hhg_ctx());
+  hhg_ctx* c = holder.get();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (stream) {
@@ -209,7 +212,7 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
     }
     c->h_lg2 = lg2;
     cudaError_t e1 = c->lg2.alloc(1025), e2 = c->diff.alloc(1025);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { delete c; return fail(HHG_ENOMEM, "fast_log2 tables"); }
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(HHG_ENOMEM, "fast_log2 tables");
     CK(cudaMemcpy(c->lg2.p, lg2.data(), 1025 * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->diff.p, diff.data(), 1025 * 4, cudaMemcpyHostToDevice));
   }
@@ -219,7 +222,7 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
   const char* env = getenv("HHG_MAX_BT_GB");
   double cap = env ? atof(env) * 1e9 : 48e9;
   c->max_bt_bytes = (size_t)std::min(cap, 0.45 * (double)free_b);
-  *out = c;
+  *out = holder.release();
   return HHG_OK;
 }
 
@@ -311,7 +314,8 @@ int hhg_db_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_off, c
     return fail(HHG_EINVAL, "hhg_db_create: bad argument");
   if (ss && !ss_off) return fail(HHG_EINVAL, "hhg_db_create: ss given without ss_off");
   CK(cudaSetDevice(ctx->device));
-  hhg_db* db = new hhg_db();
+  std::unique_ptr<hhg_db> holder(new hhg_db());   // freed on every early return below
+  hhg_db* db = holder.get();
   db->device = ctx->device;
   db->n = n;
   db->has_ss = ss != nullptr;
@@ -319,23 +323,21 @@ int hhg_db_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_off, c
   db->col_off.resize(n);
   long long tot = 0;
   for (int k = 0; k < n; ++k) {
-    if (L[k] < 1 || L[k] > 32767) { delete db; return fail(HHG_EINVAL, "target %d: length %d out of [1,32767]", k, L[k]); }
+    if (L[k] < 1 || L[k] > 32767) return fail(HHG_EINVAL, "target %d: length %d out of [1,32767]", k, L[k]);
     db->col_off[k] = tot;
     tot += L[k];
   }
   db->total_cols = tot;
   cudaError_t e;
   if ((e = db->cols.alloc((size_t)tot * 7)) != cudaSuccess || (e = db->dL.alloc(n)) != cudaSuccess ||
-      (e = db->dcol_off.alloc(n)) != cudaSuccess) {
-    delete db;
+      (e = db->dcol_off.alloc(n)) != cudaSuccess)
     return fail(HHG_ENOMEM, "hhg_db_create: %s", cudaGetErrorString(e));
-  }
   CK(cudaMemcpyAsync(db->dL.p, db->L.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(db->dcol_off.p, db->col_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   int rc = pack_profiles(ctx, n, L, p_off, tr_off, ss_off, p, tr, ss, db->col_off, tot, db->cols.p);
-  if (rc != HHG_OK) { delete db; return rc; }
+  if (rc != HHG_OK) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
-  *out = db;
+  *out = holder.release();
   return HHG_OK;
 }
 
@@ -345,17 +347,18 @@ int hhg_db_create_raw(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_of
   if (!pav) return fail(HHG_EINVAL, "hhg_db_create_raw: pav is NULL");
   int rc = hhg_db_create(ctx, n, L, p_off, tr_off, ss_off, p, tr, ss, out);
   if (rc != HHG_OK) return rc;
-  hhg_db* db = *out;
+  std::unique_ptr<hhg_db> holder(*out);
+  *out = nullptr;
+  hhg_db* db = holder.get();
   cudaError_t e;
-  if ((e = db->cols_raw.alloc(db->cols.n)) != cudaSuccess || (e = db->pav.alloc((size_t)n * 20)) != cudaSuccess) {
-    delete db; *out = nullptr;
+  if ((e = db->cols_raw.alloc(db->cols.n)) != cudaSuccess || (e = db->pav.alloc((size_t)n * 20)) != cudaSuccess)
     return fail(HHG_ENOMEM, "hhg_db_create_raw: %s", cudaGetErrorString(e));
-  }
   CK(cudaMemcpyAsync(db->cols_raw.p, db->cols.p, db->cols.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(db->pav.p, pav, (size_t)n * 20 * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   db->raw = true;
   db->prepared = false;
+  *out = holder.release();
   return HHG_OK;
 }
 
@@ -553,10 +556,10 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
 
 int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_plan** out) {
   if (!out) return fail(HHG_EINVAL, "hhg_plan_create: out is NULL");
-  hhg_plan* pl = new hhg_plan();
-  int rc = plan_build(ctx, pl, db, n, ids);
-  if (rc != HHG_OK) { delete pl; return rc; }
-  *out = pl;
+  std::unique_ptr<hhg_plan> pl(new hhg_plan());
+  int rc = plan_build(ctx, pl.get(), db, n, ids);
+  if (rc != HHG_OK) return rc;
+  *out = pl.release();
   return HHG_OK;
 }
 
@@ -795,26 +798,29 @@ int hhg_csdb_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* off, c
                     hhg_csdb** out) {
   if (!ctx || !out || n <= 0 || !L || !off || !seq) return fail(HHG_EINVAL, "hhg_csdb_create: bad argument");
   CK(cudaSetDevice(ctx->device));
-  hhg_csdb* db = new hhg_csdb();
+  std::unique_ptr<hhg_csdb> holder(new hhg_csdb());
+  hhg_csdb* db = holder.get();
   db->n = n;
+  db->device = ctx->device;
   long long tot = 0;
   for (int k = 0; k < n; ++k) tot = std::max<long long>(tot, off[k] + L[k]);
   db->total = tot;
   cudaError_t e;
   if ((e = db->dL.alloc(n)) != cudaSuccess || (e = db->doff.alloc(n)) != cudaSuccess ||
-      (e = db->seq.alloc((size_t)tot)) != cudaSuccess || (e = db->scores.alloc(n)) != cudaSuccess) {
-    delete db;
+      (e = db->seq.alloc((size_t)tot)) != cudaSuccess || (e = db->scores.alloc(n)) != cudaSuccess)
     return fail(HHG_ENOMEM, "hhg_csdb_create: %s", cudaGetErrorString(e));
-  }
   CK(cudaMemcpyAsync(db->dL.p, L, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(db->doff.p, off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(db->seq.p, seq, (size_t)tot, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  *out = db;
+  *out = holder.release();
   return HHG_OK;
 }
 
-int hhg_csdb_destroy(hhg_csdb* db) { delete db; return HHG_OK; }
+int hhg_csdb_destroy(hhg_csdb* db) {
+  if (db) { cudaSetDevice(db->device); delete db; }
+  return HHG_OK;
+}
 
 }  // extern "C"
 

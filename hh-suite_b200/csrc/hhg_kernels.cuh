@@ -139,11 +139,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// Progress-flag poll.  Deliberately a RELAXED gpu-scope load: an acquire load makes ptxas emit
-// CCTL.IVALL (L1 invalidate) which drains every in-flight prefetch at each poll (ncu: 19% of all stall
-// samples).  Ordering is still guaranteed: the boundary values are read with ld.global.cg (L2, never
-// L1) and only after the poll loop's control dependency resolved; the producer orders its st.cg data
-// before the flag with __threadfence() + st.release.
+#if HHG_USE_CPASYNC
 // 16-byte asynchronous global->shared copy (LDGSTS), L2-only (.cg): the staged target columns
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -153,17 +149,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-
-__device__ __forceinline__ void keep_alive(uint32_t v) { asm volatile("" ::"r"(v)); }
-
-__device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+#endif
 
 // log2f4 (src/hhutil-inl.h:509-541), degree-4 minimax, unfused.  x >= 0.
 // The exponent int->float conversion uses the exact magic-number form (no I2F on the hot path):
