@@ -16,10 +16,13 @@ import numpy as np
 AA_SORTED = "ACDEFGHIKLMNPQRSTVWY"      # column order in HHM files (src/hhhmm.cpp:73 of query.hhm)
 NEG = -99999.0 / 1000.0                  # what the reference stores for '*' (strinta -> -99999)/HMMSCALE
 
-# Robinson-Robinson-like background (any fixed positive vector works; values close to hhmatrices pb)
-_PB = np.array([0.0787945, 0.0151600, 0.0535222, 0.0668298, 0.0397062, 0.0695071, 0.0229198,
-                0.0590092, 0.0594422, 0.0963728, 0.0237718, 0.0414386, 0.0482904, 0.0395639,
-                0.0540978, 0.0683364, 0.0540687, 0.0673417, 0.0114135, 0.0304133], dtype=np.float64)
+# Background = the NULL line every HH-suite HHM carries (e.g. data/query.hhm:72), in 1/1000 bits, column
+# order ACDEFGHIKLMNPQRSTVWY.  Using the standard line matters: HMM::Read overwrites the global pb array
+# from each file's NULL line (src/hhhmm.cpp:540-543), so templates with different NULL lines would make the
+# reference's results depend on the (thread-racy) order in which templates are read.
+_NULL_MILLIBITS = np.array([3706, 5728, 4211, 4064, 4839, 3729, 4763, 4308, 4069, 3323, 5509, 4640, 4464, 4937,
+                            4285, 4423, 3815, 3783, 6325, 4665], dtype=np.float64)
+_PB = np.exp2(-_NULL_MILLIBITS / 1000.0)
 _PB /= _PB.sum()
 
 
@@ -79,7 +82,7 @@ def hhm_text(L: int, seed: int, name: str = "synth", with_ss: bool = False) -> s
         ss = rng.choice(list("HEC"), size=L)
         out += [">ss_pred", "".join(ss), ">ss_conf", "".join(str(d) for d in rng.integers(0, 10, L))]
     out += [">Consensus", cons.lower(), f">{name}", cons, "#"]
-    out.append("NULL   " + "\t".join(enc(p) for p in _PB) + "\t")
+    out.append("NULL   " + "\t".join(str(int(v)) for v in _NULL_MILLIBITS) + "\t")
     out.append("HMM    " + "\t".join(AA_SORTED) + "\t")
     out.append("       M->M\tM->I\tM->D\tI->M\tI->I\tD->M\tD->D\tNeff\tNeff_I\tNeff_D")
     out.append("       " + "\t".join(enc(p) for p in tr[0]) + "\t*\t*\t*\t")

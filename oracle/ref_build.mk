@@ -38,7 +38,7 @@ OBJS  = $(addprefix $(OUT)/obj/,$(addsuffix .o,$(HH_SRC))) \
         $(addprefix $(OUT)/obj/ff_,$(addsuffix .o,$(FF_SRC))) \
         $(OUT)/obj/res_crf.o $(OUT)/obj/res_cs219.o
 
-all: $(OUT)/libhhref.a $(OUT)/libhhref_shim.so
+all: $(OUT)/libhhref.a $(OUT)/libhhref_shim.so $(OUT)/hh_dropin_check
 
 $(OUT)/gen/.stamp:
 	mkdir -p $(OUT)/gen $(OUT)/obj
@@ -72,3 +72,10 @@ $(OUT)/libhhref.a: $(OBJS)
 shim: $(OUT)/libhhref_shim.so
 $(OUT)/libhhref_shim.so: oracle/ref_shim.cpp $(OUT)/libhhref.a
 	$(CXX) $(CXXFLAGS) $(INC) -shared -o $@ oracle/ref_shim.cpp -Wl,--whole-archive $(OUT)/libhhref.a -Wl,--no-whole-archive -lgomp
+
+# The drop-in check: reference front half + reference ViterbiRunner vs the C-ABI adapter (needs libhhg.so).
+dropin: $(OUT)/hh_dropin_check
+$(OUT)/hh_dropin_check: oracle/ref_gpu_adapter.cpp $(OUT)/libhhref.a hh-suite_b200/libhhg.so include/hhg.h
+	mkdir -p $(OUT)/data && cp -f $(REF)/data/query.hhm $(OUT)/data/query.hhm && chmod u+w $(OUT)/data/query.hhm
+	$(CXX) $(CXXFLAGS) $(INC) -o $@ oracle/ref_gpu_adapter.cpp -Wl,--whole-archive $(OUT)/libhhref.a -Wl,--no-whole-archive \
+	    -Lhh-suite_b200 -lhhg -Wl,-rpath,'$$ORIGIN/../../hh-suite_b200' -lgomp

@@ -1,0 +1,252 @@
+// oracle/ref_gpu_adapter.cpp -- TEST INFRASTRUCTURE: the drop-in check.
+//
+// Links the UNMODIFIED reference (oracle/_ref/libhhref.a) and the product library (libhhg.so) into one
+// binary that runs the reference's own HHalign front half (HMM::Read, PrepareQueryHMM, HMMSimd::MapOneHMM,
+// HHFileEntry::getTemplateHMM, PrepareTemplateHMM steps; src/hhalign.cpp:590-645) and then aligns the same
+// template list twice:
+//   (1) with the reference's ViterbiRunner::alignment (src/hhviterbirunner.cpp:75, AVX2, OpenMP), and
+//   (2) with GpuViterbiRunner::alignment below = the adapter of INTEGRATION.md section 2 on the C-ABI,
+// and compares every Hit the two produce: Hit.score / score_ss (bits), i1,i2,j1,j2, nsteps, matched_cols,
+// irep, lastrep and the whole path (i[], j[], states[]) for every alternative alignment.
+// It contains no reference code; it includes the reference headers at build time and is compiled by
+// oracle/ref_build.mk into oracle/_ref/hh_dropin_check (shipped prebuilt to the GPU box).
+//
+// usage: hh_dropin_check <query.hhm> <template.hhm> [more templates ...]     exit 0 = identical
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#define private public
+#define protected public
+#include "hhdecl.h"
+#include "hhhmm.h"
+#include "hhhmmsimd.h"
+#include "hhviterbi.h"
+#include "hhviterbimatrix.h"
+#include "hhviterbirunner.h"
+#include "hhmatrices.h"
+#include "hhfunc.h"
+#include "hhdatabase.h"
+#include "hhhit.h"
+#undef private
+#undef protected
+
+#include "../include/hhg.h"
+
+namespace {
+
+struct GpuHit {
+  int target, irep, lastrep;
+  float score, score_ss;
+  int i1, i2, j1, j2, nsteps, matched_cols;
+  std::vector<int> i, j;
+  std::vector<char> states;
+};
+
+#define HHG_CHECK(call)                                                        \
+  do {                                                                         \
+    if ((call) != HHG_OK) {                                                    \
+      fprintf(stderr, "hhg error: %s (%s)\n", hhg_last_error(), #call);        \
+      exit(4);                                                                 \
+    }                                                                          \
+  } while (0)
+
+// The adapter of INTEGRATION.md: same arguments as ViterbiRunner::alignment; templates are addressed by
+// their index in `dbfiles`.
+class GpuViterbiRunner {
+ public:
+  GpuViterbiRunner() { HHG_CHECK(hhg_ctx_create(0, nullptr, &ctx_)); }
+  ~GpuViterbiRunner() { if (db_) hhg_db_destroy(db_); hhg_ctx_destroy(ctx_); }
+
+  // one-time shard upload: what PrepareTemplateHMM leaves BEFORE the query-dependent null model
+  void Upload(Parameters& par, std::vector<HHEntry*>& entries, float* pb, const float S[20][20],
+              const float Sim[20][20], const float R[20][20]) {
+    std::vector<int32_t> L;
+    std::vector<int64_t> p_off, tr_off, ss_off;
+    std::vector<float> p, tr, pav;
+    std::vector<uint8_t> ss;
+    all_have_ss_ = true;
+    HMM t(MAXSEQDIS, par.maxres);
+    for (HHEntry* e : entries) {
+      int format = 0;
+      e->getTemplateHMM(par, 1, par.qsc_db, format, pb, S, Sim, &t);
+      t.AddTransitionPseudocounts(par.gapd, par.gape, par.gapf, par.gapg, par.gaph, par.gapi, par.gapb, par.gapb);
+      t.PreparePseudocounts(R);
+      t.AddAminoAcidPseudocounts(par.pc_hhm_nocontext_mode, par.pc_hhm_nocontext_a, par.pc_hhm_nocontext_b,
+                                 par.pc_hhm_nocontext_c);
+      t.CalculateAminoAcidBackground(pb);
+      L.push_back(t.L);
+      p_off.push_back((int64_t)p.size()); tr_off.push_back((int64_t)tr.size()); ss_off.push_back((int64_t)ss.size());
+      if (t.nss_pred < 0) all_have_ss_ = false;
+      for (int i = 0; i <= t.L + 1; ++i) {
+        p.insert(p.end(), t.p[i], t.p[i] + 20);
+        ss.push_back(t.nss_pred >= 0 ? (uint8_t)(t.ss_pred[i] * MAXCF + t.ss_conf[i]) : 0);
+      }
+      for (int i = 0; i <= t.L; ++i) tr.insert(tr.end(), t.tr[i], t.tr[i] + 7);
+      pav.insert(pav.end(), t.pav, t.pav + 20);
+    }
+    HHG_CHECK(hhg_db_create_raw(ctx_, (int)L.size(), L.data(), p_off.data(), tr_off.data(), ss_off.data(), p.data(),
+                                tr.data(), ss.data(), pav.data(), &db_));
+    L_ = L;
+  }
+
+  std::vector<GpuHit> alignment(Parameters& par, HMMSimd* q_simd, int n_targets, float* pb,
+                                const float S33[NSSPRED][MAXCF][NSSPRED][MAXCF]) {
+    HMM* q = q_simd->GetHMM(0);
+    std::vector<float> qp((size_t)(q->L + 2) * 20), qtr((size_t)(q->L + 1) * 7);
+    std::vector<uint8_t> qss(q->L + 2, 0);
+    for (int i = 0; i <= q->L + 1; ++i) {
+      memcpy(&qp[(size_t)i * 20], q->p[i], 80);
+      if (q->nss_pred >= 0) qss[i] = (uint8_t)(q->ss_pred[i] * MAXCF + q->ss_conf[i]);
+    }
+    for (int i = 0; i <= q->L; ++i) memcpy(&qtr[(size_t)i * 7], q->tr[i], 28);
+    // Viterbi::Align dispatch (src/hhviterbi.cpp:177) + the batch consensus of the runner (:14-22) for a
+    // homogeneous template list: PRED_PRED iff query and all templates carry a predicted ss
+    const int use_ss = (par.ssm == 2 && q->nss_pred >= 0 && all_have_ss_) ? 1 : 0;
+    hhg_params hp = {par.loc, par.egq, par.egt, par.shift, par.ssw, use_ss, par.corr, par.ssm};
+    HHG_CHECK(hhg_query_set(ctx_, q->L, qp.data(), qtr.data(), qss.data(), &S33[0][0][0][0], &hp));
+    HHG_CHECK(hhg_db_apply_null_model(ctx_, db_, q->pav, pb, par.columnscore));
+
+    std::vector<int32_t> ids(n_targets);
+    for (int k = 0; k < n_targets; ++k) ids[k] = k;
+    std::map<int, std::pair<std::vector<int32_t>, std::vector<int32_t>>> excl;   // accumulated paths per target
+    std::vector<GpuHit> ret;
+    for (int alignment = 0; alignment < par.altali && !ids.empty(); alignment++) {
+      std::vector<hhg_hit> hits(ids.size());
+      size_t cap = 0;
+      for (int id : ids) cap += (size_t)q->L + L_[id] + 2;
+      std::vector<uint8_t> paths(cap);
+      std::vector<int64_t> eoff(ids.size() + 1, 0);
+      std::vector<int32_t> ei, ej;
+      if (alignment > 0) {
+        for (size_t k = 0; k < ids.size(); ++k) {
+          auto& e = excl[ids[k]];
+          ei.insert(ei.end(), e.first.begin(), e.first.end());
+          ej.insert(ej.end(), e.second.begin(), e.second.end());
+          eoff[k + 1] = (int64_t)ei.size();
+        }
+      }
+      HHG_CHECK(hhg_viterbi_search(ctx_, db_, (int)ids.size(), ids.data(), hits.data(), paths.data(), paths.size(),
+                                   alignment ? eoff.data() : nullptr, ei.data(), ej.data()));
+      std::vector<int32_t> next;
+      for (size_t k = 0; k < ids.size(); ++k) {
+        const hhg_hit& h = hits[k];
+        GpuHit g;
+        g.target = ids[k]; g.irep = alignment + 1;                        // :257
+        g.lastrep = (h.hit_score <= par.smin) ? 1 : 0;                    // :36
+        g.score = h.hit_score; g.score_ss = h.score_ss;
+        g.i1 = h.i1; g.i2 = h.i2; g.j1 = h.j1; g.j2 = h.j2; g.nsteps = h.nsteps; g.matched_cols = h.matched_cols;
+        g.i.assign(h.nsteps + 1, 0); g.j.assign(h.nsteps + 1, 0); g.states.assign(h.nsteps + 1, 0);
+        int i = h.i2, j = h.j2;                                           // replay of Viterbi::Backtrace
+        for (int s = 1; s <= h.nsteps; ++s) {
+          const char st = (char)paths[h.path_off + s - 1];
+          g.i[s] = i; g.j[s] = j; g.states[s] = st;
+          if (s < h.nsteps) {
+            if (st == 2) { --i; --j; } else if (st == 3 || st == 4) { --j; } else { --i; }
+          }
+        }
+        ret.push_back(g);
+        if (h.hit_score > par.smin) {                                     // :260-268
+          next.push_back(ids[k]);
+          auto& e = excl[ids[k]];
+          for (int s = 1; s < h.nsteps; ++s) { e.first.push_back(g.i[s]); e.second.push_back(g.j[s]); }
+        }
+      }
+      ids.swap(next);
+    }
+    return ret;
+  }
+
+ private:
+  hhg_ctx* ctx_ = nullptr;
+  hhg_db* db_ = nullptr;
+  std::vector<int32_t> L_;
+  bool all_have_ss_ = false;
+};
+
+uint32_t bits(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 3) { fprintf(stderr, "usage: %s query.hhm template.hhm [...]\n", argv[0]); return 2; }
+  Log::reporting_level() = WARNING;
+  const char* pargv[] = {"hhalign"};
+  Parameters par(1, pargv);
+  par.nocontxt = 1;
+  par.maxres = 4096;
+  par.threads = 2;
+  float pb[21] __attribute__((aligned(32)));
+  float P[20][20] __attribute__((aligned(32))), R[20][20] __attribute__((aligned(32)));
+  float S[20][20] __attribute__((aligned(32))), Sim[20][20] __attribute__((aligned(32)));
+  static float S73[NDSSP][NSSPRED][MAXCF], S37[NSSPRED][MAXCF][NDSSP], S33[NSSPRED][MAXCF][NSSPRED][MAXCF];
+  SetSubstitutionMatrix(par.matrix, pb, P, R, S, Sim);
+  SetSecStrucSubstitutionMatrix(par.ssa, S73, S37, S33);
+
+  // ---- query: src/hhalign.cpp:610-626
+  HMM* q = new HMM(MAXSEQDIS, par.maxres);
+  HMMSimd q_vec(par.maxres);
+  {
+    FILE* f = fopen(argv[1], "r");
+    if (!f) { perror(argv[1]); return 2; }
+    char path[NAMELEN];
+    Pathname(path, argv[1]);
+    q->Read(f, par.maxcol, par.nseqdis, pb, path);
+    fclose(f);
+  }
+  char input_format = 0;
+  PrepareQueryHMM(par, input_format, q, nullptr, nullptr, pb, R);
+  q_vec.MapOneHMM(q);
+
+  std::vector<HHEntry*> entries;
+  for (int a = 2; a < argc; ++a) entries.push_back(new HHFileEntry(argv[a], par.maxres));
+
+  // ---- (1) the reference runner
+  std::vector<ViterbiMatrix*> mats(par.threads);
+  for (auto& m : mats) { m = new ViterbiMatrix(); m->AllocateBacktraceMatrix(q->L, par.maxres); }
+  std::vector<HHblitsDatabase*> nodb;
+  ViterbiRunner ref_runner(mats.data(), nodb, par.threads);
+  std::vector<Hit> ref = ref_runner.alignment(par, &q_vec, entries, par.qsc_db, pb, S, Sim, R, par.ssm, S73, S33, S37);
+
+  // ---- (2) the GPU adapter
+  GpuViterbiRunner gpu_runner;
+  gpu_runner.Upload(par, entries, pb, S, Sim, R);
+  std::vector<GpuHit> gpu = gpu_runner.alignment(par, &q_vec, (int)entries.size(), pb, S33);
+
+  // ---- compare
+  std::map<HHEntry*, int> index;
+  for (size_t k = 0; k < entries.size(); ++k) index[entries[k]] = (int)k;
+  std::map<std::pair<int, int>, const GpuHit*> gmap;
+  for (const GpuHit& g : gpu) gmap[{g.target, g.irep}] = &g;
+  int bad = 0;
+  if (ref.size() != gpu.size()) { printf("MISMATCH: %zu reference hits vs %zu gpu hits\n", ref.size(), gpu.size()); ++bad; }
+  int maxrep = 0;
+  for (Hit& h : ref) {
+    const int t = index[h.entry];
+    maxrep = std::max(maxrep, (int)h.irep);
+    auto it = gmap.find({t, h.irep});
+    if (it == gmap.end()) { printf("MISMATCH: no gpu hit for template %d irep %d\n", t, h.irep); ++bad; continue; }
+    const GpuHit& g = *it->second;
+    bool ok = bits(h.score) == bits(g.score) && bits(h.score_ss) == bits(g.score_ss) && h.i1 == g.i1 && h.i2 == g.i2 &&
+              h.j1 == g.j1 && h.j2 == g.j2 && h.nsteps == g.nsteps && h.matched_cols == g.matched_cols &&
+              h.lastrep == g.lastrep;
+    for (int s = 1; ok && s <= h.nsteps; ++s) ok = h.i[s] == g.i[s] && h.j[s] == g.j[s] && h.states[s] == g.states[s];
+    if (!ok) {
+      printf("MISMATCH: template %d (%s) irep %d: ref score %.6f (%d-%d,%d-%d, %d steps) gpu %.6f (%d-%d,%d-%d, %d steps)\n",
+             t, entries[t]->getName(), h.irep, h.score, h.i1, h.i2, h.j1, h.j2, h.nsteps, g.score, g.i1, g.i2, g.j1,
+             g.j2, g.nsteps);
+      ++bad;
+    }
+  }
+  printf("hh_dropin_check: query L=%d, %zu templates, %zu hits (up to irep %d): %s\n", q->L, entries.size(), ref.size(),
+         maxrep, bad ? "MISMATCH" : "all hits identical");
+  return bad ? 1 : 0;
+}

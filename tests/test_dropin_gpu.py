@@ -1,0 +1,51 @@
+"""The drop-in check: the reference's own HHalign front half feeding (1) the reference's
+ViterbiRunner::alignment and (2) the C-ABI adapter of INTEGRATION.md; every Hit of every alternative
+alignment must be identical.  Uses the binary oracle/_ref/hh_dropin_check (built from
+oracle/ref_gpu_adapter.cpp against the unmodified reference; shipped prebuilt to the GPU box)."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "hh_dropin_check")
+QUERY = os.path.join(ROOT, "oracle", "_ref", "data", "query.hhm")
+
+
+def _run(args):
+    r = subprocess.run([BIN] + args, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    return r
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+def test_reference_runner_vs_gpu_adapter(tmp_path):
+    from hhsuite_b200 import synth
+    # config 1: data/query.hhm vs one synthetic HMM (L=150) + itself (a strong hit with alternative alignments)
+    files = []
+    for k, L in enumerate([150, 60, 431, 300, 33, 200, 97, 120, 250, 75]):
+        f = tmp_path / f"t{k}.hhm"
+        f.write_text(synth.hhm_text(L, 100 + k, f"t{k}"))
+        files.append(str(f))
+    r = _run([QUERY, files[0]])
+    assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr
+    r = _run([QUERY, QUERY] + files)          # 11 templates: more than one 8-lane batch, self-hit re-queued 4x
+    assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr
+    assert "up to irep 4" in r.stdout or "up to irep 3" in r.stdout or "up to irep 2" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+def test_reference_runner_vs_gpu_adapter_with_ss(tmp_path):
+    """Query and all templates carry predicted secondary structure -> the reference takes the *AndSS kernels."""
+    from hhsuite_b200 import synth
+    q = tmp_path / "q.hhm"
+    q.write_text(synth.hhm_text(180, 7, "qss", with_ss=True))
+    files = []
+    for k, L in enumerate([180, 90, 140, 260, 45, 180, 75, 200, 66]):
+        f = tmp_path / f"s{k}.hhm"
+        f.write_text(synth.hhm_text(L, 7 if k in (0, 5) else 300 + k, f"s{k}", with_ss=True))   # two self-like hits
+        files.append(str(f))
+    r = _run([str(q)] + files)
+    assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr
