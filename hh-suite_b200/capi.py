@@ -31,12 +31,32 @@ HIT_DTYPE = np.dtype([("score", np.float32), ("i2", np.int32), ("j2", np.int32),
                       ("path_off", np.int32), ("hit_score", np.float32), ("score_ss", np.float32)])
 
 SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync", "hhg_ctx_launch_count",
-           "hhg_db_create", "hhg_db_create_raw", "hhg_db_apply_null_model", "hhg_debug_fastlog2_table", "hhg_db_destroy", "hhg_db_size", "hhg_db_columns", "hhg_query_set",
+           "hhg_db_create", "hhg_db_create_raw", "hhg_db_apply_null_model", "hhg_db_create_hhm", "hhg_hhm_scan", "hhg_hhm_parse",
+           "hhg_db_read_cols", "hhg_db_lengths", "hhg_db_read_pav", "hhg_db_create_packed", "hhg_debug_fastlog2_table", "hhg_db_destroy", "hhg_db_size", "hhg_db_columns", "hhg_query_set",
            "hhg_viterbi_search", "hhg_plan_create", "hhg_plan_destroy", "hhg_plan_run", "hhg_plan_run_timed", "hhg_plan_fetch", "hhg_plan_hits_devptr",
            "hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes", "hhg_plan_debug_bt",
            "hhg_csdb_create", "hhg_csdb_destroy", "hhg_prefilter_ungapped", "hhg_prefilter_ungapped_run",
            "hhg_prefilter_fetch", "hhg_prefilter_build_profile", "hhg_prefilter_corrected_score",
            "hhg_prefilter_sw", "hhg_prefilter_evalue", "hhg_prefilter_corrected_scores", "hhg_prefilter_evalues"]
+
+
+class PrepParams(C.Structure):
+    """hhg_prep_params: Parameters::gap* and pc_hhm_nocontext_* handed to PrepareTemplateHMM (src/hhfunc.cpp:170-178);
+    defaults = src/hhdecl.cpp:64-80."""
+    _fields_ = [("gapb", C.c_float), ("gapd", C.c_float), ("gape", C.c_float), ("gapf", C.c_float),
+                ("gapg", C.c_float), ("gaph", C.c_float), ("gapi", C.c_float), ("pcm", C.c_int32),
+                ("pca", C.c_float), ("pcb", C.c_float), ("pcc", C.c_float)]
+
+    @classmethod
+    def defaults(cls):
+        return cls(1.0, 0.15, 1.0, 0.6, 0.6, 0.6, 0.6, 2, 1.0, 1.5, 1.0)
+
+
+# one 112-byte column record of the resident database (include/hhg.h, hhg_db_read_cols)
+COLREC_DTYPE = np.dtype([("p", np.float32, 20), ("m2m", np.float32), ("m2d", np.float32), ("d2m", np.float32),
+                         ("d2d", np.float32), ("i2m", np.float32), ("i2i", np.float32), ("m2i", np.float32),
+                         ("ss", np.uint32)])
+assert COLREC_DTYPE.itemsize == 112
 
 
 class HhgError(RuntimeError):
@@ -73,6 +93,15 @@ def load():
     L.hhg_db_create_raw.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i64p, c_i64p, c_i64p, c_f32p, c_f32p, c_u8p,
                                     c_f32p, C.POINTER(C.c_void_p)]
     L.hhg_db_apply_null_model.argtypes = [C.c_void_p, C.c_void_p, c_f32p, c_f32p, C.c_int]
+    L.hhg_db_create_hhm.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_i64p, c_i64p, C.POINTER(PrepParams), c_f32p,
+                                    C.POINTER(C.c_void_p)]
+    L.hhg_hhm_scan.argtypes = [C.c_char_p, C.c_int64, c_i32p, c_i32p]
+    L.hhg_db_read_cols.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+    L.hhg_hhm_parse.argtypes = [C.c_char_p, C.c_int64, C.c_int32, c_i32p, c_i32p, c_u8p, c_i32p, c_f32p, c_i32p]
+    L.hhg_db_lengths.argtypes = [C.c_void_p, c_i32p]
+    L.hhg_db_read_pav.argtypes = [C.c_void_p, C.c_void_p, c_f32p]
+    L.hhg_db_create_packed.argtypes = [C.c_void_p, C.c_int, c_i32p, C.c_void_p, C.c_int, c_f32p,
+                                       C.POINTER(C.c_void_p)]
     L.hhg_debug_fastlog2_table.argtypes = [C.c_void_p, c_f32p]
     L.hhg_db_destroy.argtypes = [C.c_void_p]
     L.hhg_db_size.argtypes = [C.c_void_p]
@@ -153,6 +182,24 @@ class Context:
         self.Lq = Lq
 
 
+def hhm_scan(record: bytes):
+    """(LENG, has_ss_pred) of one HHM record; host only."""
+    L = np.zeros(1, np.int32); ss = np.zeros(1, np.int32)
+    _ck(load().hhg_hhm_scan(record, len(record), _p(L, c_i32p), _p(ss, c_i32p)))
+    return int(L[0]), bool(ss[0])
+
+
+def hhm_parse(record: bytes):
+    """The integers of one HHM record as hhg_db_create_hhm tokenises them; host only."""
+    L, has_ss = hhm_scan(record)
+    f = np.zeros((L, 20), np.int32); trn = np.zeros((L + 1, 10), np.int32); ss = np.zeros(L, np.uint8)
+    null = np.zeros(20, np.int32); neff = np.zeros(1, np.float32); has_pc = np.zeros(1, np.int32)
+    _ck(load().hhg_hhm_parse(record, len(record), L, _p(f, c_i32p), _p(trn, c_i32p), _p(ss, c_u8p), _p(null, c_i32p),
+                             _p(neff, c_f32p), _p(has_pc, c_i32p)))
+    return dict(L=L, has_ss=has_ss, f=f, tr=trn[:, :7].copy(), neff=trn[:, 7:].copy(), ss=ss, null=null,
+                neff_hmm=float(neff[0]), has_pc=int(has_pc[0]))
+
+
 class TargetDB:
     """Device-resident shard of prepared target profiles (see synth.prepared_db for the host layout)."""
 
@@ -178,6 +225,61 @@ class TargetDB:
                                         _p(pav, c_f32p), C.byref(h)))
         self.h = h
         self.n = n
+
+    @classmethod
+    def _wrap(cls, ctx, h, n):
+        self = cls.__new__(cls)
+        self.ctx, self.h, self.n = ctx, h, n
+        return self
+
+    @classmethod
+    def from_hhm(cls, ctx, data: bytes, offsets, lengths, R, params: "PrepParams | None" = None):
+        """Build the shard from HHM text records (`_hhm.ffdata` bytes + the offset/length columns of its
+        `.ffindex`): getTemplateHMM + the query-independent part of PrepareTemplateHMM, once per database.
+        R: the 20x20 pseudocount matrix (R[a][b], SetSubstitutionMatrix).  Call apply_null_model per query."""
+        off = np.ascontiguousarray(offsets, np.int64); ln = np.ascontiguousarray(lengths, np.int64)
+        n = len(off)
+        if n == 0 or len(ln) != n or off.min() < 0 or int((off + ln).max()) > len(data):
+            raise ValueError("offsets/lengths do not fit the data buffer")
+        R = np.ascontiguousarray(R, np.float32)
+        assert R.shape == (20, 20)
+        pp = params or PrepParams.defaults()
+        h = C.c_void_p()
+        buf = np.frombuffer(data, np.uint8)        # bytes or a (read-only) mmap of the ffdata file
+        _ck(ctx.L.hhg_db_create_hhm(ctx.h, n, buf.ctypes.data_as(C.c_char_p), _p(off, c_i64p), _p(ln, c_i64p),
+                                    C.byref(pp), _p(R, c_f32p), C.byref(h)))
+        self = cls._wrap(ctx, h, n)
+        self.Lh = np.zeros(n, np.int32)
+        _ck(ctx.L.hhg_db_lengths(h, _p(self.Lh, c_i32p)))
+        return self
+
+    @classmethod
+    def from_packed(cls, ctx, L, cols_raw, pav, has_ss=False):
+        """Load the resident binary format written by read_cols(0) / read_pav()."""
+        L = np.ascontiguousarray(L, np.int32)
+        cols_raw = np.ascontiguousarray(cols_raw)
+        assert cols_raw.dtype == COLREC_DTYPE and len(cols_raw) == int(L.sum())
+        pav = np.ascontiguousarray(pav, np.float32)
+        assert pav.shape == (len(L), 20)
+        h = C.c_void_p()
+        _ck(ctx.L.hhg_db_create_packed(ctx.h, len(L), _p(L, c_i32p), cols_raw.ctypes.data_as(C.c_void_p),
+                                       1 if has_ss else 0, _p(pav, c_f32p), C.byref(h)))
+        self = cls._wrap(ctx, h, len(L))
+        self.Lh = L
+        return self
+
+    def read_cols(self, which=0, first=0, count=None):
+        """Column records (COLREC_DTYPE): which=0 before the null model, 1 after apply_null_model."""
+        total = int(self.ctx.L.hhg_db_columns(self.h))
+        count = total - first if count is None else count
+        out = np.zeros(count, COLREC_DTYPE)
+        _ck(self.ctx.L.hhg_db_read_cols(self.ctx.h, self.h, which, first, count, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def read_pav(self):
+        out = np.zeros((self.n, 20), np.float32)
+        _ck(self.ctx.L.hhg_db_read_pav(self.ctx.h, self.h, _p(out, c_f32p)))
+        return out
 
     def apply_null_model(self, q_pav=None, pb=None, columnscore=1):
         q_pav = None if q_pav is None else np.ascontiguousarray(q_pav, np.float32)

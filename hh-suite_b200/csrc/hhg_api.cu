@@ -3,6 +3,7 @@
 // device memory, launches.  There is no CPU fallback: without a CUDA device every entry point fails.
 #include "../../include/hhg.h"
 #include "hhg_kernels.cuh"
+#include "hhg_hhm.cuh"
 #include "hhg_viterbi2.cuh"
 
 #include <algorithm>
@@ -15,6 +16,7 @@
 #include <cfloat>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace hhg;
@@ -385,6 +387,200 @@ int hhg_db_apply_null_model(hhg_ctx* ctx, hhg_db* db, const float* q_pav, const 
   return HHG_OK;
 }
 
+// ------------------------------------------------------------------------------ DB from HHM text records
+// HHEntry::getTemplateHMM + the query-independent part of PrepareTemplateHMM, once per database load.
+int hhg_hhm_scan(const char* rec, int64_t len, int32_t* L, int32_t* has_ss) {
+  if (!rec || len <= 0 || !L || !has_ss) return fail(HHG_EINVAL, "hhg_hhm_scan: bad argument");
+  HhmScanner sc(rec, len);
+  if (!sc.peek(L, has_ss)) return fail(HHG_EINVAL, "hhg_hhm_scan: no LENG line / not an HHM record");
+  return HHG_OK;
+}
+
+int hhg_hhm_parse(const char* rec, int64_t len, int32_t L, int32_t* f_mb, int32_t* trn_mb, uint8_t* ss,
+                  int32_t* null_mb, float* neff_hmm, int32_t* has_pc) {
+  if (!rec || len <= 0 || L < 1 || !f_mb || !trn_mb || !ss || !null_mb || !neff_hmm || !has_pc)
+    return fail(HHG_EINVAL, "hhg_hhm_parse: bad argument");
+  HhmScanner sc(rec, len);
+  std::string msg = sc.parse(L, f_mb, trn_mb, ss, null_mb, neff_hmm, has_pc);
+  if (!msg.empty()) return fail(HHG_EINVAL, "hhg_hhm_parse: %s", msg.c_str());
+  return HHG_OK;
+}
+
+int hhg_db_create_hhm(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
+                      const hhg_prep_params* pp, const float* R, hhg_db** out) {
+  if (!ctx || !out || n <= 0 || !data || !off || !len || !pp || !R)
+    return fail(HHG_EINVAL, "hhg_db_create_hhm: bad argument");
+  if (pp->pcm < 0 || pp->pcm > 2 || (pp->pcm == 2 && pp->pcc != 1.0f))
+    return fail(HHG_EINVAL, "hhg_db_create_hhm: pseudocount mode %d with pcc=%g not supported (modes 0,1 and 2 "
+                "with pcc=1, i.e. no pow(); src/hhhmm.cpp:1896-1911)", pp->pcm, (double)pp->pcc);
+  CK(cudaSetDevice(ctx->device));
+  std::unique_ptr<hhg_db> holder(new hhg_db());
+  hhg_db* db = holder.get();
+  db->device = ctx->device;
+  db->n = n;
+  db->L.resize(n);
+  db->col_off.resize(n);
+  // pass 1: lengths (LENG) and whether any record predicts secondary structure
+  long long tot = 0;
+  bool any_ss = false;
+  for (int k = 0; k < n; ++k) {
+    int32_t L = 0, has_ss = 0;
+    HhmScanner sc(data + off[k], len[k]);
+    if (len[k] <= 0 || !sc.peek(&L, &has_ss)) return fail(HHG_EINVAL, "record %d: no LENG line / not an HHM record", k);
+    if (L < 1 || L > 32767) return fail(HHG_EINVAL, "record %d: length %d out of [1,32767]", k, L);
+    db->L[k] = L;
+    db->col_off[k] = tot;
+    tot += L;
+    any_ss |= has_ss != 0;
+  }
+  db->total_cols = tot;
+  db->has_ss = any_ss;
+  cudaError_t e;
+  if ((e = db->cols.alloc((size_t)tot * 7)) != cudaSuccess || (e = db->cols_raw.alloc((size_t)tot * 7)) != cudaSuccess ||
+      (e = db->dL.alloc(n)) != cudaSuccess || (e = db->dcol_off.alloc(n)) != cudaSuccess ||
+      (e = db->pav.alloc((size_t)n * 20)) != cudaSuccess)
+    return fail(HHG_ENOMEM, "hhg_db_create_hhm: %s", cudaGetErrorString(e));
+  CK(cudaMemcpyAsync(db->dL.p, db->L.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->dcol_off.p, db->col_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  HhmPrepArgs A;
+  memcpy(A.R, R, sizeof(A.R));
+  A.gapb = pp->gapb; A.gapf = pp->gapf; A.gapg = pp->gapg; A.gaph = pp->gaph; A.gapi = pp->gapi;
+  A.pM2D = A.pM2I = (float)(pp->gapd * 0.0286);                       // src/hhhmm.cpp:1745-1752, same types
+  A.pM2M = 1 - A.pM2D - A.pM2I;
+  A.pI2I = (float)(1.0 * pp->gape / (pp->gape - 1 + 1.0 / 0.75));
+  A.pI2M = 1 - A.pI2I;
+  A.pD2D = (float)(1.0 * pp->gape / (pp->gape - 1 + 1.0 / 0.75));
+  A.pD2M = 1 - A.pD2D;
+  A.pcm = pp->pcm; A.pca = pp->pca; A.pcb = pp->pcb;
+
+  // pass 2: chunks of records -> host staging (parsed by a few threads) -> device -> k_hhm_prepare / k_hhm_pav
+  const long long kChunkCols = 2000000;
+  DevBuf<int32_t> d_f, d_trn, d_null, d_haspc;
+  DevBuf<uint8_t> d_ss;
+  DevBuf<float> d_neff;
+  DevBuf<long long> d_coff;
+  HhmStaging st;
+  std::vector<long long> coff;
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  int t0 = 0;
+  while (t0 < n) {
+    int t1 = t0;
+    long long cols = 0;
+    while (t1 < n && (cols == 0 || cols + db->L[t1] <= kChunkCols)) cols += db->L[t1++];
+    const int m = t1 - t0;
+    coff.resize(m);
+    for (int k = 0; k < m; ++k) coff[k] = db->col_off[t0 + k] - db->col_off[t0];
+    st.f_mb.assign((size_t)cols * 20, 0);
+    st.trn_mb.assign((size_t)(cols + m) * 10, 0);
+    st.ss.assign((size_t)cols, 0);
+    st.null_mb.assign((size_t)m * 20, 0);
+    st.neff_hmm.assign(m, 0.f);
+    st.has_pc.assign(m, 0);
+    std::vector<std::string> errs(hw);
+    std::vector<int> err_rec(hw, -1);
+    auto work = [&](unsigned w) {
+      for (int k = (int)w; k < m; k += (int)hw) {
+        HhmScanner sc(data + off[t0 + k], len[t0 + k]);
+        std::string msg = sc.parse(db->L[t0 + k], st.f_mb.data() + (size_t)coff[k] * 20,
+                                   st.trn_mb.data() + (size_t)(coff[k] + k) * 10, st.ss.data() + coff[k],
+                                   st.null_mb.data() + (size_t)k * 20, &st.neff_hmm[k], &st.has_pc[k]);
+        if (!msg.empty() && err_rec[w] < 0) { errs[w] = msg; err_rec[w] = t0 + k; }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < hw; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (unsigned w = 0; w < hw; ++w)
+      if (err_rec[w] >= 0) return fail(HHG_EINVAL, "record %d: %s", err_rec[w], errs[w].c_str());
+    CK(d_f.ensure(st.f_mb.size())); CK(d_trn.ensure(st.trn_mb.size())); CK(d_ss.ensure(st.ss.size()));
+    CK(d_null.ensure(st.null_mb.size())); CK(d_haspc.ensure(m)); CK(d_neff.ensure(m)); CK(d_coff.ensure(m));
+    CK(cudaMemcpyAsync(d_f.p, st.f_mb.data(), st.f_mb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_trn.p, st.trn_mb.data(), st.trn_mb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_ss.p, st.ss.data(), st.ss.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_null.p, st.null_mb.data(), st.null_mb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_haspc.p, st.has_pc.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_neff.p, st.neff_hmm.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_coff.p, coff.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ColRec* dst = reinterpret_cast<ColRec*>(db->cols_raw.p) + db->col_off[t0];
+    const int threads = 128;
+    k_hhm_prepare<<<(unsigned)((cols + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        m, db->dL.p + t0, d_coff.p, d_f.p, d_trn.p, any_ss ? d_ss.p : nullptr, d_haspc.p, A, ctx->lg2.p,
+        ctx->diff.p, dst, cols);
+    k_hhm_pav<<<(unsigned)(((long long)m * 32 + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        m, db->dL.p + t0, d_coff.p, dst, d_null.p, d_neff.p, A, db->pav.p + (size_t)t0 * 20);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));   // staging is reused by the next chunk
+    t0 = t1;
+  }
+  CK(cudaMemcpyAsync(db->cols.p, db->cols_raw.p, db->cols.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  db->raw = true;
+  db->prepared = false;
+  *out = holder.release();
+  return HHG_OK;
+}
+
+// The resident binary format: column records before the null model + pav.  read_* copy it out (to be stored
+// next to the ffindex files), hhg_db_create_packed loads it back without parsing anything.
+int hhg_db_read_cols(hhg_ctx* ctx, const hhg_db* db, int which, int64_t first, int64_t count, void* out) {
+  if (!ctx || !db || !out || first < 0 || count < 0 || first + count > db->total_cols)
+    return fail(HHG_EINVAL, "hhg_db_read_cols: bad argument");
+  if (which != 0 && which != 1) return fail(HHG_EINVAL, "hhg_db_read_cols: which must be 0 (raw) or 1 (prepared)");
+  if (which == 0 && !db->raw) return fail(HHG_EINVAL, "hhg_db_read_cols: db holds no pre-null-model records");
+  if (which == 1 && !db->prepared) return fail(HHG_EINVAL, "hhg_db_read_cols: call hhg_db_apply_null_model first");
+  CK(cudaSetDevice(ctx->device));
+  const ColRec* src = reinterpret_cast<const ColRec*>(which == 0 ? db->cols_raw.p : db->cols.p) + first;
+  CK(cudaMemcpyAsync(out, src, (size_t)count * sizeof(ColRec), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HHG_OK;
+}
+
+int hhg_db_read_pav(hhg_ctx* ctx, const hhg_db* db, float* out) {
+  if (!ctx || !db || !out || !db->raw) return fail(HHG_EINVAL, "hhg_db_read_pav: bad argument / db not raw");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, db->pav.p, (size_t)db->n * 20 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HHG_OK;
+}
+
+int hhg_db_create_packed(hhg_ctx* ctx, int n, const int32_t* L, const void* cols_raw, int has_ss,
+                         const float* pav, hhg_db** out) {
+  if (!ctx || !out || n <= 0 || !L || !cols_raw || !pav) return fail(HHG_EINVAL, "hhg_db_create_packed: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  std::unique_ptr<hhg_db> holder(new hhg_db());
+  hhg_db* db = holder.get();
+  db->device = ctx->device;
+  db->n = n;
+  db->has_ss = has_ss != 0;
+  db->L.assign(L, L + n);
+  db->col_off.resize(n);
+  long long tot = 0;
+  for (int k = 0; k < n; ++k) {
+    if (L[k] < 1 || L[k] > 32767) return fail(HHG_EINVAL, "target %d: length %d out of [1,32767]", k, L[k]);
+    db->col_off[k] = tot;
+    tot += L[k];
+  }
+  db->total_cols = tot;
+  cudaError_t e;
+  if ((e = db->cols.alloc((size_t)tot * 7)) != cudaSuccess || (e = db->cols_raw.alloc((size_t)tot * 7)) != cudaSuccess ||
+      (e = db->dL.alloc(n)) != cudaSuccess || (e = db->dcol_off.alloc(n)) != cudaSuccess ||
+      (e = db->pav.alloc((size_t)n * 20)) != cudaSuccess)
+    return fail(HHG_ENOMEM, "hhg_db_create_packed: %s", cudaGetErrorString(e));
+  CK(cudaMemcpyAsync(db->dL.p, db->L.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->dcol_off.p, db->col_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->cols_raw.p, cols_raw, (size_t)tot * sizeof(ColRec), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->cols.p, db->cols_raw.p, (size_t)tot * sizeof(ColRec), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->pav.p, pav, (size_t)n * 20 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  db->raw = true;
+  db->prepared = false;
+  *out = holder.release();
+  return HHG_OK;
+}
+
 int hhg_debug_fastlog2_table(hhg_ctx* ctx, float* lg2_out) {
   if (!ctx || !lg2_out) return fail(HHG_EINVAL, "bad argument");
   memcpy(lg2_out, ctx->h_lg2.data(), 1025 * 4);
@@ -397,6 +593,12 @@ int hhg_db_destroy(hhg_db* db) {
 }
 int hhg_db_size(const hhg_db* db) { return db ? db->n : 0; }
 long long hhg_db_columns(const hhg_db* db) { return db ? db->total_cols : 0; }
+
+int hhg_db_lengths(const hhg_db* db, int32_t* out) {
+  if (!db || !out) return fail(HHG_EINVAL, "hhg_db_lengths: bad argument");
+  memcpy(out, db->L.data(), (size_t)db->n * sizeof(int32_t));
+  return HHG_OK;
+}
 
 // --------------------------------------------------------------------------------------- query
 int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const uint8_t* ss,

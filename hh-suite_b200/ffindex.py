@@ -1,0 +1,56 @@
+"""Reader for ffindex databases (`X_hhm.ffdata` + `X_hhm.ffindex`, `X_cs219.ff*`), the container format every
+HH-suite database ships in (lib/ffindex/src/ffindex.h: ffindex_entry_t {offset, length, name}; the index is a
+text file of `name\\toffset\\tlength` lines, lengths include the trailing NUL byte of each record)."""
+from __future__ import annotations
+
+import mmap
+import os
+
+import numpy as np
+
+
+class FFIndex:
+    def __init__(self, data_path: str, index_path: str | None = None):
+        index_path = index_path or os.path.splitext(data_path)[0] + ".ffindex"
+        names, off, ln = [], [], []
+        with open(index_path, "rb") as f:
+            for line in f:
+                parts = line.rstrip(b"\n").split(b"\t")
+                if len(parts) != 3:
+                    raise ValueError(f"{index_path}: malformed index line {line!r}")
+                names.append(parts[0].decode())
+                off.append(int(parts[1])); ln.append(int(parts[2]))
+        self.names = names
+        self.offsets = np.array(off, np.int64)
+        self.lengths = np.array(ln, np.int64)
+        self._f = open(data_path, "rb")
+        size = os.fstat(self._f.fileno()).st_size
+        self.data = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_READ) if size else b""
+        if len(self.names) and int((self.offsets + self.lengths).max()) > size:
+            raise ValueError(f"{index_path}: an entry ends beyond {data_path}")
+
+    def __len__(self):
+        return len(self.names)
+
+    def record(self, k: int) -> bytes:
+        return self.data[self.offsets[k]:self.offsets[k] + self.lengths[k]]
+
+    def close(self):
+        if hasattr(self.data, "close"):
+            self.data.close()
+        self._f.close()
+
+
+def write_ffindex(data_path: str, records: list[tuple[str, bytes]], index_path: str | None = None):
+    """Write records as an ffindex pair (entries sorted by name, NUL-terminated like ffindex_build)."""
+    index_path = index_path or os.path.splitext(data_path)[0] + ".ffindex"
+    entries = []
+    with open(data_path, "wb") as d:
+        pos = 0
+        for name, blob in records:
+            d.write(blob + b"\0")
+            entries.append((name, pos, len(blob) + 1))
+            pos += len(blob) + 1
+    with open(index_path, "w") as f:
+        for name, off, ln in sorted(entries):
+            f.write(f"{name}\t{off}\t{ln}\n")

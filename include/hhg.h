@@ -102,11 +102,52 @@ int hhg_db_create_raw(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* p_of
                       const int64_t* ss_off, const float* p, const float* tr, const uint8_t* ss,
                       const float* pav, hhg_db** out);
 int hhg_db_apply_null_model(hhg_ctx* ctx, hhg_db* db, const float* q_pav, const float* pb, int columnscore);
+
+/* ---- database load straight from HHM text records (SURVEY 8a rows a10 + a11; 8f-1) ------------------------
+ * Replaces, once per database instead of once per (query, target):
+ *   HHDatabaseEntry::getTemplateHMM -> HMM::Read          src/hhdatabase.cpp:300-336, src/hhhmm.cpp:202-691
+ *   PrepareTemplateHMM up to CalculateAminoAcidBackground src/hhfunc.cpp:165-188
+ *     (AddTransitionPseudocounts src/hhhmm.cpp:1722, PreparePseudocounts :1811, AddAminoAcidPseudocounts :1874,
+ *      CalculateAminoAcidBackground :1854)
+ * The text is tokenised on the host, all arithmetic (fpow2 of the emissions, both pseudocount steps, pav) runs in
+ * CUDA kernels with the reference's operation types and order; the result is the same shard hhg_db_create_raw
+ * builds from the reference's own prepared arrays, bit for bit.  Follow with hhg_db_apply_null_model per query.
+ *
+ * data/off/len: the `_hhm.ffdata` bytes and the (offset, length) columns of its `.ffindex` (lib/ffindex/src/ffindex.h:
+ * ffindex_entry_t), n records.  Each record must be in HHM format with a NULL line (every record's own NULL line
+ * is its background, as HMM::Read sets pb before using it, src/hhhmm.cpp:540-543,666-668).  R = the 20x20
+ * pseudocount matrix of SetSubstitutionMatrix (R[a][b], src/hhfunc.cpp).  Supported pseudocount modes: 0, 1 and
+ * 2 with pcc == 1 (the default; other settings need pow() and are refused with HHG_EINVAL).
+ * Errors (malformed record, LENG/column mismatch) name the record; the reference would warn and skip. */
+typedef struct hhg_prep_params {
+  float gapb, gapd, gape, gapf, gapg, gaph, gapi; /* Parameters::gap*, defaults 1, .15, 1, .6, .6, .6, .6       */
+  int32_t pcm;                                    /* par.pc_hhm_nocontext_mode (2)                              */
+  float pca, pcb, pcc;                            /* par.pc_hhm_nocontext_a/b/c (1.0, 1.5, 1.0)                 */
+} hhg_prep_params;
+int hhg_db_create_hhm(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
+                      const hhg_prep_params* pp, const float* R, hhg_db** out);
+/* Host only: LENG and whether the record carries an ss_pred sequence (no numbers are parsed). */
+int hhg_hhm_scan(const char* rec, int64_t len, int32_t* L, int32_t* has_ss);
+/* Host only: the tokeniser hhg_db_create_hhm runs per record, exposed for inspection and CPU-side tests.
+ *   f_mb[L*20]       emission integers of columns 1..L, file (alphabetical) amino-acid order, '*' = 99999
+ *   trn_mb[(L+1)*10] rows 0..L: 7 transition integers (M2M,M2I,M2D,I2M,I2I,D2M,D2D) + Neff_M, Neff_I, Neff_D
+ *   ss[L]            ss_pred*11 + ss_conf of columns 1..L;  null_mb[20] the NULL line */
+int hhg_hhm_parse(const char* rec, int64_t len, int32_t L, int32_t* f_mb, int32_t* trn_mb, uint8_t* ss,
+                  int32_t* null_mb, float* neff_hmm, int32_t* has_pc);
+/* The resident binary database format = what the shard holds: 112-byte column records
+ *   {float p[20]; float m2m, m2d, d2m, d2d, i2m, i2i, m2i; uint32 ss}   (p before the null model)
+ * plus pav[n*20].  read_* copy them out (which: 0 = before the null model, 1 = after the last
+ * hhg_db_apply_null_model), hhg_db_create_packed loads them back without any parsing. */
+int hhg_db_read_cols(hhg_ctx* ctx, const hhg_db* db, int which, int64_t first, int64_t count, void* out);
+int hhg_db_read_pav(hhg_ctx* ctx, const hhg_db* db, float* out);
+int hhg_db_create_packed(hhg_ctx* ctx, int n, const int32_t* L, const void* cols_raw, int has_ss,
+                         const float* pav, hhg_db** out);
 /* Debug / parity: the 1025-entry lg2 table of fast_log2 the library uses for Hit.score. */
 int hhg_debug_fastlog2_table(hhg_ctx* ctx, float* lg2_out);
 int hhg_db_destroy(hhg_db* db);
 int hhg_db_size(const hhg_db* db);          /* number of targets */
 long long hhg_db_columns(const hhg_db* db); /* sum of target lengths */
+int hhg_db_lengths(const hhg_db* db, int32_t* out /* [hhg_db_size] */);
 
 /* Set the query (replaces HMMSimd::MapOneHMM).  S33: float[44*44] or NULL (needed iff use_ss). */
 int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const uint8_t* ss,

@@ -26,6 +26,21 @@ def build_oracle():
     subprocess.check_call(["make", "-C", HERE, "-s"])
 
 
+class PrepParams(C.Structure):
+    """hho_prep_params / hhg_prep_params: Parameters::gap* and pc_hhm_nocontext_* (src/hhdecl.cpp:64-80)."""
+    _fields_ = [("gapb", C.c_float), ("gapd", C.c_float), ("gape", C.c_float), ("gapf", C.c_float),
+                ("gapg", C.c_float), ("gaph", C.c_float), ("gapi", C.c_float), ("pcm", C.c_int),
+                ("pca", C.c_float), ("pcb", C.c_float), ("pcc", C.c_float)]
+
+    @classmethod
+    def defaults(cls):
+        return cls(1.0, 0.15, 1.0, 0.6, 0.6, 0.6, 0.6, 2, 1.0, 1.5, 1.0)
+
+
+# alphabetical HHM column order -> internal amino-acid numbers (s2a, src/hhdecl.h:61)
+S2A = np.array([0, 4, 3, 6, 13, 7, 8, 9, 11, 10, 12, 2, 14, 5, 1, 15, 16, 19, 17, 18])
+
+
 class Oracle:
     def __init__(self):
         path = os.path.join(HERE, "liboracle.so")
@@ -50,8 +65,59 @@ class Oracle:
         L.hho_flog2.argtypes = [C.c_float]
         L.hho_fpow2.restype = C.c_float
         L.hho_fpow2.argtypes = [C.c_float]
+        L.hho_fast_log2.restype = C.c_float
+        L.hho_fast_log2.argtypes = [C.c_float]
+        L.hho_hhm_parse.restype = C.c_int
+        L.hho_hhm_parse.argtypes = [C.c_char_p, C.c_long, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), c_i32p, c_i32p, c_i32p, c_i32p, c_u8p, c_u8p,
+                                    C.POINTER(C.c_int)]
+        L.hho_hhm_prepare.restype = C.c_int
+        L.hho_hhm_prepare.argtypes = [C.c_int, c_i32p, c_i32p, c_i32p, c_f32p, C.c_float, C.c_int,
+                                      C.POINTER(PrepParams), c_f32p, c_f32p, c_f32p, c_f32p]
         L.hho_sw_striped_byte.restype = C.c_int
         L.hho_sw_striped_byte.argtypes = [C.c_int, c_u8p, c_u8p, C.c_int, C.c_int, C.c_int, C.c_int]
+
+    def hhm_parse(self, text, maxL=4000):
+        """HMM::Read restatement: the integers of one HHM record."""
+        if isinstance(text, str):
+            text = text.encode()
+        f = np.zeros(((maxL + 2), 20), np.int32); tr = np.zeros((maxL + 1, 7), np.int32)
+        ne = np.zeros((maxL + 1, 3), np.int32); null = np.zeros(20, np.int32)
+        sp = np.zeros(maxL + 2, np.uint8); sc = np.zeros(maxL + 2, np.uint8)
+        neff = C.c_float(); has_pc = C.c_int(); has_null = C.c_int(); nss = C.c_int()
+        L = self.lib.hho_hhm_parse(text, len(text), maxL, C.byref(neff), C.byref(has_pc), C.byref(has_null),
+                                   _p(null, c_i32p), _p(f, c_i32p), _p(tr, c_i32p), _p(ne, c_i32p),
+                                   _p(sp, c_u8p), _p(sc, c_u8p), C.byref(nss))
+        if L < 0:
+            raise ValueError(f"hho_hhm_parse: {L}")
+        return dict(L=L, neff_hmm=neff.value, has_pc=has_pc.value, null=null if has_null.value else None,
+                    f=f[:L + 2].copy(), tr=tr[:L + 1].copy(), neff=ne[:L + 1].copy(),
+                    ss=(sp[:L + 2] * 11 + sc[:L + 2]).astype(np.uint8), has_ss=nss.value >= 0)
+
+    def null_to_pb(self, null_mb):
+        """pb[s2a[a]] = fpow2(-x/1000), src/hhhmm.cpp:543."""
+        pb = np.zeros(20, np.float32)
+        for a in range(20):
+            pb[S2A[a]] = self.lib.hho_fpow2(float(np.float32(-int(null_mb[a])) / np.float32(1000)))
+        return pb
+
+    def hhm_prepare(self, rec, pb, R, params=None):
+        """Query-independent part of PrepareTemplateHMM on a parsed record -> p (pre-null-model), tr, pav."""
+        pp = params or PrepParams.defaults()
+        L = rec["L"]
+        f = np.ascontiguousarray(rec["f"], np.int32); tr_mb = np.ascontiguousarray(rec["tr"], np.int32)
+        ne = np.ascontiguousarray(rec["neff"], np.int32)
+        pb = np.ascontiguousarray(pb, np.float32); R = np.ascontiguousarray(R, np.float32)
+        p = np.zeros((L + 2, 20), np.float32); tr = np.zeros((L + 1, 7), np.float32); pav = np.zeros(20, np.float32)
+        rc = self.lib.hho_hhm_prepare(L, _p(f, c_i32p), _p(tr_mb, c_i32p), _p(ne, c_i32p), _p(pb, c_f32p),
+                                      rec["neff_hmm"], rec["has_pc"], C.byref(pp), _p(R, c_f32p),
+                                      _p(p, c_f32p), _p(tr, c_f32p), _p(pav, c_f32p))
+        if rc != 0:
+            raise ValueError(f"hho_hhm_prepare: {rc}")
+        return dict(L=L, p=p, tr=tr, pav=pav, ss=rec["ss"])
+
+    def fast_log2(self, x):
+        return self.lib.hho_fast_log2(float(x))
 
     def viterbi(self, q_p, q_tr, t_p, t_tr, q_ss=None, t_ss=None, S33=None, ssw=0.11, celloff=None,
                 local=True, egq=0.0, egt=0.0, shift=-0.03, want_bt=True):
@@ -146,6 +212,8 @@ class RefShim:
         L.hhref_get_cs219.argtypes = [c_f32p]
         L.hhref_get_S33.argtypes = [c_f32p]
         L.hhref_get_pb.argtypes = [c_f32p]
+        L.hhref_get_R.argtypes = [c_f32p]
+        L.hhref_get_prep_params.argtypes = [c_f32p]
         L.hhref_stripe_query_profile.argtypes = [C.c_int, C.c_int, c_u8p]
         L.hhref_ungapped_score.argtypes = [c_u8p, C.c_int, c_u8p, C.c_int, C.c_int]
         L.hhref_sw_striped_byte.argtypes = [c_u8p, C.c_int, c_u8p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -187,6 +255,21 @@ class RefShim:
         out = np.zeros(44 * 44, np.float32)
         self.lib.hhref_get_S33(_p(out, c_f32p))
         return out
+
+    def R(self):
+        out = np.zeros(400, np.float32)
+        self.lib.hhref_get_R(_p(out, c_f32p))
+        return out.reshape(20, 20)
+
+    def pb(self):
+        out = np.zeros(20, np.float32)
+        self.lib.hhref_get_pb(_p(out, c_f32p))
+        return out
+
+    def prep_params(self):
+        v = np.zeros(11, np.float32)
+        self.lib.hhref_get_prep_params(_p(v, c_f32p))
+        return PrepParams(*[float(x) for x in v[:7]], int(v[7]), *[float(x) for x in v[8:]])
 
     # -- query
     def load_query_hhm(self, path):

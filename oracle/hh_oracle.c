@@ -336,3 +336,259 @@ float hho_fpow2(float x) {
   x = 1.0f + dx * (0.693019f + dx * (0.241404f + dx * (0.0520749f + dx * 0.0134929f)));
   return u2f(f2u(x) + ((uint32_t)lx << 23));
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * HHM text -> DP inputs: HMM::Read (src/hhhmm.cpp:202-691) and the query-independent part of
+ * PrepareTemplateHMM (src/hhfunc.cpp:165-188).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* fast_log2, src/util-inl.h:108-128.  The table is the one a real run ends up with: the first caller is
+ * HMM::AddTransitionPseudocounts in hhhmm.cpp, where log(float) binds to the double-precision C log. */
+static float g_lg2[1025], g_diff[1025];
+static int g_lg2_ready = 0;
+float hho_fast_log2(float x) {
+  if (x <= 0) return -100000;
+  if (!g_lg2_ready) {
+    float prev = 0.0f;
+    g_lg2[0] = 0.0f;
+    for (int i = 1; i <= 1024; ++i) {
+      g_lg2[i] = (float)(log((double)(float)(1024 + i)) * 1.442695041 - (double)10.0f);
+      g_diff[i - 1] = (float)((double)(g_lg2[i] - prev) * 1.2352E-4);
+      prev = g_lg2[i];
+    }
+    g_lg2_ready = 1;
+  }
+  uint32_t u = f2u(x);
+  int a = (int)((u & 0x7F800000u) >> 23) - 0x7f;
+  int b = (int)((u & 0x007FE000u) >> 13);
+  int c = (int)(u & 0x00001FFFu);
+  return (float)a + g_lg2[b] + g_diff[b] * (float)c;
+}
+
+/* strinta / strint, src/util.cpp:133-196: next integer in the string ('*' -> deflt), advancing *pp;
+ * *pp becomes NULL when the string holds no further integer. */
+static int next_int(const char** pp, int star_ok, int deflt) {
+  const char* p = *pp;
+  const char* p0 = p;
+  if (!p) return INT32_MIN;
+  while (*p != '\0' && *p != '\n' && !(*p >= '0' && *p <= '9') && !(star_ok && *p == '*')) p++;
+  if (*p == '\0' || *p == '\n') { *pp = NULL; return INT32_MIN; }
+  if (*p == '*') { *pp = p + 1; return deflt; }
+  int neg = (p > p0 && p[-1] == '-');
+  long v = 0;
+  while (*p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); p++; }
+  *pp = p;
+  return neg ? -(int)v : (int)v;
+}
+
+/* alphabetical column order of HHM files -> internal amino-acid numbers (s2a, src/hhdecl.cpp) */
+static const int kS2A[20] = {0, 4, 3, 6, 13, 7, 8, 9, 11, 10, 12, 2, 14, 5, 1, 15, 16, 19, 17, 18};
+
+static int ss_code(char c) {   /* ss2i, src/hhutil-inl.h:123-146 */
+  if (c >= 'a' && c <= 'z') c += 'A' - 'a';
+  switch (c) {
+    case '.': case '-': case 'X': return 0;
+    case 'H': return 1;
+    case 'E': return 2;
+    case 'C': case '~': case 'I': return 3;
+    case 'S': return 4; case 'T': return 5; case 'G': return 6; case 'B': return 7;
+    case ' ': case '\t': case '\n': return -1;
+  }
+  return -2;
+}
+static char ss_norm(char c) {   /* ss2ss, src/hhutil-inl.h:217-243 */
+  switch (c) {
+    case '~': case 'I': return 'C';
+    case 'i': return 'c';
+    case 'H': case 'E': case 'C': case 'S': case 'T': case 'G': case 'B':
+    case 'h': case 'e': case 'c': case 's': case 't': case 'g': case 'b': case '.': return c;
+  }
+  return '-';
+}
+static int conf_code(char c) {  /* cf2i, src/hhutil-inl.h:248-266 */
+  if (c >= '0' && c <= '9') return c - '0' + 1;
+  return 0;
+}
+
+static const char* next_line(const char* p, const char* end) {
+  while (p < end && *p != '\n') p++;
+  return p < end ? p + 1 : end;
+}
+static int blank_line(const char* p, const char* end) {
+  for (; p < end && *p != '\n'; ++p) if (*p != ' ' && *p != '\t' && *p != '\r') return 0;
+  return 1;
+}
+
+/* Parse one HHM record.  Outputs (caller-allocated, maxL columns):
+ *   f_mb[(maxL+2)*20]   the column integers of the file, ALPHABETICAL amino-acid order, '*' = 99999, rows 1..L
+ *   tr_mb[(maxL+1)*7]   transition integers rows 0..L, file order = enum order M2M,M2I,M2D,I2M,I2I,D2M,D2D
+ *   neff_mb[(maxL+1)*3] Neff_M, Neff_I, Neff_D integers rows 0..L
+ *   null_mb[20]         NULL line (alphabetical); untouched when the record has none (*has_null = 0)
+ *   ss_pred/ss_conf[maxL+2]  zero-filled, then as HMM::Read fills them (:392-446)
+ * Returns L (number of columns read), or <0 on malformed input. */
+int hho_hhm_parse(const char* text, long len, int maxL, float* neff_hmm, int* has_pc, int* has_null,
+                  int* null_mb, int* f_mb, int* tr_mb, int* neff_mb, uint8_t* ss_pred, uint8_t* ss_conf,
+                  int* nss_pred_out) {
+  const char* end = text + len;
+  const char* p = text;
+  int Lstated = 0, i = 0, nss_pred = -1, nss_conf = -1;
+  *neff_hmm = 0; *has_pc = 0; *has_null = 0;
+  memset(ss_pred, 0, (size_t)maxL + 2); memset(ss_conf, 0, (size_t)maxL + 2);
+  while (p < end && !(p[0] == '/' && p + 1 < end && p[1] == '/')) {
+    const char* line = p;
+    p = next_line(p, end);
+    if (blank_line(line, end)) continue;
+    if (!strncmp(line, "HH", 2)) continue;
+    if (!strncmp(line, "LENG", 4)) { const char* q = line + 4; Lstated = next_int(&q, 0, 0); }
+    else if (!strncmp(line, "NEFF", 4)) { *neff_hmm = strtof(line + 6, NULL); }
+    else if (!strncmp(line, "PCT", 3)) *has_pc = 1;
+    else if (!strncmp(line, "SEQ", 3)) {
+      int k = -1, l = 1, m = 1;
+      while (p < end && *p != '#') {
+        const char* s = p;
+        p = next_line(p, end);
+        if (*s == '>') {
+          k++;
+          if (!strncmp(s, ">ss_pred", 8)) nss_pred = k;
+          else if (!strncmp(s, ">ss_conf", 8)) nss_conf = k;
+          l = 1; m = 1;
+        } else if (k >= 0) {
+          for (const char* h = s; h < end && *h != '\n' && *h > '\0'; ++h) {
+            if (k == nss_pred) {
+              int c0 = ss_code(*h);
+              if (c0 >= 0 && c0 <= 3 && *h != '.') {
+                char c = ss_norm(*h);
+                if (c != '.' && !(c >= 'a' && c <= 'z') && m <= maxL) ss_pred[m++] = (uint8_t)ss_code(c);
+                l++;
+              }
+            } else if (k == nss_conf) {
+              if (*h == '-' || (*h >= '0' && *h <= '9')) { if (l <= maxL) ss_conf[l] = (uint8_t)conf_code(*h); l++; }
+            }
+          }
+        }
+      }
+      if (p < end) p = next_line(p, end);   /* the '#' line */
+    }
+    else if (!strncmp(line, "NULL", 4)) {
+      const char* q = line + 4;
+      for (int a = 0; a < 20 && q; ++a) null_mb[a] = next_int(&q, 1, 99999);
+      if (!q) return -3;
+      *has_null = 1;
+    }
+    else if (!strncmp(line, "HMM", 3)) {
+      p = next_line(p, end);                  /* transition labels */
+      const char* q = p; p = next_line(p, end);
+      for (int a = 0; a < 7 && q; ++a) tr_mb[a] = next_int(&q, 1, 99999);
+      for (int a = 0; a < 3; ++a) neff_mb[a] = next_int(&q, 1, 99999);
+      if (!q) return -4;
+      while (p < end && !(p[0] == '/' && p[1] == '/') && p[0] != '#') {
+        const char* s = p; p = next_line(p, end);
+        if (blank_line(s, end)) continue;
+        q = s + 1;
+        (void)next_int(&q, 0, 0);             /* column number */
+        ++i;
+        if (i > Lstated) return -5;
+        if (i > maxL) return -6;
+        for (int a = 0; a < 20 && q; ++a) f_mb[i * 20 + a] = next_int(&q, 1, 99999);
+        (void)next_int(&q, 0, 0);             /* l[i] */
+        if (!q) return -7;
+        q = p; p = next_line(p, end);
+        if (*q != ' ' && *q != '\t') return -8;
+        for (int a = 0; a < 7 && q; ++a) tr_mb[i * 7 + a] = next_int(&q, 1, 99999);
+        for (int a = 0; a < 3; ++a) neff_mb[i * 3 + a] = next_int(&q, 1, 99999);
+        if (!q) return -9;
+      }
+      if (p < end && p[0] == '/' && p[1] == '/') break;
+    }
+  }
+  if (nss_pred_out) *nss_pred_out = nss_pred;
+  return i;
+}
+
+typedef struct {
+  float gapb, gapd, gape, gapf, gapg, gaph, gapi;   /* Parameters::gap*, src/hhdecl.cpp:74-80 */
+  int pcm;                                          /* par.pc_hhm_nocontext_mode (:64) */
+  float pca, pcb, pcc;                              /* par.pc_hhm_nocontext_a/b/c */
+} hho_prep_params;
+
+/* HMM::Read's number conversion + AddTransitionPseudocounts (src/hhhmm.cpp:1722-1785) + PreparePseudocounts
+ * (:1811-1815) + AddAminoAcidPseudocounts (:1874-1921, modes 0,1,2 with pcc == 1) + CalculateAminoAcidBackground
+ * (:1854-1868).  pb[20] = the background in INTERNAL order that HMM::Read leaves in the global pb after this
+ * record's NULL line.  Outputs p[(L+2)*20] (pre-null-model), tr[(L+1)*7], pav[20]. */
+int hho_hhm_prepare(int L, const int* f_mb, const int* tr_mb, const int* neff_mb, const float* pb,
+                    float neff_hmm, int has_pc, const hho_prep_params* pp, const float* R /*[20][20]*/,
+                    float* p, float* tr, float* pav) {
+  float* f = (float*)malloc((size_t)(L + 2) * 20 * sizeof(float));
+  float* NM = (float*)malloc((size_t)(L + 2) * 3 * sizeof(float));
+  if (!f || !NM) { free(f); free(NM); return -1; }
+  for (int i = 1; i <= L; ++i)
+    for (int a = 0; a < 20; ++a) f[i * 20 + kS2A[a]] = hho_fpow2((float)(-f_mb[i * 20 + a]) / 1000);
+  for (int a = 0; a < 20; ++a) f[a] = f[(L + 1) * 20 + a] = pb[a];
+  for (int i = 0; i <= L; ++i) {
+    for (int k = 0; k < 7; ++k) tr[i * 7 + k] = (float)(-tr_mb[i * 7 + k]) / 1000;
+    for (int k = 0; k < 3; ++k) NM[i * 3 + k] = (float)neff_mb[i * 3 + k] / 1000;
+    if (i >= 1 && NM[i * 3] == 0) NM[i * 3] = 1;
+  }
+  if (pp->gapb > 0) {
+    float pM2D, pM2I, pM2M, pI2I, pI2M, pD2D, pD2M;
+    pM2D = pM2I = (float)(pp->gapd * 0.0286);
+    pM2M = 1 - pM2D - pM2I;
+    pI2I = (float)(1.0 * pp->gape / (pp->gape - 1 + 1.0 / 0.75));
+    pI2M = 1 - pI2I;
+    pD2D = (float)(1.0 * pp->gape / (pp->gape - 1 + 1.0 / 0.75));
+    pD2M = 1 - pD2D;
+    const float gapb = pp->gapb;
+    for (int i = 0; i <= L; ++i) {
+      float* t = tr + i * 7;
+      float p0 = (NM[i * 3] - 1) * hho_fpow2(t[M2M]) + gapb * pM2M;
+      float p1 = (NM[i * 3] - 1) * hho_fpow2(t[M2D]) + gapb * pM2D;
+      float p2 = (NM[i * 3] - 1) * hho_fpow2(t[M2I]) + gapb * pM2I;
+      if (i == 0) p1 = p2 = 0;
+      if (i == L) p1 = p2 = 0;
+      float sum = p0 + p1 + p2 + FLT_MIN;
+      t[M2M] = hho_fast_log2(p0 / sum);
+      t[M2D] = hho_fast_log2(p1 / sum) * pp->gapf;
+      t[M2I] = hho_fast_log2(p2 / sum) * pp->gapg;
+      p0 = NM[i * 3 + 1] * hho_fpow2(t[I2M]) + gapb * pI2M;
+      p1 = NM[i * 3 + 1] * hho_fpow2(t[I2I]) + gapb * pI2I;
+      sum = p0 + p1 + FLT_MIN;
+      t[I2M] = hho_fast_log2(p0 / sum);
+      t[I2I] = hho_fast_log2(p1 / sum) * pp->gapi;
+      p0 = NM[i * 3 + 2] * hho_fpow2(t[D2M]) + gapb * pD2M;
+      p1 = NM[i * 3 + 2] * hho_fpow2(t[D2D]) + gapb * pD2D;
+      if (i == L) p1 = 0;
+      sum = p0 + p1 + FLT_MIN;
+      t[D2M] = hho_fast_log2(p0 / sum);
+      t[D2D] = hho_fast_log2(p1 / sum) * pp->gaph;
+    }
+  }
+  int pcm = has_pc ? 0 : pp->pcm;
+  if (pcm == 2 && pp->pcc != 1.0f) { free(f); free(NM); return -2; }
+  if (pcm < 0 || pcm > 2) { free(f); free(NM); return -2; }
+  for (int i = 1; i <= L; ++i) {
+    const float* fi = f + i * 20;
+    float tau = 0;
+    if (pcm == 1) tau = pp->pca;
+    else if (pcm == 2) tau = (float)fmin(1.0, pp->pca / (1. + NM[i * 3] / pp->pcb));
+    for (int a = 0; a < 20; ++a) {
+      if (pcm == 0) { p[i * 20 + a] = fi[a]; continue; }
+      /* g[i][a] = ScalarProd20(R[a], f[i]): plain left-to-right sum (SSE undefined, src/hhhit-inl.h:117) */
+      const float* Ra = R + a * 20;
+      float g = fi[0] * Ra[0];
+      for (int b = 1; b < 20; ++b) g = g + fi[b] * Ra[b];
+      p[i * 20 + a] = (float)((1. - tau) * fi[a] + tau * g);
+    }
+  }
+  for (int a = 0; a < 20; ++a) pav[a] = pb[a] * 100.0f / neff_hmm;
+  for (int i = 1; i <= L; ++i)
+    for (int a = 0; a < 20; ++a) pav[a] += p[i * 20 + a];
+  float sum = 0.0f;
+  for (int a = 0; a < 20; ++a) sum += pav[a];
+  if (sum != 0.0f) {
+    float fac = (float)(1.0 / sum);
+    for (int a = 0; a < 20; ++a) pav[a] *= fac;
+  }
+  for (int a = 0; a < 20; ++a) p[a] = p[(L + 1) * 20 + a] = pav[a];
+  free(f); free(NM);
+  return 0;
+}

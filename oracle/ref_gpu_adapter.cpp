@@ -98,6 +98,34 @@ class GpuViterbiRunner {
     L_ = L;
   }
 
+  // alternative upload: hand the HHM TEXT of the files to the library (hhg_db_create_hhm); nothing of the
+  // reference's HMM::Read / PrepareTemplateHMM runs for the templates on this side.
+  void UploadText(Parameters& par, const std::vector<std::string>& files, const float R[20][20]) {
+    std::string data;
+    std::vector<int64_t> off, len;
+    all_have_ss_ = true;
+    for (const std::string& f : files) {
+      FILE* fp = fopen(f.c_str(), "rb");
+      if (!fp) { perror(f.c_str()); exit(2); }
+      std::string rec;
+      char buf[65536];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof(buf), fp)) > 0) rec.append(buf, n);
+      fclose(fp);
+      rec.push_back('\0');                                        // like an ffindex entry
+      off.push_back((int64_t)data.size()); len.push_back((int64_t)rec.size());
+      int32_t L = 0, has_ss = 0;
+      HHG_CHECK(hhg_hhm_scan(rec.data(), (int64_t)rec.size(), &L, &has_ss));
+      if (!has_ss) all_have_ss_ = false;
+      L_.push_back(L);
+      data += rec;
+    }
+    hhg_prep_params pp = {par.gapb, par.gapd, par.gape, par.gapf, par.gapg, par.gaph, par.gapi,
+                          par.pc_hhm_nocontext_mode, par.pc_hhm_nocontext_a, par.pc_hhm_nocontext_b,
+                          par.pc_hhm_nocontext_c};
+    HHG_CHECK(hhg_db_create_hhm(ctx_, (int)files.size(), data.data(), off.data(), len.data(), &pp, &R[0][0], &db_));
+  }
+
   std::vector<GpuHit> alignment(Parameters& par, HMMSimd* q_simd, int n_targets, float* pb,
                                 const float S33[NSSPRED][MAXCF][NSSPRED][MAXCF]) {
     HMM* q = q_simd->GetHMM(0);
@@ -177,7 +205,9 @@ uint32_t bits(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 }  // namespace
 
 int main(int argc, char** argv) {
-  if (argc < 3) { fprintf(stderr, "usage: %s query.hhm template.hhm [...]\n", argv[0]); return 2; }
+  bool text_loader = false;
+  if (argc > 1 && !strcmp(argv[1], "--hhm-loader")) { text_loader = true; --argc; ++argv; }
+  if (argc < 3) { fprintf(stderr, "usage: %s [--hhm-loader] query.hhm template.hhm [...]\n", argv[0]); return 2; }
   Log::reporting_level() = WARNING;
   const char* pargv[] = {"hhalign"};
   Parameters par(1, pargv);
@@ -218,7 +248,12 @@ int main(int argc, char** argv) {
 
   // ---- (2) the GPU adapter
   GpuViterbiRunner gpu_runner;
-  gpu_runner.Upload(par, entries, pb, S, Sim, R);
+  if (text_loader) {
+    std::vector<std::string> files(argv + 2, argv + argc);
+    gpu_runner.UploadText(par, files, R);
+  } else {
+    gpu_runner.Upload(par, entries, pb, S, Sim, R);
+  }
   std::vector<GpuHit> gpu = gpu_runner.alignment(par, &q_vec, (int)entries.size(), pb, S33);
 
   // ---- compare
@@ -246,6 +281,7 @@ int main(int argc, char** argv) {
       ++bad;
     }
   }
+  if (text_loader) printf("(templates loaded by hhg_db_create_hhm from the HHM text)\n");
   printf("hh_dropin_check: query L=%d, %zu templates, %zu hits (up to irep %d): %s\n", q->L, entries.size(), ref.size(),
          maxrep, bad ? "MISMATCH" : "all hits identical");
   return bad ? 1 : 0;

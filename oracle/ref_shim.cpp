@@ -155,6 +155,16 @@ int hhref_par_ssm() { return g->par->ssm; }
 // S33 table (for the SS variant): out[NSSPRED*MAXCF*NSSPRED*MAXCF]
 void hhref_get_S33(float* out) { memcpy(out, g->S33, sizeof(g->S33)); }
 void hhref_get_pb(float* out) { memcpy(out, g->pb, 20 * sizeof(float)); }
+// R[a][b] = P(a|b), the pseudocount matrix of SetSubstitutionMatrix (src/hhfunc.cpp), out[400]
+void hhref_get_R(float* out) { memcpy(out, g->R, 400 * sizeof(float)); }
+// the transition / aa pseudocount parameters PrepareTemplateHMM passes on (src/hhfunc.cpp:170-178)
+void hhref_get_prep_params(float* out11) {
+  Parameters& par = *g->par;
+  float v[11] = {par.gapb, par.gapd, par.gape, par.gapf, par.gapg, par.gaph, par.gapi,
+                 (float)par.pc_hhm_nocontext_mode, par.pc_hhm_nocontext_a, par.pc_hhm_nocontext_b,
+                 par.pc_hhm_nocontext_c};
+  memcpy(out11, v, sizeof(v));
+}
 
 // Read query HHM, add pseudocounts exactly like HHalign::run (src/hhalign.cpp:615-626), map to SIMD.
 int hhref_load_query_hhm(const char* path) {

@@ -102,6 +102,17 @@ def main():
     pb = np.zeros(20, np.float32)
     R.lib.hhref_get_pb(pb.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float)))
     G["pb"] = pb
+    # ---- HHM text -> prepared records (HMM::Read + the query-independent part of PrepareTemplateHMM)
+    G["R"] = R.R()
+    pp = R.prep_params()
+    G["prep_params"] = np.array([getattr(pp, f[0]) for f in pp._fields_], np.float32)
+    txt_ss = synth.hhm_text(60, 11, "ss60", with_ss=True)
+    open("/tmp/ss60.hhm", "w").write(txt_ss)
+    G["hhm_t150_text"] = np.frombuffer(txt.encode(), np.uint8)
+    G["hhm_ss60_text"] = np.frombuffer(txt_ss.encode(), np.uint8)
+    t = R.prepare_template_hhm_raw("/tmp/ss60.hhm", 1)
+    t2 = R.prepare_template_hhm("/tmp/ss60.hhm")
+    G["hhm_ss60_praw"], G["hhm_ss60_tr"], G["hhm_ss60_pav"], G["hhm_ss60_ss"] = t["p_raw"], t["tr"], t["pav"], t2["ss"]
     # ---- prefilter
     lib = R.cs219()
     G["cs219_lin"] = lib
