@@ -14,7 +14,7 @@
  *   ViterbiMatrix (backtrace bytes)     src/hhviterbimatrix.h:29   -> hhg_viterbi_debug_bt
  *   Prefilter::ungapped_sse_score       src/hhprefilter.h:108      -> hhg_prefilter_ungapped
  *   Prefilter::prefilter_db (stage 1)   src/hhprefilter.h:80       -> hhg_prefilter_ungapped
- *   Prefilter::swStripedByte            src/hhprefilter.h:104      -> hhg_prefilter_sw
+ *   Prefilter::swStripedByte            src/hhprefilter.h:112      -> hhg_prefilter_sw
  *   HHEntry::getTemplateHMM / HMM::Read src/hhdatabase.cpp:300, src/hhhmm.cpp:202 -> hhg_db_create_hhm
  *   PrepareTemplateHMM                  src/hhfunc.cpp:165         -> hhg_db_create_hhm + hhg_db_apply_null_model
  *
