@@ -36,7 +36,7 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_viterbi_search", "hhg_plan_create", "hhg_plan_destroy", "hhg_plan_run", "hhg_plan_run_timed", "hhg_plan_fetch", "hhg_plan_hits_devptr",
            "hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes", "hhg_plan_debug_bt",
            "hhg_csdb_create", "hhg_csdb_destroy", "hhg_prefilter_ungapped", "hhg_prefilter_ungapped_run",
-           "hhg_prefilter_fetch", "hhg_prefilter_build_profile", "hhg_prefilter_corrected_score",
+           "hhg_prefilter_fetch", "hhg_prefilter_select", "hhg_prefilter_build_profile", "hhg_prefilter_corrected_score",
            "hhg_prefilter_sw", "hhg_prefilter_evalue", "hhg_prefilter_corrected_scores", "hhg_prefilter_evalues"]
 
 
@@ -125,6 +125,8 @@ def load():
     L.hhg_csdb_destroy.argtypes = [C.c_void_p]
     L.hhg_prefilter_ungapped.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p, C.c_int, c_i32p]
     L.hhg_prefilter_ungapped_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p, C.c_int, C.c_int]
+    L.hhg_prefilter_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, c_i32p,
+                                       C.c_int, c_i32p]
     L.hhg_prefilter_fetch.argtypes = [C.c_void_p, C.c_void_p, c_i32p]
     L.hhg_prefilter_build_profile.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_u8p]
     L.hhg_prefilter_corrected_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -439,6 +441,15 @@ class CsDB:
         prof = np.ascontiguousarray(prof, np.uint8)
         _ck(self.ctx.L.hhg_prefilter_ungapped_run(self.ctx.h, self.h, prof.shape[1], _p(prof, c_u8p), offset,
                                                   1 if upload else 0))
+
+    def select(self, Lq, bit_factor=4, smax_thresh=10, min_hits=100):
+        """Stage-1 selection on the device after run(): (ids, corrected scores) of the survivors in the reference's
+        order (Prefilter::prefilter_db, src/hhprefilter.cpp:477-506)."""
+        cap = self.n
+        ids = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32); n = np.zeros(1, np.int32)
+        _ck(self.ctx.L.hhg_prefilter_select(self.ctx.h, self.h, Lq, bit_factor, smax_thresh, min_hits, _p(ids, c_i32p),
+                                            _p(sc, c_i32p), cap, _p(n, c_i32p)))
+        return ids[:n[0]].copy(), sc[:n[0]].copy()
 
     def fetch(self):
         sc = np.zeros(self.n, np.int32)

@@ -7,6 +7,7 @@
 #include "hhg_viterbi2.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -96,13 +97,17 @@ struct hhg_ctx {
   // prefilter
   DevBuf<uint8_t> pf_prof, sw_prof;
   DevBuf<int> sw_ids, sw_scores;
-  DevBuf<unsigned> pf_counter;
+  DevBuf<unsigned> pf_counter, pf_hist;
+  DevBuf<int> pf_corr, pf_ids_a, pf_score_a, pf_ids_b;
   size_t max_bt_bytes = 0;   // memory-wave budget for backtrace words
   struct hhg_plan* scratch_plan = nullptr;   // reused by hhg_viterbi_search
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
+static std::atomic<unsigned long long> g_db_serial{1};
+
 struct hhg_db {
+  const unsigned long long serial = g_db_serial.fetch_add(1);   // identity for plan reuse (addresses get recycled)
   int device = 0;
   int n = 0;
   long long total_cols = 0;
@@ -135,6 +140,8 @@ struct Wave {
 
 struct hhg_plan {
   const hhg_db* db = nullptr;
+  unsigned long long db_serial = 0;
+  int device = 0;
   int n = 0;            // requests
   int Lq = 0, R = 16, nstrips = 0, cols = 1;
   int njobs = 0;
@@ -639,7 +646,7 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   CK(cudaSetDevice(ctx->device));
   // the common case of a repeated request (same shard, same target list, same query geometry, e.g. every
   // query of a batch against the whole shard) reuses the plan: no host sort, no uploads
-  if (pl->db == db && pl->n == n && pl->Lq == ctx->Lq && pl->R == ctx->R && pl->cols == ctx->cols &&
+  if (pl->db == db && pl->db_serial == db->serial && pl->n == n && pl->Lq == ctx->Lq && pl->R == ctx->R && pl->cols == ctx->cols &&
       !pl->ids.empty() && pl->max_bt_bytes == ctx->max_bt_bytes) {
     bool same = true;
     if (ids) same = memcmp(ids, pl->ids.data(), (size_t)n * 4) == 0;
@@ -647,6 +654,8 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
     if (same) { pl->celloff = false; return HHG_OK; }
   }
   pl->db = db;
+  pl->db_serial = db->serial;
+  pl->device = db->device;
   pl->max_bt_bytes = ctx->max_bt_bytes;
   pl->cells = pl->padded_cells = pl->alg_bytes = 0;
   pl->waves.clear();
@@ -766,7 +775,7 @@ int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, h
 }
 
 int hhg_plan_destroy(hhg_plan* plan) {
-  if (plan) { if (plan->db) cudaSetDevice(plan->db->device); delete plan; }
+  if (plan) { if (plan->db) cudaSetDevice(plan->device); delete plan; }
   return HHG_OK;
 }
 double hhg_plan_cells(const hhg_plan* plan) { return plan ? plan->cells : 0; }
@@ -1197,6 +1206,77 @@ int hhg_prefilter_sw(hhg_ctx* ctx, const hhg_csdb* db, int n, const int32_t* ids
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(scores, ctx->sw_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));   // `striped` is a host temporary
+  return HHG_OK;
+}
+
+// Stage 1 of Prefilter::prefilter_db selected on the device (src/hhprefilter.cpp:477-506).  The raw ungapped
+// scores of the last hhg_prefilter_ungapped_run on this shard are corrected and histogrammed in one pass, the
+// cut is read off the histogram, survivors are compacted and only they travel to the host, where they are put
+// in the reference's order (descending by (score, index): comparePair + reverse, :489-490).
+int hhg_prefilter_select(hhg_ctx* ctx, const hhg_csdb* db, int Lq, int bit_factor, int smax_thresh,
+                         int min_hits, int32_t* ids, int32_t* scores, int cap, int* n_out) {
+  if (!ctx || !db || Lq < 1 || min_hits < 0 || !ids || !scores || cap < 0 || !n_out)
+    return fail(HHG_EINVAL, "hhg_prefilter_select: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const int n = db->n;
+  CK(ctx->pf_corr.ensure(n)); CK(ctx->pf_ids_a.ensure(n)); CK(ctx->pf_score_a.ensure(n)); CK(ctx->pf_ids_b.ensure(n));
+  CK(ctx->pf_hist.ensure(kPfHistBins + 2));
+  CK(cudaMemsetAsync(ctx->pf_hist.p, 0, (kPfHistBins + 2) * 4, ctx->stream));
+  const int blocks = std::min((n + 255) / 256, ctx->sm_count * 8);
+  k_pf_correct_hist<<<blocks, 256, 0, ctx->stream>>>(n, db->dL.p, db->scores.p, flog2_host((float)Lq), bit_factor,
+                                                     ctx->pf_corr.p, ctx->pf_hist.p);
+  ctx->launches++;
+  std::vector<unsigned> hist(kPfHistBins);
+  CK(cudaMemcpyAsync(hist.data(), ctx->pf_hist.p, kPfHistBins * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // keep while count < min_hits or score > smax_thresh  ==  everything above the threshold, but at least the
+  // min_hits best: cut = min(smax_thresh, score of the min_hits-th best); ties at the cut resolved by index
+  long long n_gt = 0;
+  auto bin_of = [](long long score) { return (int)std::min<long long>(std::max<long long>(score + kPfHistBias, 0), kPfHistBins - 1); };
+  if (bin_of(smax_thresh) <= 0 || bin_of(smax_thresh) >= kPfHistBins - 1)
+    return fail(HHG_EINVAL, "hhg_prefilter_select: smax_thresh %d outside the histogram range", smax_thresh);
+  for (int b = bin_of(smax_thresh) + 1; b < kPfHistBins; ++b) n_gt += hist[b];
+  int cut = smax_thresh, take_eq = 0;
+  long long want_eq = 0;
+  const long long need = std::min<long long>(min_hits, n);
+  if (n_gt < need) {
+    long long above = 0;
+    int b = kPfHistBins - 1;
+    for (; b >= 0; --b) {                         // highest score whose class completes the first `need` entries
+      if (above + hist[b] >= need) break;
+      above += hist[b];
+    }
+    if (b <= 0 || b >= kPfHistBins - 1)
+      return fail(HHG_EINVAL, "hhg_prefilter_select: corrected scores leave the histogram range");
+    cut = b - kPfHistBias; take_eq = 1; want_eq = need - above;
+  }
+  CK(cudaMemsetAsync(ctx->pf_hist.p + kPfHistBins, 0, 8, ctx->stream));
+  k_pf_compact<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->pf_corr.p, cut, take_eq, ctx->pf_ids_a.p,
+                                                         ctx->pf_score_a.p, ctx->pf_ids_b.p,
+                                                         ctx->pf_hist.p + kPfHistBins);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  unsigned cnt[2] = {0, 0};
+  CK(cudaMemcpyAsync(cnt, ctx->pf_hist.p + kPfHistBins, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t> a(cnt[0]), sa(cnt[0]), b(cnt[1]);
+  if (cnt[0]) {
+    CK(cudaMemcpyAsync(a.data(), ctx->pf_ids_a.p, (size_t)cnt[0] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(sa.data(), ctx->pf_score_a.p, (size_t)cnt[0] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (cnt[1]) CK(cudaMemcpyAsync(b.data(), ctx->pf_ids_b.p, (size_t)cnt[1] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::sort(b.begin(), b.end(), std::greater<int32_t>());        // ties at the cut: larger index first
+  if ((long long)b.size() > want_eq) b.resize((size_t)want_eq);
+  const long long total = (long long)a.size() + (long long)b.size();
+  *n_out = (int)total;
+  if (total > cap) return fail(HHG_EINVAL, "hhg_prefilter_select: %lld survivors exceed the output capacity %d", total, cap);
+  std::vector<std::pair<int32_t, int32_t>> v;                     // (score, index), descending
+  v.reserve((size_t)total);
+  for (size_t k = 0; k < a.size(); ++k) v.emplace_back(sa[k], a[k]);
+  std::sort(v.begin(), v.end(), std::greater<std::pair<int32_t, int32_t>>());
+  for (int32_t id : b) v.emplace_back(cut, id);                   // below all of list A, already index-descending
+  for (size_t k = 0; k < v.size(); ++k) { ids[k] = v[k].second; scores[k] = v[k].first; }
   return HHG_OK;
 }
 

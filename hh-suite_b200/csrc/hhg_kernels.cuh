@@ -945,4 +945,67 @@ __global__ void __launch_bounds__(256) k_prefilter_sw(const SwParams P) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Stage-1 selection of Prefilter::prefilter_db on the device (src/hhprefilter.cpp:477-506): the N raw scores
+// never travel to the host.  Pass 1 applies the length correction (:477) and histograms the corrected scores;
+// the host picks the cut from the 1024-bin histogram; pass 2 compacts the survivors.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPfHistBins = 1024;   // bin = corrected score + 512, clamped
+constexpr int kPfHistBias = 512;
+
+// flog2, src/util-inl.h:83-93 (the polynomial is evaluated in double, as the C++ expression promotes)
+__device__ __forceinline__ float flog2_dev(float x) {
+  if (x <= 0.f) return -128.f;
+  uint32_t u = __float_as_uint(x);
+  const float e = (float)((int)((u & 0x7F800000u) >> 23) - 0x7f);
+  x = __uint_as_float((u & 0x007FFFFFu) | 0x3f800000u);
+  x = __double2float_rn(__dsub_rn((double)x, 1.0));
+  const double xd = (double)x;
+  double y = __dadd_rn(-0.1903190, __dmul_rn(xd, 0.0440047));
+  y = __dadd_rn(0.4123442, __dmul_rn(xd, y));
+  y = __dadd_rn(-0.7077702, __dmul_rn(xd, y));
+  y = __dadd_rn(1.441740, __dmul_rn(xd, y));
+  x = __double2float_rn(__dmul_rn(xd, y));
+  return __fadd_rn(x, e);
+}
+
+__global__ void __launch_bounds__(256)
+k_pf_correct_hist(int n, const int* __restrict__ L, const int* __restrict__ raw, float flog2_Lq, int bit_factor,
+                  int* __restrict__ corr, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[kPfHistBins];
+  for (int b = threadIdx.x; b < kPfHistBins; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int c = raw[k] - (int)__fmul_rn((float)bit_factor, __fadd_rn(flog2_Lq, flog2_dev((float)L[k])));
+    corr[k] = c;
+    atomicAdd(&sh[min(max(c + kPfHistBias, 0), kPfHistBins - 1)], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < kPfHistBins; b += blockDim.x)
+    if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+
+// survivors: corr > cut  -> list A;  corr == cut && take_eq -> list B  (order restored by the caller's sort)
+__global__ void __launch_bounds__(256)
+k_pf_compact(int n, const int* __restrict__ corr, int cut, int take_eq, int* __restrict__ ids_a,
+             int* __restrict__ score_a, int* __restrict__ ids_b, unsigned int* __restrict__ counters) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = k < n ? corr[k] : INT_MIN;
+  const bool a = k < n && c > cut;
+  const bool b = k < n && take_eq && c == cut;
+  const unsigned ma = __ballot_sync(0xffffffffu, a), mb = __ballot_sync(0xffffffffu, b);
+  const int lane = threadIdx.x & 31;
+  unsigned base_a = 0, base_b = 0;
+  if (lane == 0) {
+    if (ma) base_a = atomicAdd(&counters[0], (unsigned)__popc(ma));
+    if (mb) base_b = atomicAdd(&counters[1], (unsigned)__popc(mb));
+  }
+  base_a = __shfl_sync(0xffffffffu, base_a, 0);
+  base_b = __shfl_sync(0xffffffffu, base_b, 0);
+  const unsigned below = (1u << lane) - 1u;
+  if (a) { const unsigned pos = base_a + __popc(ma & below); ids_a[pos] = k; score_a[pos] = c; }
+  if (b) ids_b[base_b + __popc(mb & below)] = k;
+}
+
 }  // namespace hhg

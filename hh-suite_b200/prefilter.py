@@ -20,25 +20,34 @@ from . import capi
 
 def prefilter_db(csdb: capi.CsDB, prof: np.ndarray, gap_open=20, gap_extend=4, score_offset=50, bit_factor=4,
                  evalue_thresh=1000.0, evalue_coarse_thresh=100000.0, smax_thresh=10, min_prefilter_hits=100,
-                 maxnumdb=20000, return_details=False):
+                 maxnumdb=20000, return_details=False, device_select=True):
+    """device_select=True (default): the stage-1 list is chosen on the GPU (hhg_prefilter_select: histogram +
+    compaction), only survivors cross PCIe.  False: all N raw scores are fetched and sorted on the host (the
+    formulation closest to the reference's loop; kept as the cross-check of the device path)."""
     L = capi.load()
     Lq = prof.shape[1]
     n = csdb.n
-    raw = csdb.ungapped(prof, score_offset)
     lens = csdb.Lh
     import ctypes as C
-    corr32 = np.zeros(n, np.int32)
-    raw32 = np.ascontiguousarray(raw, np.int32)
     lens32 = np.ascontiguousarray(lens, np.int32)
-    capi._ck(L.hhg_prefilter_corrected_scores(n, capi._p(raw32, capi.c_i32p), capi._p(lens32, capi.c_i32p), Lq,
-                                             bit_factor, capi._p(corr32, capi.c_i32p)))
-    corr = corr32.astype(np.int64)
-    order = np.lexsort((np.arange(n), corr))[::-1]          # descending (score, n)
-    # keep while count < min_prefilter_hits or score > smax_thresh: first position (>= min hits) whose
-    # score is <= smax_thresh ends the list
-    stop = np.nonzero(corr[order[min_prefilter_hits:]] <= smax_thresh)[0]
-    ncut = min_prefilter_hits + int(stop[0]) if len(stop) else n
-    first = order[:min(ncut, n)].astype(np.int32)
+    raw = corr = None
+    if device_select:
+        csdb.run(prof, score_offset)
+        first, first_scores = csdb.select(Lq, bit_factor, smax_thresh, min_prefilter_hits)
+    else:
+        raw = csdb.ungapped(prof, score_offset)
+        corr32 = np.zeros(n, np.int32)
+        raw32 = np.ascontiguousarray(raw, np.int32)
+        capi._ck(L.hhg_prefilter_corrected_scores(n, capi._p(raw32, capi.c_i32p), capi._p(lens32, capi.c_i32p), Lq,
+                                                 bit_factor, capi._p(corr32, capi.c_i32p)))
+        corr = corr32.astype(np.int64)
+        order = np.lexsort((np.arange(n), corr))[::-1]          # descending (score, n)
+        # keep while count < min_prefilter_hits or score > smax_thresh: first position (>= min hits) whose
+        # score is <= smax_thresh ends the list
+        stop = np.nonzero(corr[order[min_prefilter_hits:]] <= smax_thresh)[0]
+        ncut = min_prefilter_hits + int(stop[0]) if len(stop) else n
+        first = order[:min(ncut, n)].astype(np.int32)
+        first_scores = corr32[first]
     sw = csdb.sw(prof, ids=first, gap_open=gap_open + gap_extend, gap_extend=gap_extend, bias=score_offset) \
         if len(first) else np.zeros(0, np.int32)
     ev = np.zeros(len(first), np.float64)
@@ -57,5 +66,5 @@ def prefilter_db(csdb: capi.CsDB, prof: np.ndarray, gap_open=20, gap_extend=4, s
     out = out[:maxnumdb]
     ids = first[out] if len(out) else np.zeros(0, np.int32)
     if return_details:
-        return ids, dict(raw=raw, corrected=corr, first=first, sw=sw, evalue=ev)
+        return ids, dict(raw=raw, corrected=corr, first=first, first_scores=first_scores, sw=sw, evalue=ev)
     return ids

@@ -208,6 +208,13 @@ int hhg_prefilter_ungapped(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const uint8
 int hhg_prefilter_ungapped_run(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const uint8_t* prof_host,
                                int offset, int upload_profile);
 int hhg_prefilter_fetch(hhg_ctx* ctx, const hhg_csdb* db, int32_t* scores);
+/* Stage-1 selection of Prefilter::prefilter_db on the device (src/hhprefilter.cpp:477-506), after
+ * hhg_prefilter_ungapped_run: length correction score -= (int)(bit_factor*(flog2(Lq)+flog2(Lt))) (:477), then the
+ * list sorted descending by (score, index) (:489-490) is kept "while count < min_hits or score > smax_thresh"
+ * (:494-506).  Only the survivors leave the GPU (histogram + compaction; no N-element transfer or host sort).
+ * ids/scores[cap] receive them in the reference's order, *n_out their number (HHG_EINVAL if it exceeds cap). */
+int hhg_prefilter_select(hhg_ctx* ctx, const hhg_csdb* db, int Lq, int bit_factor, int smax_thresh,
+                         int min_hits, int32_t* ids, int32_t* scores, int cap, int* n_out);
 
 /* Host-side, once per query: the 220 x Lq byte profile of Prefilter::stripe_query_profile
  * (src/hhprefilter.cpp:356-424) in linear layout prof[k*Lq+pos].  q_p = HMM::p of the query

@@ -146,7 +146,10 @@ def test_prefilter_db_selection(hhg, gpu_ctx, oracle):
     seqs = [seqs[i] for i in perm]
     db = _db(hhg, gpu_ctx, seqs)
     kw = dict(min_prefilter_hits=20, smax_thresh=10, evalue_thresh=1000.0, evalue_coarse_thresh=100000.0, maxnumdb=40)
-    ids, det = hhg.prefilter.prefilter_db(db, prof, return_details=True, **kw)
+    ids, det = hhg.prefilter.prefilter_db(db, prof, return_details=True, device_select=False, **kw)
+    ids_dev, det_dev = hhg.prefilter.prefilter_db(db, prof, return_details=True, device_select=True, **kw)
+    assert ids_dev.tolist() == ids.tolist() and det_dev["first"].tolist() == det["first"].tolist()
+    assert det_dev["first_scores"].tolist() == det["first_scores"].tolist()
     n = len(seqs)
     raw = np.array([oracle.ungapped(prof, s, 50) for s in seqs])
     assert np.array_equal(det["raw"], raw)
@@ -172,4 +175,54 @@ def test_prefilter_db_selection(hhg, gpu_ctx, oracle):
     assert ids.tolist() == out[:40]
     planted = set(np.nonzero(perm >= 600)[0].tolist())
     assert planted <= set(ids.tolist()[:40]) or len(planted & set(ids.tolist())) >= 20
+    db.close()
+
+
+@pytest.mark.parametrize("case", ["many_above", "few_above_ties", "tiny_db", "all_tied"])
+def test_stage1_selection_on_device(hhg, gpu_ctx, oracle, case):
+    """hhg_prefilter_select (histogram + compaction on the GPU) against the reference's rule applied to oracle
+    scores: sort descending by (score, index), keep while count < min_hits or score > smax_thresh
+    (src/hhprefilter.cpp:489-506).  Cases: more survivors than min_hits; fewer (the cut falls into a class of tied
+    scores, resolved by index); a shard smaller than min_hits; every sequence identical."""
+    G = golden()
+    prof = G["pf_prof"]
+    Lq = prof.shape[1]
+    rng = np.random.default_rng({"many_above": 1, "few_above_ties": 2, "tiny_db": 3, "all_tied": 4}[case])
+    best = prof[:219].argmax(axis=0).astype(np.uint8)
+    if case == "many_above":
+        seqs = [rng.integers(0, 219, L, dtype=np.uint8) for L in rng.integers(30, 400, 3000)] + _homologs(rng, best, 150)
+        min_hits, thresh = 100, 10
+    elif case == "few_above_ties":
+        base = [rng.integers(0, 219, 120, dtype=np.uint8) for _ in range(8)]
+        seqs = [base[int(rng.integers(0, 8))] for _ in range(2500)] + _homologs(rng, best, 7)    # 8 score classes
+        min_hits, thresh = 300, 10
+    elif case == "tiny_db":
+        seqs = [rng.integers(0, 219, L, dtype=np.uint8) for L in rng.integers(30, 200, 37)]
+        min_hits, thresh = 100, 10
+    else:
+        one = rng.integers(0, 219, 150, dtype=np.uint8)
+        seqs = [one] * 1000
+        min_hits, thresh = 64, 10
+    perm = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in perm]
+    db = _db(hhg, gpu_ctx, seqs)
+    db.run(prof, 50)
+    ids, sc = db.select(Lq, 4, thresh, min_hits)
+    cache = {}
+    def score(s):
+        key = s.tobytes()
+        if key not in cache:
+            cache[key] = oracle.lib.hho_ungapped_corrected(oracle.ungapped(prof, s, 50), Lq, len(s), 4)
+        return cache[key]
+    corr = [score(s) for s in seqs]
+    order = sorted(range(len(seqs)), key=lambda k: (corr[k], k), reverse=True)
+    want = []
+    for k in order:
+        if len(want) >= min_hits and corr[k] <= thresh:
+            break
+        want.append(k)
+    assert ids.tolist() == want
+    assert sc.tolist() == [corr[k] for k in want]
+    if case == "few_above_ties":
+        assert len(want) == min_hits and corr[want[-1]] <= thresh       # the tie class really was cut by index
     db.close()

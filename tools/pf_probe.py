@@ -10,6 +10,20 @@ import hhsuite_b200 as hh  # noqa: E402
 from hhsuite_b200 import synth  # noqa: E402
 
 
+def _host_select(hh, db, lq):
+    raw = db.fetch()
+    L = hh.capi.load()
+    corr = np.zeros(db.n, np.int32)
+    hh.capi._ck(L.hhg_prefilter_corrected_scores(db.n, hh.capi._p(np.ascontiguousarray(raw, np.int32), hh.capi.c_i32p),
+                                                hh.capi._p(np.ascontiguousarray(db.Lh, np.int32), hh.capi.c_i32p), lq, 4,
+                                                hh.capi._p(corr, hh.capi.c_i32p)))
+    order = np.lexsort((np.arange(db.n), corr))[::-1]
+    stop = np.nonzero(corr[order[100:]] <= 10)[0]
+    ncut = 100 + int(stop[0]) if len(stop) else db.n
+    first = order[:ncut]
+    return first, corr[first]
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
     lq = int(sys.argv[2]) if len(sys.argv) > 2 else 400
@@ -33,6 +47,25 @@ def main():
     sc = db.fetch()
     print(f"prefilter ungapped: n={n} Lq={lq} {ms:.3f} ms  {cells / ms / 1e9:.2f} Tcells/s  "
           f"({float(cs['L'].sum()) / ms / 1e6:.1f} GB/s of cs219 bytes) max score {sc.max()} mean {sc.mean():.1f}")
+    # a real query profile (golden: data/query.hhm, Lq=431) so that scores spread like a real search
+    G = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "golden_v1.npz"))
+    rprof = np.ascontiguousarray(G["pf_prof"])
+    lq_r = rprof.shape[1]
+    db.run(rprof, 50, upload=True)
+    ctx.sync()
+    lq_saved, lq = lq, lq_r
+    # stage-1 selection: device (histogram + compaction) vs host (fetch N scores, correct, sort), wall clock
+    for name, fn in (("device select", lambda: db.select(lq, 4, 10, 100)),
+                     ("host fetch+sort", lambda: _host_select(hh, db, lq))):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            r = fn()
+        dt = (time.perf_counter() - t0) / 3
+        print(f"stage-1 selection (real profile Lq={lq}), {name}: {dt * 1e3:.2f} ms, {len(r[0])} survivors")
+    lq = lq_saved
+    db.run(prof, 50, upload=True)
+    ctx.sync()
     try:
         from oracle.binding import RefShim
         R = RefShim()
