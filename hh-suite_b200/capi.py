@@ -36,7 +36,8 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_viterbi_search", "hhg_plan_create", "hhg_plan_destroy", "hhg_plan_run", "hhg_plan_run_timed", "hhg_plan_fetch", "hhg_plan_hits_devptr",
            "hhg_plan_cells", "hhg_plan_padded_cells", "hhg_plan_algorithmic_bytes", "hhg_plan_debug_bt",
            "hhg_csdb_create", "hhg_csdb_destroy", "hhg_prefilter_ungapped", "hhg_prefilter_ungapped_run",
-           "hhg_prefilter_fetch", "hhg_prefilter_select", "hhg_prefilter_build_profile", "hhg_prefilter_corrected_score",
+           "hhg_prefilter_fetch", "hhg_prefilter_select", "hhg_log2lin", "hhg_mac_query_set", "hhg_mac_realign",
+           "hhg_mac_debug_posterior", "hhg_prefilter_build_profile", "hhg_prefilter_corrected_score",
            "hhg_prefilter_sw", "hhg_prefilter_evalue", "hhg_prefilter_corrected_scores", "hhg_prefilter_evalues"]
 
 
@@ -57,6 +58,17 @@ COLREC_DTYPE = np.dtype([("p", np.float32, 20), ("m2m", np.float32), ("m2d", np.
                          ("d2d", np.float32), ("i2m", np.float32), ("i2i", np.float32), ("m2i", np.float32),
                          ("ss", np.uint32)])
 assert COLREC_DTYPE.itemsize == 112
+
+
+class MacParams(C.Structure):
+    """hhg_mac_params: par.loc, par.shift, par.mact."""
+    _fields_ = [("local", C.c_int32), ("shift", C.c_float), ("mact", C.c_float)]
+
+
+MAC_HIT_DTYPE = np.dtype([("i1", np.int32), ("i2", np.int32), ("j1", np.int32), ("j2", np.int32), ("nsteps", np.int32),
+                          ("matched_cols", np.int32), ("sum_of_probs", np.float32), ("flags", np.int32),
+                          ("pforward", np.float64), ("path_off", np.int64)])
+assert MAC_HIT_DTYPE.itemsize == 48
 
 
 class HhgError(RuntimeError):
@@ -127,6 +139,12 @@ def load():
     L.hhg_prefilter_ungapped_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p, C.c_int, C.c_int]
     L.hhg_prefilter_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, c_i32p,
                                        C.c_int, c_i32p]
+    L.hhg_log2lin.argtypes = [C.c_int64, c_f32p, c_f32p]
+    L.hhg_mac_query_set.argtypes = [C.c_void_p, C.c_int, c_f32p, c_f32p]
+    L.hhg_mac_realign.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, c_i32p, c_i64p, c_i32p, c_i32p, c_i64p,
+                                  c_i32p, c_i32p, C.POINTER(MacParams), C.c_void_p, c_i32p, c_i32p, c_u8p, c_f32p,
+                                  C.c_size_t]
+    L.hhg_mac_debug_posterior.argtypes = [C.c_void_p, C.c_int, c_f32p]
     L.hhg_prefilter_fetch.argtypes = [C.c_void_p, C.c_void_p, c_i32p]
     L.hhg_prefilter_build_profile.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_u8p]
     L.hhg_prefilter_corrected_score.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -182,6 +200,70 @@ class Context:
         _ck(self.L.hhg_query_set(self.h, Lq, _p(p, c_f32p), _p(tr, c_f32p), _p(ss, c_u8p), _p(S33, c_f32p),
                                  C.byref(par)))
         self.Lq = Lq
+
+
+def log2lin(tr):
+    """HMM::Log2LinTransitionProbs(1.0) on a host array (through the C library's pow, like the reference)."""
+    tr = np.ascontiguousarray(tr, np.float32)
+    out = np.empty_like(tr)
+    _ck(load().hhg_log2lin(tr.size, _p(tr, c_f32p), _p(out, c_f32p)))
+    return out
+
+
+def mac_query_set(ctx, q_p, q_tr_lin):
+    """Query for MAC realignment: HMM::p and the LINEAR transitions (log2lin(q_tr))."""
+    q_p = np.ascontiguousarray(q_p, np.float32); q_tr_lin = np.ascontiguousarray(q_tr_lin, np.float32)
+    Lq = q_p.shape[0] - 2
+    assert q_tr_lin.shape == (Lq + 1, 7)
+    _ck(ctx.L.hhg_mac_query_set(ctx.h, Lq, _p(q_p, c_f32p), _p(q_tr_lin, c_f32p)))
+    ctx.mac_Lq = Lq
+
+
+def mac_realign(ctx, db, targets, vits, excl=None, local=True, shift=-0.03, mact=0.35):
+    """PosteriorDecoder::realign for a batch of hits.  vits[r] = (i1, i2, j1, j2, nsteps, i_steps, j_steps) with
+    1-based step arrays (Hit.i / Hit.j); excl[r] = (alt_i, alt_j) of earlier MAC alignments of that template or None.
+    Returns (hits[MAC_HIT_DTYPE], list of dict(i, j, states, P_posterior) with 1-based step arrays)."""
+    n = len(targets)
+    targets = np.ascontiguousarray(targets, np.int32)
+    vit = np.zeros((n, 5), np.int32)
+    voff = np.zeros(n + 1, np.int64)
+    for r, v in enumerate(vits):
+        vit[r] = v[:5]
+        voff[r + 1] = voff[r] + v[4]
+    vi = np.zeros(max(int(voff[-1]), 1), np.int32); vj = np.zeros_like(vi)
+    for r, v in enumerate(vits):
+        ns = v[4]
+        vi[voff[r]:voff[r + 1]] = np.asarray(v[5])[1:ns + 1]
+        vj[voff[r]:voff[r + 1]] = np.asarray(v[6])[1:ns + 1]
+    eoff = ei = ej = None
+    if excl is not None:
+        eoff = np.zeros(n + 1, np.int64)
+        for r, e in enumerate(excl):
+            eoff[r + 1] = eoff[r] + (len(e[0]) if e is not None else 0)
+        ei = np.zeros(max(int(eoff[-1]), 1), np.int32); ej = np.zeros_like(ei)
+        for r, e in enumerate(excl):
+            if e is not None and len(e[0]):
+                ei[eoff[r]:eoff[r + 1]] = e[0]; ej[eoff[r]:eoff[r + 1]] = e[1]
+    cap = int(np.sum(ctx.mac_Lq + db.Lh[np.clip(targets, 0, db.n - 1)].astype(np.int64) + 2))
+    hits = np.zeros(n, MAC_HIT_DTYPE)
+    oi = np.zeros(cap, np.int32); oj = np.zeros(cap, np.int32); os_ = np.zeros(cap, np.uint8); op = np.zeros(cap, np.float32)
+    pp = MacParams(1 if local else 0, shift, mact)
+    _ck(ctx.L.hhg_mac_realign(ctx.h, db.h, n, _p(targets, c_i32p), _p(vit, c_i32p), _p(voff, c_i64p), _p(vi, c_i32p),
+                              _p(vj, c_i32p), _p(eoff, c_i64p), _p(ei, c_i32p), _p(ej, c_i32p), C.byref(pp),
+                              hits.ctypes.data_as(C.c_void_p), _p(oi, c_i32p), _p(oj, c_i32p), _p(os_, c_u8p),
+                              _p(op, c_f32p), cap))
+    paths = []
+    for r in range(n):
+        o, ns = int(hits["path_off"][r]), int(hits["nsteps"][r])
+        paths.append(dict(i=oi[o:o + ns + 1].copy(), j=oj[o:o + ns + 1].copy(), states=os_[o:o + ns + 1].copy(),
+                          P_posterior=op[o:o + ns + 1].copy()))
+    return hits, paths
+
+
+def mac_debug_posterior(ctx, request, Lt):
+    out = np.zeros((ctx.mac_Lq + 1, Lt + 1), np.float32)
+    _ck(ctx.L.hhg_mac_debug_posterior(ctx.h, request, _p(out, c_f32p)))
+    return out
 
 
 def hhm_scan(record: bytes):

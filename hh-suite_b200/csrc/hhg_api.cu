@@ -4,6 +4,7 @@
 #include "../../include/hhg.h"
 #include "hhg_kernels.cuh"
 #include "hhg_hhm.cuh"
+#include "hhg_mac.cuh"
 #include "hhg_viterbi2.cuh"
 
 #include <algorithm>
@@ -99,6 +100,16 @@ struct hhg_ctx {
   DevBuf<int> sw_ids, sw_scores;
   DevBuf<unsigned> pf_counter, pf_hist;
   DevBuf<int> pf_corr, pf_ids_a, pf_score_a, pf_ids_b;
+  // MAC realignment (hhg_mac_*): query in linear transition space + grow-only scratch of the last call
+  int mac_Lq = 0;
+  DevBuf<float> mac_qp, mac_qtr, mac_ttr, mac_post, mac_out_post;
+  DevBuf<uint8_t> mac_off, mac_bt, mac_out_states;
+  DevBuf<double> mac_rows, mac_scale;
+  DevBuf<long long> mac_i64;
+  DevBuf<int> mac_i32, mac_out_i, mac_out_j, mac_flag;
+  DevBuf<MacHitOut> mac_out;
+  std::vector<long long> mac_cell_off;   // of the last call (debug fetch)
+  std::vector<int> mac_Lt;
   size_t max_bt_bytes = 0;   // memory-wave budget for backtrace words
   struct hhg_plan* scratch_plan = nullptr;   // reused by hhg_viterbi_search
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1002,6 +1013,168 @@ int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids
   if (rc == HHG_OK) rc = hhg_plan_run(ctx, pl);
   if (rc == HHG_OK) rc = hhg_plan_fetch(ctx, pl, hits, paths, paths_cap);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------ MAC realignment
+// HMM::Log2LinTransitionProbs(1.0) (src/hhhmm.cpp:2305-2313) for host arrays: tr = pow(2.0f, 1.0f * tr), which with
+// float arguments is the C library's powf.  Host only.
+int hhg_log2lin(int64_t n, const float* in, float* out) {
+  if (n < 0 || !in || !out) return fail(HHG_EINVAL, "hhg_log2lin: bad argument");
+  for (int64_t k = 0; k < n; ++k) out[k] = ::powf(2.0f, 1.0f * in[k]);
+  return HHG_OK;
+}
+
+int hhg_mac_query_set(hhg_ctx* ctx, int Lq, const float* q_p, const float* q_tr_lin) {
+  if (!ctx || Lq < 1 || Lq > 32767 || !q_p || !q_tr_lin) return fail(HHG_EINVAL, "hhg_mac_query_set: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<float> tr(q_tr_lin, q_tr_lin + (size_t)(Lq + 1) * 7);
+  // PosteriorDecoderRunner::initializeQueryHMMTransitions, src/hhposteriordecoderrunner.cpp:145-155
+  // (enum order M2M,M2I,M2D,I2M,I2I,D2M,D2D)
+  tr[1] = tr[2] = tr[3] = tr[4] = tr[5] = tr[6] = 0.0f;
+  float* e = tr.data() + (size_t)Lq * 7;
+  e[0] = 1.0f; e[1] = e[2] = e[3] = e[4] = 0.0f; e[5] = 1.0f; e[6] = 0.0f;
+  CK(ctx->mac_qp.ensure((size_t)(Lq + 2) * 20)); CK(ctx->mac_qtr.ensure(tr.size()));
+  CK(cudaMemcpyAsync(ctx->mac_qp.p, q_p, (size_t)(Lq + 2) * 80, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->mac_qtr.p, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->mac_Lq = Lq;
+  return HHG_OK;
+}
+
+int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target, const int32_t* vit,
+                    const int64_t* vit_off, const int32_t* vit_i, const int32_t* vit_j, const int64_t* excl_off,
+                    const int32_t* excl_i, const int32_t* excl_j, const hhg_mac_params* par, hhg_mac_hit* hits,
+                    int32_t* out_i, int32_t* out_j, uint8_t* out_states, float* out_post, size_t path_cap) {
+  if (!ctx || !db || n <= 0 || !target || !vit || !vit_off || !vit_i || !vit_j || !par || !hits || !out_i || !out_j ||
+      !out_states || !out_post)
+    return fail(HHG_EINVAL, "hhg_mac_realign: bad argument");
+  if (ctx->mac_Lq <= 0) return fail(HHG_EINVAL, "hhg_mac_realign: call hhg_mac_query_set first");
+  if (!db->prepared) return fail(HHG_EINVAL, "hhg_mac_realign: shard has no null model applied");
+  if (excl_off && (!excl_i || !excl_j)) return fail(HHG_EINVAL, "hhg_mac_realign: excl_off without excl_i/excl_j");
+  CK(cudaSetDevice(ctx->device));
+  const int Lq = ctx->mac_Lq;
+  static_assert(sizeof(MacHitOut) == sizeof(hhg_mac_hit), "hhg_mac_hit layout");
+  std::vector<long long> rec0(n), tr_off(n), cell_off(n), row_off(n), path_off(n);
+  std::vector<int> Lt(n);
+  long long ntr = 0, ncell = 0, nrow = 0, npath = 0;
+  for (int r = 0; r < n; ++r) {
+    const int t = target[r];
+    if (t < 0 || t >= db->n) return fail(HHG_EINVAL, "request %d: target id %d out of range", r, t);
+    const int L = db->L[t];
+    const int32_t* v = vit + (size_t)r * 5;
+    const long long ns = vit_off[r + 1] - vit_off[r];
+    if (v[4] != ns || ns < 0) return fail(HHG_EINVAL, "request %d: nsteps %d but %lld path entries", r, v[4], ns);
+    if (v[0] < 1 || v[1] > Lq || v[0] > v[1] || v[2] < 1 || v[3] > L || v[2] > v[3])
+      return fail(HHG_EINVAL, "request %d: Viterbi end points (%d-%d, %d-%d) outside 1..%d x 1..%d", r, v[0], v[1], v[2], v[3], Lq, L);
+    for (long long s = vit_off[r]; s < vit_off[r + 1]; ++s)
+      if (vit_i[s] < 1 || vit_i[s] > Lq || vit_j[s] < 1 || vit_j[s] > L)
+        return fail(HHG_EINVAL, "request %d: Viterbi path leaves the matrix", r);
+    if (excl_off)
+      for (long long s = excl_off[r]; s < excl_off[r + 1]; ++s)
+        if (excl_i[s] < 1 || excl_i[s] > Lq || excl_j[s] < 1 || excl_j[s] > L)
+          return fail(HHG_EINVAL, "request %d: excluded alignment leaves the matrix", r);
+    rec0[r] = db->col_off[t]; Lt[r] = L;
+    tr_off[r] = ntr; ntr += (long long)(L + 1) * 7;
+    cell_off[r] = ncell; ncell += (long long)(Lq + 1) * (L + 1);
+    row_off[r] = nrow; nrow += 10LL * (L + 3);
+    path_off[r] = npath; npath += (long long)Lq + L + 2;
+  }
+  if ((size_t)npath > path_cap) return fail(HHG_EINVAL, "hhg_mac_realign: path buffers hold %zu entries, %lld needed", path_cap, npath);
+  const long long nvit = vit_off[n], nexcl = excl_off ? excl_off[n] : 0;
+  // device staging: one int64 block {rec0, tr_off, cell_off, row_off, path_off, vit_off[n+1], excl_off[n+1]},
+  // one int32 block {Lt, vit[5n], vit_i, vit_j, excl_i, excl_j}
+  std::vector<long long> h64;
+  h64.insert(h64.end(), rec0.begin(), rec0.end());
+  h64.insert(h64.end(), tr_off.begin(), tr_off.end());
+  h64.insert(h64.end(), cell_off.begin(), cell_off.end());
+  h64.insert(h64.end(), row_off.begin(), row_off.end());
+  h64.insert(h64.end(), path_off.begin(), path_off.end());
+  for (int r = 0; r <= n; ++r) h64.push_back(vit_off[r] - vit_off[0]);
+  for (int r = 0; r <= n; ++r) h64.push_back(excl_off ? excl_off[r] - excl_off[0] : 0);
+  std::vector<int> h32;
+  h32.insert(h32.end(), Lt.begin(), Lt.end());
+  h32.insert(h32.end(), vit, vit + (size_t)n * 5);
+  h32.insert(h32.end(), vit_i + vit_off[0], vit_i + vit_off[0] + nvit);
+  h32.insert(h32.end(), vit_j + vit_off[0], vit_j + vit_off[0] + nvit);
+  if (excl_off) {
+    h32.insert(h32.end(), excl_i + excl_off[0], excl_i + excl_off[0] + (nexcl - excl_off[0]));
+    h32.insert(h32.end(), excl_j + excl_off[0], excl_j + excl_off[0] + (nexcl - excl_off[0]));
+  }
+  const long long nex = excl_off ? nexcl - excl_off[0] : 0;
+  CK(ctx->mac_i64.ensure(h64.size())); CK(ctx->mac_i32.ensure(h32.size()));
+  CK(ctx->mac_ttr.ensure((size_t)ntr)); CK(ctx->mac_post.ensure((size_t)ncell)); CK(ctx->mac_off.ensure((size_t)ncell));
+  CK(ctx->mac_bt.ensure((size_t)ncell)); CK(ctx->mac_rows.ensure((size_t)nrow)); CK(ctx->mac_scale.ensure((size_t)n * (Lq + 3)));
+  CK(ctx->mac_out.ensure(n)); CK(ctx->mac_out_i.ensure((size_t)npath)); CK(ctx->mac_out_j.ensure((size_t)npath));
+  CK(ctx->mac_out_states.ensure((size_t)npath)); CK(ctx->mac_out_post.ensure((size_t)npath));
+  CK(cudaMemcpyAsync(ctx->mac_i64.p, h64.data(), h64.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->mac_i32.p, h32.data(), h32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->mac_bt.p, 0, (size_t)ncell, ctx->stream));
+  const long long* d64 = ctx->mac_i64.p;
+  const int* d32 = ctx->mac_i32.p;
+  MacArgs A{};
+  A.n = n; A.Lq = Lq; A.local = par->local ? 1 : 0; A.mact = par->mact;
+  A.Cshift = ::pow(2.0, par->shift);                       // src/hhforwardalgorithm.cpp:16
+  A.q_p = ctx->mac_qp.p; A.q_tr = ctx->mac_qtr.p;
+  A.cols = reinterpret_cast<const ColRec*>(db->cols.p);
+  A.rec0 = d64; A.tr_off = d64 + n; A.cell_off = d64 + 2 * n; A.row_off = d64 + 3 * n; A.path_off = const_cast<long long*>(d64 + 4 * n);
+  A.vit_off = d64 + 5 * n; A.excl_off = excl_off ? d64 + 5 * n + (n + 1) : nullptr;
+  A.Lt = d32; A.vit = d32 + n; A.vit_i = d32 + 6 * n; A.vit_j = d32 + 6 * n + nvit;
+  A.excl_i = d32 + 6 * n + 2 * nvit; A.excl_j = d32 + 6 * n + 2 * nvit + nex;
+  A.t_tr = ctx->mac_ttr.p;
+  A.post = ctx->mac_post.p; A.off = ctx->mac_off.p; A.bt = ctx->mac_bt.p; A.rows = ctx->mac_rows.p;
+  A.scale = ctx->mac_scale.p; A.out = ctx->mac_out.p;
+  A.out_i = ctx->mac_out_i.p; A.out_j = ctx->mac_out_j.p; A.out_states = ctx->mac_out_states.p; A.out_post = ctx->mac_out_post.p;
+  // template transitions in linear space: gather the log2 rows on the device, powf on the host (a few threads),
+  // boundary rows as initializeForAlignment sets them, back to the device
+  k_mac_gather_tr<<<dim3(8, n), 128, 0, ctx->stream>>>(n, A.cols, A.rec0, A.Lt, A.tr_off, ctx->mac_ttr.p);
+  ctx->launches++;
+  {
+    std::vector<float> htr((size_t)ntr);
+    CK(cudaMemcpyAsync(htr.data(), ctx->mac_ttr.p, (size_t)ntr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto work = [&](unsigned w) {
+      for (int r = (int)w; r < n; r += (int)hw) {
+        float* tr = htr.data() + tr_off[r];
+        const int L = Lt[r];
+        for (int i = 1; i < L; ++i)
+          for (int k = 0; k < 7; ++k) tr[(size_t)i * 7 + k] = ::powf(2.0f, 1.0f * tr[(size_t)i * 7 + k]);
+        float* b = tr;                 // t.tr[0]: M2M = 1, everything else 0
+        b[0] = 1.0f; b[1] = b[2] = b[3] = b[4] = b[5] = b[6] = 0.0f;
+        float* e = tr + (size_t)L * 7; // t.tr[L]: M2M = D2M = 1
+        e[0] = 1.0f; e[1] = e[2] = e[3] = e[4] = 0.0f; e[5] = 1.0f; e[6] = 0.0f;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < hw; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (auto& th : pool) th.join();
+    CK(cudaMemcpyAsync(ctx->mac_ttr.p, htr.data(), (size_t)ntr * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  k_mac_band<<<n, 256, 0, ctx->stream>>>(A);
+  k_mac_realign<<<n, 32, 0, ctx->stream>>>(A);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hits, ctx->mac_out.p, (size_t)n * sizeof(MacHitOut), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_i, ctx->mac_out_i.p, (size_t)npath * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_j, ctx->mac_out_j.p, (size_t)npath * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_states, ctx->mac_out_states.p, (size_t)npath, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_post, ctx->mac_out_post.p, (size_t)npath * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->mac_cell_off = cell_off;
+  ctx->mac_Lt = Lt;
+  return HHG_OK;
+}
+
+int hhg_mac_debug_posterior(hhg_ctx* ctx, int request, float* out) {
+  if (!ctx || !out || request < 0 || request >= (int)ctx->mac_cell_off.size())
+    return fail(HHG_EINVAL, "hhg_mac_debug_posterior: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const size_t cells = (size_t)(ctx->mac_Lq + 1) * (ctx->mac_Lt[request] + 1);
+  CK(cudaMemcpyAsync(out, ctx->mac_post.p + ctx->mac_cell_off[request], cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HHG_OK;
 }
 
 // ------------------------------------------------------------------------------------ prefilter

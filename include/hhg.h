@@ -195,6 +195,47 @@ double hhg_plan_algorithmic_bytes(const hhg_plan* plan);
  * ViterbiMatrix cell format, row-major bt[i*(Lt+1)+j] (host buffer of (Lq+1)*(Lt+1) bytes). */
 int hhg_plan_debug_bt(hhg_ctx* ctx, hhg_plan* plan, int k, uint8_t* bt);
 
+/* ---- MAC realignment of reported hits (the step after Viterbi) -------------------------------
+ * Replaces PosteriorDecoder::realign (src/hhposteriordecoder.cpp:85-118) for a batch of hits of one query:
+ * cell-off band around each hit's Viterbi path (maskViterbiAlignment :207-237) minus earlier MAC alignments of the
+ * same template (excludeMACAlignment :242-258), Forward / Backward in double with the reference's row scaling
+ * (src/hhforwardalgorithm.cpp, src/hhbackwardalgorithm.cpp), the MAC dynamic programme over posterior - mact
+ * (src/hhmacalgorithm.cpp) and its backtrace (src/hhbacktracemac.cpp:112-210).  One warp per hit; every value is
+ * computed with the reference's operation order and types, so posteriors, Pforward and paths are bit-identical.
+ * Not covered: the secondary-structure term (hit.ssm2 != 0), self-alignment (hit.self), exclstr regions.
+ *
+ * hhg_mac_query_set: q_p = HMM::p of the query, q_tr_lin = HMM::tr after Log2LinTransitionProbs(1.0)
+ *   (src/hhposteriordecoderrunner.cpp:48); the boundary rows are reset here like initializeQueryHMMTransitions.
+ * hhg_mac_realign, request r: target[r] = shard id (its records and transitions come from the resident shard; the
+ *   linear transition probabilities are powf() of the shard's log2 values, computed by the host libm like the
+ *   reference's HMM::Log2LinTransitionProbs);
+ *   vit[5r..] = i1,i2,j1,j2,nsteps and vit_i/vit_j[vit_off[r] .. vit_off[r+1]) = Hit.i / Hit.j of steps 1..nsteps of
+ *   the Viterbi alignment; excl_*: the (i,j) pairs of all earlier MAC alignments of this template (Hit.alt_i /
+ *   alt_j, concatenated), or excl_off == NULL.
+ * Outputs: hits[r]; the MAC path of request r sits at path_off..path_off+nsteps in out_i/out_j/out_states/out_post
+ *   (index 0 unused, states 2 = MM, 4 = IM, 6 = MI; out_post = Hit.P_posterior).  path_cap >= sum(Lq + Lt + 2). */
+typedef struct hhg_mac_params {
+  int32_t local; /* par.loc   */
+  float shift;   /* par.shift */
+  float mact;    /* par.mact  */
+} hhg_mac_params;
+typedef struct hhg_mac_hit {
+  int32_t i1, i2, j1, j2, nsteps, matched_cols;
+  float sum_of_probs; /* Hit.sum_of_probs */
+  int32_t flags;
+  double pforward;    /* Hit.Pforward     */
+  int64_t path_off;
+} hhg_mac_hit;
+/* Host only: HMM::Log2LinTransitionProbs(1.0), src/hhhmm.cpp:2305-2313, on n values. */
+int hhg_log2lin(int64_t n, const float* in, float* out);
+int hhg_mac_query_set(hhg_ctx* ctx, int Lq, const float* q_p, const float* q_tr_lin);
+int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target, const int32_t* vit,
+                    const int64_t* vit_off, const int32_t* vit_i, const int32_t* vit_j, const int64_t* excl_off,
+                    const int32_t* excl_i, const int32_t* excl_j, const hhg_mac_params* par, hhg_mac_hit* hits,
+                    int32_t* out_i, int32_t* out_j, uint8_t* out_states, float* out_post, size_t path_cap);
+/* Debug / parity: the posterior matrix of request `request` of the last hhg_mac_realign, (Lq+1) x (Lt+1) floats. */
+int hhg_mac_debug_posterior(hhg_ctx* ctx, int request, float* out);
+
 /* ---- cs219 ungapped prefilter (stage 1 of Prefilter::prefilter_db, src/hhprefilter.cpp:466-482) */
 int hhg_csdb_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* off, const uint8_t* seq,
                     hhg_csdb** out);

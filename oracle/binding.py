@@ -74,6 +74,13 @@ class Oracle:
         L.hho_hhm_prepare.restype = C.c_int
         L.hho_hhm_prepare.argtypes = [C.c_int, c_i32p, c_i32p, c_i32p, c_f32p, C.c_float, C.c_int,
                                       C.POINTER(PrepParams), c_f32p, c_f32p, c_f32p, c_f32p]
+        L.hho_log2lin.restype = C.c_float
+        L.hho_log2lin.argtypes = [C.c_float]
+        L.hho_mac_realign.restype = C.c_int
+        L.hho_mac_realign.argtypes = [C.c_int, c_f32p, c_f32p, C.c_int, c_f32p, c_f32p, C.c_int, C.c_float, C.c_float,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, c_i32p, C.c_int, c_i32p,
+                                      c_i32p, c_i32p, c_i32p, c_f32p, C.POINTER(C.c_double), c_i32p, c_i32p, c_u8p,
+                                      c_f32p, c_f32p]
         L.hho_sw_striped_byte.restype = C.c_int
         L.hho_sw_striped_byte.argtypes = [C.c_int, c_u8p, c_u8p, C.c_int, C.c_int, C.c_int, C.c_int]
 
@@ -118,6 +125,39 @@ class Oracle:
 
     def fast_log2(self, x):
         return self.lib.hho_fast_log2(float(x))
+
+    def log2lin(self, tr):
+        """HMM::Log2LinTransitionProbs(1.0), src/hhhmm.cpp:2305-2313."""
+        tr = np.asarray(tr, np.float32)
+        out = np.array([self.lib.hho_log2lin(float(v)) for v in tr.reshape(-1)], np.float32)
+        return out.reshape(tr.shape)
+
+    def mac_realign(self, q_p, q_tr_lin, t_p, t_tr_lin, vit, excl=(), local=True, shift=-0.03, mact=0.35):
+        """PosteriorDecoder::realign restated (no SS term).  vit = (i1, i2, j1, j2, nsteps, i_steps, j_steps)."""
+        Lq = q_p.shape[0] - 2; Lt = t_p.shape[0] - 2
+        q_p = np.ascontiguousarray(q_p, np.float32); q_tr_lin = np.ascontiguousarray(q_tr_lin, np.float32)
+        t_p = np.ascontiguousarray(t_p, np.float32); t_tr_lin = np.ascontiguousarray(t_tr_lin, np.float32)
+        i1, i2, j1, j2, n, vi, vj = vit
+        vi = np.ascontiguousarray(vi, np.int32); vj = np.ascontiguousarray(vj, np.int32)
+        eo = np.zeros(len(excl) + 1, np.int32)
+        for k, (a, b) in enumerate(excl):
+            eo[k + 1] = eo[k] + len(a)
+        ei = np.ascontiguousarray(np.concatenate([np.asarray(a, np.int32) for a, _ in excl]) if excl else np.zeros(1, np.int32))
+        ej = np.ascontiguousarray(np.concatenate([np.asarray(b, np.int32) for _, b in excl]) if excl else np.zeros(1, np.int32))
+        cap = Lq + Lt + 4
+        res = np.zeros(6, np.int32); sp = np.zeros(1, np.float32); pf = C.c_double()
+        oi = np.zeros(cap, np.int32); oj = np.zeros(cap, np.int32); ost = np.zeros(cap, np.uint8)
+        ops = np.zeros(cap, np.float32); post = np.zeros((Lq + 1, Lt + 1), np.float32)
+        nn = self.lib.hho_mac_realign(Lq, _p(q_p, c_f32p), _p(q_tr_lin, c_f32p), Lt, _p(t_p, c_f32p), _p(t_tr_lin, c_f32p),
+                                      1 if local else 0, shift, mact, i1, i2, j1, j2, n, _p(vi, c_i32p), _p(vj, c_i32p),
+                                      len(excl), _p(eo, c_i32p), _p(ei, c_i32p), _p(ej, c_i32p), _p(res, c_i32p),
+                                      _p(sp, c_f32p), C.byref(pf), _p(oi, c_i32p), _p(oj, c_i32p), _p(ost, c_u8p),
+                                      _p(ops, c_f32p), _p(post, c_f32p))
+        if nn < 0:
+            raise RuntimeError(f"hho_mac_realign: {nn}")
+        return dict(i1=int(res[0]), i2=int(res[1]), j1=int(res[2]), j2=int(res[3]), nsteps=int(res[4]),
+                    matched_cols=int(res[5]), sum_of_probs=float(sp[0]), Pforward=pf.value, i=oi[:nn + 1].copy(),
+                    j=oj[:nn + 1].copy(), states=ost[:nn + 1].copy(), P_posterior=ops[:nn + 1].copy(), post=post)
 
     def viterbi(self, q_p, q_tr, t_p, t_tr, q_ss=None, t_ss=None, S33=None, ssw=0.11, celloff=None,
                 local=True, egq=0.0, egt=0.0, shift=-0.03, want_bt=True):
@@ -213,6 +253,11 @@ class RefShim:
         L.hhref_get_S33.argtypes = [c_f32p]
         L.hhref_get_pb.argtypes = [c_f32p]
         L.hhref_get_R.argtypes = [c_f32p]
+        L.hhref_mac_realign.argtypes = [C.c_int, c_f32p, c_f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, c_i32p,
+                                        C.c_int, c_i32p, c_i32p, c_i32p,
+                                        c_i32p, c_f32p, C.POINTER(C.c_double), c_i32p, c_i32p, C.c_char_p,
+                                        c_f32p, c_f32p, c_f32p, c_f32p]
         L.hhref_get_prep_params.argtypes = [c_f32p]
         L.hhref_stripe_query_profile.argtypes = [C.c_int, C.c_int, c_u8p]
         L.hhref_ungapped_score.argtypes = [c_u8p, C.c_int, c_u8p, C.c_int, C.c_int]
@@ -324,6 +369,40 @@ class RefShim:
         if L < 0:
             raise IOError(path)
         return dict(L=L, p_raw=p_raw[:L + 2].copy(), p=p_prep[:L + 2].copy(), tr=tr[:L + 1].copy(), pav=pav)
+
+    def mac_realign(self, t_p, t_tr, vit, excl=(), local=True, shift=-0.03, mact=0.35, corr=0.1, min_overlap=0,
+                    want_post=True):
+        """PosteriorDecoder::realign for one hit of the loaded query.  vit = (i1, i2, j1, j2, nsteps, i_steps,
+        j_steps) of the Viterbi alignment (step arrays 1-based like Hit.i/Hit.j); excl = list of (alt_i, alt_j)
+        of previous MAC alignments of this template."""
+        Lq = self.Lq
+        Lt = t_p.shape[0] - 2
+        t_p = np.ascontiguousarray(t_p, np.float32); t_tr = np.ascontiguousarray(t_tr, np.float32)
+        i1, i2, j1, j2, n, vi, vj = vit
+        vi = np.ascontiguousarray(vi, np.int32); vj = np.ascontiguousarray(vj, np.int32)
+        eo = np.zeros(len(excl) + 1, np.int32)
+        for k, (a, b) in enumerate(excl):
+            eo[k + 1] = eo[k] + len(a)
+        ei = np.ascontiguousarray(np.concatenate([np.asarray(a, np.int32) for a, _ in excl]) if excl else np.zeros(1, np.int32))
+        ej = np.ascontiguousarray(np.concatenate([np.asarray(b, np.int32) for _, b in excl]) if excl else np.zeros(1, np.int32))
+        cap = Lq + Lt + 4
+        res = np.zeros(6, np.int32); fres = np.zeros(2, np.float32); pf = C.c_double()
+        oi = np.zeros(cap, np.int32); oj = np.zeros(cap, np.int32); ost = C.create_string_buffer(cap)
+        ops = np.zeros(cap, np.float32)
+        post = np.zeros((Lq + 1, Lt + 1), np.float32) if want_post else None
+        ttl = np.zeros((Lt + 1, 7), np.float32); qtl = np.zeros((Lq + 1, 7), np.float32)
+        nn = self.lib.hhref_mac_realign(Lt, _p(t_p, c_f32p), _p(t_tr, c_f32p), 1 if local else 0, shift, mact, corr,
+                                        min_overlap, i1, i2, j1, j2, n, _p(vi, c_i32p), _p(vj, c_i32p),
+                                        len(excl), _p(eo, c_i32p), _p(ei, c_i32p), _p(ej, c_i32p),
+                                        _p(res, c_i32p), _p(fres, c_f32p), C.byref(pf), _p(oi, c_i32p), _p(oj, c_i32p),
+                                        ost, _p(ops, c_f32p), _p(post, c_f32p), _p(ttl, c_f32p), _p(qtl, c_f32p))
+        if nn < 0:
+            raise RuntimeError(f"hhref_mac_realign: {nn}")
+        st = np.frombuffer(ost.raw, np.uint8)[:nn + 1].copy()
+        return dict(i1=int(res[0]), i2=int(res[1]), j1=int(res[2]), j2=int(res[3]), nsteps=int(res[4]),
+                    matched_cols=int(res[5]), sum_of_probs=float(fres[0]), Pforward=pf.value, i=oi[:nn + 1].copy(),
+                    j=oj[:nn + 1].copy(), states=st, P_posterior=ops[:nn + 1].copy(), post=post, t_tr_lin=ttl,
+                    q_tr_lin=qtl)
 
     def fast_log2_table(self):
         """lg2[0..1024] of the reference's fast_log2 (x in [1,2): a=0, c=0 -> returns lg2[b] exactly)."""

@@ -592,3 +592,223 @@ int hho_hhm_prepare(int L, const int* f_mb, const int* tr_mb, const int* neff_mb
   free(f); free(NM);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * MAC realignment of one hit: PosteriorDecoder::realign (src/hhposteriordecoder.cpp:85-118) =
+ * cell-off band around the Viterbi path (maskViterbiAlignment :207-237, FWD_BKW_PATHWITDH = 40) minus previous
+ * MAC alignments (excludeMACAlignment :242-258), Forward (src/hhforwardalgorithm.cpp), Backward
+ * (src/hhbackwardalgorithm.cpp), MAC DP (src/hhmacalgorithm.cpp), MAC backtrace (src/hhbacktracemac.cpp:112-210).
+ * No secondary-structure term (hit.ssm2 == 0), hit.self == 0.  All double/float types and the order of every
+ * product and sum follow the C++ expressions.
+ *   q_tr / t_tr: LINEAR transition probabilities (HMM::Log2LinTransitionProbs, src/hhhmm.cpp:2305); the boundary
+ *   rows are reset here as initializeQueryHMMTransitions (src/hhposteriordecoderrunner.cpp:145-155) and
+ *   initializeForAlignment (src/hhposteriordecoder.cpp:158-167) do.
+ * ---------------------------------------------------------------------------------------------- */
+/* ScalarProd20 of src/hhhit-inl.h:117-122 (the non-SSE return statement): left-to-right sum */
+static inline float dot20_seq(const float* qi, const float* tj) {
+  float s = tj[0] * qi[0];
+  for (int a = 1; a < 20; ++a) s = s + tj[a] * qi[a];
+  return s;
+}
+
+/* HMM::Log2LinTransitionProbs, src/hhhmm.cpp:2311: pow(2.0f, beta * tr) with float arguments = the C library's powf */
+float hho_log2lin(float x) { return powf(2.0f, 1.0f * x); }
+
+typedef struct { double mm, gd, im, dg, mi; } hho_fb_cell;
+
+int hho_mac_realign(int Lq, const float* q_p, const float* q_tr_in, int Lt, const float* t_p, const float* t_tr_in,
+                    int local, float shift, float mact, int i1, int i2, int j1, int j2, int nsteps,
+                    const int* vit_i, const int* vit_j, int excl_n, const int* excl_off, const int* excl_i,
+                    const int* excl_j, int* res, float* sum_of_probs, double* pforward, int* out_i, int* out_j,
+                    uint8_t* out_states, float* out_post_steps, float* post /* (Lq+1)*(Lt+1) */) {
+  const int W = Lt + 1;
+  uint8_t* off = (uint8_t*)calloc((size_t)(Lq + 1) * W, 1);
+  uint8_t* bt = (uint8_t*)calloc((size_t)(Lq + 1) * W, 1);
+  float* qtr = (float*)malloc((size_t)(Lq + 1) * 7 * sizeof(float));
+  float* ttr = (float*)malloc((size_t)(Lt + 1) * 7 * sizeof(float));
+  hho_fb_cell* prev = (hho_fb_cell*)calloc((size_t)Lt + 3, sizeof(hho_fb_cell));
+  hho_fb_cell* curr = (hho_fb_cell*)calloc((size_t)Lt + 3, sizeof(hho_fb_cell));
+  double* scale = (double*)calloc((size_t)Lq + 3, sizeof(double));
+  float* Sp = (float*)calloc((size_t)Lt + 2, sizeof(float));
+  float* Sc = (float*)calloc((size_t)Lt + 2, sizeof(float));
+  if (!off || !bt || !qtr || !ttr || !prev || !curr || !scale || !Sp || !Sc) return -1;
+  memcpy(qtr, q_tr_in, (size_t)(Lq + 1) * 7 * sizeof(float));
+  memcpy(ttr, t_tr_in, (size_t)(Lt + 1) * 7 * sizeof(float));
+  qtr[M2D] = qtr[M2I] = qtr[I2M] = qtr[I2I] = qtr[D2M] = qtr[D2D] = 0.0f;
+  { float* e = qtr + Lq * 7; e[M2M] = 1.0f; e[M2D] = e[M2I] = e[I2M] = e[I2I] = 0.0f; e[D2M] = 1.0f; e[D2D] = 0.0f; }
+  ttr[M2M] = 1.0f; ttr[M2D] = ttr[M2I] = ttr[I2M] = ttr[I2I] = ttr[D2M] = ttr[D2D] = 0.0f;
+  { float* e = ttr + Lt * 7; e[M2M] = 1.0f; e[M2D] = e[M2I] = e[I2M] = e[I2I] = 0.0f; e[D2M] = 1.0f; e[D2D] = 0.0f; }
+#define OFF(i, j) off[(size_t)(i) * W + (j)]
+#define BT(i, j) bt[(size_t)(i) * W + (j)]
+#define POST(i, j) post[(size_t)(i) * W + (j)]
+#define QT(i, k) qtr[(size_t)(i) * 7 + (k)]
+#define TT(j, k) ttr[(size_t)(j) * 7 + (k)]
+  /* band around the Viterbi path */
+  for (int i = 1; i <= Lq; ++i)
+    for (int j = 1; j <= Lt; ++j) OFF(i, j) = !((i < i1 && j < j1) || (i > i2 && j > j2));
+  for (int s = nsteps; s >= 1; --s) {
+    int lo = vit_i[s] - 40 < 1 ? 1 : vit_i[s] - 40, hi = vit_i[s] + 40 > Lq ? Lq : vit_i[s] + 40;
+    for (int i = lo; i <= hi; ++i) OFF(i, vit_j[s]) = 0;
+  }
+  for (int s = nsteps; s >= 1; --s) {
+    int lo = vit_j[s] - 40 < 1 ? 1 : vit_j[s] - 40, hi = vit_j[s] + 40 > Lt ? Lt : vit_j[s] + 40;
+    for (int j = lo; j <= hi; ++j) OFF(vit_i[s], j) = 0;
+  }
+  for (int e = 0; e < excl_n; ++e)
+    for (int k = excl_off[e]; k < excl_off[e + 1]; ++k) {
+      const int i = excl_i[k], j = excl_j[k];
+      for (int ii = (i - 2 < 1 ? 1 : i - 2); ii <= (i + 2 > Lq ? Lq : i + 2); ++ii) OFF(ii, j) = 1;
+      for (int jj = (j - 2 < 1 ? 1 : j - 2); jj <= (j + 2 > Lt ? Lt : j + 2); ++jj) OFF(i, jj) = 1;
+    }
+  memset(post, 0, (size_t)(Lq + 1) * W * sizeof(float));
+
+  /* ---- Forward */
+  double pmin = local ? 1.0 : 0.0;
+  const double Cshift = pow(2.0, shift);
+  double scale_prod = 1.0;
+  const float one = hho_fpow2(0.0f);           /* fpow2(ScoreSS) with ssm2 == 0 */
+  for (int j = 1; j <= Lt; ++j) {
+    if (OFF(1, j)) { memset(&curr[j], 0, sizeof(hho_fb_cell)); continue; }
+    curr[j].mm = dot20_seq(q_p + 20, t_p + (size_t)j * 20) * Cshift;
+    curr[j].mi = curr[j].dg = 0.0;
+    curr[j].im = curr[j - 1].mm * QT(1, M2I) * TT(j - 1, M2M) + curr[j - 1].im * QT(1, I2I) * TT(j - 1, M2M);
+    curr[j].gd = curr[j - 1].mm * TT(j - 1, M2D) + curr[j - 1].gd * TT(j - 1, D2D);
+  }
+  for (int j = 0; j <= Lt; ++j) { POST(1, j) = (float)curr[j].mm; prev[j] = curr[j]; }
+  scale[0] = scale[1] = scale[2] = 1.0;
+  for (int i = 2; i <= Lq; ++i) {
+    if (scale_prod < DBL_MIN * 100) scale_prod = 0.0; else scale_prod *= scale[i];
+    if (OFF(i, 1)) memset(&curr[1], 0, sizeof(hho_fb_cell));
+    else {
+      curr[1].mm = scale_prod * one * dot20_seq(q_p + (size_t)i * 20, t_p + 20) * Cshift;
+      curr[1].im = curr[1].gd = 0.0;
+      curr[1].mi = scale[i] * (prev[1].mm * QT(i - 1, M2M) * TT(1, M2I) + prev[1].mi * QT(i - 1, M2M) * TT(1, I2I));
+      curr[1].dg = scale[i] * (prev[1].mm * QT(i - 1, M2D) + prev[1].dg * QT(i - 1, D2D));
+    }
+    POST(i, 1) = (float)curr[1].mm;
+    double Pmax_i = 0;
+    memset(curr + 2, 0, (size_t)Lt * sizeof(hho_fb_cell));
+    for (int j = 2; j <= Lt; ++j) {
+      if (OFF(i, j)) continue;
+      curr[j].mm = dot20_seq(q_p + (size_t)i * 20, t_p + (size_t)j * 20) * Cshift * one * scale[i] *
+                   (pmin + prev[j - 1].mm * QT(i - 1, M2M) * TT(j - 1, M2M) + prev[j - 1].gd * QT(i - 1, M2M) * TT(j - 1, D2M) +
+                    prev[j - 1].im * QT(i - 1, I2M) * TT(j - 1, M2M) + prev[j - 1].dg * QT(i - 1, D2M) * TT(j - 1, M2M) +
+                    prev[j - 1].mi * QT(i - 1, M2M) * TT(j - 1, I2M));
+      curr[j].gd = (curr[j - 1].mm * TT(j - 1, M2D) + curr[j - 1].gd * TT(j - 1, D2D));
+      curr[j].im = (curr[j - 1].mm * QT(i, M2I) * TT(j - 1, M2M) + curr[j - 1].im * QT(i, I2I) * TT(j - 1, M2M));
+      curr[j].dg = scale[i] * (prev[j].mm * QT(i - 1, M2D) + prev[j].dg * QT(i - 1, D2D));
+      curr[j].mi = scale[i] * (prev[j].mm * QT(i - 1, M2M) * TT(j, M2I) + prev[j].mi * QT(i - 1, M2M) * TT(j, I2I));
+      Pmax_i = fmax(Pmax_i, curr[j].mm);
+    }
+    for (int j = 0; j <= Lt; ++j) POST(i, j) = (float)curr[j].mm;
+    { hho_fb_cell* x = prev; prev = curr; curr = x; }
+    pmin *= scale[i];
+    if (pmin < DBL_MIN * 100) pmin = 0.0;
+    scale[i + 1] = 1.0 / (Pmax_i + 1.0);
+  }
+  double Pf;
+  if (local) {
+    Pf = 1.0;
+    for (int i = 1; i <= Lq; ++i) {
+      for (int j = 1; j <= Lt; ++j) Pf += POST(i, j);
+      Pf *= scale[i + 1];
+    }
+  } else {
+    Pf = 0.0;
+    for (int i = 1; i < Lq; ++i) Pf = (Pf + POST(i, Lt) * scale[i + 1]);
+    for (int j = 1; j <= Lt; ++j) Pf += POST(Lq, j);
+    Pf *= scale[Lq + 1];
+  }
+  *pforward = Pf;
+
+  /* ---- Backward, posterior = F * B / Pforward written over the forward values */
+  scale_prod = scale[Lq + 1];
+  for (int j = Lt; j >= 1; --j) {
+    if (OFF(Lq, j)) { POST(Lq, j) = 0.0f; prev[j].mm = 0.0; }
+    else { prev[j].mm = scale[Lq + 1]; POST(Lq, j) = (float)(POST(Lq, j) * scale[Lq + 1] / Pf); }
+    prev[j].mi = prev[j].dg = 0.0;
+  }
+  pmin = local ? scale[Lq + 1] : 0.0;
+  for (int i = Lq - 1; i >= 1; --i) {
+    scale_prod *= scale[i + 1];
+    if (scale_prod < DBL_MIN * 100) scale_prod = 0.0;
+    if (OFF(i, Lt)) { POST(i, Lt) = 0.0f; curr[Lt].mm = 0.0; }
+    else { curr[Lt].mm = scale_prod; POST(i, Lt) = (float)(POST(i, Lt) * scale_prod / Pf); }
+    pmin *= scale[i + 1];
+    if (pmin < DBL_MIN * 100) pmin = 0.0;
+    curr[Lt].im = curr[Lt].mi = curr[Lt].dg = curr[Lt].gd = 0.0;
+    if (Lt > 1) memset(curr + 1, 0, (size_t)(Lt - 1) * sizeof(hho_fb_cell));
+    for (int j = Lt - 1; j >= 1; --j) {
+      if (OFF(i, j)) continue;
+      const double pmatch = prev[j + 1].mm * dot20_seq(q_p + (size_t)(i + 1) * 20, t_p + (size_t)(j + 1) * 20) * one *
+                            Cshift * scale[i + 1];
+      curr[j].mm = (+pmin + pmatch * QT(i, M2M) * TT(j, M2M) + curr[j + 1].gd * TT(j, M2D) +
+                    curr[j + 1].im * QT(i, M2I) * TT(j, M2M) + prev[j].dg * QT(i, M2D) * scale[i + 1] +
+                    prev[j].mi * QT(i, M2M) * TT(j, M2I) * scale[i + 1]);
+      curr[j].gd = (+pmatch * QT(i, M2M) * TT(j, D2M) + curr[j + 1].gd * TT(j, D2D));
+      curr[j].im = (+pmatch * QT(i, I2M) * TT(j, M2M) + curr[j + 1].im * QT(i, I2I) * TT(j, M2M));
+      curr[j].dg = (+pmatch * QT(i, D2M) * TT(j, M2M) + prev[j].dg * QT(i, D2D) * scale[i + 1]);
+      curr[j].mi = (+pmatch * QT(i, M2M) * TT(j, I2M) + prev[j].mi * QT(i, M2M) * TT(j, I2I) * scale[i + 1]);
+    }
+    for (int j = 1; j <= Lt - 1; ++j) POST(i, j) *= (float)(curr[j].mm / Pf);
+    { hho_fb_cell* x = prev; prev = curr; curr = x; }
+  }
+
+  /* ---- MAC dynamic programming (float) */
+  float score_MAC = -FLT_MAX;
+  int mi2 = 0, mj2 = 0;
+  for (int j = 0; j <= Lt; ++j) Sp[j] = 0.0f;
+  BT(0, 0) = 0;
+  for (int i = 1; i <= Lq; ++i) {
+    Sc[0] = 0.0f;
+    for (int j = 1; j <= Lt; ++j) {
+      if (OFF(i, j)) { Sc[j] = -FLT_MIN; BT(i, j) = ST_STOP; continue; }
+      const float term1 = POST(i, j) - mact;
+      const float term2 = Sp[j - 1] + POST(i, j) - mact;
+      const float term3 = (float)(Sp[j] - 0.5 * mact);
+      const float term4 = (float)(Sc[j - 1] - 0.5 * mact);
+      float mx; uint8_t st;
+      if (term1 > term2) { mx = term1; st = ST_STOP; } else { mx = term2; st = ST_MM; }
+      if (term3 > mx) { mx = term3; st = ST_MI; }
+      if (term4 > mx) { mx = term4; st = ST_IM; }
+      Sc[j] = mx; BT(i, j) = st;
+      if (mx > score_MAC && (local || i == Lq)) { mi2 = i; mj2 = j; score_MAC = mx; }
+    }
+    if (!local && Sc[Lt] > score_MAC) { mi2 = i; mj2 = Lt; score_MAC = Sc[Lt]; }
+    for (int j = 0; j <= Lt; ++j) Sp[j] = Sc[j];
+  }
+
+  /* ---- MAC backtrace */
+  for (int i = 0; i <= Lq; ++i) BT(i, 1) = ST_STOP;
+  for (int j = 1; j <= Lt; ++j) BT(1, j) = ST_STOP;
+  int matched = 1, step = 0, i = mi2, j = mj2;
+  uint8_t state = ST_MM;
+  if (BT(i, j) != ST_MM) {
+    out_i[0] = i; out_j[0] = j;
+  } else {
+    while (state != ST_STOP) {
+      ++step;
+      out_states[step] = state = BT(i, j);
+      out_i[step] = i; out_j[step] = j;
+      if (state == ST_MM) matched++;
+      if (state == ST_MM) { i--; j--; }
+      else if (state == ST_IM) j--;
+      else if (state == ST_MI) i--;
+    }
+  }
+  res[0] = out_i[step]; res[1] = mi2; res[2] = out_j[step]; res[3] = mj2; res[4] = step; res[5] = matched;
+  if (step) out_states[step] = ST_MM;
+  float sum = 0.0f;                             /* Hit::sum_of_probs is a float accumulator (src/hhhit.h:97) */
+  for (int s = 1; s <= step; ++s) {
+    if (out_states[s] == ST_MM) { out_post_steps[s] = POST(out_i[s], out_j[s]); sum += out_post_steps[s]; }
+    else out_post_steps[s] = 0.0f;
+  }
+  *sum_of_probs = sum;
+#undef OFF
+#undef BT
+#undef POST
+#undef QT
+#undef TT
+  free(off); free(bt); free(qtr); free(ttr); free(prev); free(curr); free(scale); free(Sp); free(Sc);
+  return step;
+}

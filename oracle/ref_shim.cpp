@@ -44,6 +44,9 @@
 #include "hhfunc.h"
 #include "hhprefilter.h"
 #include "hhhit.h"
+#include "hhposteriordecoder.h"
+#include "hhposteriordecoderrunner.h"
+#include "hhposteriormatrix.h"
 #include "cs219.lib.h"
 #undef private
 #undef protected
@@ -242,6 +245,115 @@ int hhref_prepare_template_hhm_raw(const char* path, int columnscore, float* p_r
   export_hmm(t, p_prep, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   delete t;
   return L;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MAC realignment of ONE hit (PosteriorDecoder::realign, src/hhposteriordecoder.cpp:85-118) around its
+// Viterbi alignment.  Query = the loaded query (a copy is put into linear transition space exactly like
+// PosteriorDecoderRunner::executeComputation, src/hhposteriordecoderrunner.cpp:48-52).
+//   t_p/t_tr: prepared template as handed to the Viterbi kernel (null model included, log2 transitions)
+//   vit_i/vit_j[1..nsteps]: the Viterbi path (Hit.i / Hit.j), i1..j2 its end points
+//   excl_n previous MAC alignments of the same template: concatenated (i,j) lists, excl_off[excl_n+1]
+// Outputs: MAC path out_i/out_j/out_states[1..nsteps'], P_posterior per step, res[6] = {i1,i2,j1,j2,nsteps,
+// matched_cols}, fres[2] = {sum_of_probs, forward score before restoreHitValues}, *pforward,
+// post[(Lq+1)*(Lt+1)] the posterior matrix (optional).
+int hhref_mac_realign(int Lt, const float* t_p, const float* t_tr, int local, float shift, float mact, float corr,
+                      int min_overlap, int i1, int i2, int j1, int j2, int nsteps, const int* vit_i,
+                      const int* vit_j, int excl_n, const int* excl_off, const int* excl_i, const int* excl_j,
+                      int* res, float* fres, double* pforward, int* out_i, int* out_j, char* out_states,
+                      float* out_post_steps, float* post, float* t_tr_lin_out, float* q_tr_lin_out) {
+  const int Lq = g->q->L;
+  if (Lt + 2 > g->maxres) return -2;
+  // query copy in linear space
+  HMM* q = new HMM(MAXSEQDIS, g->maxres);
+  *q = *g->q;
+  q->trans_lin = 0;
+  q->Log2LinTransitionProbs(1.0);
+  {
+    PosteriorDecoderRunner r(nullptr, nullptr, 1, 0.0f, g->S73, g->S33, g->S37);
+    r.initializeQueryHMMTransitions(*q);
+  }
+  HMM* t = new HMM(MAXSEQDIS, g->maxres);
+  fill_hmm(t, Lt, t_p, t_tr, nullptr, nullptr, nullptr);
+  t->trans_lin = 0;
+  t->Log2LinTransitionProbs(1.0);
+  Hit hit;
+  hit.L = Lt;
+  hit.self = 0;
+  hit.i1 = i1; hit.i2 = i2; hit.j1 = j1; hit.j2 = j2; hit.nsteps = nsteps;
+  hit.i = new int[i2 + j2 + 2]; hit.j = new int[i2 + j2 + 2]; hit.states = new char[i2 + j2 + 2];
+  for (int s = 1; s <= nsteps; ++s) { hit.i[s] = vit_i[s]; hit.j[s] = vit_j[s]; hit.states[s] = 0; }
+  hit.ssm1 = hit.ssm2 = 0;
+  hit.score = hit.score_ss = hit.score_aass = 0; hit.Pval = hit.Pvalt = hit.logPval = hit.logPvalt = 0;
+  hit.Eval = hit.logEval = hit.Probab = 0;
+  PosteriorMatrix pm;
+  pm.allocateMatrix(Lq, Lt);
+  ViterbiMatrix vm;
+  vm.AllocateBacktraceMatrix(Lq, Lt);
+  for (int i = 0; i <= Lq; ++i) memset(vm.getRow(i), 0, (size_t)(Lt + 1) * VECSIZE_FLOAT);
+  PosteriorDecoder dec(Lt, local != 0, Lq, 0.0f, g->S73, g->S33, g->S37);
+  std::vector<std::vector<int>*> keep;
+  std::vector<PosteriorDecoder::MACBacktraceResult> excl;
+  for (int e = 0; e < excl_n; ++e) {
+    std::vector<int>* ai = new std::vector<int>(excl_i + excl_off[e], excl_i + excl_off[e + 1]);
+    std::vector<int>* aj = new std::vector<int>(excl_j + excl_off[e], excl_j + excl_off[e + 1]);
+    keep.push_back(ai); keep.push_back(aj);
+    excl.push_back(PosteriorDecoder::MACBacktraceResult(ai, aj));
+  }
+  // realign() minus restoreHitValues' effect on what we export: run the public entry, then read the fields
+  dec.realign(*q, *t, hit, pm, vm, excl, nullptr, nullptr, min_overlap, shift, mact, corr);
+  res[0] = hit.i1; res[1] = hit.i2; res[2] = hit.j1; res[3] = hit.j2; res[4] = hit.nsteps; res[5] = hit.matched_cols;
+  fres[0] = hit.sum_of_probs; fres[1] = 0;
+  *pforward = hit.Pforward;
+  for (int s = 0; s <= hit.nsteps; ++s) {
+    out_i[s] = hit.i[s]; out_j[s] = hit.j[s]; out_states[s] = s ? hit.states[s] : 0;
+    out_post_steps[s] = (s && hit.P_posterior) ? hit.P_posterior[s] : 0.f;
+  }
+  if (post)
+    for (int i = 0; i <= Lq; ++i)
+      for (int j = 0; j <= Lt; ++j) post[(size_t)i * (Lt + 1) + j] = (i && j) ? pm.getPosteriorValue(i, j) : 0.f;
+  if (t_tr_lin_out) for (int i = 0; i <= Lt; ++i) for (int k = 0; k < 7; ++k) t_tr_lin_out[i * 7 + k] = t->tr[i][k];
+  if (q_tr_lin_out) for (int i = 0; i <= Lq; ++i) for (int k = 0; k < 7; ++k) q_tr_lin_out[i * 7 + k] = q->tr[i][k];
+  const int n = hit.nsteps;
+  for (auto v : keep) delete v;
+  pm.DeleteProbabilityMatrix();
+  delete q; delete t;
+  return n;
+}
+
+// Debug: forward pass only (same setup as hhref_mac_realign), exports the forward matrix and the scale factors.
+int hhref_mac_forward_only(int Lt, const float* t_p, const float* t_tr, int local, float shift, int i1, int i2, int j1,
+                           int j2, int nsteps, const int* vit_i, const int* vit_j, float* fwd, double* scale_out,
+                           double* pforward) {
+  const int Lq = g->q->L;
+  HMM* q = new HMM(MAXSEQDIS, g->maxres);
+  *q = *g->q;
+  q->trans_lin = 0;
+  q->Log2LinTransitionProbs(1.0);
+  { PosteriorDecoderRunner r(nullptr, nullptr, 1, 0.0f, g->S73, g->S33, g->S37); r.initializeQueryHMMTransitions(*q); }
+  HMM* t = new HMM(MAXSEQDIS, g->maxres);
+  fill_hmm(t, Lt, t_p, t_tr, nullptr, nullptr, nullptr);
+  t->trans_lin = 0;
+  t->Log2LinTransitionProbs(1.0);
+  Hit hit;
+  hit.L = Lt; hit.self = 0;
+  hit.i1 = i1; hit.i2 = i2; hit.j1 = j1; hit.j2 = j2; hit.nsteps = nsteps;
+  hit.i = new int[i2 + j2 + 2]; hit.j = new int[i2 + j2 + 2]; hit.states = new char[i2 + j2 + 2];
+  for (int s = 1; s <= nsteps; ++s) { hit.i[s] = vit_i[s]; hit.j[s] = vit_j[s]; hit.states[s] = 0; }
+  hit.ssm1 = hit.ssm2 = 0;
+  PosteriorMatrix pm; pm.allocateMatrix(Lq, Lt);
+  ViterbiMatrix vm; vm.AllocateBacktraceMatrix(Lq, Lt);
+  for (int i = 0; i <= Lq; ++i) memset(vm.getRow(i), 0, (size_t)(Lt + 1) * VECSIZE_FLOAT);
+  PosteriorDecoder dec(Lt, local != 0, Lq, 0.0f, g->S73, g->S33, g->S37);
+  dec.initializeForAlignment(*q, *t, hit, vm, 0, t->L, 0);
+  dec.forwardAlgorithm(*q, *t, hit, pm, vm, shift, 0);
+  for (int i = 0; i <= Lq; ++i)
+    for (int j = 0; j <= Lt; ++j) fwd[(size_t)i * (Lt + 1) + j] = (i && j) ? pm.getPosteriorValue(i, j) : 0.f;
+  for (int i = 0; i <= Lq + 1; ++i) scale_out[i] = dec.scale[i];
+  *pforward = hit.Pforward;
+  pm.DeleteProbabilityMatrix();
+  delete q; delete t;
+  return 0;
 }
 
 // fast_log2 of the reference (table-based, src/util-inl.h:108-128) and Score() (src/hhhit-inl.h:132)

@@ -113,6 +113,30 @@ def main():
     t = R.prepare_template_hhm_raw("/tmp/ss60.hhm", 1)
     t2 = R.prepare_template_hhm("/tmp/ss60.hhm")
     G["hhm_ss60_praw"], G["hhm_ss60_tr"], G["hhm_ss60_pav"], G["hhm_ss60_ss"] = t["p_raw"], t["tr"], t["pav"], t2["ss"]
+    # ---- MAC realignment (PosteriorDecoder::realign) of the config-1 hits around their Viterbi alignments
+    q = R.load_query_hhm(os.path.join(REFDATA, "query.hhm"))
+    for name, path, mact in (("t150", "/tmp/synth150.hhm", 0.0), ("tself", os.path.join(REFDATA, "query.hhm"), 0.35)):
+        tt = R.prepare_template_hhm(path)
+        res = R.viterbi([(tt["p"], tt["tr"], None)])
+        sc, i2, j2, bt = res[0]
+        n, i_s, j_s, st, mc = R.backtrace(0)
+        m = R.mac_realign(tt["p"], tt["tr"], (int(i_s[n]), i2, int(j_s[n]), j2, n, i_s, j_s), mact=mact)
+        G[f"mac_{name}_vit"] = np.array([int(i_s[n]), i2, int(j_s[n]), j2, n], np.int32)
+        G[f"mac_{name}_vit_i"], G[f"mac_{name}_vit_j"] = i_s[:n + 1].astype(np.int32), j_s[:n + 1].astype(np.int32)
+        G[f"mac_{name}_res"] = np.array([m["i1"], m["i2"], m["j1"], m["j2"], m["nsteps"], m["matched_cols"]], np.int32)
+        G[f"mac_{name}_f"] = np.array([m["sum_of_probs"], mact], np.float32)
+        G[f"mac_{name}_pforward"] = np.array([m["Pforward"]], np.float64)
+        G[f"mac_{name}_i"], G[f"mac_{name}_j"], G[f"mac_{name}_states"] = m["i"], m["j"], m["states"]
+        G[f"mac_{name}_ppost"] = m["P_posterior"]
+        G[f"mac_{name}_post_sha"] = sha(m["post"][1:, 1:])
+        if name == "tself":      # second MAC alignment of the same template: the first one is excluded
+            m2 = R.mac_realign(tt["p"], tt["tr"], (int(i_s[n]), i2, int(j_s[n]), j2, n, i_s, j_s), mact=mact,
+                               excl=[(m["i"][1:], m["j"][1:])])
+            G["mac_tself2_res"] = np.array([m2["i1"], m2["i2"], m2["j1"], m2["j2"], m2["nsteps"], m2["matched_cols"]], np.int32)
+            G["mac_tself2_pforward"] = np.array([m2["Pforward"]], np.float64)
+            G["mac_tself2_i"], G["mac_tself2_j"], G["mac_tself2_ppost"] = m2["i"], m2["j"], m2["P_posterior"]
+        if name == "t150":
+            G["mac_q_tr_lin"] = m["q_tr_lin"]
     # ---- prefilter
     lib = R.cs219()
     G["cs219_lin"] = lib
