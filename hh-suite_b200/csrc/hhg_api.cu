@@ -8,6 +8,7 @@
 #include "hhg_viterbi2.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -105,7 +106,7 @@ struct hhg_ctx {
   DevBuf<float> mac_qp, mac_qtr, mac_ttr, mac_post, mac_out_post;
   DevBuf<uint8_t> mac_off, mac_bt, mac_out_states;
   DevBuf<double> mac_rows, mac_scale;
-  DevBuf<long long> mac_i64;
+  DevBuf<long long> mac_i64, mac_dbg;
   DevBuf<int> mac_i32, mac_out_i, mac_out_j, mac_flag;
   DevBuf<MacHitOut> mac_out;
   std::vector<long long> mac_cell_off;   // of the last call (debug fetch)
@@ -1052,6 +1053,13 @@ int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target
   if (!db->prepared) return fail(HHG_EINVAL, "hhg_mac_realign: shard has no null model applied");
   if (excl_off && (!excl_i || !excl_j)) return fail(HHG_EINVAL, "hhg_mac_realign: excl_off without excl_i/excl_j");
   CK(cudaSetDevice(ctx->device));
+  const bool timing = getenv("HHG_MAC_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+  };
+  const auto t_begin = now();
+  double t_prep = 0, t_lin = 0, t_kern = 0;
   const int Lq = ctx->mac_Lq;
   static_assert(sizeof(MacHitOut) == sizeof(hhg_mac_hit), "hhg_mac_hit layout");
   std::vector<long long> rec0(n), tr_off(n), cell_off(n), row_off(n), path_off(n);
@@ -1076,7 +1084,7 @@ int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target
     rec0[r] = db->col_off[t]; Lt[r] = L;
     tr_off[r] = ntr; ntr += (long long)(L + 1) * 7;
     cell_off[r] = ncell; ncell += (long long)(Lq + 1) * (L + 1);
-    row_off[r] = nrow; nrow += 10LL * (L + 3);
+    row_off[r] = nrow; nrow += 10LL * (L + 3) + (L + 3 + 7) / 8 + 1;   // + the cell-off row of the fallback path
     path_off[r] = npath; npath += (long long)Lq + L + 2;
   }
   if ((size_t)npath > path_cap) return fail(HHG_EINVAL, "hhg_mac_realign: path buffers hold %zu entries, %lld needed", path_cap, npath);
@@ -1124,6 +1132,8 @@ int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target
   A.post = ctx->mac_post.p; A.off = ctx->mac_off.p; A.bt = ctx->mac_bt.p; A.rows = ctx->mac_rows.p;
   A.scale = ctx->mac_scale.p; A.out = ctx->mac_out.p;
   A.out_i = ctx->mac_out_i.p; A.out_j = ctx->mac_out_j.p; A.out_states = ctx->mac_out_states.p; A.out_post = ctx->mac_out_post.p;
+  t_prep = ms_since(t_begin);
+  const auto t_lin0 = now();
   // template transitions in linear space: gather the log2 rows on the device, powf on the host (a few threads),
   // boundary rows as initializeForAlignment sets them, back to the device
   k_mac_gather_tr<<<dim3(8, n), 128, 0, ctx->stream>>>(n, A.cols, A.rec0, A.Lt, A.tr_off, ctx->mac_ttr.p);
@@ -1152,16 +1162,45 @@ int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target
     CK(cudaMemcpyAsync(ctx->mac_ttr.p, htr.data(), (size_t)ntr * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
+  t_lin = ms_since(t_lin0);
+  const auto t_k0 = now();
   k_mac_band<<<n, 256, 0, ctx->stream>>>(A);
-  k_mac_realign<<<n, 32, 0, ctx->stream>>>(A);
+  {
+    // working set in shared memory (109 bytes per template column) for templates up to ~600 columns: 64 KB per warp
+    // keeps 3 warps per SM resident (500 hits over 148 SMs need 3.4); longer templates use the global scratch
+    int Lmax = 0;
+    for (int r = 0; r < n; ++r) Lmax = std::max(Lmax, Lt[r]);
+    const size_t want = (size_t)109 * (Lmax + 3);
+    const size_t smem = std::min<size_t>(want, 64 * 1024);
+    CK(cudaFuncSetAttribute(k_mac_realign, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    A.smem_rows = (int)smem;
+    if (timing) { CK(ctx->mac_dbg.ensure((size_t)n * 12)); A.dbg = ctx->mac_dbg.p; }
+    k_mac_realign<<<n, 32, smem, ctx->stream>>>(A);
+  }
   ctx->launches += 2;
   CK(cudaGetLastError());
+  if (timing) { CK(cudaStreamSynchronize(ctx->stream)); t_kern = ms_since(t_k0); }
+  const auto t_d0 = now();
   CK(cudaMemcpyAsync(hits, ctx->mac_out.p, (size_t)n * sizeof(MacHitOut), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(out_i, ctx->mac_out_i.p, (size_t)npath * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(out_j, ctx->mac_out_j.p, (size_t)npath * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(out_states, ctx->mac_out_states.p, (size_t)npath, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(out_post, ctx->mac_out_post.p, (size_t)npath * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (timing) {
+    std::vector<long long> d((size_t)n * 12);
+    CK(cudaMemcpy(d.data(), ctx->mac_dbg.p, d.size() * 8, cudaMemcpyDeviceToHost));
+    int big = 0;
+    for (int r = 1; r < n; ++r) if (Lt[r] > Lt[big]) big = r;
+    for (int r : {0, big}) {
+      fprintf(stderr, "  request %d (Lt=%d) Mcycles: fwdA %.2f fwdScan %.2f fwdEnd %.2f Pf %.2f bwdA %.2f bwdB %.2f bwdC %.2f macA %.2f macScan %.2f bt %.2f\n",
+              r, Lt[r], d[r * 12 + 0] / 1e6, d[r * 12 + 1] / 1e6, d[r * 12 + 2] / 1e6, d[r * 12 + 3] / 1e6, d[r * 12 + 4] / 1e6,
+              d[r * 12 + 5] / 1e6, d[r * 12 + 6] / 1e6, d[r * 12 + 7] / 1e6, d[r * 12 + 8] / 1e6, d[r * 12 + 9] / 1e6);
+    }
+  }
+  if (timing)
+    fprintf(stderr, "hhg_mac_realign: n=%d cells=%lld  prep+H2D %.2f ms, transitions (gather, powf, H2D) %.2f ms, "
+            "kernels %.2f ms, D2H %.2f ms, total %.2f ms\n", n, ncell, t_prep, t_lin, t_kern, ms_since(t_d0), ms_since(t_begin));
   ctx->mac_cell_off = cell_off;
   ctx->mac_Lt = Lt;
   return HHG_OK;

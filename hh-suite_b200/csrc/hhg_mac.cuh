@@ -49,6 +49,8 @@ struct MacArgs {
   float* post; uint8_t* off; uint8_t* bt;
   const long long* row_off;            // [n] offset (in doubles) of 10*(Lt+3) row buffers
   double* rows;
+  long long* dbg;                      // optional [n*12] per-phase clock64 totals (HHG_MAC_TIMING)
+  int smem_rows;                       // bytes of dynamic shared memory available for the row buffers
   double* scale;                       // [n*(Lq+3)]
   MacHitOut* out;
   long long* path_off;                 // [n] into out_i/out_j/out_states/out_post
@@ -122,22 +124,39 @@ __global__ void __launch_bounds__(256) k_mac_band(const MacArgs A) {
 }
 
 // Forward + Pforward + Backward + MAC DP + backtrace: one warp per request.
+// Row buffers live in shared memory when 10*(Lt+3) doubles fit (A.smem_rows), else in the global scratch.
+// The sequential recurrences are written so that the scanning lanes execute ONE instruction stream with per-lane
+// coefficients (a multiplication by 1.0 is exact, so "x*a + v*b" and "(x*a)*c + (v*b)*c" share the shape
+// (x*A)*B + (v*C)*D); lanes that differ only in operands do not serialise.
 __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
+  extern __shared__ __align__(16) unsigned char mac_smem[];
   const int r = blockIdx.x, lane = threadIdx.x;
   const int Lq = A.Lq, Lt = A.Lt[r], W = Lt + 1;
   const uint8_t* off = A.off + A.cell_off[r];
   uint8_t* bt = A.bt + A.cell_off[r];
   float* post = A.post + A.cell_off[r];
   const ColRec* tcol = A.cols + A.rec0[r] - 1;            // tcol[j] = record of column j (1-based)
-  const float* ttr = A.t_tr + A.tr_off[r];
+  const float* ttr_g = A.t_tr + A.tr_off[r];
   const float* qtr = A.q_tr;
   double* scale = A.scale + (size_t)r * (Lq + 3);
   const size_t RS = (size_t)Lt + 3;
-  double* base = A.rows + A.row_off[r];
+  // per-warp working set: 10 row buffers (doubles), the template's linear transitions, the cell-off flags of the
+  // current row.  In shared memory when it fits; the sequential scans below then never wait for global memory.
+  const size_t need = 10 * RS * sizeof(double) + 7 * RS * sizeof(float) + RS;
+  const bool in_smem = need <= (size_t)A.smem_rows;
+  double* base = in_smem ? reinterpret_cast<double*>(mac_smem) : A.rows + A.row_off[r];
+  float* ttr_s = in_smem ? reinterpret_cast<float*>(mac_smem + 10 * RS * sizeof(double)) : nullptr;
+  uint8_t* offrow = in_smem ? mac_smem + 10 * RS * sizeof(double) + 7 * RS * sizeof(float)
+                            : reinterpret_cast<uint8_t*>(A.rows + A.row_off[r] + 10 * RS);
   double *Pm = base, *Pg = base + RS, *Pi = base + 2 * RS, *Pd = base + 3 * RS, *Px = base + 4 * RS;
   double *Cm = base + 5 * RS, *Cg = base + 6 * RS, *Ci = base + 7 * RS, *Cd = base + 8 * RS, *Cx = base + 9 * RS;
   const double Cshift = A.Cshift;
   const unsigned FULL = 0xffffffffu;
+  if (in_smem) {
+    for (int k = lane; k < (Lt + 1) * 7; k += 32) ttr_s[k] = ttr_g[k];
+    __syncwarp();
+  }
+  const float* ttr = in_smem ? ttr_s : ttr_g;
 #define OFFC(i, j) off[(size_t)(i) * W + (j)]
 #define QT(i, k) qtr[(size_t)(i) * 7 + (k)]
 #define TT(j, k) ttr[(size_t)(j) * 7 + (k)]
@@ -145,21 +164,49 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
                          t_ = Pd; Pd = Cd; Cd = t_; t_ = Px; Px = Cx; Cx = t_; } while (0)
   enum { M2M = 0, M2I = 1, M2D = 2, I2M = 3, I2I = 4, D2M = 5, D2D = 6 };
 
+  // Forward scan of row i (lanes 0 and 1):  GD: v = Cm[j-1]*t.M2D[j-1] + v*t.D2D[j-1]
+  //                                          IM: v = Cm[j-1]*q.M2I[i]*t.M2M[j-1] + v*q.I2I[i]*t.M2M[j-1]
+  // both as (x*A)*B + (v*C)*D with A,B,C,D per lane; off cells reset v to 0.
+  // Lane 2 accumulates Pforward in the same stream: Pf += (float)Cm[j] in row-major order, Pf *= scale[i+1] at the
+  // end of each row (src/hhforwardalgorithm.cpp:151-166) -- shape (x*1)*1 + (v*1)*1, never reset.
+  double Pf_acc = A.local ? 1.0 : 0.0;
+  auto fwd_scan = [&](int i, int jfirst) {
+    if (lane < 3) {
+      const float qa = QT(i, M2I), qc = QT(i, I2I);
+      double* __restrict__ dst = lane == 0 ? Cg : (lane == 1 ? Ci : Cx + RS - 1);   // lane 2: dummy slot
+      const double* __restrict__ cm = Cm;
+      const float* __restrict__ tt = ttr;
+      const uint8_t* __restrict__ of = offrow;
+      const int ka = lane == 0 ? M2D : M2M, kc = lane == 0 ? D2D : M2M;
+      double v = lane == 2 ? Pf_acc : 0.0;
+      if (lane == 2 && jfirst == 2 && A.local) v += (double)(float)cm[1];
+      if (jfirst == 2 && lane < 2) dst[1] = 0.0;
+#pragma unroll 4
+      for (int j = jfirst; j <= Lt; ++j) {
+        const float ta = tt[(j - 1) * 7 + ka], tc = tt[(j - 1) * 7 + kc];
+        const float a1 = lane == 0 ? ta : (lane == 1 ? qa : 1.0f), b1 = lane == 1 ? ta : 1.0f;
+        const float c1 = lane == 0 ? tc : (lane == 1 ? qc : 1.0f), d1 = lane == 1 ? tc : 1.0f;
+        const double x = lane == 2 ? (double)(float)cm[j] : cm[j - 1];
+        const double nv = (x * a1) * b1 + (v * c1) * d1;
+        v = (lane < 2 && of[j]) ? 0.0 : nv;
+        if (lane < 2) dst[j] = v;
+      }
+      if (lane == 2) Pf_acc = v;
+    }
+  };
+
+  long long tk[12] = {0,0,0,0,0,0,0,0,0,0,0,0}; long long t0_ = clock64();
+#define TICK(k) do { const long long t1_ = clock64(); tk[k] += t1_ - t0_; t0_ = t1_; } while (0)
   // ------------------------------------------------------------------ Forward, row 1
   for (int j = lane; j <= Lt + 1; j += 32) { Cm[j] = Cg[j] = Ci[j] = Cd[j] = Cx[j] = 0.0; Pm[j] = Pg[j] = Pi[j] = Pd[j] = Px[j] = 0.0; }
   __syncwarp();
-  for (int j = 1 + lane; j <= Lt; j += 32)
-    if (!OFFC(1, j)) Cm[j] = (double)mac_dot20(A.q_p + 20, tcol[j].p) * Cshift;
-  __syncwarp();
-  if (lane < 2) {
-    double v = 0.0;
-    for (int j = 1; j <= Lt; ++j) {
-      if (OFFC(1, j)) v = 0.0;
-      else if (lane == 0) v = Cm[j - 1] * TT(j - 1, M2D) + v * TT(j - 1, D2D);
-      else v = Cm[j - 1] * QT(1, M2I) * TT(j - 1, M2M) + v * QT(1, I2I) * TT(j - 1, M2M);
-      if (lane == 0) Cg[j] = v; else Ci[j] = v;
-    }
+  for (int j = 1 + lane; j <= Lt; j += 32) {
+    const uint8_t o = OFFC(1, j);
+    offrow[j] = o;
+    if (!o) Cm[j] = (double)mac_dot20(A.q_p + 20, tcol[j].p) * Cshift;
   }
+  __syncwarp();
+  fwd_scan(1, 1);
   __syncwarp();
   for (int j = lane; j <= Lt; j += 32) post[(size_t)W + j] = (float)Cm[j];
   SWAP_ROWS();
@@ -177,7 +224,9 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
     double pmax = 0.0;
     for (int j = 1 + lane; j <= Lt; j += 32) {
       double mm = 0.0, dg = 0.0, mi = 0.0;
-      if (!OFFC(i, j)) {
+      const uint8_t o = OFFC(i, j);
+      offrow[j] = o;
+      if (!o) {
         const float pf = mac_dot20(qi, tcol[j].p);
         if (j == 1) {
           mm = scale_prod * 1.0f * pf * Cshift;
@@ -194,17 +243,9 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
       Cm[j] = mm; Cd[j] = dg; Cx[j] = mi;
     }
     __syncwarp();
-    if (lane < 2) {                                       // GD (lane 0) and IM (lane 1): sequential along the row
-      const float q_m2i = QT(i, M2I), q_i2i = QT(i, I2I);
-      double v = 0.0;
-      if (lane == 0) Cg[1] = 0.0; else Ci[1] = 0.0;
-      for (int j = 2; j <= Lt; ++j) {
-        if (OFFC(i, j)) v = 0.0;
-        else if (lane == 0) v = (Cm[j - 1] * TT(j - 1, M2D) + v * TT(j - 1, D2D));
-        else v = (Cm[j - 1] * q_m2i * TT(j - 1, M2M) + v * q_i2i * TT(j - 1, M2M));
-        if (lane == 0) Cg[j] = v; else Ci[j] = v;
-      }
-    }
+    TICK(0);
+    fwd_scan(i, 2);
+    TICK(1);
 #pragma unroll
     for (int o = 16; o; o >>= 1) pmax = fmax(pmax, __shfl_xor_sync(FULL, pmax, o));
     __syncwarp();
@@ -212,27 +253,24 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
     SWAP_ROWS();
     pmin *= sc_i;
     if (pmin < DBL_MIN * 100) pmin = 0.0;
-    if (lane == 0) scale[i + 1] = 1.0 / (pmax + 1.0);
+    const double sc_next = 1.0 / (pmax + 1.0);           // every lane holds pmax after the reduction
+    if (lane == 0) scale[i + 1] = sc_next;
+    if (A.local) Pf_acc *= sc_next;                       // lane 2's copy is the live one
     __syncwarp();
+    TICK(2);
   }
 
-  // ------------------------------------------------------------------ Pforward (sequential sum, row-major)
+  // ------------------------------------------------------------------ Pforward
   double Pf = 0.0;
-  if (lane == 0) {
-    if (A.local) {
-      Pf = 1.0;
-      for (int i = 1; i <= Lq; ++i) {
-        const float* row = post + (size_t)i * W;
-        for (int j = 1; j <= Lt; ++j) Pf += row[j];
-        Pf *= scale[i + 1];
-      }
-    } else {
-      for (int i = 1; i < Lq; ++i) Pf = (Pf + post[(size_t)i * W + Lt] * scale[i + 1]);
-      for (int j = 1; j <= Lt; ++j) Pf += post[(size_t)Lq * W + j];
-      Pf *= scale[Lq + 1];
-    }
+  if (A.local) {
+    Pf = Pf_acc;                                          // accumulated by lane 2 during the forward scans
+  } else if (lane == 2) {                                 // global mode: last column and last row only (:167-173)
+    for (int i = 1; i < Lq; ++i) Pf = (Pf + post[(size_t)i * W + Lt] * scale[i + 1]);
+    for (int j = 1; j <= Lt; ++j) Pf += post[(size_t)Lq * W + j];
+    Pf *= scale[Lq + 1];
   }
-  Pf = __shfl_sync(FULL, Pf, 0);
+  Pf = __shfl_sync(FULL, Pf, 2);
+  TICK(3);
 
   // ------------------------------------------------------------------ Backward
   const double sc_last = scale[Lq + 1];
@@ -255,87 +293,121 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
     const float* qn = A.q_p + (size_t)(i + 1) * 20;
     const float q_m2m = QT(i, M2M), q_m2i = QT(i, M2I), q_m2d = QT(i, M2D), q_i2m = QT(i, I2M), q_i2i = QT(i, I2I),
                 q_d2m = QT(i, D2M), q_d2d = QT(i, D2D);
-    // phase A: pmatch-dependent parts that need only the row below: pm (stored in Cd as scratch? no: own array)
-    // Cx <- mi, Cd <- dg, and the partial sums of mm/gd/im that do not involve curr[j+1]
+    // phase A (lanes = columns): pmatch -> Cm (scratch), DG, MI; the cell in column Lt
     for (int j = 1 + lane; j <= Lt; j += 32) {
+      const uint8_t o = OFFC(i, j);
+      offrow[j] = o;
       if (j == Lt) {
         float* pp = post + (size_t)i * W + Lt;
-        if (OFFC(i, Lt)) { *pp = 0.0f; Cm[Lt] = 0.0; }
+        if (o) { *pp = 0.0f; Cm[Lt] = 0.0; }
         else { Cm[Lt] = scale_prod; *pp = (float)(*pp * scale_prod / Pf); }
         Cg[Lt] = Ci[Lt] = Cd[Lt] = Cx[Lt] = 0.0;
-      } else if (OFFC(i, j)) {
+      } else if (o) {
         Cm[j] = Cg[j] = Ci[j] = Cd[j] = Cx[j] = 0.0;
       } else {
         const double pmatch = Pm[j + 1] * mac_dot20(qn, tcol[j + 1].p) * 1.0f * Cshift * sc_n;
         Cd[j] = (+pmatch * q_d2m * TT(j, M2M) + Pd[j] * q_d2d * sc_n);
         Cx[j] = (+pmatch * q_m2m * TT(j, I2M) + Px[j] * q_m2m * TT(j, I2I) * sc_n);
-        Cm[j] = pmatch;                                  // completed by the scan below
+        Cm[j] = pmatch;
       }
     }
     __syncwarp();
-    if (lane == 0) {                                      // right-to-left: GD, IM, then MM which needs both
-      double g = 0.0, im = 0.0;                           // curr[Lt].gd = curr[Lt].im = 0
+    TICK(4);
+    // phase B (lanes 0 and 1, right to left):  GD: v = pmatch*q.M2M*t.D2M[j] + v*t.D2D[j]
+    //                                           IM: v = pmatch*q.I2M*t.M2M[j] + v*q.I2I*t.M2M[j]
+    if (lane < 2) {
+      double* __restrict__ dst = lane == 0 ? Cg : Ci;
+      const double* __restrict__ cm = Cm;
+      const float* __restrict__ tt = ttr;
+      const uint8_t* __restrict__ of = offrow;
+      const float a1 = lane == 0 ? q_m2m : q_i2m;
+      const int kb = lane == 0 ? D2M : M2M, kc = lane == 0 ? D2D : M2M;
+      double v = 0.0;
+#pragma unroll 4
       for (int j = Lt - 1; j >= 1; --j) {
-        if (OFFC(i, j)) { g = 0.0; im = 0.0; continue; }
-        const double pmatch = Cm[j];
-        const double mm = (+pmin + pmatch * q_m2m * TT(j, M2M) + g * TT(j, M2D) + im * q_m2i * TT(j, M2M) +
-                           Pd[j] * q_m2d * sc_n + Px[j] * q_m2m * TT(j, M2I) * sc_n);
-        const double g2 = (+pmatch * q_m2m * TT(j, D2M) + g * TT(j, D2D));
-        const double i2 = (+pmatch * q_i2m * TT(j, M2M) + im * q_i2i * TT(j, M2M));
-        Cm[j] = mm; Cg[j] = g2; Ci[j] = i2;
-        g = g2; im = i2;
+        const float tb = tt[j * 7 + kb], tc = tt[j * 7 + kc];
+        const float c1 = lane == 0 ? tc : q_i2i, d1 = lane == 0 ? 1.0f : tc;
+        const double nv = (cm[j] * a1) * tb + (v * c1) * d1;
+        v = of[j] ? 0.0 : nv;
+        dst[j] = v;
       }
     }
     __syncwarp();
-    for (int j = 1 + lane; j <= Lt - 1; j += 32) post[(size_t)i * W + j] *= (float)(Cm[j] / Pf);
+    TICK(5);
+    // phase C (lanes = columns): MM from pmatch, the finished GD / IM of column j+1 and the row below
+    for (int j = 1 + lane; j <= Lt - 1; j += 32) {
+      double mm = 0.0;
+      if (!offrow[j]) {
+        const double pmatch = Cm[j];
+        mm = (+pmin + pmatch * q_m2m * TT(j, M2M) + Cg[j + 1] * TT(j, M2D) + Ci[j + 1] * q_m2i * TT(j, M2M) +
+              Pd[j] * q_m2d * sc_n + Px[j] * q_m2m * TT(j, M2I) * sc_n);
+      }
+      Cm[j] = mm;
+      post[(size_t)i * W + j] *= (float)(mm / Pf);
+    }
     SWAP_ROWS();
     __syncwarp();
+    TICK(6);
   }
 
   // ------------------------------------------------------------------ MAC dynamic programming (float)
+  // S_curr[j-1] - 0.5*mact is written in double in the reference; with 0.5*mact exactly a float (halving is exact)
+  // and |S| < 2^28 * 0.5*mact or S in {0, -FLT_MIN}, the difference of the two floats is exact in double, so
+  // rounding it once to float equals the float subtraction used here.
   float* Sp = reinterpret_cast<float*>(base);
   float* Sc = Sp + RS;
-  float* T12 = Sc + RS;                                   // max(term1, term2) candidates per column
-  float* T3 = T12 + RS;
-  uint8_t* st12 = reinterpret_cast<uint8_t*>(T3 + RS);
+  float* T123 = Sc + RS;                                  // best of term1..term3 per column
+  uint8_t* st123 = reinterpret_cast<uint8_t*>(T123 + RS);
   __syncwarp();
   for (int j = lane; j <= Lt; j += 32) Sp[j] = 0.0f;
   const float mact = A.mact;
   const double half_mact = 0.5 * mact;
+  const float half_f = (float)half_mact;
+  const bool half_exact = (double)half_f == half_mact;
   float score_MAC = -FLT_MAX;
   int mi2 = 0, mj2 = 0;
   if (lane == 0) bt[0] = 0;
   __syncwarp();
   for (int i = 1; i <= Lq; ++i) {
     for (int j = 1 + lane; j <= Lt; j += 32) {
-      if (OFFC(i, j)) continue;
+      const uint8_t o = OFFC(i, j);
+      offrow[j] = o;
+      if (o) continue;
       const float p = post[(size_t)i * W + j];
       const float term1 = __fsub_rn(p, mact);
       const float term2 = __fsub_rn(__fadd_rn(Sp[j - 1], p), mact);
-      if (term1 > term2) { T12[j] = term1; st12[j] = 0; } else { T12[j] = term2; st12[j] = 2; }
-      T3[j] = (float)((double)Sp[j] - half_mact);
+      const float term3 = (float)((double)Sp[j] - half_mact);
+      float mx; uint8_t st;
+      if (term1 > term2) { mx = term1; st = 0; } else { mx = term2; st = 2; }
+      if (term3 > mx) { mx = term3; st = 6; }             // MI
+      T123[j] = mx; st123[j] = st;
     }
     __syncwarp();
+    TICK(7);
     if (lane == 0) {
       float left = 0.0f;                                  // S_curr[jmin-1] = 0
       Sc[0] = 0.0f;
+      uint8_t* __restrict__ btrow = bt + (size_t)i * W;
+      const float* __restrict__ t123 = T123;
+      const uint8_t* __restrict__ s123 = st123;
+      const uint8_t* __restrict__ of = offrow;
+      float* __restrict__ sc_row = Sc;
+      const bool can_end = A.local || i == Lq;
+#pragma unroll 4
       for (int j = 1; j <= Lt; ++j) {
-        float mx; uint8_t st;
-        if (OFFC(i, j)) { mx = -FLT_MIN; st = 0; }
-        else {
-          mx = T12[j]; st = st12[j];
-          const float t3 = T3[j];
-          if (t3 > mx) { mx = t3; st = 6; }               // MI
-          const float t4 = (float)((double)left - half_mact);
-          if (t4 > mx) { mx = t4; st = 4; }               // IM
-          if (mx > score_MAC && (A.local || i == Lq)) { mi2 = i; mj2 = j; score_MAC = mx; }
-        }
-        Sc[j] = mx; bt[(size_t)i * W + j] = st;
+        const float t4 = half_exact ? __fsub_rn(left, half_f) : (float)((double)left - half_mact);
+        float mx = t123[j]; uint8_t st = s123[j];
+        if (t4 > mx) { mx = t4; st = 4; }                 // IM
+        const bool o = of[j] != 0;
+        mx = o ? -FLT_MIN : mx; st = o ? (uint8_t)0 : st;
+        if (!o && can_end && mx > score_MAC) { mi2 = i; mj2 = j; score_MAC = mx; }
+        sc_row[j] = mx; btrow[j] = st;
         left = mx;
       }
       if (!A.local && Sc[Lt] > score_MAC) { mi2 = i; mj2 = Lt; score_MAC = Sc[Lt]; }
     }
     __syncwarp();
+    TICK(8);
     { float* t_ = Sp; Sp = Sc; Sc = t_; }
   }
 
@@ -370,7 +442,10 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
     }
     o.sum_of_probs = sum; o.flags = 0; o.pforward = Pf; o.path_off = po;
     A.out[r] = o;
+    TICK(9);
+    if (A.dbg) for (int k = 0; k < 12; ++k) A.dbg[(size_t)r * 12 + k] = tk[k];
   }
+#undef TICK
 #undef OFFC
 #undef QT
 #undef TT

@@ -17,6 +17,7 @@
  *   Prefilter::swStripedByte            src/hhprefilter.h:112      -> hhg_prefilter_sw
  *   HHEntry::getTemplateHMM / HMM::Read src/hhdatabase.cpp:300, src/hhhmm.cpp:202 -> hhg_db_create_hhm
  *   PrepareTemplateHMM                  src/hhfunc.cpp:165         -> hhg_db_create_hhm + hhg_db_apply_null_model
+ *   PosteriorDecoder::realign           src/hhposteriordecoder.h:67 -> hhg_mac_realign
  *
  * Error convention: every function returns 0 on success or a negative HHG_E* code;
  * hhg_last_error() returns a thread-local message.  (The reference logs and exit()s,
