@@ -88,7 +88,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln)
+            self.lines.append((time.time(), ln))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
@@ -99,7 +105,12 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        # nvidia-smi needs ~0.2 s to start, so it is launched before the warm-up; only samples that arrived inside
+        # the timed region count
+        t0 = getattr(self, "t_begin", 0.0)
+        t1 = getattr(self, "t_end", float("inf"))
+        inside = [(ts, ln) for ts, ln in self.lines if t0 <= ts <= t1 + 0.02]
+        for ts, ln in (inside or self.lines[-3:]):      # a very short region may fall between two samples
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -265,14 +276,15 @@ def main():
         plan.run()
         return topk_exchange(hits_dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # before the warm-up: nvidia-smi takes a moment to deliver its first sample
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_begin()
     l0 = ctx.launches
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -283,6 +295,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = ctx.launches - l0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
