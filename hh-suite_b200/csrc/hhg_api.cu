@@ -107,7 +107,9 @@ struct hhg_ctx {
   DevBuf<uint8_t> mac_off, mac_bt, mac_out_states;
   DevBuf<double> mac_rows, mac_scale;
   DevBuf<long long> mac_i64, mac_dbg;
-  DevBuf<int> mac_i32, mac_out_i, mac_out_j, mac_flag;
+  DevBuf<int> mac_i32, mac_out_i, mac_out_j, mac_flag, mac_map;
+  cudaStream_t aux_stream = nullptr;     // long-template launch of hhg_mac_realign
+  cudaEvent_t aux_ev[2] = {nullptr, nullptr};
   DevBuf<MacHitOut> mac_out;
   std::vector<long long> mac_cell_off;   // of the last call (debug fetch)
   std::vector<int> mac_Lt;
@@ -252,6 +254,8 @@ int hhg_ctx_destroy(hhg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->scratch_plan) hhg_plan_destroy(ctx->scratch_plan);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->aux_ev) if (e) cudaEventDestroy(e);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return HHG_OK;
@@ -1084,7 +1088,7 @@ int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target
     rec0[r] = db->col_off[t]; Lt[r] = L;
     tr_off[r] = ntr; ntr += (long long)(L + 1) * 7;
     cell_off[r] = ncell; ncell += (long long)(Lq + 1) * (L + 1);
-    row_off[r] = nrow; nrow += 10LL * (L + 3) + (L + 3 + 7) / 8 + 1;   // + the cell-off row of the fallback path
+    row_off[r] = nrow; nrow += 11LL * (L + 3) + (L + 3 + 7) / 8 + 1;   // + the cell-off row of the fallback path
     path_off[r] = npath; npath += (long long)Lq + L + 2;
   }
   if ((size_t)npath > path_cap) return fail(HHG_EINVAL, "hhg_mac_realign: path buffers hold %zu entries, %lld needed", path_cap, npath);
@@ -1166,18 +1170,51 @@ int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target
   const auto t_k0 = now();
   k_mac_band<<<n, 256, 0, ctx->stream>>>(A);
   {
-    // working set in shared memory (109 bytes per template column) for templates up to ~600 columns: 64 KB per warp
-    // keeps 3 warps per SM resident (500 hits over 148 SMs need 3.4); longer templates use the global scratch
-    int Lmax = 0;
-    for (int r = 0; r < n; ++r) Lmax = std::max(Lmax, Lt[r]);
-    const size_t want = (size_t)109 * (Lmax + 3);
-    const size_t smem = std::min<size_t>(want, 64 * 1024);
-    CK(cudaFuncSetAttribute(k_mac_realign, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    A.smem_rows = (int)smem;
+    // working set in shared memory (117 bytes per template column).  Requests whose templates fit 64 KB (Lt <= ~555)
+    // run 3 warps per SM on the main stream; longer ones get their own launch with a window of up to 200 KB on an
+    // auxiliary stream so that they overlap the rest; beyond that the kernel falls back to the global scratch.
+    const size_t kSmall = 64 * 1024, kLarge = 200 * 1024;
+    std::vector<int> small_ids, large_ids;
+    size_t small_need = 0, large_need = 0;
+    for (int r = 0; r < n; ++r) {
+      const size_t need = (size_t)117 * (Lt[r] + 3);
+      if (need <= kSmall) { small_ids.push_back(r); small_need = std::max(small_need, need); }
+      else { large_ids.push_back(r); large_need = std::max(large_need, need); }
+    }
+    CK(cudaFuncSetAttribute(k_mac_realign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLarge));
     if (timing) { CK(ctx->mac_dbg.ensure((size_t)n * 12)); A.dbg = ctx->mac_dbg.p; }
-    k_mac_realign<<<n, 32, smem, ctx->stream>>>(A);
+    if (large_ids.empty()) {
+      A.smem_rows = (int)small_need;
+      k_mac_realign<<<n, 32, small_need, ctx->stream>>>(A);
+      ctx->launches++;
+    } else {
+      std::vector<int> map(small_ids);
+      map.insert(map.end(), large_ids.begin(), large_ids.end());
+      CK(ctx->mac_map.ensure(map.size()));
+      CK(cudaMemcpyAsync(ctx->mac_map.p, map.data(), map.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      if (!ctx->aux_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->aux_ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->aux_ev[1], cudaEventDisableTiming));
+      }
+      CK(cudaEventRecord(ctx->aux_ev[0], ctx->stream));              // band + inputs ready
+      CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
+      MacArgs AL = A;
+      const size_t lsm = std::min(large_need, kLarge);
+      AL.smem_rows = (int)lsm;
+      AL.req_map = ctx->mac_map.p + small_ids.size();
+      k_mac_realign<<<(unsigned)large_ids.size(), 32, lsm, ctx->aux_stream>>>(AL);
+      CK(cudaEventRecord(ctx->aux_ev[1], ctx->aux_stream));
+      if (!small_ids.empty()) {
+        A.smem_rows = (int)small_need;
+        A.req_map = ctx->mac_map.p;
+        k_mac_realign<<<(unsigned)small_ids.size(), 32, small_need, ctx->stream>>>(A);
+      }
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));
+      ctx->launches += small_ids.empty() ? 1 : 2;
+    }
   }
-  ctx->launches += 2;
+  ctx->launches += 1;
   CK(cudaGetLastError());
   if (timing) { CK(cudaStreamSynchronize(ctx->stream)); t_kern = ms_since(t_k0); }
   const auto t_d0 = now();

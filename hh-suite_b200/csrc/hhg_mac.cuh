@@ -49,6 +49,7 @@ struct MacArgs {
   float* post; uint8_t* off; uint8_t* bt;
   const long long* row_off;            // [n] offset (in doubles) of 10*(Lt+3) row buffers
   double* rows;
+  const int* req_map;                  // optional: blockIdx.x -> request (launches over a subset of the requests)
   long long* dbg;                      // optional [n*12] per-phase clock64 totals (HHG_MAC_TIMING)
   int smem_rows;                       // bytes of dynamic shared memory available for the row buffers
   double* scale;                       // [n*(Lq+3)]
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256) k_mac_band(const MacArgs A) {
 // (x*A)*B + (v*C)*D); lanes that differ only in operands do not serialise.
 __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
   extern __shared__ __align__(16) unsigned char mac_smem[];
-  const int r = blockIdx.x, lane = threadIdx.x;
+  const int r = A.req_map ? A.req_map[blockIdx.x] : (int)blockIdx.x, lane = threadIdx.x;
   const int Lq = A.Lq, Lt = A.Lt[r], W = Lt + 1;
   const uint8_t* off = A.off + A.cell_off[r];
   uint8_t* bt = A.bt + A.cell_off[r];
@@ -142,14 +143,15 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
   const size_t RS = (size_t)Lt + 3;
   // per-warp working set: 10 row buffers (doubles), the template's linear transitions, the cell-off flags of the
   // current row.  In shared memory when it fits; the sequential scans below then never wait for global memory.
-  const size_t need = 10 * RS * sizeof(double) + 7 * RS * sizeof(float) + RS;
+  const size_t need = 11 * RS * sizeof(double) + 7 * RS * sizeof(float) + RS;
   const bool in_smem = need <= (size_t)A.smem_rows;
   double* base = in_smem ? reinterpret_cast<double*>(mac_smem) : A.rows + A.row_off[r];
-  float* ttr_s = in_smem ? reinterpret_cast<float*>(mac_smem + 10 * RS * sizeof(double)) : nullptr;
-  uint8_t* offrow = in_smem ? mac_smem + 10 * RS * sizeof(double) + 7 * RS * sizeof(float)
-                            : reinterpret_cast<uint8_t*>(A.rows + A.row_off[r] + 10 * RS);
+  float* ttr_s = in_smem ? reinterpret_cast<float*>(mac_smem + 11 * RS * sizeof(double)) : nullptr;
+  uint8_t* offrow = in_smem ? mac_smem + 11 * RS * sizeof(double) + 7 * RS * sizeof(float)
+                            : reinterpret_cast<uint8_t*>(A.rows + A.row_off[r] + 11 * RS);
   double *Pm = base, *Pg = base + RS, *Pi = base + 2 * RS, *Pd = base + 3 * RS, *Px = base + 4 * RS;
   double *Cm = base + 5 * RS, *Cg = base + 6 * RS, *Ci = base + 7 * RS, *Cd = base + 8 * RS, *Cx = base + 9 * RS;
+  double* Xp = base + 10 * RS;                             // per-row addends of the Pforward lane
   const double Cshift = A.Cshift;
   const unsigned FULL = 0xffffffffu;
   if (in_smem) {
@@ -167,29 +169,37 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
   // Forward scan of row i (lanes 0 and 1):  GD: v = Cm[j-1]*t.M2D[j-1] + v*t.D2D[j-1]
   //                                          IM: v = Cm[j-1]*q.M2I[i]*t.M2M[j-1] + v*q.I2I[i]*t.M2M[j-1]
   // both as (x*A)*B + (v*C)*D with A,B,C,D per lane; off cells reset v to 0.
-  // Lane 2 accumulates Pforward in the same stream: Pf += (float)Cm[j] in row-major order, Pf *= scale[i+1] at the
-  // end of each row (src/hhforwardalgorithm.cpp:151-166) -- shape (x*1)*1 + (v*1)*1, never reset.
+  // The addend of every chain does not depend on the chain itself, so all lanes precompute it (fwd_pre) and the scan
+  // is v = pre[j] + (v*C)*D -- three FP64 instructions per column step instead of five.  Lane 2 accumulates
+  // Pforward in the same stream: Pf += (float)Cm[j] in row-major order, Pf *= scale[i+1] at the end of each row
+  // (src/hhforwardalgorithm.cpp:151-166), never reset.
   double Pf_acc = A.local ? 1.0 : 0.0;
+  auto fwd_pre = [&](int i) {
+    const float qa = QT(i, M2I);
+    for (int j = 1 + lane; j <= Lt; j += 32) {
+      const double cm1 = Cm[j - 1];
+      Cg[j] = (cm1 * TT(j - 1, M2D));
+      Ci[j] = (cm1 * qa) * TT(j - 1, M2M);
+      Xp[j] = (double)(float)Cm[j];
+    }
+  };
   auto fwd_scan = [&](int i, int jfirst) {
     if (lane < 3) {
-      const float qa = QT(i, M2I), qc = QT(i, I2I);
-      double* __restrict__ dst = lane == 0 ? Cg : (lane == 1 ? Ci : Cx + RS - 1);   // lane 2: dummy slot
-      const double* __restrict__ cm = Cm;
+      const float qc = QT(i, I2I);
+      double* __restrict__ dst = lane == 0 ? Cg : (lane == 1 ? Ci : Xp);
       const float* __restrict__ tt = ttr;
       const uint8_t* __restrict__ of = offrow;
-      const int ka = lane == 0 ? M2D : M2M, kc = lane == 0 ? D2D : M2M;
+      const int kc = lane == 0 ? D2D : M2M;
       double v = lane == 2 ? Pf_acc : 0.0;
-      if (lane == 2 && jfirst == 2 && A.local) v += (double)(float)cm[1];
+      if (lane == 2 && jfirst == 2) v += dst[1];          // (only the local-mode value of Pf_acc is used)
       if (jfirst == 2 && lane < 2) dst[1] = 0.0;
 #pragma unroll 4
       for (int j = jfirst; j <= Lt; ++j) {
-        const float ta = tt[(j - 1) * 7 + ka], tc = tt[(j - 1) * 7 + kc];
-        const float a1 = lane == 0 ? ta : (lane == 1 ? qa : 1.0f), b1 = lane == 1 ? ta : 1.0f;
+        const float tc = tt[(j - 1) * 7 + kc];
         const float c1 = lane == 0 ? tc : (lane == 1 ? qc : 1.0f), d1 = lane == 1 ? tc : 1.0f;
-        const double x = lane == 2 ? (double)(float)cm[j] : cm[j - 1];
-        const double nv = (x * a1) * b1 + (v * c1) * d1;
+        const double nv = dst[j] + (v * c1) * d1;
         v = (lane < 2 && of[j]) ? 0.0 : nv;
-        if (lane < 2) dst[j] = v;
+        dst[j] = v;
       }
       if (lane == 2) Pf_acc = v;
     }
@@ -205,6 +215,8 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
     offrow[j] = o;
     if (!o) Cm[j] = (double)mac_dot20(A.q_p + 20, tcol[j].p) * Cshift;
   }
+  __syncwarp();
+  fwd_pre(1);
   __syncwarp();
   fwd_scan(1, 1);
   __syncwarp();
@@ -242,6 +254,8 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
       }
       Cm[j] = mm; Cd[j] = dg; Cx[j] = mi;
     }
+    __syncwarp();
+    fwd_pre(i);
     __syncwarp();
     TICK(0);
     fwd_scan(i, 2);
@@ -309,6 +323,8 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
         Cd[j] = (+pmatch * q_d2m * TT(j, M2M) + Pd[j] * q_d2d * sc_n);
         Cx[j] = (+pmatch * q_m2m * TT(j, I2M) + Px[j] * q_m2m * TT(j, I2I) * sc_n);
         Cm[j] = pmatch;
+        Cg[j] = (pmatch * q_m2m) * TT(j, D2M);            // addends of the GD / IM chains
+        Ci[j] = (pmatch * q_i2m) * TT(j, M2M);
       }
     }
     __syncwarp();
@@ -317,17 +333,15 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
     //                                           IM: v = pmatch*q.I2M*t.M2M[j] + v*q.I2I*t.M2M[j]
     if (lane < 2) {
       double* __restrict__ dst = lane == 0 ? Cg : Ci;
-      const double* __restrict__ cm = Cm;
       const float* __restrict__ tt = ttr;
       const uint8_t* __restrict__ of = offrow;
-      const float a1 = lane == 0 ? q_m2m : q_i2m;
-      const int kb = lane == 0 ? D2M : M2M, kc = lane == 0 ? D2D : M2M;
+      const int kc = lane == 0 ? D2D : M2M;
       double v = 0.0;
 #pragma unroll 4
       for (int j = Lt - 1; j >= 1; --j) {
-        const float tb = tt[j * 7 + kb], tc = tt[j * 7 + kc];
+        const float tc = tt[j * 7 + kc];
         const float c1 = lane == 0 ? tc : q_i2i, d1 = lane == 0 ? 1.0f : tc;
-        const double nv = (cm[j] * a1) * tb + (v * c1) * d1;
+        const double nv = dst[j] + (v * c1) * d1;
         v = of[j] ? 0.0 : nv;
         dst[j] = v;
       }
