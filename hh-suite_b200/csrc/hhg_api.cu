@@ -107,7 +107,7 @@ struct hhg_ctx {
   DevBuf<uint8_t> mac_off, mac_bt, mac_out_states;
   DevBuf<double> mac_rows, mac_scale;
   DevBuf<long long> mac_i64, mac_dbg;
-  DevBuf<int> mac_i32, mac_out_i, mac_out_j, mac_flag, mac_map;
+  DevBuf<int> mac_i32, mac_out_i, mac_out_j, mac_map;
   cudaStream_t aux_stream = nullptr;     // long-template launch of hhg_mac_realign
   cudaEvent_t aux_ev[2] = {nullptr, nullptr};
   DevBuf<MacHitOut> mac_out;
