@@ -54,3 +54,23 @@ def write_ffindex(data_path: str, records: list[tuple[str, bytes]], index_path: 
     with open(index_path, "w") as f:
         for name, off, ln in sorted(entries):
             f.write(f"{name}\t{off}\t{ln}\n")
+
+
+def cs219_arrays(ff: FFIndex):
+    """(L, off, seq) for capi.CsDB from an `X_cs219` ffindex in the binary column-state format, as
+    Prefilter::init_prefilter reads it (src/hhprefilter.cpp:314-335): record n = `length[n] = entry->length - 1`
+    state bytes followed by NUL.  The old text format (records starting with '>') is refused like checkCSFormat does
+    (:337-352)."""
+    seq = np.frombuffer(ff.data, np.uint8)
+    L = (ff.lengths - 1).astype(np.int32)
+    if len(L) and L.min() < 1:
+        raise ValueError("cs219 database has an empty record")
+    for k in range(min(5, len(ff))):
+        if seq[ff.offsets[k]] == ord(">"):
+            raise ValueError("cs219 database is in the old text format; rebuild it with cstranslate -b (binary)")
+    return L, ff.offsets.copy(), seq
+
+
+def hhm_arrays(ff: FFIndex):
+    """(data, offsets, lengths) of an `X_hhm` ffindex for capi.TargetDB.from_hhm."""
+    return ff.data, ff.offsets.copy(), ff.lengths.copy()

@@ -116,3 +116,22 @@ def test_ffindex_roundtrip(tmp_path):
     got = {n: ff.record(k) for k, n in enumerate(ff.names)}
     assert got == {n: b + b"\0" for n, b in recs}
     ff.close()
+
+
+def test_cs219_ffindex_arrays(tmp_path):
+    """init_prefilter's view of a binary cs219 database: length = entry length - 1, pointers into the data file."""
+    from hhsuite_b200 import ffindex
+    rng = np.random.default_rng(4)
+    seqs = {f"s{k:03d}": rng.integers(0, 219, int(L), dtype=np.uint8).tobytes() for k, L in enumerate([5, 1, 300, 77])}
+    ffindex.write_ffindex(str(tmp_path / "db_cs219.ffdata"), list(seqs.items()))
+    ff = ffindex.FFIndex(str(tmp_path / "db_cs219.ffdata"))
+    L, off, seq = ffindex.cs219_arrays(ff)
+    assert L.tolist() == [len(seqs[n]) for n in ff.names]
+    for k, n in enumerate(ff.names):
+        assert seq[off[k]:off[k] + L[k]].tobytes() == seqs[n] and seq[off[k] + L[k]] == 0
+    ff.close()
+    ffindex.write_ffindex(str(tmp_path / "old_cs219.ffdata"), [("a", b">a\nABCDEF")])
+    ff = ffindex.FFIndex(str(tmp_path / "old_cs219.ffdata"))
+    with pytest.raises(ValueError, match="old text format"):
+        ffindex.cs219_arrays(ff)
+    ff.close()
