@@ -37,7 +37,10 @@ class FFIndex:
 
     def close(self):
         if hasattr(self.data, "close"):
-            self.data.close()
+            try:
+                self.data.close()
+            except BufferError:       # numpy views of the mapping are still alive; the map goes with the last of them
+                pass
         self._f.close()
 
 
