@@ -135,3 +135,46 @@ def test_cs219_ffindex_arrays(tmp_path):
     with pytest.raises(ValueError, match="old text format"):
         ffindex.cs219_arrays(ff)
     ff.close()
+
+
+def test_tokeniser_fuzz_never_crashes_and_agrees_with_oracle(oracle):
+    """Truncated / corrupted / spliced HHM records (what a damaged ffindex entry looks like): the product tokeniser
+    must either refuse the record or return exactly the integers the oracle's parser reads."""
+    from hhsuite_b200 import capi, synth
+    G = golden()
+    rng = np.random.default_rng(0)
+    base = [synth.hhm_text(L, 900 + k, f"f{k}", with_ss=bool(k % 2)).encode() for k, L in enumerate([3, 17, 60])]
+    base.append(G["hhm_ss60_text"].tobytes())
+    accepted = rejected = 0
+    for it in range(800):
+        t = bytearray(base[it % len(base)])
+        mode = it % 5
+        if mode == 0:
+            t = t[:int(rng.integers(0, len(t)))]
+        elif mode == 1:
+            for _ in range(int(rng.integers(1, 20))):
+                t[int(rng.integers(0, len(t)))] = int(rng.integers(0, 256))
+        elif mode == 2:
+            lines = bytes(t).split(b"\n"); del lines[int(rng.integers(0, len(lines)))]; t = bytearray(b"\n".join(lines))
+        elif mode == 3:
+            lines = bytes(t).split(b"\n"); k = int(rng.integers(0, len(lines))); lines.insert(k, lines[k])
+            t = bytearray(b"\n".join(lines))
+        else:
+            k = int(rng.integers(0, len(t)))
+            t[k:k] = bytes(rng.integers(0, 256, int(rng.integers(1, 50)), dtype=np.uint8))
+        t = bytes(t)
+        if not t:
+            continue
+        try:
+            a = capi.hhm_parse(t)
+        except capi.HhgError:
+            rejected += 1
+            continue
+        accepted += 1
+        try:
+            b = oracle.hhm_parse(t, maxL=a["L"] + 5)
+        except ValueError:
+            continue
+        if b["L"] == a["L"]:
+            assert np.array_equal(a["f"], b["f"][1:a["L"] + 1]) and np.array_equal(a["tr"], b["tr"]), it
+    assert accepted > 100 and rejected > 100
