@@ -57,12 +57,32 @@ struct __align__(32) BndSlot {
 };
 static_assert(sizeof(BndSlot) == 32, "BndSlot must be one 32-byte sector");
 
+// HHG_SLOT_EVICT_LAST=1 (build variant, off by default; drafted for round 2, not yet measured): tag the slot
+// accesses with an L2 evict_last policy so that the 8 GB stream of backtrace words (stored evict_first) does not
+// push the 13 MB of live hand-off slots of a job group out to DRAM between two strips.
+#ifndef HHG_SLOT_EVICT_LAST
+#define HHG_SLOT_EVICT_LAST 0
+#endif
+#if HHG_SLOT_EVICT_LAST
+__device__ __forceinline__ uint64_t slot_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+#endif
 __device__ __forceinline__ void st_slot(BndSlot* p, float mm, float dg, float mi, float gd, float im,
                                         uint32_t tag) {
+#if HHG_SLOT_EVICT_LAST
+  asm volatile("st.relaxed.gpu.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p),
+               "r"(__float_as_uint(mm)), "r"(__float_as_uint(dg)), "r"(__float_as_uint(mi)),
+               "r"(__float_as_uint(gd)), "r"(__float_as_uint(im)), "r"(tag), "r"(0u), "r"(0u), "l"(slot_policy())
+               : "memory");
+#else
   asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
                "r"(__float_as_uint(mm)), "r"(__float_as_uint(dg)), "r"(__float_as_uint(mi)),
                "r"(__float_as_uint(gd)), "r"(__float_as_uint(im)), "r"(tag), "r"(0u), "r"(0u)
                : "memory");
+#endif
 }
 // pad0/pad1 are returned so the caller can keep their registers live until the slot is consumed: a dead
 // destination register of an in-flight load gets reused by ptxas and the re-use then stalls on the load
@@ -70,10 +90,17 @@ __device__ __forceinline__ void st_slot(BndSlot* p, float mm, float dg, float mi
 __device__ __forceinline__ void ld_slot(const BndSlot* p, float& mm, float& dg, float& mi, float& gd,
                                         float& im, uint32_t& tag, uint32_t& x, uint32_t& y) {
   uint32_t a, b, c, d, e;
+#if HHG_SLOT_EVICT_LAST
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(tag), "=r"(x), "=r"(y)
+               : "l"(p), "l"(slot_policy())
+               : "memory");
+#else
   asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(tag), "=r"(x), "=r"(y)
                : "l"(p)
                : "memory");
+#endif
   mm = __uint_as_float(a); dg = __uint_as_float(b); mi = __uint_as_float(c);
   gd = __uint_as_float(d); im = __uint_as_float(e);
 }
