@@ -11,7 +11,11 @@
 // It contains no reference code; it includes the reference headers at build time and is compiled by
 // oracle/ref_build.mk into oracle/_ref/hh_dropin_check (shipped prebuilt to the GPU box).
 //
-// usage: hh_dropin_check <query.hhm> <template.hhm> [more templates ...]     exit 0 = identical
+// usage: hh_dropin_check [--hhm-loader] [--mac] <query.hhm> <template.hhm> [more templates ...]   exit 0 = identical
+//   --hhm-loader  templates are loaded by hhg_db_create_hhm from the HHM text instead of the reference's preparation
+//   --mac         additionally realign every hit: PosteriorDecoderRunner::executeComputation vs hhg_mac_realign
+//                 (written in round 1, first exercised on a GPU in round 2; the MAC parity of round 1 is established
+//                 by tests/test_mac_gpu.py against the same reference code through oracle/ref_shim.cpp)
 
 #include <algorithm>
 #include <cstdio>
@@ -36,6 +40,9 @@
 #include "hhfunc.h"
 #include "hhdatabase.h"
 #include "hhhit.h"
+#include "hhposteriordecoder.h"
+#include "hhposteriordecoderrunner.h"
+#include "hhposteriormatrix.h"
 #undef private
 #undef protected
 
@@ -193,6 +200,67 @@ class GpuViterbiRunner {
     return ret;
   }
 
+  // The adapter of INTEGRATION.md section 2b: PosteriorDecoderRunner::executeComputation on the C-ABI.  `vit` are the
+  // Viterbi hits to realign; q is the query AFTER the reference put it into linear transition space.
+  struct GpuMac { int target, irep, i1, i2, j1, j2, nsteps, matched_cols; float sum_of_probs; double pforward;
+                  std::vector<int> i, j; std::vector<char> states; std::vector<float> post; };
+  std::vector<GpuMac> realign(Parameters& par, HMM* q, const std::vector<GpuHit>& vit) {
+    std::vector<float> qp((size_t)(q->L + 2) * 20), qtr((size_t)(q->L + 1) * 7);
+    for (int i = 0; i <= q->L + 1; ++i) memcpy(&qp[(size_t)i * 20], q->p[i], 80);
+    for (int i = 0; i <= q->L; ++i) memcpy(&qtr[(size_t)i * 7], q->tr[i], 28);
+    HHG_CHECK(hhg_mac_query_set(ctx_, q->L, qp.data(), qtr.data()));
+    std::map<int, std::vector<const GpuHit*>> by_target;                 // alignments_map + sort by irep (:54-66)
+    for (const GpuHit& h : vit) if (h.nsteps > 0) by_target[h.target].push_back(&h);
+    for (auto& kv : by_target)
+      std::sort(kv.second.begin(), kv.second.end(), [](const GpuHit* a, const GpuHit* b) { return a->irep < b->irep; });
+    std::map<int, std::pair<std::vector<int32_t>, std::vector<int32_t>>> alt;   // Hit.alt_i / alt_j per template
+    std::vector<GpuMac> out;
+    for (size_t round = 0;; ++round) {
+      std::vector<const GpuHit*> batch;
+      for (auto& kv : by_target) if (kv.second.size() > round) batch.push_back(kv.second[round]);
+      if (batch.empty()) break;
+      std::vector<int32_t> target, vitv, vi, vj, ei, ej;
+      std::vector<int64_t> voff(1, 0), eoff(1, 0);
+      size_t cap = 0;
+      for (const GpuHit* h : batch) {
+        target.push_back(h->target);
+        const int32_t v5[5] = {h->i1, h->i2, h->j1, h->j2, h->nsteps};
+        vitv.insert(vitv.end(), v5, v5 + 5);
+        vi.insert(vi.end(), h->i.begin() + 1, h->i.end()); vj.insert(vj.end(), h->j.begin() + 1, h->j.end());
+        voff.push_back((int64_t)vi.size());
+        auto& a = alt[h->target];
+        ei.insert(ei.end(), a.first.begin(), a.first.end()); ej.insert(ej.end(), a.second.begin(), a.second.end());
+        eoff.push_back((int64_t)ei.size());
+        cap += (size_t)q->L + L_[h->target] + 2;
+      }
+      if (ei.empty()) { ei.push_back(0); ej.push_back(0); }
+      std::vector<hhg_mac_hit> mh(batch.size());
+      std::vector<int32_t> oi(cap), oj(cap);
+      std::vector<uint8_t> os(cap);
+      std::vector<float> op(cap);
+      hhg_mac_params mp = {par.loc, par.shift, par.mact};
+      HHG_CHECK(hhg_mac_realign(ctx_, db_, (int)batch.size(), target.data(), vitv.data(), voff.data(), vi.data(), vj.data(),
+                                round ? eoff.data() : nullptr, ei.data(), ej.data(), &mp, mh.data(), oi.data(), oj.data(),
+                                os.data(), op.data(), cap));
+      for (size_t k = 0; k < batch.size(); ++k) {
+        const hhg_mac_hit& m = mh[k];
+        GpuMac g;
+        g.target = batch[k]->target; g.irep = batch[k]->irep;
+        g.i1 = m.i1; g.i2 = m.i2; g.j1 = m.j1; g.j2 = m.j2; g.nsteps = m.nsteps; g.matched_cols = m.matched_cols;
+        g.sum_of_probs = m.sum_of_probs; g.pforward = m.pforward;
+        g.i.assign(oi.begin() + m.path_off, oi.begin() + m.path_off + m.nsteps + 1);
+        g.j.assign(oj.begin() + m.path_off, oj.begin() + m.path_off + m.nsteps + 1);
+        g.states.assign(os.begin() + m.path_off, os.begin() + m.path_off + m.nsteps + 1);
+        g.post.assign(op.begin() + m.path_off, op.begin() + m.path_off + m.nsteps + 1);
+        auto& a = alt[g.target];                                         // backtraceMAC pushes every visited (i,j)
+        if (m.nsteps) { a.first.insert(a.first.end(), g.i.begin() + 1, g.i.end()); a.second.insert(a.second.end(), g.j.begin() + 1, g.j.end()); }
+        else { a.first.push_back(g.i[0]); a.second.push_back(g.j[0]); }
+        out.push_back(g);
+      }
+    }
+    return out;
+  }
+
  private:
   hhg_ctx* ctx_ = nullptr;
   hhg_db* db_ = nullptr;
@@ -205,9 +273,14 @@ uint32_t bits(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 }  // namespace
 
 int main(int argc, char** argv) {
-  bool text_loader = false;
-  if (argc > 1 && !strcmp(argv[1], "--hhm-loader")) { text_loader = true; --argc; ++argv; }
-  if (argc < 3) { fprintf(stderr, "usage: %s [--hhm-loader] query.hhm template.hhm [...]\n", argv[0]); return 2; }
+  bool text_loader = false, with_mac = false;
+  while (argc > 1 && argv[1][0] == '-' && argv[1][1] == '-') {
+    if (!strcmp(argv[1], "--hhm-loader")) text_loader = true;
+    else if (!strcmp(argv[1], "--mac")) with_mac = true;
+    else break;
+    --argc; ++argv;
+  }
+  if (argc < 3) { fprintf(stderr, "usage: %s [--hhm-loader] [--mac] query.hhm template.hhm [...]\n", argv[0]); return 2; }
   Log::reporting_level() = WARNING;
   const char* pargv[] = {"hhalign"};
   Parameters par(1, pargv);
@@ -282,6 +355,40 @@ int main(int argc, char** argv) {
     }
   }
   if (text_loader) printf("(templates loaded by hhg_db_create_hhm from the HHM text)\n");
+  // ---- (3) optional: MAC realignment of all hits, reference runner vs C-ABI
+  if (with_mac && !bad) {
+    std::vector<PosteriorMatrix*> pms(par.threads);
+    int Lmax = 0;
+    for (Hit& h : ref) Lmax = std::max(Lmax, (int)h.L);
+    for (auto& pm : pms) { pm = new PosteriorMatrix(); pm->allocateMatrix(q->L, Lmax + 2); }
+    std::vector<Hit*> hit_ptrs;
+    for (Hit& h : ref) if (h.nsteps > 0) hit_ptrs.push_back(&h);
+    par.ssw = par.ssw_realign;                                           // src/hhalign.cpp:651
+    PosteriorDecoderRunner prunner(pms.data(), mats.data(), par.threads, par.ssw, S73, S33, S37);
+    prunner.executeComputation(*q, hit_ptrs, par, par.qsc_db, pb, S, Sim, R);   // puts q into linear space, realigns in place
+    std::vector<GpuViterbiRunner::GpuMac> gm = gpu_runner.realign(par, q, gpu);
+    std::map<std::pair<int, int>, const GpuViterbiRunner::GpuMac*> mmap;
+    for (const auto& g : gm) mmap[{g.target, g.irep}] = &g;
+    int mbad = 0;
+    for (Hit* hp : hit_ptrs) {
+      Hit& h = *hp;
+      auto it = mmap.find({index[h.entry], h.irep});
+      if (it == mmap.end()) { printf("MAC MISMATCH: no gpu result for template %d irep %d\n", index[h.entry], h.irep); ++mbad; continue; }
+      const auto& g = *it->second;
+      bool ok = h.i1 == g.i1 && h.i2 == g.i2 && h.j1 == g.j1 && h.j2 == g.j2 && h.nsteps == g.nsteps &&
+                h.matched_cols == g.matched_cols && bits(h.sum_of_probs) == bits(g.sum_of_probs) && h.Pforward == g.pforward;
+      for (int s = 1; ok && s <= h.nsteps; ++s)
+        ok = h.i[s] == g.i[s] && h.j[s] == g.j[s] && h.states[s] == g.states[s] && bits(h.P_posterior[s]) == bits(g.post[s]);
+      if (!ok) {
+        printf("MAC MISMATCH: template %d irep %d: ref %d-%d,%d-%d %d steps sum %.6f Pf %.17g | gpu %d-%d,%d-%d %d steps sum %.6f Pf %.17g\n",
+               index[h.entry], h.irep, h.i1, h.i2, h.j1, h.j2, h.nsteps, h.sum_of_probs, h.Pforward, g.i1, g.i2, g.j1, g.j2,
+               g.nsteps, g.sum_of_probs, g.pforward);
+        ++mbad;
+      }
+    }
+    printf("hh_dropin_check --mac: %zu hits realigned: %s\n", hit_ptrs.size(), mbad ? "MISMATCH" : "all MAC alignments identical");
+    bad += mbad;
+  }
   printf("hh_dropin_check: query L=%d, %zu templates, %zu hits (up to irep %d): %s\n", q->L, entries.size(), ref.size(),
          maxrep, bad ? "MISMATCH" : "all hits identical");
   return bad ? 1 : 0;
