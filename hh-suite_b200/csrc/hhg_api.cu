@@ -1125,6 +1125,7 @@ int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target
   const int* d32 = ctx->mac_i32.p;
   MacArgs A{};
   A.n = n; A.Lq = Lq; A.local = par->local ? 1 : 0; A.mact = par->mact;
+  { const char* e = getenv("HHG_MAC_BANDSCAN"); A.band_scan = (e && atoi(e) == 1) ? 1 : 0; }   // opt-in, see hhg_mac.cuh
   A.Cshift = ::pow(2.0, par->shift);                       // src/hhforwardalgorithm.cpp:16
   A.q_p = ctx->mac_qp.p; A.q_tr = ctx->mac_qtr.p;
   A.cols = reinterpret_cast<const ColRec*>(db->cols.p);

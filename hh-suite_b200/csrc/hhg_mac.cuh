@@ -16,6 +16,7 @@
 // No secondary-structure term (hit.ssm2 == 0) and no self-alignment mode.
 #pragma once
 #include <cfloat>
+#include <climits>
 #include <cstdint>
 
 namespace hhg {
@@ -49,6 +50,7 @@ struct MacArgs {
   float* post; uint8_t* off; uint8_t* bt;
   const long long* row_off;            // [n] offset (in doubles) of 10*(Lt+3) row buffers
   double* rows;
+  int band_scan;                       // opt-in (HHG_MAC_BANDSCAN=1): scans visit only [first, last] active column of a row
   const int* req_map;                  // optional: blockIdx.x -> request (launches over a subset of the requests)
   long long* dbg;                      // optional [n*12] per-phase clock64 totals (HHG_MAC_TIMING)
   int smem_rows;                       // bytes of dynamic shared memory available for the row buffers
@@ -174,12 +176,25 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
   // Pforward in the same stream: Pf += (float)Cm[j] in row-major order, Pf *= scale[i+1] at the end of each row
   // (src/hhforwardalgorithm.cpp:151-166), never reset.
   double Pf_acc = A.local ? 1.0 : 0.0;
+  // Band-limited scans (A.band_scan): outside [jlo, jhi] every cell of the row is switched off, where the reference
+  // computes exact zeros (GD = IM = 0, posterior 0 -> Pforward += 0.0 is a no-op) and every chain re-enters an active
+  // run with v = 0; visiting only the active span therefore gives the same bits with ~Lt/band fewer dependent steps.
+  // fwd_pre leaves the final zeros in the switched-off cells so the span can skip them.
+  const bool bs = A.band_scan != 0;
+  int jlo = 1, jhi = Lt;
+  auto row_span = [&](int lo, int hi) {          // warp-wide first/last active column of the row just staged
+    if (!bs) { jlo = 1; jhi = Lt; return; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { lo = min(lo, __shfl_xor_sync(FULL, lo, o)); hi = max(hi, __shfl_xor_sync(FULL, hi, o)); }
+    jlo = lo; jhi = hi;
+  };
   auto fwd_pre = [&](int i) {
     const float qa = QT(i, M2I);
     for (int j = 1 + lane; j <= Lt; j += 32) {
       const double cm1 = Cm[j - 1];
-      Cg[j] = (cm1 * TT(j - 1, M2D));
-      Ci[j] = (cm1 * qa) * TT(j - 1, M2M);
+      const bool dead = bs && offrow[j];
+      Cg[j] = dead ? 0.0 : (cm1 * TT(j - 1, M2D));
+      Ci[j] = dead ? 0.0 : (cm1 * qa) * TT(j - 1, M2M);
       Xp[j] = (double)(float)Cm[j];
     }
   };
@@ -193,8 +208,9 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
       double v = lane == 2 ? Pf_acc : 0.0;
       if (lane == 2 && jfirst == 2) v += dst[1];          // (only the local-mode value of Pf_acc is used)
       if (jfirst == 2 && lane < 2) dst[1] = 0.0;
+      const int jbeg = max(jfirst, jlo), jend = jhi;
 #pragma unroll 4
-      for (int j = jfirst; j <= Lt; ++j) {
+      for (int j = jbeg; j <= jend; ++j) {
         const float tc = tt[(j - 1) * 7 + kc];
         const float c1 = lane == 0 ? tc : (lane == 1 ? qc : 1.0f), d1 = lane == 1 ? tc : 1.0f;
         const double nv = dst[j] + (v * c1) * d1;
@@ -210,10 +226,14 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
   // ------------------------------------------------------------------ Forward, row 1
   for (int j = lane; j <= Lt + 1; j += 32) { Cm[j] = Cg[j] = Ci[j] = Cd[j] = Cx[j] = 0.0; Pm[j] = Pg[j] = Pi[j] = Pd[j] = Px[j] = 0.0; }
   __syncwarp();
-  for (int j = 1 + lane; j <= Lt; j += 32) {
-    const uint8_t o = OFFC(1, j);
-    offrow[j] = o;
-    if (!o) Cm[j] = (double)mac_dot20(A.q_p + 20, tcol[j].p) * Cshift;
+  {
+    int lo = INT_MAX, hi = 0;
+    for (int j = 1 + lane; j <= Lt; j += 32) {
+      const uint8_t o = OFFC(1, j);
+      offrow[j] = o;
+      if (!o) { Cm[j] = (double)mac_dot20(A.q_p + 20, tcol[j].p) * Cshift; lo = min(lo, j); hi = max(hi, j); }
+    }
+    row_span(lo, hi);
   }
   __syncwarp();
   fwd_pre(1);
@@ -234,11 +254,13 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
     const float q_m2m = QT(i - 1, M2M), q_i2m = QT(i - 1, I2M), q_d2m = QT(i - 1, D2M), q_m2d = QT(i - 1, M2D),
                 q_d2d = QT(i - 1, D2D);
     double pmax = 0.0;
+    int lo_ = INT_MAX, hi_ = 0;
     for (int j = 1 + lane; j <= Lt; j += 32) {
       double mm = 0.0, dg = 0.0, mi = 0.0;
       const uint8_t o = OFFC(i, j);
       offrow[j] = o;
       if (!o) {
+        lo_ = min(lo_, j); hi_ = max(hi_, j);
         const float pf = mac_dot20(qi, tcol[j].p);
         if (j == 1) {
           mm = scale_prod * 1.0f * pf * Cshift;
@@ -254,6 +276,7 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
       }
       Cm[j] = mm; Cd[j] = dg; Cx[j] = mi;
     }
+    row_span(lo_, hi_);
     __syncwarp();
     fwd_pre(i);
     __syncwarp();
@@ -308,9 +331,11 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
     const float q_m2m = QT(i, M2M), q_m2i = QT(i, M2I), q_m2d = QT(i, M2D), q_i2m = QT(i, I2M), q_i2i = QT(i, I2I),
                 q_d2m = QT(i, D2M), q_d2d = QT(i, D2D);
     // phase A (lanes = columns): pmatch -> Cm (scratch), DG, MI; the cell in column Lt
+    int lo_ = INT_MAX, hi_ = 0;
     for (int j = 1 + lane; j <= Lt; j += 32) {
       const uint8_t o = OFFC(i, j);
       offrow[j] = o;
+      if (!o) { lo_ = min(lo_, j); hi_ = max(hi_, j); }
       if (j == Lt) {
         float* pp = post + (size_t)i * W + Lt;
         if (o) { *pp = 0.0f; Cm[Lt] = 0.0; }
@@ -327,6 +352,7 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
         Ci[j] = (pmatch * q_i2m) * TT(j, M2M);
       }
     }
+    row_span(lo_, hi_);
     __syncwarp();
     TICK(4);
     // phase B (lanes 0 and 1, right to left):  GD: v = pmatch*q.M2M*t.D2M[j] + v*t.D2D[j]
@@ -337,8 +363,9 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
       const uint8_t* __restrict__ of = offrow;
       const int kc = lane == 0 ? D2D : M2M;
       double v = 0.0;
+      const int jbeg = min(jhi, Lt - 1), jend = max(jlo, 1);
 #pragma unroll 4
-      for (int j = Lt - 1; j >= 1; --j) {
+      for (int j = jbeg; j >= jend; --j) {
         const float tc = tt[j * 7 + kc];
         const float c1 = lane == 0 ? tc : q_i2i, d1 = lane == 0 ? 1.0f : tc;
         const double nv = dst[j] + (v * c1) * d1;
@@ -383,10 +410,12 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
   if (lane == 0) bt[0] = 0;
   __syncwarp();
   for (int i = 1; i <= Lq; ++i) {
+    int lo_ = INT_MAX, hi_ = 0;
     for (int j = 1 + lane; j <= Lt; j += 32) {
       const uint8_t o = OFFC(i, j);
       offrow[j] = o;
-      if (o) continue;
+      if (o) { if (bs) Sc[j] = -FLT_MIN; continue; }     // (bt of a switched-off cell stays STOP = 0 from the memset)
+      lo_ = min(lo_, j); hi_ = max(hi_, j);
       const float p = post[(size_t)i * W + j];
       const float term1 = __fsub_rn(p, mact);
       const float term2 = __fsub_rn(__fadd_rn(Sp[j - 1], p), mact);
@@ -396,10 +425,11 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
       if (term3 > mx) { mx = term3; st = 6; }             // MI
       T123[j] = mx; st123[j] = st;
     }
+    row_span(lo_, hi_);
     __syncwarp();
     TICK(7);
     if (lane == 0) {
-      float left = 0.0f;                                  // S_curr[jmin-1] = 0
+      float left = jlo == 1 ? 0.0f : -FLT_MIN;            // S_curr[0] = 0; left of an active run sits a switched-off cell
       Sc[0] = 0.0f;
       uint8_t* __restrict__ btrow = bt + (size_t)i * W;
       const float* __restrict__ t123 = T123;
@@ -408,7 +438,7 @@ __global__ void __launch_bounds__(32) k_mac_realign(const MacArgs A) {
       float* __restrict__ sc_row = Sc;
       const bool can_end = A.local || i == Lq;
 #pragma unroll 4
-      for (int j = 1; j <= Lt; ++j) {
+      for (int j = jlo; j <= jhi; ++j) {
         const float t4 = half_exact ? __fsub_rn(left, half_f) : (float)((double)left - half_mact);
         float mx = t123[j]; uint8_t st = s123[j];
         if (t4 > mx) { mx = t4; st = 4; }                 // IM
