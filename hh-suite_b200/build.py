@@ -7,13 +7,17 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "hhg_api.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "hhg_kernels.cuh"), os.path.join(HERE, "csrc", "hhg_viterbi2.cuh"),
-        os.path.join(os.path.dirname(HERE), "include", "hhg.h")]
+import glob  # noqa: E402
+
+# every source the library is built from: a stale .so after editing any kernel header is a parity trap
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu*")) + glob.glob(os.path.join(HERE, "csrc", "*.h")) +
+              glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h")))
 OUT = os.path.join(HERE, "libhhg.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-fmad=false",            # belt and braces: the kernels use explicit _rn intrinsics anyway
-         "-Xcompiler", "-fPIC", "-shared"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",   # host-side flog2/fpow2 must not be fused either
+         "-diag-suppress", "177", "-shared"]
 
 
 def stale() -> bool:

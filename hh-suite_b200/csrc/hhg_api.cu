@@ -5,7 +5,6 @@
 #include "hhg_kernels.cuh"
 #include "hhg_hhm.cuh"
 #include "hhg_mac.cuh"
-#include "hhg_viterbi2.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -87,8 +86,7 @@ struct hhg_ctx {
   long long launches = 0;
   // query
   int Lq = 0, R = 16, nstrips = 0;
-  int group_jobs = 64;   // work-item interleave (see k_viterbi)
-  int cols = 1;          // target columns per query-row visit: 1 = k_viterbi, 2 = k_viterbi2
+  int group_jobs = 16;   // work-item interleave (see k_viterbi): 16 jobs x nstrips items keep the group L2-resident
   uint32_t epoch = 0;    // run counter feeding the boundary-slot tags
   DevBuf<float4> qrec;
   DevBuf<float> S33;
@@ -135,6 +133,7 @@ struct hhg_db {
   DevBuf<float4> cols_raw;   // pre-null-model records
   DevBuf<float> pav;         // [n*20] template average aa frequencies
   bool prepared = true;
+  unsigned long long cols_version = 1;   // bumped whenever `cols` is rewritten (hhg_db_apply_null_model)
 };
 
 struct hhg_csdb {
@@ -157,20 +156,23 @@ struct hhg_plan {
   unsigned long long db_serial = 0;
   int device = 0;
   int n = 0;            // requests
-  int Lq = 0, R = 16, nstrips = 0, cols = 1;
+  int Lq = 0, R = 16, nstrips = 0;
   int njobs = 0;
   double cells = 0, padded_cells = 0, alg_bytes = 0;
   std::vector<int> ids;          // request -> target id
   std::vector<int> order;        // sorted position -> request index
   std::vector<int> req_job, req_lane;   // per request
   std::vector<int> job_Lmax;
-  std::vector<long long> job_bt_off, job_bnd_off, job_co_off, path_off;
+  std::vector<long long> job_bt_off, job_bnd_off, job_co_off, job_jc_off, path_off;
+  long long jc_total = 0;                 // float4 in the job-interleaved operand stream
+  unsigned long long jc_version = 0;      // db->cols_version the stream was built from (0 = never)
   std::vector<Wave> waves;
   long long path_total = 0;
   // device
   DevBuf<int> d_job_target, d_job_Lmax, d_req_job, d_req_lane, d_req_Lt, d_req_target;
   DevBuf<float> d_S;
-  DevBuf<long long> d_job_bt_off, d_job_bnd_off, d_job_co_off, d_path_off;
+  DevBuf<long long> d_job_bt_off, d_job_bnd_off, d_job_co_off, d_job_jc_off, d_path_off;
+  DevBuf<float4> d_jcols;
   DevBuf<uint32_t> d_bt, d_co;
   DevBuf<BndSlot> d_bnd;
   DevBuf<float> d_strip_score;
@@ -221,7 +223,6 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
     c->own_stream = true;
   }
   c->R = strip_rows();
-  { const char* ce = getenv("HHG_COLS"); c->cols = (ce && atoi(ce) == 2) ? 2 : 1; }
   {
     // fast_log2 tables exactly as the reference fills them on first use (src/util-inl.h:113-121):
     // lg2[i] = log2(1 + i/1024) via the C library's double-precision log (that is the overload the
@@ -239,7 +240,7 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
     CK(cudaMemcpy(c->lg2.p, lg2.data(), 1025 * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->diff.p, diff.data(), 1025 * 4, cudaMemcpyHostToDevice));
   }
-  { const char* ge = getenv("HHG_GROUP_JOBS"); c->group_jobs = ge ? std::max(1, atoi(ge)) : 64; }
+  { const char* ge = getenv("HHG_GROUP_JOBS"); c->group_jobs = ge ? std::max(1, atoi(ge)) : 16; }
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const char* env = getenv("HHG_MAX_BT_GB");
@@ -407,6 +408,7 @@ int hhg_db_apply_null_model(hhg_ctx* ctx, hhg_db* db, const float* q_pav, const 
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   db->prepared = true;
+  db->cols_version++;
   return HHG_OK;
 }
 
@@ -662,7 +664,7 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   CK(cudaSetDevice(ctx->device));
   // the common case of a repeated request (same shard, same target list, same query geometry, e.g. every
   // query of a batch against the whole shard) reuses the plan: no host sort, no uploads
-  if (pl->db == db && pl->db_serial == db->serial && pl->n == n && pl->Lq == ctx->Lq && pl->R == ctx->R && pl->cols == ctx->cols &&
+  if (pl->db == db && pl->db_serial == db->serial && pl->n == n && pl->Lq == ctx->Lq && pl->R == ctx->R &&
       !pl->ids.empty() && pl->max_bt_bytes == ctx->max_bt_bytes) {
     bool same = true;
     if (ids) same = memcmp(ids, pl->ids.data(), (size_t)n * 4) == 0;
@@ -677,7 +679,7 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   pl->waves.clear();
   pl->celloff = false;
   pl->n = n;
-  pl->Lq = ctx->Lq; pl->R = ctx->R; pl->nstrips = ctx->nstrips; pl->cols = ctx->cols;
+  pl->Lq = ctx->Lq; pl->R = ctx->R; pl->nstrips = ctx->nstrips;
   pl->ids.resize(n);
   for (int k = 0; k < n; ++k) {
     const int id = ids ? ids[k] : k;
@@ -694,17 +696,18 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   pl->req_job.resize(n); pl->req_lane.resize(n);
   pl->job_Lmax.resize(pl->njobs);
   pl->job_bt_off.resize(pl->njobs); pl->job_bnd_off.resize(pl->njobs); pl->job_co_off.resize(pl->njobs);
+  pl->job_jc_off.resize(pl->njobs);
+  pl->jc_version = 0;
   std::vector<int> job_target((size_t)pl->njobs * 32);
   std::vector<int> req_Lt(n);
   const int rowgroups = pl->nstrips * pl->R / 4;
-  long long bnd = 0, co = 0;
+  long long bnd = 0, co = 0, jc = 0;
   size_t wave_bt = 0;   // words in the current wave
   Wave w;
   for (int jb = 0; jb < pl->njobs; ++jb) {
     const int first = jb * 32;
     const int cnt = std::min(32, n - first);
     int Lmax = db->L[pl->ids[pl->order[first]]];
-    if (pl->cols == 2) Lmax += (Lmax & 1);   // the 2-column kernel sweeps column pairs
     pl->job_Lmax[jb] = Lmax;
     for (int l = 0; l < 32; ++l) {
       const int rq = pl->order[first + std::min(l, cnt - 1)];   // padded lanes repeat the last target
@@ -723,6 +726,8 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
     pl->job_bnd_off[jb] = bnd;
     bnd += (long long)(Lmax + 1) * 32;
     pl->job_co_off[jb] = co;
+    pl->job_jc_off[jb] = jc;
+    jc += (long long)Lmax * 224;
     co += (long long)pl->nstrips * (Lmax + 1) * 32;
     pl->padded_cells += (double)pl->nstrips * pl->R * (double)Lmax * 32.0;
   }
@@ -747,12 +752,14 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   }
   if (po > 0x7fffffffLL) return fail(HHG_EINVAL, "plan too large: %lld path bytes (> 2^31-1); split the request", po);
   pl->path_total = po;
+  pl->jc_total = jc;
   pl->alg_bytes = cols_sum * 112.0 + pl->cells * 1.0 + (double)sizeof(HitRec) * n;
 
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   A(pl->d_job_target.ensure(job_target.size())); A(pl->d_job_Lmax.ensure(pl->njobs));
   A(pl->d_job_bt_off.ensure(pl->njobs)); A(pl->d_job_bnd_off.ensure(pl->njobs)); A(pl->d_job_co_off.ensure(pl->njobs));
+  A(pl->d_job_jc_off.ensure(pl->njobs)); A(pl->d_jcols.ensure((size_t)jc));
   A(pl->d_req_job.ensure(n)); A(pl->d_req_lane.ensure(n)); A(pl->d_req_Lt.ensure(n)); A(pl->d_path_off.ensure(n));
   A(pl->d_req_target.ensure(n)); A(pl->d_S.ensure((size_t)po));
   A(pl->d_bt.ensure(max_wave_words));
@@ -772,6 +779,7 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   CK(cudaMemcpyAsync(pl->d_job_bt_off.p, pl->job_bt_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_job_bnd_off.p, pl->job_bnd_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_job_co_off.p, pl->job_co_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(pl->d_job_jc_off.p, pl->job_jc_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_req_job.p, pl->req_job.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_req_lane.p, pl->req_lane.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(pl->d_req_Lt.p, req_Lt.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -831,10 +839,8 @@ static int set_exclusions(hhg_ctx* ctx, hhg_plan* pl, const int64_t* excl_off, c
 }  // extern "C"
 
 template <int R>
-static int launch_viterbi(hhg_ctx* ctx, const VitParams& P, bool local, bool ss, bool co, int items, int cols = 1) {
-  const size_t smem = (size_t)kWarpsPerCta * R * 112 +
-                      (HHG_USE_CPASYNC ? (size_t)kWarpsPerCta * kStages * 32 * 112 : 0) + 64 +
-                      (ss ? 44 * 44 * 4 : 0);
+static int launch_viterbi(hhg_ctx* ctx, const VitParams& P, bool local, bool ss, bool co, int items) {
+  const size_t smem = (size_t)kWarpsPerCta * R * 112 + 64 + (ss ? 44 * 44 * 4 : 0);
   void (*kern)(const VitParams) = nullptr;
 #define PICK(L_, S_, C_) kern = k_viterbi<R, L_, S_, C_>
   if (local) { if (ss) { if (co) PICK(true, true, true); else PICK(true, true, false); }
@@ -842,16 +848,6 @@ static int launch_viterbi(hhg_ctx* ctx, const VitParams& P, bool local, bool ss,
   else       { if (ss) { if (co) PICK(false, true, true); else PICK(false, true, false); }
                else    { if (co) PICK(false, false, true); else PICK(false, false, false); } }
 #undef PICK
-  {
-    if (cols == 2) {
-#define PICK2(L_, S_, C_) kern = k_viterbi2<R, L_, S_, C_>
-      if (local) { if (ss) { if (co) PICK2(true, true, true); else PICK2(true, true, false); }
-                   else    { if (co) PICK2(true, false, true); else PICK2(true, false, false); } }
-      else       { if (ss) { if (co) PICK2(false, true, true); else PICK2(false, true, false); }
-                   else    { if (co) PICK2(false, false, true); else PICK2(false, false, false); } }
-#undef PICK2
-    }
-  }
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem));
@@ -870,7 +866,7 @@ extern "C" {
 
 static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
   if (!ctx || !pl) return fail(HHG_EINVAL, "hhg_plan_run: bad argument");
-  if (pl->Lq != ctx->Lq || pl->R != ctx->R || pl->cols != ctx->cols) return fail(HHG_EINVAL, "plan was made for another query length");
+  if (pl->Lq != ctx->Lq || pl->R != ctx->R) return fail(HHG_EINVAL, "plan was made for another query length");
   const hhg_db* db = pl->db;
   if (!db->prepared) return fail(HHG_EINVAL, "raw db: call hhg_db_apply_null_model for the current query first");
   if (ctx->par.use_ss && (!db->has_ss || !ctx->has_ss || !ctx->has_S33))
@@ -880,12 +876,26 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
   ctx->epoch = (ctx->epoch + 1) & 0xFFFFFu;   // slot tags of earlier runs never match (20-bit epoch)
   if (ctx->epoch == 0) ctx->epoch = 1;
   CK(cudaMemsetAsync(pl->d_counter.p, 0, pl->waves.size() * 4, st));
+  if (pl->jc_version != db->cols_version) {
+    // (re)build the job-interleaved operand stream: once per plan, and again after every
+    // hhg_db_apply_null_model (the prepared emissions changed)
+    int maxL = 0;
+    for (int jb = 0; jb < pl->njobs; ++jb) maxL = std::max(maxL, pl->job_Lmax[jb]);
+    dim3 grid((unsigned)pl->njobs, (unsigned)std::min(64, (maxL + 7) / 8), 1);
+    k_interleave_cols<<<grid, 256, 0, st>>>(pl->njobs, pl->d_job_target.p, pl->d_job_Lmax.p, pl->d_job_jc_off.p,
+                                            db->cols.p, db->dcol_off.p, db->dL.p, pl->d_jcols.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    pl->jc_version = db->cols_version;
+  }
   for (size_t wi = 0; wi < pl->waves.size(); ++wi) {
     const Wave& w = pl->waves[wi];
     const int nj = w.job_end - w.job_begin;
     VitParams P{};
     P.qrec = ctx->qrec.p; P.Lq = pl->Lq; P.nstrips = pl->nstrips;
-    P.cols = db->cols.p; P.col_off = db->dcol_off.p; P.Lt = db->dL.p;
+    P.Lt = db->dL.p;
+    P.jcols = pl->d_jcols.p;
+    P.job_jc_off = pl->d_job_jc_off.p + w.job_begin;
     P.njobs = nj;
     P.job_target = pl->d_job_target.p + (size_t)w.job_begin * 32;
     P.job_Lmax = pl->d_job_Lmax.p + w.job_begin;
@@ -907,9 +917,9 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
     const int items = nj * pl->nstrips;
     int rc;
     if (timed) CK(cudaEventRecord(ctx->ev[0], st));
-    if (pl->R == 8) rc = launch_viterbi<8>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items, pl->cols);
-    else if (pl->R == 12) rc = launch_viterbi<12>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items, pl->cols);
-    else rc = launch_viterbi<16>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items, pl->cols);
+    if (pl->R == 8) rc = launch_viterbi<8>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
+    else if (pl->R == 12) rc = launch_viterbi<12>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
+    else rc = launch_viterbi<16>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
     if (rc != HHG_OK) return rc;
     if (timed) CK(cudaEventRecord(ctx->ev[1], st));
     // backtrace of this wave's requests.  Requests are addressed through the sorted order: the

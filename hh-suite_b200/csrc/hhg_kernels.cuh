@@ -14,8 +14,10 @@
 //     values of its R rows in registers; the R query rows (20 emissions + 7 transitions each)
 //     are TMA-bulk-staged (cp.async.bulk + mbarrier) into the warp's shared-memory slice and
 //     read back as warp-uniform broadcast LDS.128.
-//   * target operands stream from HBM as 112-byte column records (7 x LDG.128 per lane per
-//     column, register-prefetched one column ahead).
+//   * target operands stream from a JOB-INTERLEAVED copy of the job's column records,
+//     [column][k = 0..6][lane] float4 (built per plan by k_interleave_cols), so each of the 7 loads of a
+//     column is ONE coalesced 512-byte warp request (4 L1TEX wavefronts instead of 32 when every lane
+//     reads its own 112-byte record), register-prefetched one column ahead.
 //   * 1 backtrace byte per cell, packed 4 rows per 32-bit word and stored lane-interleaved so
 //     every warp store writes one full 128-byte line.
 // Arithmetic is the reference's, operation for operation (unfused fp32 mul/add in the same order,
@@ -25,18 +27,19 @@
 #include <float.h>
 #include <stdint.h>
 
-// Build-time experiment switches (defaults = the measured best; see DESIGN.md "kernel history").
-#ifndef HHG_USE_CPASYNC
-#define HHG_USE_CPASYNC 0   // 1: stage target columns in smem with cp.async; 0: register prefetch (__ldg)
+#ifndef HHG_CTAS_R8
+#define HHG_CTAS_R8 3   // resident CTAs per SM the R<=12 kernels are compiled for (3 -> 168 registers, 4 -> 128)
 #endif
-#ifndef HHG_QDB
-#define HHG_QDB 0           // 1: double-buffer the query row registers
+#ifndef HHG_JC_EVICT_LAST
+#define HHG_JC_EVICT_LAST 0   // 1: operand-stream loads carry an L2 evict_last policy (they are re-read by every strip)
+#endif
+#ifndef HHG_MAX3
+#define HHG_MAX3 1   // MM-state maximum as 3-input maxima + equality selects (same bits, fewer ALU-pipe instructions)
 #endif
 
 namespace hhg {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kStages = 3;         // cp.async ring depth for the target column records
 
 struct __align__(16) ColRec {      // one profile column = operands of DP cell (., j)   (112 B)
   float p[20];
@@ -111,9 +114,11 @@ struct VitParams {
   int Lq;
   int nstrips;
   // database shard
-  const float4* cols;        // column records of all targets
-  const long long* col_off;  // [n_targets] first column record of target t
   const int* Lt;             // [n_targets]
+  // plan: the job-interleaved operand stream, [job][column 1..Lmax][k 0..6][lane] float4 (lanes shorter than
+  // the job repeat their last column; the cells computed there are never used)
+  const float4* jcols;
+  const long long* job_jc_off;   // [njobs] offset (in float4) of the job's stream
   // plan
   int njobs;
   const int* job_target;     // [njobs*32] target id (padded lanes repeat a valid id)
@@ -166,18 +171,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-#if HHG_USE_CPASYNC
-// 16-byte asynchronous global->shared copy (LDGSTS), L2-only (.cg): the staged target columns
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-#endif
-
 // log2f4 (src/hhutil-inl.h:509-541), degree-4 minimax, unfused.  x >= 0.
 // The exponent int->float conversion uses the exact magic-number form (no I2F on the hot path):
 // bits(8388608.0f) + eb is the float 8388608+eb; subtracting 8388735 (=2^23+127) is exact.
@@ -236,6 +229,20 @@ __device__ __forceinline__ float dot20_dev(const unsigned long long (&t)[10], co
   return __fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3));
 }
 
+// one 16-byte operand of the job-interleaved stream: L2-only load (a line is read once per strip and SM)
+__device__ __forceinline__ float4 ld_jc(const float4* p) {
+#if HHG_JC_EVICT_LAST
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  float4 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+#else
+  return __ldcg(p);
+#endif
+}
+
 #define HHG_NEG (-FLT_MAX)
 
 // ---------------------------------------------------------------------------------------------
@@ -243,22 +250,15 @@ __device__ __forceinline__ float dot20_dev(const unsigned long long (&t)[10], co
 // CELLOFF: cell-off bit input (alternative alignments / excluded regions).
 // ---------------------------------------------------------------------------------------------
 template <int R, bool LOCAL, bool SS, bool CELLOFF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? HHG_CTAS_R8 : 2)
     k_viterbi(const VitParams P) {
   static_assert(R % 4 == 0, "R must be a multiple of 4");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // smem carve-up: [warps][R] query records | [warps][kStages][32 lanes] target column records |
-  // mbarriers | (SS) the S33 table
+  // smem carve-up: [warps][R] query records | mbarriers | (SS) the S33 table
   float4* qs = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * R * 7;
-#if HHG_USE_CPASYNC
-  float4* tstage = reinterpret_cast<float4*>(smem_raw + (size_t)kWarpsPerCta * R * 112) +
-                   ((size_t)warp * kStages * 32 + lane) * 7;   // this lane's slot in stage 0
-  constexpr size_t kBarOff = (size_t)kWarpsPerCta * R * 112 + (size_t)kWarpsPerCta * kStages * 32 * 112;
-#else
   constexpr size_t kBarOff = (size_t)kWarpsPerCta * R * 112;
-#endif
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kBarOff);
   float* s33 = reinterpret_cast<float*>(smem_raw + kBarOff + 64);
   uint64_t* bar = bars + warp;
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
     const int t = P.job_target[job * 32 + lane];
     const int Lt = P.Lt[t];
     const int Lmax = P.job_Lmax[job];
-    const float4* tc = P.cols + (size_t)P.col_off[t] * 7;
+    const float4* jc = P.jcols + P.job_jc_off[job] + lane;   // operand k of column j: jc[((j-1)*7+k)*32]
     uint32_t* btj = P.bt + P.job_bt_off[job] + lane;
     const size_t bt_row_stride = (size_t)(Lmax + 1) * 32;   // words per 4-row group
     BndSlot* bnd = P.bnd + P.job_bnd_off[job] + lane;
@@ -322,23 +322,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
     float best = HHG_NEG;
     int bi = 0, bj = 0;
 
-#if !HHG_USE_CPASYNC
-    // first column record (register prefetch, one column ahead)
+    // first column (register prefetch, one column ahead); L2-only loads: a line is read once per strip
     float4 nx[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) nx[k] = __ldg(tc + k);   // Lt >= 1
-#else
-    // target column records: cp.async ring, kStages-1 columns in flight (columns clamp at Lt so
-    // lanes shorter than the job keep re-reading their last column)
-#pragma unroll
-    for (int c = 1; c < kStages; ++c) {
-      const float4* src = tc + (size_t)(min(c, Lt) - 1) * 7;
-      float4* dst = tstage + (size_t)(c % kStages) * 32 * 7;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) cp_async16(dst + k, src + k);
-      cp_async_commit();
-    }
-#endif
+    for (int k = 0; k < 7; ++k) nx[k] = ld_jc(jc + k * 32);   // Lmax >= 1
 
     // boundary values of column 1 (strips > 0): issue the slot load now, validate the tag at use
     float nMM = 0.f, nDG = 0.f, nMI = 0.f, nGD = 0.f, nIM = 0.f;
@@ -349,7 +336,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
     parity ^= 1u;
 
     for (int j = 1; j <= Lmax; ++j) {
-#if !HHG_USE_CPASYNC
       // ---- current column operands (from the prefetch registers), prefetch the next column
       unsigned long long tp[10];
       tp[0] = pack2(nx[0].x, nx[0].y); tp[1] = pack2(nx[0].z, nx[0].w);
@@ -361,39 +347,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
       const float t_i2m = nx[6].x, t_i2i = nx[6].y, t_m2i = nx[6].z;
       const uint32_t t_ss = __float_as_uint(nx[6].w);
       {
-        const int jn = min(j + 1, Lt);            // clamp: lanes shorter than the job keep re-reading
-        const float4* src = tc + (size_t)(jn - 1) * 7;
+        const float4* src = jc + (size_t)(min(j + 1, Lmax) - 1) * 224;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) nx[k] = __ldg(src + k);
+        for (int k = 0; k < 7; ++k) nx[k] = ld_jc(src + k * 32);
       }
-#else
-      // ---- current column operands from the staging ring; refill the slot freed by column j-1
-      cp_async_wait<kStages - 2>();
-      {
-        const float4* src = tc + (size_t)(min(j + kStages - 1, Lt) - 1) * 7;
-        float4* dst = tstage + (size_t)((j + kStages - 1) % kStages) * 32 * 7;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) cp_async16(dst + k, src + k);
-        cp_async_commit();
-      }
-      unsigned long long tp[10];
-      float t_m2m, t_m2d, t_d2m, t_d2d, t_i2m, t_i2i, t_m2i;
-      uint32_t t_ss;
-      {
-        const float4* cur = tstage + (size_t)(j % kStages) * 32 * 7;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const float4 v = cur[k];
-          tp[2 * k] = pack2(v.x, v.y);
-          tp[2 * k + 1] = pack2(v.z, v.w);
-        }
-        const float4 va = cur[5], vb = cur[6];
-        t_m2m = va.x; t_m2d = va.y; t_d2m = va.z; t_d2d = va.w;
-        t_i2m = vb.x; t_i2i = vb.y; t_m2i = vb.z;
-        t_ss = __float_as_uint(vb.w);
-      }
-
-#endif
 
       // ---- boundary row i0 at column j: slot prefetched during column j-1; spin (per lane) until the
       // producer strip's tag is there, then prefetch column j+1
@@ -420,29 +377,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
 
       // (t_ss & P.zero) is 0; it only keeps the 4th register of the prefetch LDG.128 live (see ld_slot)
       uint32_t word = SS ? 0u : (t_ss & P.zero);
-      // query rows are double-buffered in registers: row r+1 is fetched (broadcast LDS.128) before
-      // row r is computed so the shared-memory latency overlaps the arithmetic
-#if HHG_QDB
-      float4 qn[7];
-#pragma unroll
-      for (int k = 0; k < 7; ++k) qn[k] = qs[k];
-#endif
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         float4 q[5];
-#if HHG_QDB
-#pragma unroll
-        for (int k = 0; k < 5; ++k) q[k] = qn[k];
-        const float4 qa = qn[5], qb = qn[6];
-        if (r + 1 < R) {
-#pragma unroll
-          for (int k = 0; k < 7; ++k) qn[k] = qs[(r + 1) * 7 + k];
-        }
-#else
 #pragma unroll
         for (int k = 0; k < 5; ++k) q[k] = qs[r * 7 + k];
         const float4 qa = qs[r * 7 + 5], qb = qs[r * 7 + 6];
-#endif
         const float q_m2m = qa.x, q_m2d = qa.y, q_d2m = qa.z, q_d2d = qa.w;
         const float q_i2m = qb.x, q_i2i = qb.y, q_m2i = qb.z;
 
@@ -450,22 +390,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
 
         // 5-way maximum with the reference's strict-'>' / first-wins rule, :241-273
         uint32_t b;
-        float mm, c;
-        c = __fadd_rn(__fadd_rn(dMM, q_m2m), t_m2m);
-        b = (c > smin) ? 2u : 0u;
-        mm = fmaxf(smin, c);
-        c = __fadd_rn(__fadd_rn(dGD, q_m2m), t_d2m);
-        b = (c > mm) ? 3u : b;
-        mm = fmaxf(mm, c);
-        c = __fadd_rn(__fadd_rn(dIM, q_i2m), t_m2m);
-        b = (c > mm) ? 4u : b;
-        mm = fmaxf(mm, c);
-        c = __fadd_rn(__fadd_rn(dDG, q_d2m), t_m2m);
-        b = (c > mm) ? 5u : b;
-        mm = fmaxf(mm, c);
-        c = __fadd_rn(__fadd_rn(dMI, q_m2m), t_i2m);
-        b = (c > mm) ? 6u : b;
-        mm = fmaxf(mm, c);
+        float mm;
+        const float c1 = __fadd_rn(__fadd_rn(dMM, q_m2m), t_m2m);
+        const float c2 = __fadd_rn(__fadd_rn(dGD, q_m2m), t_d2m);
+        const float c3 = __fadd_rn(__fadd_rn(dIM, q_i2m), t_m2m);
+        const float c4 = __fadd_rn(__fadd_rn(dDG, q_d2m), t_m2m);
+        const float c5 = __fadd_rn(__fadd_rn(dMI, q_m2m), t_i2m);
+#if HHG_MAX3
+        // the winner of the strict-'>' chain is the FIRST candidate (order STOP, MM, GD, IM, DG, MI) that attains
+        // the maximum: three 3-input maxima (FMNMX3) + five equality selects instead of five max + five '>' selects
+        mm = fmaxf(fmaxf(smin, c1), c2);
+        mm = fmaxf(fmaxf(mm, c3), c4);
+        mm = fmaxf(mm, c5);
+        b = 6u;
+        b = (c4 == mm) ? 5u : b;
+        b = (c3 == mm) ? 4u : b;
+        b = (c2 == mm) ? 3u : b;
+        b = (c1 == mm) ? 2u : b;
+        b = (smin == mm) ? 0u : b;
+#else
+        b = (c1 > smin) ? 2u : 0u; mm = fmaxf(smin, c1);
+        b = (c2 > mm) ? 3u : b;    mm = fmaxf(mm, c2);
+        b = (c3 > mm) ? 4u : b;    mm = fmaxf(mm, c3);
+        b = (c4 > mm) ? 5u : b;    mm = fmaxf(mm, c4);
+        b = (c5 > mm) ? 6u : b;    mm = fmaxf(mm, c5);
+#endif
 
         float Si = log2f4_dev(dot20_dev(tp, q, P.one2));                       // :277
         if (SS) {
@@ -535,9 +484,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)
     const size_t o = ((size_t)job * P.nstrips + s) * 32 + lane;
     P.strip_score[o] = best;
     P.strip_ij[o] = (bi << 16) | bj;
-#if HHG_USE_CPASYNC
-    cp_async_wait<0>();
-#endif
     __syncwarp();   // all lanes done with the smem slice before the next TMA overwrites it
   }
 }
@@ -776,6 +722,28 @@ __global__ void k_pack_cols(int n, const int* L, const long long* col_off, const
   r.i2i = t0[4]; r.m2i = t0[1];
   r.ss = ss ? (uint32_t)ss[ss_off[t] + j] : 0u;
   out[c] = r;
+}
+
+// Build the job-interleaved operand stream of a plan from the shard's column records: warp per (job, column),
+// lane = the job's lane.  Each lane copies its own 112-byte record (7 x 16 B) of column min(j, Lt) into
+// out[job_jc_off[job] + ((j-1)*7 + k)*32 + lane]: the seven stores of a warp are full 512-byte lines.
+__global__ void __launch_bounds__(256)
+k_interleave_cols(int njobs, const int* __restrict__ job_target, const int* __restrict__ job_Lmax,
+                  const long long* __restrict__ job_jc_off, const float4* __restrict__ cols,
+                  const long long* __restrict__ col_off, const int* __restrict__ Lt, float4* __restrict__ out) {
+  const int job = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int Lmax = job_Lmax[job];
+  const int t = job_target[job * 32 + lane];
+  const int L = Lt[t];
+  const float4* src0 = cols + (size_t)col_off[t] * 7;
+  float4* dst0 = out + job_jc_off[job] + lane;
+  for (int j = blockIdx.y * 8 + (threadIdx.x >> 5) + 1; j <= Lmax; j += gridDim.y * 8) {
+    const float4* src = src0 + (size_t)(min(j, L) - 1) * 7;
+    float4* dst = dst0 + (size_t)(j - 1) * 224;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) dst[k * 32] = __ldg(src + k);
+  }
 }
 
 // Rasterise excluded alignments into the cell-off bit words (Viterbi::ExcludeAlignment,
