@@ -38,7 +38,9 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_csdb_create", "hhg_csdb_destroy", "hhg_prefilter_ungapped", "hhg_prefilter_ungapped_run",
            "hhg_prefilter_fetch", "hhg_prefilter_select", "hhg_log2lin", "hhg_mac_query_set", "hhg_mac_realign",
            "hhg_mac_debug_posterior", "hhg_prefilter_build_profile", "hhg_prefilter_corrected_score",
-           "hhg_prefilter_sw", "hhg_prefilter_evalue", "hhg_prefilter_corrected_scores", "hhg_prefilter_evalues"]
+           "hhg_prefilter_sw", "hhg_prefilter_evalue", "hhg_prefilter_corrected_scores", "hhg_prefilter_evalues",
+           "hhg_comm_unique_id", "hhg_comm_create", "hhg_comm_destroy", "hhg_comm_rank", "hhg_comm_world",
+           "hhg_plan_topk", "hhg_plan_topk_paths", "hhg_ctx_last_plan"]
 
 
 class PrepParams(C.Structure):
@@ -64,6 +66,10 @@ class MacParams(C.Structure):
     """hhg_mac_params: par.loc, par.shift, par.mact."""
     _fields_ = [("local", C.c_int32), ("shift", C.c_float), ("mact", C.c_float)]
 
+
+# hhg_topk_rec: one record of the merged multi-GPU hit list (include/hhg.h)
+TOPK_DTYPE = np.dtype([("target", np.int32), ("owner", np.int32), ("hit", HIT_DTYPE), ("key", np.uint64)])
+assert TOPK_DTYPE.itemsize == 56
 
 MAC_HIT_DTYPE = np.dtype([("i1", np.int32), ("i2", np.int32), ("j1", np.int32), ("j2", np.int32), ("nsteps", np.int32),
                           ("matched_cols", np.int32), ("sum_of_probs", np.float32), ("flags", np.int32),
@@ -155,6 +161,16 @@ def load():
                                         C.POINTER(C.c_double)]
     L.hhg_prefilter_sw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, C.c_int, c_u8p, C.c_int, C.c_int, C.c_int,
                                    c_i32p]
+    L.hhg_comm_unique_id.argtypes = [C.c_void_p]
+    L.hhg_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.hhg_comm_destroy.argtypes = [C.c_void_p]
+    L.hhg_comm_rank.argtypes = [C.c_void_p]
+    L.hhg_comm_world.argtypes = [C.c_void_p]
+    L.hhg_plan_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int32, c_i32p, C.c_void_p,
+                                c_i32p]
+    L.hhg_plan_topk_paths.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, c_u8p]
+    L.hhg_ctx_last_plan.argtypes = [C.c_void_p]
+    L.hhg_ctx_last_plan.restype = C.c_void_p
     _lib = L
     return L
 
@@ -388,6 +404,49 @@ class TargetDB:
             self.h = None
 
 
+class Comm:
+    """hhg_comm: one rank of the NCCL communicator behind the C-ABI (world == 1: no NCCL involved)."""
+
+    def __init__(self, ctx: Context, rank: int = 0, world: int = 1, unique_id: bytes | None = None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        _ck(ctx.L.hhg_comm_create(ctx.h, rank, world, buf, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _ck(load().hhg_comm_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hhg_comm_destroy(self.h)
+            self.h = None
+
+
+def plan_topk(ctx: Context, plan_handle, comm: Comm | None, K: int, by_hit_score: bool = False, id_base: int = 0,
+              global_ids=None):
+    """hhg_plan_topk on a raw plan handle: the merged K best hit records (TOPK_DTYPE) on every rank."""
+    out = np.zeros(K, TOPK_DTYPE)
+    n = C.c_int32(0)
+    gi = None if global_ids is None else np.ascontiguousarray(global_ids, np.int32)
+    _ck(ctx.L.hhg_plan_topk(ctx.h, plan_handle, comm.h if comm is not None else None, K, 1 if by_hit_score else 0,
+                            id_base, _p(gi, c_i32p), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+    return out[:n.value]
+
+
+def plan_topk_paths(ctx: Context, plan_handle, comm: Comm | None, recs: np.ndarray, width: int | None = None):
+    """hhg_plan_topk_paths: [len(recs), width] uint8 state strings of the merged list, zero padded."""
+    recs = np.ascontiguousarray(recs)
+    width = int(width or max(1, int(recs["hit"]["nsteps"].max()) if len(recs) else 1))
+    out = np.zeros((len(recs), width), np.uint8)
+    _ck(ctx.L.hhg_plan_topk_paths(ctx.h, plan_handle, comm.h if comm is not None else None, len(recs),
+                                  recs.ctypes.data_as(C.c_void_p), width, _p(out, c_u8p)))
+    return out
+
+
 class Plan:
     def __init__(self, ctx: Context, db: TargetDB, ids=None):
         self.ctx, self.db = ctx, db
@@ -417,6 +476,12 @@ class Plan:
         _ck(self.ctx.L.hhg_plan_fetch(self.ctx.h, self.h, hits.ctypes.data_as(C.c_void_p), _p(paths, c_u8p),
                                       self.path_cap if want_paths else 0))
         return hits, paths
+
+    def topk(self, K, comm=None, by_hit_score=False, id_base=0, global_ids=None):
+        return plan_topk(self.ctx, self.h, comm, K, by_hit_score, id_base, global_ids)
+
+    def topk_paths(self, recs, comm=None, width=None):
+        return plan_topk_paths(self.ctx, self.h, comm, recs, width)
 
     def debug_bt(self, k):
         Lt = int(self.db.Lh[self.ids[k]])

@@ -5,6 +5,9 @@
 #include "hhg_kernels.cuh"
 #include "hhg_hhm.cuh"
 #include "hhg_mac.cuh"
+#include "hhg_topk.cuh"
+
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -16,6 +19,7 @@
 #include <memory>
 #include <cmath>
 #include <cfloat>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -184,6 +188,12 @@ struct hhg_plan {
   DevBuf<long long> d_compact_off;
   std::vector<long long> h_compact_off;
   DevBuf<HitRec> d_hits;
+  // top-K selection / exchange scratch (hhg_plan_topk)
+  DevBuf<unsigned long long> d_keys;
+  DevBuf<int> d_gids;
+  DevBuf<TopkState> d_topk_state;
+  DevBuf<TopkRec> d_topk_local, d_topk_all;
+  DevBuf<uint8_t> d_topk_paths;
   DevBuf<uint8_t> d_paths;
   // cell-off input (optional)
   bool celloff = false;
@@ -997,6 +1007,7 @@ int hhg_plan_fetch(hhg_ctx* ctx, hhg_plan* pl, hhg_hit* hits, uint8_t* paths, si
 }
 
 void* hhg_plan_hits_devptr(hhg_plan* plan) { return plan ? (void*)plan->d_hits.p : nullptr; }
+hhg_plan* hhg_ctx_last_plan(hhg_ctx* ctx) { return ctx ? ctx->scratch_plan : nullptr; }
 
 int hhg_plan_debug_bt(hhg_ctx* ctx, hhg_plan* pl, int k, uint8_t* bt) {
   if (!ctx || !pl || !bt || k < 0 || k >= pl->n) return fail(HHG_EINVAL, "hhg_plan_debug_bt: bad argument");
@@ -1029,6 +1040,169 @@ int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids
   if (rc == HHG_OK) rc = hhg_plan_fetch(ctx, pl, hits, paths, paths_cap);
   return rc;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------ multi-GPU: NCCL behind the C-ABI
+// NCCL is bound at run time (dlopen "libnccl.so.2"): a single-GPU user needs no NCCL at all, and inside a process
+// that already loaded a copy (e.g. PyTorch's bundled one) the same copy is used.  Only the stable core entry
+// points are needed; their prototypes are restated here (nccl.h: ncclGetUniqueId :146, ncclCommInitRank :160,
+// ncclCommDestroy :181, ncclAllGather :425, ncclAllReduce, ncclGetErrorString).
+namespace {
+typedef struct ncclComm* nccl_comm_t;
+typedef struct { char internal[128]; } nccl_uid_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+const char* g_nccl_err = nullptr;
+
+int nccl_load() {
+  std::call_once(g_nccl_once, [] {
+    const char* names[] = {getenv("HHG_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm) continue;
+      g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { g_nccl_err = "libnccl.so.2 not found (set HHG_NCCL_LIB)"; return; }
+#define SYM(f) *(void**)(&g_nccl.f) = dlsym(g_nccl.lib, "nccl" #f); if (!g_nccl.f) g_nccl_err = "NCCL symbol nccl" #f " missing"
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllGather); SYM(AllReduce); SYM(GetErrorString);
+#undef SYM
+  });
+  return g_nccl_err ? fail(HHG_ECUDA, "%s", g_nccl_err) : HHG_OK;
+}
+#define NCK(expr)                                                                                           \
+  do {                                                                                                      \
+    int r__ = (expr);                                                                                       \
+    if (r__ != 0) return fail(HHG_ECUDA, "%s: NCCL error %d (%s)", #expr, r__, g_nccl.GetErrorString(r__)); \
+  } while (0)
+}  // namespace
+
+struct hhg_comm {
+  int rank = 0, world = 1, device = 0;
+  nccl_comm_t comm = nullptr;
+};
+
+extern "C" {
+
+int hhg_comm_unique_id(void* id128) {
+  if (!id128) return fail(HHG_EINVAL, "hhg_comm_unique_id: id is NULL");
+  int rc = nccl_load();
+  if (rc != HHG_OK) return rc;
+  nccl_uid_t id;
+  NCK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return HHG_OK;
+}
+
+int hhg_comm_create(hhg_ctx* ctx, int rank, int world, const void* id128, hhg_comm** out) {
+  if (!ctx || !out || world < 1 || rank < 0 || rank >= world || (world > 1 && !id128))
+    return fail(HHG_EINVAL, "hhg_comm_create: bad argument");
+  std::unique_ptr<hhg_comm> c(new hhg_comm());
+  c->rank = rank; c->world = world; c->device = ctx->device;
+  if (world > 1) {
+    int rc = nccl_load();
+    if (rc != HHG_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    nccl_uid_t id;
+    memcpy(&id, id128, sizeof id);
+    NCK(g_nccl.CommInitRank(&c->comm, world, id, rank));
+  }
+  *out = c.release();
+  return HHG_OK;
+}
+
+int hhg_comm_destroy(hhg_comm* c) {
+  if (!c) return HHG_OK;
+  if (c->comm) { cudaSetDevice(c->device); g_nccl.CommDestroy(c->comm); }
+  delete c;
+  return HHG_OK;
+}
+
+int hhg_comm_rank(const hhg_comm* c) { return c ? c->rank : 0; }
+int hhg_comm_world(const hhg_comm* c) { return c ? c->world : 1; }
+
+// Top-K of the last run of `plan`, merged over all ranks of `comm` (NULL / world 1: this GPU only).
+int hhg_plan_topk(hhg_ctx* ctx, hhg_plan* pl, hhg_comm* comm, int K, int by_hit_score, int32_t id_base,
+                  const int32_t* global_ids, hhg_topk_rec* out, int* n_out) {
+  static_assert(sizeof(hhg_topk_rec) == sizeof(TopkRec), "hhg_topk_rec / TopkRec layout");
+  if (!ctx || !pl || K < 1 || !out || !n_out) return fail(HHG_EINVAL, "hhg_plan_topk: bad argument");
+  if (comm && comm->world > 1 && comm->device != ctx->device) return fail(HHG_EINVAL, "hhg_plan_topk: comm lives on another device");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n = pl->n;
+  const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+  const int kl = std::min(K, n);
+  CK(pl->d_keys.ensure((size_t)n)); CK(pl->d_topk_state.ensure(1));
+  CK(pl->d_topk_local.ensure((size_t)K)); CK(pl->d_topk_all.ensure((size_t)K * world));
+  if (global_ids) {
+    CK(pl->d_gids.ensure((size_t)n));
+    CK(cudaMemcpyAsync(pl->d_gids.p, global_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  }
+  TopkState init{};
+  init.krem = (unsigned)kl;
+  CK(cudaMemcpyAsync(pl->d_topk_state.p, &init, sizeof init, cudaMemcpyHostToDevice, st));
+  const int threads = 256, blocks = (n + threads - 1) / threads;
+  k_topk_keys<<<blocks, threads, 0, st>>>(n, pl->d_hits.p, by_hit_score, id_base, global_ids ? pl->d_gids.p : nullptr, pl->d_keys.p);
+  const int hblocks = std::min(blocks, ctx->sm_count * 4);
+  for (int p = 7; p >= 0; --p) {
+    k_topk_hist<<<hblocks, threads, 0, st>>>(n, pl->d_keys.p, p, pl->d_topk_state.p);
+    k_topk_scan<<<1, 256, 0, st>>>(pl->d_topk_state.p);
+  }
+  k_topk_emit<<<blocks, threads, 0, st>>>(n, pl->d_keys.p, pl->d_hits.p, rank, pl->d_topk_state.p, pl->d_topk_local.p, K);
+  ctx->launches += 18;
+  if (kl < K) { k_topk_pad<<<(K - kl + 255) / 256, 256, 0, st>>>(pl->d_topk_local.p, kl, K); ctx->launches++; }
+  CK(cudaGetLastError());
+  const TopkRec* src = pl->d_topk_local.p;
+  if (world > 1) {
+    NCK(g_nccl.AllGather(pl->d_topk_local.p, pl->d_topk_all.p, (size_t)K * sizeof(TopkRec), /*ncclChar*/ 0, comm->comm, st));
+    src = pl->d_topk_all.p;
+  }
+  std::vector<TopkRec> all((size_t)K * world);
+  CK(cudaMemcpyAsync(all.data(), src, all.size() * sizeof(TopkRec), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  // merge: keys are unique and totally ordered (score descending, global id ascending)
+  all.erase(std::remove_if(all.begin(), all.end(), [](const TopkRec& r) { return r.target < 0; }), all.end());
+  std::sort(all.begin(), all.end(), [](const TopkRec& a, const TopkRec& b) { return a.key < b.key; });
+  const int m = (int)std::min<size_t>(all.size(), (size_t)K);
+  memcpy(out, all.data(), (size_t)m * sizeof(TopkRec));
+  *n_out = m;
+  return HHG_OK;
+}
+
+// State strings of the merged list: out[r*width .. ] = path of recs[r] (nsteps bytes, zero padded), on every rank.
+int hhg_plan_topk_paths(hhg_ctx* ctx, hhg_plan* pl, hhg_comm* comm, int n_rec, const hhg_topk_rec* recs, int width,
+                        uint8_t* out) {
+  if (!ctx || !pl || n_rec < 0 || !recs || width < 1 || !out) return fail(HHG_EINVAL, "hhg_plan_topk_paths: bad argument");
+  if (n_rec == 0) return HHG_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+  CK(pl->d_topk_all.ensure((size_t)n_rec));
+  CK(pl->d_topk_paths.ensure((size_t)n_rec * width));
+  CK(cudaMemcpyAsync(pl->d_topk_all.p, recs, (size_t)n_rec * sizeof(TopkRec), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(pl->d_topk_paths.p, 0, (size_t)n_rec * width, st));
+  k_topk_paths<<<n_rec, 128, 0, st>>>(n_rec, pl->d_topk_all.p, rank, pl->d_paths.p, width, pl->d_topk_paths.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (world > 1)
+    NCK(g_nccl.AllReduce(pl->d_topk_paths.p, pl->d_topk_paths.p, (size_t)n_rec * width, /*ncclUint8*/ 1, /*ncclSum*/ 0, comm->comm, st));
+  CK(cudaMemcpyAsync(out, pl->d_topk_paths.p, (size_t)n_rec * width, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return HHG_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------ MAC realignment
 // HMM::Log2LinTransitionProbs(1.0) (src/hhhmm.cpp:2305-2313) for host arrays: tr = pow(2.0f, 1.0f * tr), which with

@@ -138,12 +138,10 @@ def stage2_merge(cand: np.ndarray, ev: np.ndarray, min_hits: int, evalue_thresh:
     cap at maxnumdb (:590).  Returns global ids in the reference's output order."""
     keep = np.nonzero(ev < evalue_coarse)[0]
     order = keep[np.lexsort((cand[keep], ev[keep]))]
-    out = []
-    for k in order:
-        if len(out) >= min_hits and ev[k] > evalue_thresh:
-            break
-        out.append(int(cand[k]))
-    return np.array(out[:maxnumdb], np.int64)
+    # keep while count < min_hits or ev <= evalue_thresh: the first position >= min_hits with ev > thresh ends the list
+    tail = np.nonzero(ev[order[min_hits:]] > evalue_thresh)[0]
+    ncut = min_hits + int(tail[0]) if len(tail) else len(order)
+    return np.asarray(cand, np.int64)[order[:min(ncut, maxnumdb)]]
 
 
 def sharded_prefilter(score_stage1, score_stage2, local_ids: np.ndarray, local_len: np.ndarray, n_global: int,
@@ -159,30 +157,29 @@ def sharded_prefilter(score_stage1, score_stage2, local_ids: np.ndarray, local_l
     database size).  Returns the global ids kept, identical on every rank and identical to the single-process result."""
     from . import capi
     import ctypes as C
+    local_ids = np.asarray(local_ids, np.int64)
+    local_len = np.asarray(local_len, np.int64)
     li, sc = score_stage1()
-    cand = np.stack([np.asarray(local_ids, np.int64)[li], np.asarray(sc, np.int64)], axis=1) if len(li) else \
-        np.zeros((0, 2), np.int64)
+    li = np.asarray(li, np.int64)
+    cand = np.stack([local_ids[li], np.asarray(sc, np.int64)], axis=1) if len(li) else np.zeros((0, 2), np.int64)
     first = stage1_merge(_allgather_var(cand, device), min_hits, smax_thresh)
-    # stage 2 on the members this rank owns
-    g2l = {int(g): x for x, g in enumerate(np.asarray(local_ids, np.int64)[li])}
-    own = [int(g) for g in first[:, 0] if int(g) in g2l]
-    own_local = np.array([li[g2l[g]] for g in own], np.int32)
-    rows = np.zeros((0, 2), np.int64)
-    if len(own):
+    # stage 2 on the members this rank owns: a global id is mine iff it occurs in my (id-sorted) shard; every member
+    # of `first` that is mine was one of my own stage-1 candidates (first is a subset of the union of the candidates)
+    g = first[:, 0]
+    x = np.searchsorted(local_ids, g)
+    x[x >= len(local_ids)] = 0
+    mine = local_ids[x] == g if len(local_ids) else np.zeros(len(g), bool)
+    own_local = x[mine].astype(np.int32)
+    rows = np.zeros((0, 3), np.int64)
+    if len(own_local):
         sw = np.ascontiguousarray(score_stage2(own_local), np.int32)
-        rows = np.stack([np.array(own, np.int64), sw.astype(np.int64)], axis=1)
+        rows = np.stack([g[mine], sw.astype(np.int64), local_len[own_local]], axis=1)     # (id, score, length)
     allrows = _allgather_var(rows, device)
-    # E-values with the global N; the length of each candidate travels implicitly: recompute from the owner's row
-    lens = np.zeros(len(allrows), np.int32)
-    own_set = {g: int(local_len[own_local[k]]) for k, g in enumerate(own)}
-    lrows = np.array([[g, own_set[g]] for g in own], np.int64).reshape(-1, 2)
-    alll = _allgather_var(lrows, device)
-    lmap = {int(g): int(l) for g, l in alll}
-    for k, g in enumerate(allrows[:, 0]):
-        lens[k] = lmap[int(g)]
+    # E-values with the GLOBAL database size
     ev = np.zeros(len(allrows), np.float64)
     if len(allrows):
         sw32 = np.ascontiguousarray(allrows[:, 1], np.int32)
+        lens = np.ascontiguousarray(allrows[:, 2], np.int32)
         capi._ck(capi.load().hhg_prefilter_evalues(len(allrows), capi._p(sw32, capi.c_i32p), capi._p(lens, capi.c_i32p),
                                                    n_global, Lq, bit_factor, ev.ctypes.data_as(C.POINTER(C.c_double))))
     return stage2_merge(allrows[:, 0], ev, min_hits, evalue_thresh, evalue_coarse, maxnumdb)

@@ -192,6 +192,41 @@ double hhg_plan_padded_cells(const hhg_plan* plan);
 /* Algorithmic bytes of one run: 112 B per target column + 1 B per cell + 32 B per hit */
 double hhg_plan_algorithmic_bytes(const hhg_plan* plan);
 
+/* ---- multi-GPU: database sharded by target, hit lists merged over NCCL ------------------------------
+ * The reference has no GPU or multi-device layer (its MPI front end distributes QUERIES, src/hhblits_mpi.cpp:135);
+ * what must be kept is the result: every target aligned exactly once, one merged hit list ordered like a
+ * single-process search (src/hhblits.cpp:890-905), global database size in the E-values.  One process (or host
+ * thread) per GPU; each owns a shard (hhg_db) and a communicator.
+ *   hhg_comm_unique_id : rank 0 obtains the 128-byte rendezvous id (ncclGetUniqueId) and hands it to the other
+ *                        ranks by any means (argv, file, MPI, a shared variable between threads);
+ *   hhg_comm_create    : collective over all ranks (ncclCommInitRank on the context's device); world == 1 needs
+ *                        no NCCL at all.  NCCL is loaded at run time (libnccl.so.2; override with HHG_NCCL_LIB).
+ *   hhg_plan_topk      : after hhg_plan_run / hhg_viterbi_search on every rank: selects this rank's K best hit
+ *                        records on the GPU (radix select on a 64-bit key: score descending, GLOBAL target id
+ *                        ascending), exchanges them with ONE ncclAllGather of K*56 bytes per rank and returns the
+ *                        merged K best on every rank.  by_hit_score: 0 = raw Viterbi score, 1 = Hit.score.
+ *                        Global id of request k = global_ids ? global_ids[k] : id_base + k  (host array of plan-n).
+ *   hhg_plan_topk_paths: the state strings of the merged list (one ncclAllReduce of n_rec*width bytes; each row has
+ *                        exactly one owner).  out[r*width ..] = path of recs[r], zero padded; width >= max nsteps. */
+typedef struct hhg_comm hhg_comm;
+typedef struct hhg_topk_rec {
+  int32_t target;   /* global target id                          */
+  int32_t owner;    /* rank whose shard holds it                 */
+  hhg_hit hit;      /* the owner's hit record (path_off is local to the owner) */
+  uint64_t key;     /* ordering key, ascending = better          */
+} hhg_topk_rec;
+int hhg_comm_unique_id(void* id128);
+int hhg_comm_create(hhg_ctx* ctx, int rank, int world, const void* id128, hhg_comm** out);
+int hhg_comm_destroy(hhg_comm* comm);
+int hhg_comm_rank(const hhg_comm* comm);
+int hhg_comm_world(const hhg_comm* comm);
+int hhg_plan_topk(hhg_ctx* ctx, hhg_plan* plan, hhg_comm* comm, int K, int by_hit_score, int32_t id_base,
+                  const int32_t* global_ids, hhg_topk_rec* out, int* n_out);
+int hhg_plan_topk_paths(hhg_ctx* ctx, hhg_plan* plan, hhg_comm* comm, int n_rec, const hhg_topk_rec* recs, int width,
+                        uint8_t* out);
+/* The plan hhg_viterbi_search used last on this context (for hhg_plan_topk after a host-buffer search). */
+hhg_plan* hhg_ctx_last_plan(hhg_ctx* ctx);
+
 /* Debug / parity: raw backtrace bytes of request k of the last run of `plan` in the reference's
  * ViterbiMatrix cell format, row-major bt[i*(Lt+1)+j] (host buffer of (Lq+1)*(Lt+1) bytes). */
 int hhg_plan_debug_bt(hhg_ctx* ctx, hhg_plan* plan, int k, uint8_t* bt);

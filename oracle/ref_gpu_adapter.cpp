@@ -11,7 +11,11 @@
 // It contains no reference code; it includes the reference headers at build time and is compiled by
 // oracle/ref_build.mk into oracle/_ref/hh_dropin_check (shipped prebuilt to the GPU box).
 //
-// usage: hh_dropin_check [--hhm-loader] [--mac] <query.hhm> <template.hhm> [more templates ...]   exit 0 = identical
+// usage: hh_dropin_check [--hhm-loader] [--mac] [--gpus N] <query.hhm> <template.hhm> [more templates ...]   exit 0 = identical
+//   --gpus N      shard the templates over N GPUs (template k -> GPU k mod N), one host thread + hhg_ctx + hhg_comm
+//                 per GPU; every Hit must still equal the reference's, and the hit list merged over NCCL by
+//                 hhg_plan_topk / hhg_plan_topk_paths (K = all templates, key = Hit.score) must be the reference's
+//                 first-alignment hits in (score descending, template index ascending) order, paths included
 //   --hhm-loader  templates are loaded by hhg_db_create_hhm from the HHM text instead of the reference's preparation
 //   --mac         additionally realign every hit: PosteriorDecoderRunner::executeComputation vs hhg_mac_realign
 //                 (written in round 1, first exercised on a GPU in round 2; the MAC parity of round 1 is established
@@ -26,6 +30,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #define private public
@@ -70,8 +75,18 @@ struct GpuHit {
 // their index in `dbfiles`.
 class GpuViterbiRunner {
  public:
-  GpuViterbiRunner() { HHG_CHECK(hhg_ctx_create(0, nullptr, &ctx_)); }
-  ~GpuViterbiRunner() { if (db_) hhg_db_destroy(db_); hhg_ctx_destroy(ctx_); }
+  explicit GpuViterbiRunner(int device = 0) { HHG_CHECK(hhg_ctx_create(device, nullptr, &ctx_)); }
+  ~GpuViterbiRunner() { if (comm_) hhg_comm_destroy(comm_); if (db_) hhg_db_destroy(db_); hhg_ctx_destroy(ctx_); }
+
+  // multi-GPU: this runner owns the templates global_ids[0..] of the whole list and is rank `rank` of `world`
+  void JoinComm(int rank, int world, const void* uid, const std::vector<int32_t>& global_ids, int n_total) {
+    HHG_CHECK(hhg_comm_create(ctx_, rank, world, uid, &comm_));
+    gids_ = global_ids;
+    n_total_ = n_total;
+  }
+  std::vector<hhg_topk_rec> merged;      // the merged first-alignment hit list (every rank holds the same)
+  std::vector<uint8_t> merged_paths;     // [merged.size() x merged_width]
+  int merged_width = 0;
 
   // one-time shard upload: what PrepareTemplateHMM leaves BEFORE the query-dependent null model
   void Upload(Parameters& par, std::vector<HHEntry*>& entries, float* pb, const float S[20][20],
@@ -171,11 +186,23 @@ class GpuViterbiRunner {
       }
       HHG_CHECK(hhg_viterbi_search(ctx_, db_, (int)ids.size(), ids.data(), hits.data(), paths.data(), paths.size(),
                                    alignment ? eoff.data() : nullptr, ei.data(), ej.data()));
+      if (comm_ && alignment == 0) {
+        // merged hit list of the first alignment round over all GPUs (collective: every rank calls it)
+        merged.resize(n_total_);
+        int m = 0;
+        HHG_CHECK(hhg_plan_topk(ctx_, hhg_ctx_last_plan(ctx_), comm_, n_total_, 1, 0, gids_.data(), merged.data(), &m));
+        merged.resize(m);
+        merged_width = 1;
+        for (const hhg_topk_rec& r : merged) merged_width = std::max(merged_width, (int)r.hit.nsteps);
+        merged_paths.assign((size_t)m * merged_width, 0);
+        HHG_CHECK(hhg_plan_topk_paths(ctx_, hhg_ctx_last_plan(ctx_), comm_, m, merged.data(), merged_width,
+                                      merged_paths.data()));
+      }
       std::vector<int32_t> next;
       for (size_t k = 0; k < ids.size(); ++k) {
         const hhg_hit& h = hits[k];
         GpuHit g;
-        g.target = ids[k]; g.irep = alignment + 1;                        // :257
+        g.target = gids_.empty() ? ids[k] : gids_[ids[k]]; g.irep = alignment + 1;   // :257 (global template index)
         g.lastrep = (h.hit_score <= par.smin) ? 1 : 0;                    // :36
         g.score = h.hit_score; g.score_ss = h.score_ss;
         g.i1 = h.i1; g.i2 = h.i2; g.j1 = h.j1; g.j2 = h.j2; g.nsteps = h.nsteps; g.matched_cols = h.matched_cols;
@@ -264,6 +291,9 @@ class GpuViterbiRunner {
  private:
   hhg_ctx* ctx_ = nullptr;
   hhg_db* db_ = nullptr;
+  hhg_comm* comm_ = nullptr;
+  std::vector<int32_t> gids_;
+  int n_total_ = 0;
   std::vector<int32_t> L_;
   bool all_have_ss_ = false;
 };
@@ -274,12 +304,15 @@ uint32_t bits(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 
 int main(int argc, char** argv) {
   bool text_loader = false, with_mac = false;
+  int gpus = 1;
   while (argc > 1 && argv[1][0] == '-' && argv[1][1] == '-') {
     if (!strcmp(argv[1], "--hhm-loader")) text_loader = true;
     else if (!strcmp(argv[1], "--mac")) with_mac = true;
+    else if (!strcmp(argv[1], "--gpus") && argc > 2) { gpus = atoi(argv[2]); --argc; ++argv; }
     else break;
     --argc; ++argv;
   }
+  if (gpus > 1 && with_mac) { fprintf(stderr, "--mac is checked on one GPU\n"); return 2; }
   if (argc < 3) { fprintf(stderr, "usage: %s [--hhm-loader] [--mac] query.hhm template.hhm [...]\n", argv[0]); return 2; }
   Log::reporting_level() = WARNING;
   const char* pargv[] = {"hhalign"};
@@ -321,13 +354,48 @@ int main(int argc, char** argv) {
 
   // ---- (2) the GPU adapter
   GpuViterbiRunner gpu_runner;
-  if (text_loader) {
-    std::vector<std::string> files(argv + 2, argv + argc);
-    gpu_runner.UploadText(par, files, R);
+  std::vector<GpuHit> gpu;
+  std::vector<hhg_topk_rec> merged;
+  std::vector<uint8_t> merged_paths;
+  int merged_width = 0;
+  if (gpus <= 1) {
+    if (text_loader) {
+      std::vector<std::string> files(argv + 2, argv + argc);
+      gpu_runner.UploadText(par, files, R);
+    } else {
+      gpu_runner.Upload(par, entries, pb, S, Sim, R);
+    }
+    gpu = gpu_runner.alignment(par, &q_vec, (int)entries.size(), pb, S33);
   } else {
-    gpu_runner.Upload(par, entries, pb, S, Sim, R);
+    // the shard of GPU r = templates r, r+gpus, ...; uploads run on this thread (they call into the reference),
+    // the searches run concurrently, one host thread per GPU, and meet in hhg_plan_topk
+    char uid[128];
+    HHG_CHECK(hhg_comm_unique_id(uid));
+    std::vector<std::unique_ptr<GpuViterbiRunner>> runners;
+    std::vector<std::vector<int32_t>> gid(gpus);
+    for (int r = 0; r < gpus; ++r) {
+      runners.emplace_back(new GpuViterbiRunner(r));
+      std::vector<HHEntry*> mine;
+      std::vector<std::string> files;
+      for (size_t k = r; k < entries.size(); k += gpus) { gid[r].push_back((int32_t)k); mine.push_back(entries[k]); files.push_back(argv[2 + k]); }
+      if (mine.empty()) { fprintf(stderr, "--gpus %d needs at least %d templates\n", gpus, gpus); return 2; }
+      if (text_loader) runners[r]->UploadText(par, files, R); else runners[r]->Upload(par, mine, pb, S, Sim, R);
+    }
+    std::vector<std::vector<GpuHit>> part(gpus);
+    std::vector<std::thread> th;
+    for (int r = 0; r < gpus; ++r)
+      th.emplace_back([&, r] {
+        runners[r]->JoinComm(r, gpus, uid, gid[r], (int)entries.size());
+        part[r] = runners[r]->alignment(par, &q_vec, (int)gid[r].size(), pb, S33);
+      });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < gpus; ++r) gpu.insert(gpu.end(), part[r].begin(), part[r].end());
+    merged = runners[0]->merged; merged_paths = runners[0]->merged_paths; merged_width = runners[0]->merged_width;
+    for (int r = 1; r < gpus; ++r)
+      if (runners[r]->merged.size() != merged.size() ||
+          memcmp(runners[r]->merged.data(), merged.data(), merged.size() * sizeof(hhg_topk_rec)) ||
+          runners[r]->merged_paths != merged_paths) { printf("MISMATCH: rank %d holds a different merged list\n", r); return 1; }
   }
-  std::vector<GpuHit> gpu = gpu_runner.alignment(par, &q_vec, (int)entries.size(), pb, S33);
 
   // ---- compare
   std::map<HHEntry*, int> index;
@@ -353,6 +421,27 @@ int main(int argc, char** argv) {
              g.j2, g.nsteps);
       ++bad;
     }
+  }
+  if (gpus > 1) {
+    // the NCCL-merged list must be the reference's first-alignment hits, best Hit.score first, template index on ties
+    std::vector<Hit*> first;
+    for (Hit& h : ref) if (h.irep == 1) first.push_back(&h);
+    std::sort(first.begin(), first.end(), [&](Hit* a, Hit* b) {
+      if (a->score != b->score) return a->score > b->score;
+      return index[a->entry] < index[b->entry];
+    });
+    int mbad = first.size() != merged.size();
+    for (size_t r = 0; !mbad && r < first.size(); ++r) {
+      const Hit& h = *first[r];
+      const hhg_topk_rec& m = merged[r];
+      bool ok = m.target == index[h.entry] && m.owner == m.target % gpus && bits(m.hit.hit_score) == bits(h.score) &&
+                m.hit.i1 == h.i1 && m.hit.i2 == h.i2 && m.hit.j1 == h.j1 && m.hit.j2 == h.j2 && m.hit.nsteps == h.nsteps;
+      for (int s = 1; ok && s <= h.nsteps; ++s) ok = merged_paths[r * merged_width + s - 1] == (uint8_t)h.states[s];
+      if (!ok) { printf("MERGE MISMATCH at rank-list position %zu: template %d vs reference template %d\n", r, m.target, index[h.entry]); ++mbad; }
+    }
+    printf("hh_dropin_check --gpus %d: merged list of %zu hits over NCCL: %s\n", gpus, merged.size(),
+           mbad ? "MISMATCH" : "identical to the reference's sorted first-round hits, paths included");
+    bad += mbad;
   }
   if (text_loader) printf("(templates loaded by hhg_db_create_hhm from the HHM text)\n");
   // ---- (3) optional: MAC realignment of all hits, reference runner vs C-ABI

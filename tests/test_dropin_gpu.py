@@ -49,3 +49,42 @@ def test_reference_runner_vs_gpu_adapter_with_ss(tmp_path):
         files.append(str(f))
     r = _run([str(q)] + files)
     assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+def test_mac_realignment_in_the_dropin_check(tmp_path):
+    """--mac: PosteriorDecoderRunner::executeComputation vs hhg_mac_realign on every Viterbi hit (INTEGRATION.md 2b)."""
+    from hhsuite_b200 import synth
+    files = []
+    for k, L in enumerate([150, 431, 300, 97, 200]):
+        f = tmp_path / f"m{k}.hhm"
+        f.write_text(synth.hhm_text(L, 500 + k, f"m{k}"))
+        files.append(str(f))
+    r = _run(["--mac", QUERY, QUERY] + files)
+    assert r.returncode == 0 and "all MAC alignments identical" in r.stdout and "all hits identical" in r.stdout, \
+        r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpus_behind_the_c_abi(tmp_path):
+    """--gpus 2: C++ only (no torch): templates sharded over two GPUs, one host thread + hhg_ctx + hhg_comm each;
+    all Hits equal the reference's and the NCCL-merged list (hhg_plan_topk + hhg_plan_topk_paths) equals the
+    reference's first-round hits sorted by (Hit.score desc, template index asc)."""
+    from hhsuite_b200 import synth
+    files = []
+    for k, L in enumerate([150, 60, 431, 300, 33, 200, 97, 120, 250, 75, 150]):     # 150 twice: seeds differ
+        f = tmp_path / f"g{k}.hhm"
+        f.write_text(synth.hhm_text(L, 100 + k, f"g{k}"))
+        files.append(str(f))
+    r = _run(["--gpus", "2", QUERY, QUERY] + files + [files[3]])                    # files[3] twice: an exact score tie
+    assert r.returncode == 0 and "all hits identical" in r.stdout and "identical to the reference's sorted" in r.stdout, \
+        r.stdout + r.stderr
