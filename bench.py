@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 TOPK = 500          # realign_max of the reference (src/hhdecl.cpp): records exchanged per rank
 BASE_SEED = 1000
 # instructions per 32-cell row visit of k_viterbi<16,local> (ncu smsp__inst_executed / row visits, profiles/r2_*)
-WARP_INSTR_PER_ROW_VISIT = 105.5
+WARP_INSTR_PER_ROW_VISIT = 105.7
 
 
 def parse_args():

@@ -71,13 +71,14 @@ struct DevBuf {
   }
 };
 
+// strip height forced by the environment (developer / test knob), or 0 = chosen per plan (plan_strip_rows)
 int strip_rows() {
   const char* e = getenv("HHG_STRIP_ROWS");
   if (e) {
     int r = atoi(e);
     if (r == 8 || r == 12 || r == 16) return r;
   }
-  return 16;
+  return 0;
 }
 
 }  // namespace
@@ -89,7 +90,7 @@ struct hhg_ctx {
   int sm_count = 0;
   long long launches = 0;
   // query
-  int Lq = 0, R = 16, nstrips = 0;
+  int Lq = 0, R = 0;     // R: forced strip height (HHG_STRIP_ROWS) or 0 = per plan
   int group_jobs = 16;   // work-item interleave (see k_viterbi): 16 jobs x nstrips items keep the group L2-resident
   uint32_t epoch = 0;    // run counter feeding the boundary-slot tags
   DevBuf<float4> qrec;
@@ -100,6 +101,7 @@ struct hhg_ctx {
   hhg_params par{1, 0.f, 0.f, -0.03f, 0.11f, 0, 0.1f, 2};
   // prefilter
   DevBuf<uint8_t> pf_prof, sw_prof;
+  DevBuf<uint8_t> pf_edge[2];   // per-column hand-off between query tiles of the ungapped prefilter (Lq > 512)
   DevBuf<int> sw_ids, sw_scores;
   DevBuf<unsigned> pf_counter, pf_hist;
   DevBuf<int> pf_corr, pf_ids_a, pf_score_a, pf_ids_b;
@@ -643,8 +645,7 @@ int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const u
   CK(cudaSetDevice(ctx->device));
   ctx->par = *par;
   ctx->Lq = Lq;
-  ctx->nstrips = (Lq + ctx->R - 1) / ctx->R;
-  const int rows = ctx->nstrips * ctx->R;
+  const int rows = (Lq + 47) / 48 * 48;   // zero padded to a multiple of every strip height (8, 12, 16)
   CK(ctx->qrec.ensure((size_t)rows * 7));
   CK(cudaMemsetAsync(ctx->qrec.p, 0, (size_t)rows * 112, ctx->stream));
   // pack with the same kernel as the DB (a one-profile shard)
@@ -665,6 +666,16 @@ int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const u
 }
 
 // ---------------------------------------------------------------------------------------- plan
+// Strip height of a plan.  Whole-shard scans have work items to spare and take R = 16 (least per-column overhead,
+// 253 GCUPS).  A small request (the few thousand survivors of the prefilter) is latency bound: its longest job is one
+// serial sweep over Lmax columns per strip, so halving the strip height halves that critical path and doubles the
+// number of work items that can run side by side.
+static int plan_strip_rows(const hhg_ctx* ctx, int n) {
+  if (ctx->R) return ctx->R;
+  const long long items16 = (long long)((n + 31) / 32) * ((ctx->Lq + 15) / 16);
+  return items16 >= 4LL * ctx->sm_count * 8 ? 16 : 8;
+}
+
 // (Re)build a plan in place; device buffers only ever grow, so a plan object that is reused across
 // searches (hhg_viterbi_search keeps one per context) does not touch cudaMalloc in steady state.
 static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const int32_t* ids) {
@@ -674,7 +685,7 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   CK(cudaSetDevice(ctx->device));
   // the common case of a repeated request (same shard, same target list, same query geometry, e.g. every
   // query of a batch against the whole shard) reuses the plan: no host sort, no uploads
-  if (pl->db == db && pl->db_serial == db->serial && pl->n == n && pl->Lq == ctx->Lq && pl->R == ctx->R &&
+  if (pl->db == db && pl->db_serial == db->serial && pl->n == n && pl->Lq == ctx->Lq && pl->R == plan_strip_rows(ctx, n) &&
       !pl->ids.empty() && pl->max_bt_bytes == ctx->max_bt_bytes) {
     bool same = true;
     if (ids) same = memcmp(ids, pl->ids.data(), (size_t)n * 4) == 0;
@@ -689,7 +700,7 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   pl->waves.clear();
   pl->celloff = false;
   pl->n = n;
-  pl->Lq = ctx->Lq; pl->R = ctx->R; pl->nstrips = ctx->nstrips;
+  pl->Lq = ctx->Lq; pl->R = plan_strip_rows(ctx, n); pl->nstrips = (pl->Lq + pl->R - 1) / pl->R;
   pl->ids.resize(n);
   for (int k = 0; k < n; ++k) {
     const int id = ids ? ids[k] : k;
@@ -876,7 +887,7 @@ extern "C" {
 
 static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
   if (!ctx || !pl) return fail(HHG_EINVAL, "hhg_plan_run: bad argument");
-  if (pl->Lq != ctx->Lq || pl->R != ctx->R) return fail(HHG_EINVAL, "plan was made for another query length");
+  if (pl->Lq != ctx->Lq) return fail(HHG_EINVAL, "plan was made for another query length");
   const hhg_db* db = pl->db;
   if (!db->prepared) return fail(HHG_EINVAL, "raw db: call hhg_db_apply_null_model for the current query first");
   if (ctx->par.use_ss && (!db->has_ss || !ctx->has_ss || !ctx->has_S33))
@@ -1033,11 +1044,21 @@ int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids
   if (!ctx) return fail(HHG_EINVAL, "ctx is NULL");
   if (!ctx->scratch_plan) ctx->scratch_plan = new hhg_plan();
   hhg_plan* pl = ctx->scratch_plan;
+  static const bool timing = getenv("HHG_TIMING") != nullptr;   // developer aid: host-side phase times on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t0 = now();
   int rc = plan_build(ctx, pl, db, n, ids);
   if (rc != HHG_OK) return rc;
+  auto t1 = now();
   rc = set_exclusions(ctx, pl, excl_off, excl_i, excl_j);
   if (rc == HHG_OK) rc = hhg_plan_run(ctx, pl);
+  if (timing) cudaStreamSynchronize(ctx->stream);
+  auto t2 = now();
   if (rc == HHG_OK) rc = hhg_plan_fetch(ctx, pl, hits, paths, paths_cap);
+  if (timing) {
+    auto ms = [](decltype(t0) a, decltype(t0) b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[hhg] viterbi_search n=%d: plan %.3f ms, run (device) %.3f ms, fetch %.3f ms\n", n, ms(t0, t1), ms(t1, t2), ms(t2, now()));
+  }
   return rc;
 }
 
@@ -1471,63 +1492,80 @@ int hhg_csdb_destroy(hhg_csdb* db) {
 
 template <int WB>
 static int launch_prefilter(hhg_ctx* ctx, const PfParams& P) {
-  const size_t smem = (size_t)220 * WB * 32 * 2;
+  const size_t smem = (size_t)220 * WB * 32 * 4;
   auto kern = k_prefilter_ungapped<WB>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem));
   if (per_sm < 1) return fail(HHG_ECUDA, "prefilter kernel does not fit on an SM");
-  kern<<<ctx->sm_count * per_sm, 256, smem, ctx->stream>>>(P);
+  kern<<<ctx->sm_count * per_sm, 512, smem, ctx->stream>>>(P);
   ctx->launches++;
   CK(cudaGetLastError());
   return HHG_OK;
 }
 
+// registers per lane of one query tile (64 positions per register): the smallest size that covers the query in one
+// tile, else full 512-position tiles (225 KB of shared memory)
 static int prefilter_wb(int Lq) {
-  static const int kWB[] = {2, 4, 6, 7, 8, 10, 12, 16};
+  static const int kWB[] = {1, 2, 3, 4, 5, 6, 7, 8};
   for (int wb : kWB) if (Lq <= 64 * wb) return wb;
-  return 0;
+  return 8;
 }
 
 extern "C" {
 
 int hhg_prefilter_ungapped_run(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const uint8_t* prof_host,
                                int offset, int upload_profile) {
-  if (!ctx || !db || Lq < 1) return fail(HHG_EINVAL, "hhg_prefilter_ungapped_run: bad argument");
+  if (!ctx || !db || Lq < 1 || offset < 0 || offset > 255) return fail(HHG_EINVAL, "hhg_prefilter_ungapped_run: bad argument");
   const int WB = prefilter_wb(Lq);
-  if (!WB) return fail(HHG_EINVAL, "prefilter: query length %d > 1024 not supported yet (profile must fit in shared memory)", Lq);
+  const int tile_pos = 64 * WB;
+  const int ntiles = (Lq + tile_pos - 1) / tile_pos;
+  const size_t tile_words = (size_t)220 * WB * 32;
   CK(cudaSetDevice(ctx->device));
   if (upload_profile) {
     if (!prof_host) return fail(HHG_EINVAL, "profile is NULL");
-    // repack [220][Lq] bytes into [220][WB][32 lanes] halfwords: lane l owns positions l*2WB .. +2WB-1
-    std::vector<uint8_t> packed((size_t)220 * WB * 32 * 2, 0);
-    for (int k = 0; k < 220; ++k)
-      for (int l = 0; l < 32; ++l)
+    // repack [220][Lq] bytes into [tile][220][WB][32 lanes] words: lane l of a tile owns its positions
+    // l*2WB .. +2WB-1; word w = (position l*2WB+w | position l*2WB+WB+w), each as the s16 value p - offset
+    std::vector<uint32_t> packed(tile_words * ntiles);
+    const uint32_t pad = (uint32_t)(uint16_t)(int16_t)(-offset);
+    for (int t = 0; t < ntiles; ++t)
+      for (int k = 0; k < 220; ++k)
         for (int w = 0; w < WB; ++w)
-          for (int h = 0; h < 2; ++h) {
-            const int pos = l * 2 * WB + 2 * w + h;
-            if (pos < Lq) packed[(((size_t)k * WB + w) * 32 + l) * 2 + h] = prof_host[(size_t)k * Lq + pos];
+          for (int l = 0; l < 32; ++l) {
+            const int plo = t * tile_pos + l * 2 * WB + w, phi = plo + WB;
+            const uint32_t lo = plo < Lq ? (uint32_t)(uint16_t)(int16_t)((int)prof_host[(size_t)k * Lq + plo] - offset) : pad;
+            const uint32_t hi = phi < Lq ? (uint32_t)(uint16_t)(int16_t)((int)prof_host[(size_t)k * Lq + phi] - offset) : pad;
+            packed[(size_t)t * tile_words + ((size_t)k * WB + w) * 32 + l] = lo | (hi << 16);
           }
-    CK(ctx->pf_prof.ensure(packed.size()));
-    CK(cudaMemcpyAsync(ctx->pf_prof.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->pf_prof.ensure(packed.size() * 4));
+    CK(cudaMemcpyAsync(ctx->pf_prof.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
-  CK(ctx->pf_counter.ensure(1));
-  CK(cudaMemsetAsync(ctx->pf_counter.p, 0, 4, ctx->stream));
-  PfParams P{};
-  P.n = db->n; P.L = db->dL.p; P.off = db->doff.p; P.seq = db->seq.p;
-  P.prof16 = reinterpret_cast<const uint16_t*>(ctx->pf_prof.p);
-  P.Lq = Lq; P.offset = offset; P.scores = db->scores.p; P.counter = ctx->pf_counter.p;
-  switch (WB) {
-    case 2: return launch_prefilter<2>(ctx, P);
-    case 4: return launch_prefilter<4>(ctx, P);
-    case 6: return launch_prefilter<6>(ctx, P);
-    case 7: return launch_prefilter<7>(ctx, P);
-    case 8: return launch_prefilter<8>(ctx, P);
-    case 10: return launch_prefilter<10>(ctx, P);
-    case 12: return launch_prefilter<12>(ctx, P);
-    default: return launch_prefilter<16>(ctx, P);
+  CK(ctx->pf_counter.ensure((size_t)ntiles));
+  CK(cudaMemsetAsync(ctx->pf_counter.p, 0, 4 * (size_t)ntiles, ctx->stream));
+  if (ntiles > 1) { CK(ctx->pf_edge[0].ensure((size_t)db->total)); CK(ctx->pf_edge[1].ensure((size_t)db->total)); }
+  for (int t = 0; t < ntiles; ++t) {
+    PfParams P{};
+    P.n = db->n; P.L = db->dL.p; P.off = db->doff.p; P.seq = db->seq.p;
+    P.prof32 = reinterpret_cast<const uint32_t*>(ctx->pf_prof.p) + (size_t)t * tile_words;
+    P.offset = offset; P.tile = t; P.last_tile = (t == ntiles - 1);
+    P.edge_in = ntiles > 1 ? ctx->pf_edge[(t + 1) & 1].p : nullptr;
+    P.edge_out = ntiles > 1 ? ctx->pf_edge[t & 1].p : nullptr;
+    P.scores = db->scores.p; P.counter = ctx->pf_counter.p + t;
+    int rc;
+    switch (WB) {
+      case 1: rc = launch_prefilter<1>(ctx, P); break;
+      case 2: rc = launch_prefilter<2>(ctx, P); break;
+      case 3: rc = launch_prefilter<3>(ctx, P); break;
+      case 4: rc = launch_prefilter<4>(ctx, P); break;
+      case 5: rc = launch_prefilter<5>(ctx, P); break;
+      case 6: rc = launch_prefilter<6>(ctx, P); break;
+      case 7: rc = launch_prefilter<7>(ctx, P); break;
+      default: rc = launch_prefilter<8>(ctx, P); break;
+    }
+    if (rc != HHG_OK) return rc;
   }
+  return HHG_OK;
 }
 
 // Host-side query profile of the prefilter (once per query; Prefilter::stripe_query_profile,
@@ -1609,8 +1647,10 @@ int hhg_prefilter_sw(hhg_ctx* ctx, const hhg_csdb* db, int n, const int32_t* ids
   if (!ctx || !db || n < 1 || Lq < 1 || !prof || !scores) return fail(HHG_EINVAL, "hhg_prefilter_sw: bad argument");
   const int W = (Lq + 31) / 32;
   const size_t prof_bytes = (size_t)220 * W * 32;
-  const size_t smem = prof_bytes + (size_t)8 * 3 * W * 32;
-  if (smem > 227 * 1024) return fail(HHG_EINVAL, "prefilter sw: query length %d too long for shared memory", Lq);
+  const size_t work_bytes = (size_t)8 * 3 * W * 32;             // H/H/E columns of the 8 warps of a CTA
+  const bool prof_smem = prof_bytes + work_bytes <= 227 * 1024;   // else the striped profile is read through L1/L2
+  const size_t smem = (prof_smem ? prof_bytes : 0) + work_bytes;
+  if (smem > 227 * 1024) return fail(HHG_EINVAL, "prefilter sw: query length %d too long (working columns exceed shared memory)", Lq);
   CK(cudaSetDevice(ctx->device));
   for (int k = 0; ids && k < n; ++k)
     if (ids[k] < 0 || ids[k] >= db->n) return fail(HHG_EINVAL, "prefilter sw: id %d out of range", ids[k]);
@@ -1630,12 +1670,13 @@ int hhg_prefilter_sw(hhg_ctx* ctx, const hhg_csdb* db, int n, const int32_t* ids
   P.n = n; P.ids = ids ? ctx->sw_ids.p : nullptr; P.L = db->dL.p; P.off = db->doff.p; P.seq = db->seq.p;
   P.prof = ctx->sw_prof.p; P.W = W; P.gap_open = gap_open; P.gap_extend = gap_extend; P.bias = bias;
   P.scores = ctx->sw_scores.p; P.counter = ctx->pf_counter.p;
-  CK(cudaFuncSetAttribute(k_prefilter_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void (*swk)(const SwParams) = prof_smem ? k_prefilter_sw<true> : k_prefilter_sw<false>;
+  CK(cudaFuncSetAttribute(swk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prefilter_sw, 256, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, swk, 256, smem));
   if (per_sm < 1) return fail(HHG_ECUDA, "prefilter sw kernel does not fit on an SM");
   const int grid = std::min(ctx->sm_count * per_sm, (n + 7) / 8);
-  k_prefilter_sw<<<grid, 256, smem, ctx->stream>>>(P);
+  swk<<<grid, 256, smem, ctx->stream>>>(P);
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(scores, ctx->sw_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));

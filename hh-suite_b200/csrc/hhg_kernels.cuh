@@ -773,46 +773,52 @@ __global__ void k_celloff_raster(int n_steps, const int* step_req, const int* st
 // ---------------------------------------------------------------------------------------------
 // cs219 ungapped prefilter (Prefilter::ungapped_sse_score, src/hhprefilter.cpp:214-275).
 //   S(i,j) = max(0, min(255, S(i-1,j-1) + prof[x_j][i]) - offset);  score = max over all cells.
-// One warp per database sequence; lane l owns the CONTIGUOUS query positions [l*2*WB, (l+1)*2*WB), two
-// positions per 32-bit register as s16x2.  The u8-saturating recurrence maps 1:1 onto the sm_90+/sm_100
-// DPX instructions: min(a+b, 255) = __viaddmin_s16x2, max(t-offset, 0) = __viaddmax_s16x2, running
-// maximum = __vimax3_s16x2 (3 instructions per 2 cells; the byte-SIMD __vaddus4 family is emulated on
-// this architecture, ~17 instructions per cell).  The diagonal dependency is a 16-bit funnel shift
-// between neighbouring registers plus ONE shuffle per column for the lane-boundary carry.
-// The query profile (220 x Lq bytes) sits in shared memory as [state][word][lane] halfwords, so the 32
-// lanes of a warp read 64 contiguous bytes (conflict-free).
+// One warp per database sequence.  The query is cut into TILES of 64*WB positions (WB <= 8, one launch per
+// tile, so a query of any length works); inside a tile lane l owns the contiguous positions
+// [l*2WB, (l+1)*2WB) as WB registers of two 16-bit values: register w holds position l*2WB + w in its low
+// half and l*2WB + WB + w in its high half.  With that pairing the diagonal predecessor of BOTH halves of
+// register w is register w-1, so the sweep needs no funnel shifts: one byte-permute per column builds the
+// carry into register 0 (low half: last position of lane l-1 via one shuffle, high half: position WB-1 of
+// the own lane).  The u8-saturating recurrence is exact in 16-bit integers:
+//   min(S + p, 255) - offset = min(S + (p - offset), 255 - offset),  then max(., 0)
+// = ONE DPX instruction per two cells, __viaddmin_s16x2_relu(S, p - offset, 255 - offset); the running
+// maximum takes one __vimax3_s16x2 per two registers.  The profile (p - offset as s16x2, [state][w][lane]
+// words, 28 KB per WB) sits in shared memory; the 32 lanes of a warp read 128 contiguous bytes.
+// Tile t > 0 needs S of the previous tile's last position at column j-1: tile t-1 stores that byte per
+// column (edge_out), tile t reads it (edge_in); the per-sequence maximum is combined across tiles in `scores`.
+// Positions past the end of the query carry p = 0: their S is always < the diagonal predecessor's (or 0) and
+// never changes the maximum.
 // ---------------------------------------------------------------------------------------------
 struct PfParams {
   int n;
   const int* L;
   const long long* off;
   const uint8_t* seq;
-  const uint16_t* prof16;   // [220][WB][32] halfwords: 2 consecutive query positions of one lane
-  int Lq;
+  const uint32_t* prof32;   // this tile's profile: [220][WB][32] words (p - offset | p - offset) as s16x2
   int offset;
-  int* scores;
+  int tile, last_tile;      // tile index; 1 if no further tile follows
+  const uint8_t* edge_in;   // [sum L] S(last position of tile-1, column) per sequence column (tile > 0)
+  uint8_t* edge_out;        // [sum L] written when !last_tile
+  int* scores;              // running maximum over the tiles launched so far
   unsigned int* counter;
 };
 
-template <int WB>   // 32-bit s16x2 registers per lane: covers Lq <= 64*WB
-__global__ void __launch_bounds__(256) k_prefilter_ungapped(const PfParams P) {
+template <int WB>   // 32-bit s16x2 registers per lane: the tile covers 64*WB query positions
+__global__ void __launch_bounds__(512) k_prefilter_ungapped(const PfParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint16_t* sprof = reinterpret_cast<uint16_t*>(smem_raw);   // [220][WB][32]
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.prof16);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
-    for (int idx = threadIdx.x; idx < 220 * WB * 16; idx += blockDim.x) dst[idx] = src[idx];
-  }
+  uint32_t* sprof = reinterpret_cast<uint32_t*>(smem_raw);   // [220][WB][32]
+  for (int idx = threadIdx.x; idx < 220 * WB * 32; idx += blockDim.x) sprof[idx] = P.prof32[idx];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const uint32_t cap = 0x00FF00FFu;                                        // 255 | 255
-  const uint32_t noff = (uint32_t)((-P.offset) & 0xFFFF) * 0x00010001u;    // -offset | -offset
+  const uint32_t cap = (uint32_t)(255 - P.offset) * 0x00010001u;           // 255 - offset | 255 - offset
+  const bool first_tile = P.tile == 0;
   for (;;) {
     int n = 0;
     if (lane == 0) n = (int)atomicAdd(P.counter, 1u);
     n = __shfl_sync(0xffffffffu, n, 0);
     if (n >= P.n) break;
-    const uint8_t* x = P.seq + P.off[n];
+    const long long o = P.off[n];
+    const uint8_t* x = P.seq + o;
     const int L = P.L[n];
     uint32_t S[WB];
 #pragma unroll
@@ -820,30 +826,38 @@ __global__ void __launch_bounds__(256) k_prefilter_ungapped(const PfParams P) {
     uint32_t smax = 0;
     for (int j0 = 0; j0 < L; j0 += 32) {
       const int xl = (j0 + lane < L) ? (int)x[j0 + lane] : 0;
+      // carry into the tile at column j = S(last position of the previous tile, column j-1)
+      int el = 0;
+      if (!first_tile && j0 + lane >= 1 && j0 + lane <= L) el = (int)P.edge_in[o + j0 + lane - 1];
       const int cnt = min(32, L - j0);
+      uint32_t eout = 0;
       for (int jj = 0; jj < cnt; ++jj) {
         const int xs = __shfl_sync(0xffffffffu, xl, jj);
-        const uint16_t* prow = sprof + (size_t)xs * (WB * 32) + lane;
-        // carry into this lane's first position: last position (high half of the last register) of
-        // lane-1 in the previous column; lane 0 starts every diagonal at 0
-        uint32_t carry = __shfl_up_sync(0xffffffffu, S[WB - 1], 1);
-        if (lane == 0) carry = 0;
+        const uint32_t* prow = sprof + (size_t)xs * (WB * 32) + lane;
+        uint32_t up = __shfl_up_sync(0xffffffffu, S[WB - 1], 1);
+        const uint32_t ein = first_tile ? 0u : (uint32_t)__shfl_sync(0xffffffffu, el, jj);   // warp-uniform branch
+        if (lane == 0) up = ein << 16;
+        // register 0's diagonal inputs: low half <- high half of `up` (position l*2WB-1), high half <- low half
+        // of the own last register (position l*2WB+WB-1)
+        const uint32_t carry = __byte_perm(up, S[WB - 1], 0x5432);
 #pragma unroll
-        for (int w = WB - 1; w >= 0; --w) {
-          const uint32_t below = (w > 0) ? S[w - 1] : carry;
-          const uint32_t diag = __funnelshift_l(below, S[w], 16);          // positions shifted up by one
-          const uint32_t pr = __byte_perm((uint32_t)prow[w * 32], 0u, 0x4140);   // u8,u8 -> s16x2
-          uint32_t v = __viaddmin_s16x2(diag, pr, cap);                     // min(S + prof, 255)
-          v = __viaddmax_s16x2(v, noff, 0u);                                // max(. - offset, 0)
-          S[w] = v;
-          smax = __vimax3_s16x2(smax, v, 0u);
+        for (int w = WB - 1; w >= 1; --w) S[w] = __viaddmin_s16x2_relu(S[w - 1], prow[w * 32], cap);
+        S[0] = __viaddmin_s16x2_relu(carry, prow[0], cap);
+#pragma unroll
+        for (int w = 0; w + 1 < WB; w += 2) smax = __vimax3_s16x2(smax, S[w], S[w + 1]);
+        if (WB & 1) smax = __vimax3_s16x2(smax, S[WB - 1], 0u);
+        if (!P.last_tile) {
+          // S(last position of this tile, column j0+jj): lane 31, last register, high half; lane jj keeps it
+          const uint32_t e = __shfl_sync(0xffffffffu, S[WB - 1] >> 16, 31);
+          if (lane == jj) eout = e;
         }
       }
+      if (!P.last_tile && lane < cnt) P.edge_out[o + j0 + lane] = (uint8_t)eout;
     }
     uint32_t m = max(smax & 0xFFFFu, smax >> 16);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) P.scores[n] = (int)m;
+    for (int k = 16; k > 0; k >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, k));
+    if (lane == 0) P.scores[n] = first_tile ? (int)m : max(P.scores[n], (int)m);
   }
 }
 
@@ -868,18 +882,19 @@ struct SwParams {
   unsigned int* counter;
 };
 
+template <bool PROF_SMEM>   // false: the striped profile does not fit in shared memory (Lq > ~900) and is read from L2
 __global__ void __launch_bounds__(256) k_prefilter_sw(const SwParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int W = P.W;
-  uint8_t* sprof = smem_raw;                                   // [220][W][32]
-  {
+  const uint8_t* sprof = PROF_SMEM ? smem_raw : P.prof;        // [220][W][32]
+  if (PROF_SMEM) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(P.prof);
     uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
     for (int idx = threadIdx.x; idx < 220 * W * 8; idx += blockDim.x) dst[idx] = src[idx];
+    __syncthreads();
   }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* Hst = smem_raw + (size_t)220 * W * 32 + (size_t)warp * 3 * W * 32 + lane;   // + j*32
+  uint8_t* Hst = smem_raw + (PROF_SMEM ? (size_t)220 * W * 32 : 0) + (size_t)warp * 3 * W * 32 + lane;   // + j*32
   uint8_t* Hld = Hst + (size_t)W * 32;
   uint8_t* E = Hld + (size_t)W * 32;
   const int go = P.gap_open, ge = P.gap_extend, bias = P.bias;

@@ -24,10 +24,11 @@ def test_prefilter_goldens(hhg, gpu_ctx):
     db.close()
 
 
-@pytest.mark.parametrize("Lq", [1, 31, 64, 65, 130, 400, 431, 449, 1000, 1024])
+@pytest.mark.parametrize("Lq", [1, 31, 64, 65, 130, 192, 257, 400, 431, 449, 512, 513, 1000, 1024, 1025, 1500, 2100])
 def test_prefilter_oracle_parity(hhg, gpu_ctx, oracle, Lq):
-    """Ragged random DB incl. L=1 and sequences far longer than the query; every supported register
-    tiling (WB) of the kernel; planted high-scoring diagonals so saturation at 255 is exercised."""
+    """Ragged random DB incl. L=1 and sequences far longer than the query; every register tiling (WB = 1..8) of the
+    kernel and queries of 2..5 tiles of 512 positions (the reference has no length limit, src/hhprefilter.cpp:214-275);
+    planted high-scoring diagonals so saturation at 255 is exercised, also across tile boundaries."""
     rng = np.random.default_rng(Lq)
     prof = rng.integers(30, 75, (220, Lq), dtype=np.uint8)         # offset 50 +- noise like real profiles
     prof[219] = 49
@@ -48,12 +49,13 @@ def test_prefilter_oracle_parity(hhg, gpu_ctx, oracle, Lq):
     db.close()
 
 
-def test_prefilter_vs_compiled_reference(hhg, gpu_ctx, refshim, oracle, tmp_path):
+@pytest.mark.parametrize("QL", [300, 1100])
+def test_prefilter_vs_compiled_reference(hhg, gpu_ctx, refshim, oracle, tmp_path, QL):
     """Query profile from the reference's own stripe_query_profile (striped AVX2 layout un-striped here),
-    scores from its ungapped_sse_score."""
+    scores from its ungapped_sse_score.  QL=1100: three query tiles on the GPU, W=35 stripes in the reference."""
     from hhsuite_b200 import synth
     f = tmp_path / "q.hhm"
-    f.write_text(synth.hhm_text(300, 12, "q300"))
+    f.write_text(synth.hhm_text(QL, 12, f"q{QL}"))
     q = refshim.load_query_hhm(str(f))
     qc, W = refshim.stripe_query_profile(50, 4)
     Lq = q["L"]
@@ -70,11 +72,18 @@ def test_prefilter_vs_compiled_reference(hhg, gpu_ctx, refshim, oracle, tmp_path
     db.close()
 
 
-def test_prefilter_rejects_overlong_query(hhg, gpu_ctx):
-    db = _db(hhg, gpu_ctx, [np.zeros(10, np.uint8)])
-    with pytest.raises(hhg.HhgError):
-        db.ungapped(np.zeros((220, 1025), np.uint8), 50)
-    db.close()
+def test_prefilter_offsets_and_extreme_profiles(hhg, gpu_ctx, oracle):
+    """The exact 16-bit rewrite min(S+p,255)-offset = min(S+(p-offset),255-offset) for every kind of byte: profile
+    values 0 and 255, offsets 0 / 1 / 50 / 255, a two-tile query."""
+    rng = np.random.default_rng(99)
+    seqs = [rng.integers(0, 220, L, dtype=np.uint8) for L in [1, 40, 333, 900]]
+    for Lq in (70, 600):
+        for offset in (0, 1, 50, 255):
+            prof = rng.choice(np.array([0, 1, 49, 50, 51, 128, 254, 255], np.uint8), (220, Lq))
+            seqs2 = seqs + [prof[:219].argmax(axis=0).astype(np.uint8)]
+            db = _db(hhg, gpu_ctx, seqs2)
+            assert db.ungapped(prof, offset).tolist() == [oracle.ungapped(prof, s, offset) for s in seqs2], (Lq, offset)
+            db.close()
 
 
 def test_host_profile_builder_matches_reference(hhg):
@@ -94,12 +103,12 @@ def _homologs(rng, best, n):
     return out
 
 
-@pytest.mark.parametrize("Lq", [20, 64, 130, 431])
+@pytest.mark.parametrize("Lq", [20, 64, 130, 431, 900, 929, 1500])
 def test_gapped_sw_oracle_parity(hhg, gpu_ctx, oracle, Lq):
     """Stage 2 (swStripedByte, lazy-F quirk and all) against the lane-exact oracle emulation."""
     G = golden()
     rng = np.random.default_rng(100 + Lq)
-    prof = G["pf_prof"][:, :Lq].copy() if Lq <= 431 else None
+    prof = G["pf_prof"][:, :Lq].copy() if Lq <= 431 else np.tile(G["pf_prof"], (1, 4))[:, :Lq].copy()   # > 928: profile stays in L2
     best = prof[:219].argmax(axis=0).astype(np.uint8)
     seqs = [rng.integers(0, 219, L, dtype=np.uint8) for L in [1, 2, 33, 500] + list(rng.integers(5, 300, 60))]
     seqs += _homologs(rng, best, 30) if Lq > 3 else []
