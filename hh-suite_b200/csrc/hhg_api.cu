@@ -93,6 +93,7 @@ struct hhg_ctx {
   int Lq = 0, R = 0;     // R: forced strip height (HHG_STRIP_ROWS) or 0 = per plan
   int group_jobs = 16;   // work-item interleave (see k_viterbi): 16 jobs x nstrips items keep the group L2-resident
   uint32_t epoch = 0;    // run counter feeding the boundary-slot tags
+  uint32_t epoch_window = 1;   // number of times the 20-bit epoch has wrapped (+1)
   DevBuf<float4> qrec;
   DevBuf<float> S33;
   DevBuf<float> lg2, diff;   // fast_log2 tables for Hit.score
@@ -181,6 +182,7 @@ struct hhg_plan {
   DevBuf<float4> d_jcols;
   DevBuf<uint32_t> d_bt, d_co;
   DevBuf<BndSlot> d_bnd;
+  uint32_t bnd_epoch_window = 0;   // epoch window in which d_bnd was last cleared
   DevBuf<float> d_strip_score;
   DevBuf<int> d_strip_ij;
   DevBuf<unsigned> d_counter;
@@ -221,8 +223,10 @@ int hhg_ctx_create(int device, void* stream, hhg_ctx** out) {
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10)
-    return fail(HHG_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+  // sm_100a code only loads on compute capability 10.0; the fence-free 256-bit slot hand-off of k_viterbi was
+  // validated on exactly that part (tests/test_kernel_variants_gpu.py stress test)
+  if (prop.major != 10 || prop.minor != 0)
+    return fail(HHG_ENODEV, "device %d is sm_%d%d; this library is built and validated for sm_100a (B200) only", device,
                 prop.major, prop.minor);
   std::unique_ptr<hhg_ctx> holder(new hhg_ctx());
   hhg_ctx* c = holder.get();
@@ -834,9 +838,20 @@ static int set_exclusions(hhg_ctx* ctx, hhg_plan* pl, const int64_t* excl_off, c
   if (!excl_off) return HHG_OK;
   const long long total = excl_off[pl->n];
   if (total <= 0) return HHG_OK;
+  // validate like hhg_mac_realign does: k_celloff_raster indexes the mask with these values
+  if (excl_off[0] != 0) return fail(HHG_EINVAL, "excl_off[0] must be 0");
+  if (!excl_i || !excl_j) return fail(HHG_EINVAL, "excl_i / excl_j are NULL");
   std::vector<int> sreq((size_t)total);
-  for (int k = 0; k < pl->n; ++k)
-    for (long long s = excl_off[k]; s < excl_off[k + 1]; ++s) sreq[(size_t)s] = k;
+  for (int k = 0; k < pl->n; ++k) {
+    if (excl_off[k + 1] < excl_off[k]) return fail(HHG_EINVAL, "excl_off is not monotonic at request %d", k);
+    const int Lt = pl->db->L[pl->ids[k]];
+    for (long long s = excl_off[k]; s < excl_off[k + 1]; ++s) {
+      if (excl_i[s] < 1 || excl_i[s] > pl->Lq || excl_j[s] < 1 || excl_j[s] > Lt)
+        return fail(HHG_EINVAL, "excluded step %lld of request %d is (%d,%d), outside 1..%d x 1..%d", s - excl_off[k], k,
+                    excl_i[s], excl_j[s], pl->Lq, Lt);
+      sreq[(size_t)s] = k;
+    }
+  }
   size_t co_words = 0;
   for (int jb = 0; jb < pl->njobs; ++jb) co_words += (size_t)pl->nstrips * (pl->job_Lmax[jb] + 1) * 32;
   CK(pl->d_co.ensure(co_words));
@@ -894,8 +909,15 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
     return fail(HHG_EINVAL, "use_ss requested but query/db/S33 carry no ss information");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  ctx->epoch = (ctx->epoch + 1) & 0xFFFFFu;   // slot tags of earlier runs never match (20-bit epoch)
-  if (ctx->epoch == 0) ctx->epoch = 1;
+  // slot tags of earlier runs never match (20-bit epoch in the tag) ... unless the epoch has wrapped since this plan's
+  // slots were last cleared: then a slot left over from exactly 2^20 runs ago would look valid, so clear them once
+  // per epoch window
+  ctx->epoch = (ctx->epoch + 1) & 0xFFFFFu;
+  if (ctx->epoch == 0) { ctx->epoch = 1; ctx->epoch_window++; }
+  if (pl->bnd_epoch_window != ctx->epoch_window) {
+    if (pl->d_bnd.p) CK(cudaMemsetAsync(pl->d_bnd.p, 0, pl->d_bnd.n * sizeof(BndSlot), st));
+    pl->bnd_epoch_window = ctx->epoch_window;
+  }
   CK(cudaMemsetAsync(pl->d_counter.p, 0, pl->waves.size() * 4, st));
   if (pl->jc_version != db->cols_version) {
     // (re)build the job-interleaved operand stream: once per plan, and again after every
@@ -1330,7 +1352,7 @@ int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target
   const int* d32 = ctx->mac_i32.p;
   MacArgs A{};
   A.n = n; A.Lq = Lq; A.local = par->local ? 1 : 0; A.mact = par->mact;
-  { const char* e = getenv("HHG_MAC_BANDSCAN"); A.band_scan = (e && atoi(e) == 1) ? 1 : 0; }   // opt-in, see hhg_mac.cuh
+  { const char* e = getenv("HHG_MAC_BANDSCAN"); A.band_scan = (e && atoi(e) == 0) ? 0 : 1; }   // default on (2.5x); 0 = full-row scans
   A.Cshift = ::pow(2.0, par->shift);                       // src/hhforwardalgorithm.cpp:16
   A.q_p = ctx->mac_qp.p; A.q_tr = ctx->mac_qtr.p;
   A.cols = reinterpret_cast<const ColRec*>(db->cols.p);

@@ -27,12 +27,6 @@
 #include <float.h>
 #include <stdint.h>
 
-#ifndef HHG_CTAS_R8
-#define HHG_CTAS_R8 3   // resident CTAs per SM the R<=12 kernels are compiled for (3 -> 168 registers, 4 -> 128)
-#endif
-#ifndef HHG_JC_EVICT_LAST
-#define HHG_JC_EVICT_LAST 0   // 1: operand-stream loads carry an L2 evict_last policy (they are re-read by every strip)
-#endif
 #ifndef HHG_MAX3
 #define HHG_MAX3 1   // MM-state maximum as 3-input maxima + equality selects (same bits, fewer ALU-pipe instructions)
 #endif
@@ -60,32 +54,15 @@ struct __align__(32) BndSlot {
 };
 static_assert(sizeof(BndSlot) == 32, "BndSlot must be one 32-byte sector");
 
-// HHG_SLOT_EVICT_LAST=1 (build variant, off by default; drafted for round 2, not yet measured): tag the slot
-// accesses with an L2 evict_last policy so that the 8 GB stream of backtrace words (stored evict_first) does not
-// push the 13 MB of live hand-off slots of a job group out to DRAM between two strips.
-#ifndef HHG_SLOT_EVICT_LAST
-#define HHG_SLOT_EVICT_LAST 0
-#endif
-#if HHG_SLOT_EVICT_LAST
-__device__ __forceinline__ uint64_t slot_policy() {
-  uint64_t pol;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-#endif
+// The tag is stored three times (tag, ~tag in pad0, tag in pad1): a consumer accepts a slot only when all three
+// agree, so a torn view of the 32 bytes (PTX does not promise single-copy atomicity of a vector access as a whole,
+// sm_100 delivers it as one sector transaction) is detected and simply re-read instead of being consumed.
 __device__ __forceinline__ void st_slot(BndSlot* p, float mm, float dg, float mi, float gd, float im,
                                         uint32_t tag) {
-#if HHG_SLOT_EVICT_LAST
-  asm volatile("st.relaxed.gpu.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p),
-               "r"(__float_as_uint(mm)), "r"(__float_as_uint(dg)), "r"(__float_as_uint(mi)),
-               "r"(__float_as_uint(gd)), "r"(__float_as_uint(im)), "r"(tag), "r"(0u), "r"(0u), "l"(slot_policy())
-               : "memory");
-#else
   asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
                "r"(__float_as_uint(mm)), "r"(__float_as_uint(dg)), "r"(__float_as_uint(mi)),
-               "r"(__float_as_uint(gd)), "r"(__float_as_uint(im)), "r"(tag), "r"(0u), "r"(0u)
+               "r"(__float_as_uint(gd)), "r"(__float_as_uint(im)), "r"(tag), "r"(~tag), "r"(tag)
                : "memory");
-#endif
 }
 // pad0/pad1 are returned so the caller can keep their registers live until the slot is consumed: a dead
 // destination register of an in-flight load gets reused by ptxas and the re-use then stalls on the load
@@ -93,19 +70,16 @@ __device__ __forceinline__ void st_slot(BndSlot* p, float mm, float dg, float mi
 __device__ __forceinline__ void ld_slot(const BndSlot* p, float& mm, float& dg, float& mi, float& gd,
                                         float& im, uint32_t& tag, uint32_t& x, uint32_t& y) {
   uint32_t a, b, c, d, e;
-#if HHG_SLOT_EVICT_LAST
-  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-               : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(tag), "=r"(x), "=r"(y)
-               : "l"(p), "l"(slot_policy())
-               : "memory");
-#else
   asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(tag), "=r"(x), "=r"(y)
                : "l"(p)
                : "memory");
-#endif
   mm = __uint_as_float(a); dg = __uint_as_float(b); mi = __uint_as_float(c);
   gd = __uint_as_float(d); im = __uint_as_float(e);
+}
+// slot valid for tag t: tag == t, pad0 == ~t, pad1 == t
+__device__ __forceinline__ bool slot_ok(uint32_t tag, uint32_t pad0, uint32_t pad1, uint32_t want) {
+  return ((tag ^ want) | (pad0 ^ ~want) | (pad1 ^ want)) == 0u;
 }
 
 struct VitParams {
@@ -229,19 +203,9 @@ __device__ __forceinline__ float dot20_dev(const unsigned long long (&t)[10], co
   return __fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3));
 }
 
-// one 16-byte operand of the job-interleaved stream: L2-only load (a line is read once per strip and SM)
-__device__ __forceinline__ float4 ld_jc(const float4* p) {
-#if HHG_JC_EVICT_LAST
-  uint64_t pol;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  float4 v;
-  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-  return v;
-#else
-  return __ldcg(p);
-#endif
-}
+// one 16-byte operand of the job-interleaved stream: L2-only load (a line is read once per strip and SM; an L2
+// evict_last policy on these loads was measured and changes nothing, profiles/r2_probe_max3_groupsize_dram.txt)
+__device__ __forceinline__ float4 ld_jc(const float4* p) { return __ldcg(p); }
 
 #define HHG_NEG (-FLT_MAX)
 
@@ -250,7 +214,7 @@ __device__ __forceinline__ float4 ld_jc(const float4* p) {
 // CELLOFF: cell-off bit input (alternative alignments / excluded regions).
 // ---------------------------------------------------------------------------------------------
 template <int R, bool LOCAL, bool SS, bool CELLOFF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? HHG_CTAS_R8 : 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)   // 168 / 255 registers; 4 CTAs (128 registers) spill and lose 8%
     k_viterbi(const VitParams P) {
   static_assert(R % 4 == 0, "R must be a multiple of 4");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -359,8 +323,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? HHG_CTAS_R8 : 2
         tMM = __fmul_rn((float)(-j), P.egt);   // :148
         tDG = tMI = tGD = tIM = HHG_NEG;
       } else {
-        // pads are always 0 in a valid slot; testing them keeps their registers live (see ld_slot)
-        while (((ntag ^ tag_in) | npad0 | npad1) != 0u) {
+        // all three copies of the tag must agree (also keeps the pad registers live, see ld_slot)
+        while (!slot_ok(ntag, npad0, npad1, tag_in)) {
           __nanosleep(20);
           ld_slot(bnd + (size_t)j * 32, nMM, nDG, nMI, nGD, nIM, ntag, npad0, npad1);
         }

@@ -50,7 +50,7 @@ struct MacArgs {
   float* post; uint8_t* off; uint8_t* bt;
   const long long* row_off;            // [n] offset (in doubles) of 10*(Lt+3) row buffers
   double* rows;
-  int band_scan;                       // opt-in (HHG_MAC_BANDSCAN=1): scans visit only [first, last] active column of a row
+  int band_scan;                       // default 1 (HHG_MAC_BANDSCAN=0 disables): scans visit only [first, last] active column of a row
   const int* req_map;                  // optional: blockIdx.x -> request (launches over a subset of the requests)
   long long* dbg;                      // optional [n*12] per-phase clock64 totals (HHG_MAC_TIMING)
   int smem_rows;                       // bytes of dynamic shared memory available for the row buffers

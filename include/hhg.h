@@ -167,6 +167,10 @@ int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const u
  *                  src/hhviterbirunner.cpp:277-288): for request k, the path steps
  *                  excl_i/excl_j[excl_off[k] .. excl_off[k+1]) are masked with the +-40 cross of
  *                  Viterbi::ExcludeAlignment.  NULL = no cell-off (AlignWithOutCellOff variants).
+ *                  Pass steps 1 .. nsteps-1 of every earlier alignment of that target: the reference's loop is
+ *                  `for (step = 1; step < nsteps; step++)` (src/hhviterbi.cpp:61-77), the last step is NOT masked.
+ *                  excl_off must start at 0 and be monotonic, 1 <= excl_i <= Lq, 1 <= excl_j <= Lt of the request's
+ *                  target; anything else is refused with HHG_EINVAL.
  * All host buffers; copies in and out are part of the call. */
 int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_hit* hits,
                        uint8_t* paths, size_t paths_cap, const int64_t* excl_off,

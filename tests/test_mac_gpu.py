@@ -9,6 +9,14 @@ from tests.util import bits, golden
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[0, 1], ids=["fullscan", "bandscan"], autouse=True)
+def band_scan(request, monkeypatch):
+    """Every MAC test runs with both scan modes of k_mac_realign: full-row scans and the band-limited scans
+    (HHG_MAC_BANDSCAN, read per call by hhg_mac_realign); results must be bit-identical either way."""
+    monkeypatch.setenv("HHG_MAC_BANDSCAN", str(request.param))
+    return request.param
+
+
 def _check(gpu_hit, gpu_path, want):
     for f in ("i1", "i2", "j1", "j2", "nsteps", "matched_cols"):
         assert int(gpu_hit[f]) == want[f], f
