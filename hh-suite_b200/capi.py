@@ -40,7 +40,8 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_mac_debug_posterior", "hhg_prefilter_build_profile", "hhg_prefilter_corrected_score",
            "hhg_prefilter_sw", "hhg_prefilter_evalue", "hhg_prefilter_corrected_scores", "hhg_prefilter_evalues",
            "hhg_comm_unique_id", "hhg_comm_create", "hhg_comm_destroy", "hhg_comm_rank", "hhg_comm_world",
-           "hhg_plan_topk", "hhg_plan_topk_paths", "hhg_ctx_last_plan"]
+           "hhg_plan_topk", "hhg_plan_topk_by_key", "hhg_plan_topk_paths", "hhg_ctx_last_plan",
+           "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order"]
 
 
 class PrepParams(C.Structure):
@@ -168,6 +169,13 @@ def load():
     L.hhg_comm_world.argtypes = [C.c_void_p]
     L.hhg_plan_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int32, c_i32p, C.c_void_p,
                                 c_i32p]
+    L.hhg_plan_topk_by_key.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f32p, C.c_int32, c_i32p, C.c_void_p,
+                                       c_i32p]
+    L.hhg_hitlist_pvalues.argtypes = [C.c_int, c_f32p, c_f32p, c_i32p, c_f32p, c_i32p, C.c_int, C.c_float, C.c_int,
+                                      C.c_int, C.c_int, C.c_float, C.c_void_p]
+    L.hhg_hitlist_hhblits_evalues.argtypes = [C.c_int, C.c_void_p, c_f32p, C.c_float, C.c_int, C.c_float, C.c_float,
+                                              C.c_float, C.c_double]
+    L.hhg_hitlist_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, c_i32p]
     L.hhg_plan_topk_paths.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, c_u8p]
     L.hhg_ctx_last_plan.argtypes = [C.c_void_p]
     L.hhg_ctx_last_plan.restype = C.c_void_p
@@ -434,6 +442,50 @@ def plan_topk(ctx: Context, plan_handle, comm: Comm | None, K: int, by_hit_score
     gi = None if global_ids is None else np.ascontiguousarray(global_ids, np.int32)
     _ck(ctx.L.hhg_plan_topk(ctx.h, plan_handle, comm.h if comm is not None else None, K, 1 if by_hit_score else 0,
                             id_base, _p(gi, c_i32p), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+    return out[:n.value]
+
+
+STATS_DTYPE = np.dtype([("Pval", np.float64), ("logPval", np.float64), ("Eval", np.float64), ("logEval", np.float64),
+                        ("score_aass", np.float32), ("Probab", np.float32), ("lamda", np.float32), ("mu", np.float32)])
+
+
+def hitlist_pvalues(score, score_ss, Lt, t_neff, Lq, q_neff, N_searched, loc=True, ssm=2, ssw=0.11, hit_has_ss=None):
+    """HitList::CalculatePvalues on arrays (host side of the library): returns STATS_DTYPE records."""
+    n = len(score)
+    out = np.zeros(n, STATS_DTYPE)
+    s = np.ascontiguousarray(score, np.float32); ss = np.ascontiguousarray(score_ss, np.float32)
+    L = np.ascontiguousarray(Lt, np.int32); ne = np.ascontiguousarray(t_neff, np.float32)
+    hs = None if hit_has_ss is None else np.ascontiguousarray(hit_has_ss, np.int32)
+    _ck(load().hhg_hitlist_pvalues(n, _p(s, c_f32p), _p(ss, c_f32p), _p(L, c_i32p), _p(ne, c_f32p), _p(hs, c_i32p), Lq,
+                                   q_neff, N_searched, 1 if loc else 0, ssm, ssw, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def hitlist_hhblits_evalues(stats, t_neff, q_neff, dbsize, alphaa=0.4, alphab=0.02, alphac=0.1, prefilter_evalue_thresh=1000.0):
+    """HitList::CalculateHHblitsEvalues: overwrites Eval / logEval of `stats` in place."""
+    ne = np.ascontiguousarray(t_neff, np.float32)
+    _ck(load().hhg_hitlist_hhblits_evalues(len(stats), stats.ctypes.data_as(C.c_void_p), _p(ne, c_f32p), q_neff, dbsize,
+                                           alphaa, alphab, alphac, prefilter_evalue_thresh))
+    return stats
+
+
+def hitlist_order(stats, files=None):
+    """HitList::SortList order (score_aass ascending, then file name)."""
+    n = len(stats)
+    order = np.zeros(n, np.int32)
+    farr = None if files is None else (C.c_char_p * n)(*[f.encode() for f in files])
+    _ck(load().hhg_hitlist_order(n, stats.ctypes.data_as(C.c_void_p), farr, _p(order, c_i32p)))
+    return order
+
+
+def plan_topk_by_key(ctx: Context, plan_handle, comm, K: int, key, id_base: int = 0, global_ids=None):
+    """hhg_plan_topk_by_key: merged K best by a caller-supplied per-request value (ascending = better)."""
+    out = np.zeros(K, TOPK_DTYPE)
+    n = C.c_int32(0)
+    key = np.ascontiguousarray(key, np.float32)
+    gi = None if global_ids is None else np.ascontiguousarray(global_ids, np.int32)
+    _ck(ctx.L.hhg_plan_topk_by_key(ctx.h, plan_handle, comm.h if comm is not None else None, K, _p(key, c_f32p), id_base,
+                                   _p(gi, c_i32p), out.ctypes.data_as(C.c_void_p), C.byref(n)))
     return out[:n.value]
 
 

@@ -6,6 +6,7 @@
 #include "hhg_hhm.cuh"
 #include "hhg_mac.cuh"
 #include "hhg_topk.cuh"
+#include "hhg_hitlist.h"
 
 #include <dlfcn.h>
 
@@ -195,6 +196,7 @@ struct hhg_plan {
   // top-K selection / exchange scratch (hhg_plan_topk)
   DevBuf<unsigned long long> d_keys;
   DevBuf<int> d_gids;
+  DevBuf<float> d_user_key;
   DevBuf<TopkState> d_topk_state;
   DevBuf<TopkRec> d_topk_local, d_topk_all;
   DevBuf<uint8_t> d_topk_paths;
@@ -1174,8 +1176,8 @@ int hhg_comm_rank(const hhg_comm* c) { return c ? c->rank : 0; }
 int hhg_comm_world(const hhg_comm* c) { return c ? c->world : 1; }
 
 // Top-K of the last run of `plan`, merged over all ranks of `comm` (NULL / world 1: this GPU only).
-int hhg_plan_topk(hhg_ctx* ctx, hhg_plan* pl, hhg_comm* comm, int K, int by_hit_score, int32_t id_base,
-                  const int32_t* global_ids, hhg_topk_rec* out, int* n_out) {
+static int plan_topk_impl(hhg_ctx* ctx, hhg_plan* pl, hhg_comm* comm, int K, int by_hit_score, const float* user_key,
+                          int32_t id_base, const int32_t* global_ids, hhg_topk_rec* out, int* n_out) {
   static_assert(sizeof(hhg_topk_rec) == sizeof(TopkRec), "hhg_topk_rec / TopkRec layout");
   if (!ctx || !pl || K < 1 || !out || !n_out) return fail(HHG_EINVAL, "hhg_plan_topk: bad argument");
   if (comm && comm->world > 1 && comm->device != ctx->device) return fail(HHG_EINVAL, "hhg_plan_topk: comm lives on another device");
@@ -1190,11 +1192,16 @@ int hhg_plan_topk(hhg_ctx* ctx, hhg_plan* pl, hhg_comm* comm, int K, int by_hit_
     CK(pl->d_gids.ensure((size_t)n));
     CK(cudaMemcpyAsync(pl->d_gids.p, global_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   }
+  if (user_key) {
+    CK(pl->d_user_key.ensure((size_t)n));
+    CK(cudaMemcpyAsync(pl->d_user_key.p, user_key, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  }
   TopkState init{};
   init.krem = (unsigned)kl;
   CK(cudaMemcpyAsync(pl->d_topk_state.p, &init, sizeof init, cudaMemcpyHostToDevice, st));
   const int threads = 256, blocks = (n + threads - 1) / threads;
-  k_topk_keys<<<blocks, threads, 0, st>>>(n, pl->d_hits.p, by_hit_score, id_base, global_ids ? pl->d_gids.p : nullptr, pl->d_keys.p);
+  k_topk_keys<<<blocks, threads, 0, st>>>(n, pl->d_hits.p, by_hit_score, id_base, global_ids ? pl->d_gids.p : nullptr,
+                                            user_key ? pl->d_user_key.p : nullptr, pl->d_keys.p);
   const int hblocks = std::min(blocks, ctx->sm_count * 4);
   for (int p = 7; p >= 0; --p) {
     k_topk_hist<<<hblocks, threads, 0, st>>>(n, pl->d_keys.p, p, pl->d_topk_state.p);
@@ -1219,6 +1226,17 @@ int hhg_plan_topk(hhg_ctx* ctx, hhg_plan* pl, hhg_comm* comm, int K, int by_hit_
   memcpy(out, all.data(), (size_t)m * sizeof(TopkRec));
   *n_out = m;
   return HHG_OK;
+}
+
+int hhg_plan_topk(hhg_ctx* ctx, hhg_plan* pl, hhg_comm* comm, int K, int by_hit_score, int32_t id_base,
+                  const int32_t* global_ids, hhg_topk_rec* out, int* n_out) {
+  return plan_topk_impl(ctx, pl, comm, K, by_hit_score, nullptr, id_base, global_ids, out, n_out);
+}
+
+int hhg_plan_topk_by_key(hhg_ctx* ctx, hhg_plan* pl, hhg_comm* comm, int K, const float* key, int32_t id_base,
+                         const int32_t* global_ids, hhg_topk_rec* out, int* n_out) {
+  if (!key) return fail(HHG_EINVAL, "hhg_plan_topk_by_key: key is NULL");
+  return plan_topk_impl(ctx, pl, comm, K, 0, key, id_base, global_ids, out, n_out);
 }
 
 // State strings of the merged list: out[r*width .. ] = path of recs[r] (nsteps bytes, zero padded), on every rank.

@@ -37,14 +37,17 @@ __device__ __forceinline__ uint32_t orderable_f32(float f) {   // monotone incre
   return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
 }
 
+// user_key != NULL: caller-supplied ranking value per request, ASCENDING = better (e.g. the reference's score_aass)
 __global__ void __launch_bounds__(256)
 k_topk_keys(int n, const HitRec* __restrict__ hits, int by_hit_score, int id_base, const int* __restrict__ gids,
-            unsigned long long* __restrict__ keys) {
+            const float* __restrict__ user_key, unsigned long long* __restrict__ keys) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const float s = by_hit_score ? hits[k].hit_score : hits[k].score;
   const uint32_t gid = (uint32_t)(gids ? gids[k] : id_base + k);
-  keys[k] = ((unsigned long long)(~orderable_f32(s)) << 32) | gid;
+  uint32_t hi;
+  if (user_key) hi = orderable_f32(user_key[k]);
+  else hi = ~orderable_f32(by_hit_score ? hits[k].hit_score : hits[k].score);
+  keys[k] = ((unsigned long long)hi << 32) | gid;
 }
 
 // pass p (7 = most significant byte first): histogram byte p of the keys whose bytes above p equal the prefix

@@ -196,6 +196,28 @@ double hhg_plan_padded_cells(const hhg_plan* plan);
 /* Algorithmic bytes of one run: 112 B per target column + 1 B per cell + 32 B per hit */
 double hhg_plan_algorithmic_bytes(const hhg_plan* plan);
 
+/* ---- hit-list statistics (host side of the library, no GPU needed) ---------------------------
+ * HitList::CalculatePvalues (src/hhhitlist.cpp:499-531): per hit the EVD parameters lamda, mu from the neural-network
+ * regression over (query length, template length, query Neff, template Neff) (src/hhhitlist-inl.h:14-69), then
+ * logPval / Pval (src/hhhit-inl.h:44-53) and Hit::CalcEvalScoreProbab (src/hhhit.h:134-194): Eval = Pval * N_searched,
+ * score_aass (the list's sort key, more negative = better) and Probab.
+ *   score / score_ss : Hit.score / Hit.score_ss (hhg_hit.hit_score / score_ss);  Lt, t_neff: template length and
+ *   Neff_HMM;  hit_has_ss[k] != 0 iff the hit was scored with secondary structure (Hit.ssm1 || Hit.ssm2), may be NULL;
+ *   loc, ssm, ssw = par.loc, par.ssm, par.ssw;  N_searched = number of database HMMs searched (global, all shards).
+ * hhg_hitlist_hhblits_evalues (HitList::CalculateHHblitsEvalues, src/hhhitlist.cpp:465-494) overwrites Eval / logEval
+ * with the prefilter-corrected composite E-value.  hhg_hitlist_order = HitList::SortList with Hit::operator<
+ * (src/hhhit.h:116-126): ascending score_aass, then file name (strcmp; file may be NULL), then input order. */
+typedef struct hhg_hit_stats {
+  double Pval, logPval, Eval, logEval;
+  float score_aass, Probab, lamda, mu;
+} hhg_hit_stats;
+int hhg_hitlist_pvalues(int n, const float* score, const float* score_ss, const int32_t* Lt, const float* t_neff,
+                        const int32_t* hit_has_ss, int Lq, float q_neff, int N_searched, int loc, int ssm, float ssw,
+                        hhg_hit_stats* out);
+int hhg_hitlist_hhblits_evalues(int n, hhg_hit_stats* stats, const float* t_neff, float q_neff, int dbsize, float alphaa,
+                                float alphab, float alphac, double prefilter_evalue_thresh);
+int hhg_hitlist_order(int n, const hhg_hit_stats* stats, const char* const* file, int32_t* order);
+
 /* ---- multi-GPU: database sharded by target, hit lists merged over NCCL ------------------------------
  * The reference has no GPU or multi-device layer (its MPI front end distributes QUERIES, src/hhblits_mpi.cpp:135);
  * what must be kept is the result: every target aligned exactly once, one merged hit list ordered like a
@@ -226,6 +248,10 @@ int hhg_comm_rank(const hhg_comm* comm);
 int hhg_comm_world(const hhg_comm* comm);
 int hhg_plan_topk(hhg_ctx* ctx, hhg_plan* plan, hhg_comm* comm, int K, int by_hit_score, int32_t id_base,
                   const int32_t* global_ids, hhg_topk_rec* out, int* n_out);
+/* Same, ranked by a caller-supplied value per request, ASCENDING = better: key[k] = hhg_hit_stats.score_aass of
+ * request k (hhg_hitlist_pvalues) gives exactly the reference's list order (Hit::operator<, src/hhhit.h:116-126). */
+int hhg_plan_topk_by_key(hhg_ctx* ctx, hhg_plan* plan, hhg_comm* comm, int K, const float* key, int32_t id_base,
+                         const int32_t* global_ids, hhg_topk_rec* out, int* n_out);
 int hhg_plan_topk_paths(hhg_ctx* ctx, hhg_plan* plan, hhg_comm* comm, int n_rec, const hhg_topk_rec* recs, int width,
                         uint8_t* out);
 /* The plan hhg_viterbi_search used last on this context (for hhg_plan_topk after a host-buffer search). */

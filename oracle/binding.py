@@ -482,6 +482,33 @@ class RefShim:
                                            _p(sc, c_f32p))
         return sec, cells.value, sc
 
+    # -- hit-list statistics
+    def hitlist_stats(self, score, score_ss, L, neff, qL, qneff, N_searched, loc=1, ssm=2, ssw=0.11, ssm2=None, files=None,
+                      hhblits=False, dbsize=1, alphaa=0.4, alphab=0.02, alphac=0.1, pf_evalue_thresh=1000.0):
+        """HitList::CalculatePvalues (+ CalculateHHblitsEvalues) of the compiled reference on synthetic hits."""
+        n = len(score)
+        score = np.ascontiguousarray(score, np.float32); score_ss = np.ascontiguousarray(score_ss, np.float32)
+        L = np.ascontiguousarray(L, np.int32); neff = np.ascontiguousarray(neff, np.float32)
+        s2 = None if ssm2 is None else np.ascontiguousarray(ssm2, np.int32)
+        farr = None
+        if files is not None:
+            farr = (C.c_char_p * n)(*[f.encode() for f in files])
+        out = dict(Pval=np.zeros(n), logPval=np.zeros(n), Eval=np.zeros(n), logEval=np.zeros(n),
+                   score_aass=np.zeros(n, np.float32), Probab=np.zeros(n, np.float32), order=np.zeros(n, np.int32))
+        dp = C.POINTER(C.c_double)
+        self.lib.hhref_hitlist_stats.argtypes = [C.c_int, c_f32p, c_f32p, c_i32p, c_f32p, c_i32p, C.c_void_p, C.c_int,
+                                                 C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                                 C.c_float, C.c_float, C.c_float, C.c_double, dp, dp, dp, dp, c_f32p,
+                                                 c_f32p, c_i32p]
+        m = self.lib.hhref_hitlist_stats(n, _p(score, c_f32p), _p(score_ss, c_f32p), _p(L, c_i32p), _p(neff, c_f32p),
+                                         _p(s2, c_i32p), farr, qL, qneff, N_searched, loc, ssm, ssw, 1 if hhblits else 0,
+                                         dbsize, alphaa, alphab, alphac, pf_evalue_thresh,
+                                         out["Pval"].ctypes.data_as(dp), out["logPval"].ctypes.data_as(dp),
+                                         out["Eval"].ctypes.data_as(dp), out["logEval"].ctypes.data_as(dp),
+                                         _p(out["score_aass"], c_f32p), _p(out["Probab"], c_f32p), _p(out["order"], c_i32p))
+        assert m == n
+        return out
+
     # -- prefilter
     def cs219(self):
         out = np.zeros((219, 20), np.float32)

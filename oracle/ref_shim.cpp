@@ -44,6 +44,7 @@
 #include "hhfunc.h"
 #include "hhprefilter.h"
 #include "hhhit.h"
+#include "hhhitlist.h"
 #include "hhposteriordecoder.h"
 #include "hhposteriordecoderrunner.h"
 #include "hhposteriormatrix.h"
@@ -574,3 +575,44 @@ double hhref_ungapped_bench(const unsigned char* qc, int Lq, int N, const unsign
 }
 
 }  // extern "C"
+
+
+// ---------------------------------------------------------------- hit-list statistics (a13)
+// Build a HitList of n Hits carrying (score, score_ss, L, Neff_HMM, ssm2, file), run the reference's
+// HitList::CalculatePvalues (src/hhhitlist.cpp:499) and optionally CalculateHHblitsEvalues (:465), return the per-hit
+// values (indexed by input position via Hit.index) and the list order after each sort.
+extern "C" int hhref_hitlist_stats(int n, const float* score, const float* score_ss, const int* L, const float* neff,
+                                   const int* ssm2, const char* const* file, int qL, float qneff, int N_searched, int loc,
+                                   int ssm, float ssw, int hhblits, int dbsize, float alphaa, float alphab, float alphac,
+                                   double pf_evalue_thresh, double* pval, double* logpval, double* eval, double* logeval,
+                                   float* score_aass, float* probab, int* order) {
+  HitList* hl = new HitList();
+  HMM q(2, qL + 2);
+  q.L = qL;
+  q.Neff_HMM = qneff;
+  std::vector<char*> names(n);
+  for (int k = 0; k < n; ++k) {
+    Hit h;
+    h.score = score[k]; h.score_ss = score_ss[k]; h.L = L[k]; h.Neff_HMM = neff[k];
+    h.ssm1 = 0; h.ssm2 = ssm2 ? ssm2[k] : 0;
+    h.nfirst = k;                 // carries the input position through the sorts
+    names[k] = strdup(file ? file[k] : "x");
+    h.file = names[k];
+    hl->Push(h);
+  }
+  hl->N_searched = N_searched;
+  hl->CalculatePvalues(&q, (char)loc, (char)ssm, ssw);
+  if (hhblits) hl->CalculateHHblitsEvalues(&q, dbsize, alphaa, alphab, alphac, pf_evalue_thresh);
+  int pos = 0;
+  hl->Reset();
+  while (!hl->End()) {
+    Hit h = hl->ReadNext();
+    const int k = h.nfirst;
+    pval[k] = h.Pval; logpval[k] = h.logPval; eval[k] = h.Eval; logeval[k] = h.logEval;
+    score_aass[k] = h.score_aass; probab[k] = h.Probab;
+    order[pos++] = k;
+  }
+  for (char* p : names) free(p);
+  delete hl;
+  return pos;
+}

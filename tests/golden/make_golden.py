@@ -160,6 +160,24 @@ def main():
         G[f"pf_ref{k}"] = np.array([R.ungapped(qc, s, 50), R.sw_byte(qc, s, 24, 4, 50)], np.int32)
     np.savez_compressed(OUT, **G)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(G), "arrays")
+    hitlist_goldens(R)
+
+
+def hitlist_goldens(R):
+    """hitlist_v1.npz: HitList::CalculatePvalues / CalculateHHblitsEvalues / SortList of the compiled reference on
+    the seeded synthetic hit lists of tests/test_hitlist_cpu.py (same `cases()`)."""
+    from tests.test_hitlist_cpu import cases
+    H = {}
+    for i, c in enumerate(cases()):
+        hb = c["hb"] or {}
+        ref = R.hitlist_stats(c["score"], c["score_ss"], c["L"], c["neff"], c["qL"], c["qneff"], c["N"], c["loc"], c["ssm"],
+                              c["ssw"], c["ssm2"], c["files"], hhblits=c["hb"] is not None, dbsize=hb.get("dbsize", 1),
+                              pf_evalue_thresh=hb.get("thresh", 1.0))
+        for f, v in ref.items():
+            H[f"c{i}_{f}"] = v
+    out = os.path.join(os.path.dirname(OUT), "hitlist_v1.npz")
+    np.savez_compressed(out, **H)
+    print("wrote", out, os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":

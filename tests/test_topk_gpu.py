@@ -110,3 +110,24 @@ def test_sharded_search_merges_to_the_single_gpu_list(hhg, world):
         owners = np.array([next(k for k in range(world) if t in set(parts[k].tolist())) for t in rec["target"]])
         assert np.array_equal(rec["owner"], owners)
         assert np.array_equal(rows, ref_rows)
+
+
+def test_topk_by_score_aass_is_the_reference_list_order(hhg, gpu_ctx):
+    """Rank by the reference's sort key: score_aass from hhg_hitlist_pvalues (HitList::CalculatePvalues), ascending;
+    the device selection must reproduce the host order (ties by global id)."""
+    (qp, qtr), tg = _make(600, 12)
+    gpu_ctx.set_query(qp, qtr)
+    db = hhg.TargetDB.from_profiles(gpu_ctx, tg)
+    plan = hhg.Plan(gpu_ctx, db)
+    plan.run()
+    hits, _ = plan.fetch(want_paths=False)
+    rng = np.random.default_rng(1)
+    neff = rng.uniform(1, 12, 600).astype(np.float32)
+    Lt = np.array([t[0].shape[0] - 2 for t in tg], np.int32)
+    st = hhg.capi.hitlist_pvalues(hits["hit_score"], hits["score_ss"], Lt, neff, 120, 5.5, 600)
+    gids = np.arange(600, dtype=np.int32)[::-1].copy()
+    rec = hhg.capi.plan_topk_by_key(gpu_ctx, plan.h, None, 150, st["score_aass"], global_ids=gids)
+    exp = np.lexsort((gids, st["score_aass"]))[:150]
+    assert np.array_equal(rec["target"], gids[exp])
+    assert np.array_equal(rec["hit"]["hit_score"].view(np.uint32), hits["hit_score"][exp].view(np.uint32))
+    plan.close(); db.close()
