@@ -41,7 +41,7 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_prefilter_sw", "hhg_prefilter_evalue", "hhg_prefilter_corrected_scores", "hhg_prefilter_evalues",
            "hhg_comm_unique_id", "hhg_comm_create", "hhg_comm_destroy", "hhg_comm_rank", "hhg_comm_world",
            "hhg_plan_topk", "hhg_plan_topk_by_key", "hhg_plan_topk_paths", "hhg_ctx_last_plan",
-           "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order"]
+           "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order", "hhg_early_stop_sum", "hhg_set_use_ss"]
 
 
 class PrepParams(C.Structure):
@@ -176,6 +176,10 @@ def load():
     L.hhg_hitlist_hhblits_evalues.argtypes = [C.c_int, C.c_void_p, c_f32p, C.c_float, C.c_int, C.c_float, C.c_float,
                                               C.c_float, C.c_double]
     L.hhg_hitlist_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, c_i32p]
+    L.hhg_early_stop_sum.argtypes = [C.c_int, c_f32p, c_i32p, c_f32p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float,
+                                     C.c_float, C.c_float, C.c_double]
+    L.hhg_early_stop_sum.restype = C.c_float
+    L.hhg_set_use_ss.argtypes = [C.c_void_p, C.c_int]
     L.hhg_plan_topk_paths.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, c_u8p]
     L.hhg_ctx_last_plan.argtypes = [C.c_void_p]
     L.hhg_ctx_last_plan.restype = C.c_void_p
@@ -467,6 +471,15 @@ def hitlist_hhblits_evalues(stats, t_neff, q_neff, dbsize, alphaa=0.4, alphab=0.
     _ck(load().hhg_hitlist_hhblits_evalues(len(stats), stats.ctypes.data_as(C.c_void_p), _p(ne, c_f32p), q_neff, dbsize,
                                            alphaa, alphab, alphac, prefilter_evalue_thresh))
     return stats
+
+
+def early_stop_sum(score, Lt, t_neff, Lq, q_neff, prefilter=True, dbsize=1, alphaa=0.4, alphab=0.02, alphac=0.1,
+                   prefilter_evalue_thresh=1000.0):
+    """ViterbiRunner::calculateEarlyStop over one chunk of hits."""
+    s = np.ascontiguousarray(score, np.float32); L = np.ascontiguousarray(Lt, np.int32)
+    ne = np.ascontiguousarray(t_neff, np.float32)
+    return float(load().hhg_early_stop_sum(len(s), _p(s, c_f32p), _p(L, c_i32p), _p(ne, c_f32p), Lq, q_neff,
+                                           1 if prefilter else 0, dbsize, alphaa, alphab, alphac, prefilter_evalue_thresh))
 
 
 def hitlist_order(stats, files=None):

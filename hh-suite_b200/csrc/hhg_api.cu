@@ -671,6 +671,15 @@ int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const u
   return HHG_OK;
 }
 
+// Switch the PRED_PRED secondary-structure term on/off for the following searches without re-sending the query
+// (Viterbi::Align picks the *AndSS kernels per 8-target batch, src/hhviterbirunner.cpp:14-26).
+int hhg_set_use_ss(hhg_ctx* ctx, int use_ss) {
+  if (!ctx) return fail(HHG_EINVAL, "ctx is NULL");
+  if (use_ss && (!ctx->has_ss || !ctx->has_S33)) return fail(HHG_EINVAL, "hhg_set_use_ss: the query was set without ss / S33");
+  ctx->par.use_ss = use_ss ? 1 : 0;
+  return HHG_OK;
+}
+
 // ---------------------------------------------------------------------------------------- plan
 // Strip height of a plan.  Whole-shard scans have work items to spare and take R = 16 (least per-column overhead,
 // 253 GCUPS).  A small request (the few thousand survivors of the prefilter) is latency bound: its longest job is one

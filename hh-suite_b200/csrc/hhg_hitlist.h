@@ -123,6 +123,34 @@ int hhg_hitlist_hhblits_evalues(int n, hhg_hit_stats* stats, const float* t_neff
   return HHG_OK;
 }
 
+// ViterbiRunner::calculateEarlyStop, src/hhviterbirunner.cpp:213-247: the sum over one chunk's hits of 1/(1+Eval) that
+// hhblits compares with chunk_size * filter_thresh (:178-188).  The reference evaluates this one in FLOAT where
+// CalculateHHblitsEvalues uses double, and feeds the already normalised Neff/10 into alpha; both reproduced.
+float hhg_early_stop_sum(int n, const float* score, const int32_t* Lt, const float* t_neff, int Lq, float q_neff_hmm,
+                         int prefilter, int dbsize, float alphaa, float alphab, float alphac,
+                         double prefilter_evalue_thresh) {
+  using namespace hhg_hitlist;
+  const float LOG1000 = (float)log(1000.0);                        // src/hhdecl.h:48
+  float early_stop_result = 0.0f;
+  for (int k = 0; k < n; ++k) {
+    float q_len = (float)(log(Lq) / LOG1000);
+    float hit_len = (float)(log(Lt[k]) / LOG1000);
+    float q_neff = (float)(q_neff_hmm / 10.0);
+    float hit_neff = (float)(t_neff[k] / 10.0);
+    float lamda = lamda_NN(q_len, hit_len, q_neff, hit_neff);
+    float mu = mu_NN(q_len, hit_len, q_neff, hit_neff);
+    const double logPval = logPvalue(score[k], lamda, mu);
+    float alpha = 0;
+    float log_Pcut = (float)log(prefilter_evalue_thresh / dbsize);
+    float log_dbsize = (float)log(dbsize);
+    if (prefilter) alpha = alphaa + alphab * (hit_neff - 1) * (1 - alphac * (q_neff - 1));
+    const double Eval = exp(logPval + log_dbsize + (alpha * log_Pcut));
+    float eval_normalized = (float)(1.0 / (1.0 + Eval));
+    early_stop_result += eval_normalized;
+  }
+  return early_stop_result;
+}
+
 int hhg_hitlist_order(int n, const hhg_hit_stats* stats, const char* const* file, int32_t* order) {
   if (n < 0 || (n > 0 && (!stats || !order))) return HHG_EINVAL;
   std::iota(order, order + n, 0);

@@ -157,6 +157,11 @@ int hhg_db_lengths(const hhg_db* db, int32_t* out /* [hhg_db_size] */);
 int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const uint8_t* ss,
                   const float* S33, const hhg_params* par);
 
+/* Switch the PRED_PRED ss term of the following searches on/off (hhg_params.use_ss) without re-sending the query: the
+ * reference decides it per 8-target batch (consensus over the lanes, src/hhviterbirunner.cpp:14-26), so a runner
+ * splits a mixed target list into the two groups.  Needs a query set with ss and S33. */
+int hhg_set_use_ss(hhg_ctx* ctx, int use_ss);
+
 /* Align the current query against `n` targets of `db` (ids == NULL: all targets in db order).
  *   hits[n]      : one record per requested target, in request order.
  *   paths        : caller buffer of `paths_cap` bytes (>= sum of nsteps; sum(Lq+Lt+2) always suffices)
@@ -217,6 +222,12 @@ int hhg_hitlist_pvalues(int n, const float* score, const float* score_ss, const 
 int hhg_hitlist_hhblits_evalues(int n, hhg_hit_stats* stats, const float* t_neff, float q_neff, int dbsize, float alphaa,
                                 float alphab, float alphac, double prefilter_evalue_thresh);
 int hhg_hitlist_order(int n, const hhg_hit_stats* stats, const char* const* file, int32_t* order);
+/* ViterbiRunner::calculateEarlyStop (src/hhviterbirunner.cpp:213-247): sum over the hits of one chunk of 2000
+ * database entries of 1/(1+Eval); hhblits stops aligning further chunks of the first alignment round when the sum is
+ * below chunk_size * par.filter_thresh (:178-188).  score = Hit.score; prefilter = par.prefilter; dbsize = par.dbsize. */
+float hhg_early_stop_sum(int n, const float* score, const int32_t* Lt, const float* t_neff, int Lq, float q_neff,
+                         int prefilter, int dbsize, float alphaa, float alphab, float alphac,
+                         double prefilter_evalue_thresh);
 
 /* ---- multi-GPU: database sharded by target, hit lists merged over NCCL ------------------------------
  * The reference has no GPU or multi-device layer (its MPI front end distributes QUERIES, src/hhblits_mpi.cpp:135);

@@ -509,6 +509,16 @@ class RefShim:
         assert m == n
         return out
 
+    def early_stop(self, score, L, neff, qL, qneff, prefilter=True, dbsize=1, alphaa=0.4, alphab=0.02, alphac=0.1,
+                   thresh=1000.0):
+        score = np.ascontiguousarray(score, np.float32); L = np.ascontiguousarray(L, np.int32)
+        neff = np.ascontiguousarray(neff, np.float32)
+        self.lib.hhref_early_stop.argtypes = [C.c_int, c_f32p, c_i32p, c_f32p, C.c_int, C.c_float, C.c_int, C.c_int,
+                                              C.c_float, C.c_float, C.c_float, C.c_double]
+        self.lib.hhref_early_stop.restype = C.c_float
+        return float(self.lib.hhref_early_stop(len(score), _p(score, c_f32p), _p(L, c_i32p), _p(neff, c_f32p), qL, qneff,
+                                               1 if prefilter else 0, dbsize, alphaa, alphab, alphac, thresh))
+
     # -- prefilter
     def cs219(self):
         out = np.zeros((219, 20), np.float32)

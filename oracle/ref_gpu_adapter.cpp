@@ -98,6 +98,7 @@ class GpuViterbiRunner {
     all_have_ss_ = true;
     HMM t(MAXSEQDIS, par.maxres);
     for (HHEntry* e : entries) {
+      seqlen_.push_back(e->sequence_length);
       int format = 0;
       e->getTemplateHMM(par, 1, par.qsc_db, format, pb, S, Sim, &t);
       t.AddTransitionPseudocounts(par.gapd, par.gape, par.gapf, par.gapg, par.gaph, par.gapi, par.gapb, par.gapb);
@@ -108,6 +109,9 @@ class GpuViterbiRunner {
       L.push_back(t.L);
       p_off.push_back((int64_t)p.size()); tr_off.push_back((int64_t)tr.size()); ss_off.push_back((int64_t)ss.size());
       if (t.nss_pred < 0) all_have_ss_ = false;
+      neff_.push_back(t.Neff_HMM);
+      has_pred_.push_back(t.nss_pred >= 0 ? 1 : 0);
+      has_dssp_.push_back(t.nss_dssp >= 0 ? 1 : 0);
       for (int i = 0; i <= t.L + 1; ++i) {
         p.insert(p.end(), t.p[i], t.p[i] + 20);
         ss.push_back(t.nss_pred >= 0 ? (uint8_t)(t.ss_pred[i] * MAXCF + t.ss_conf[i]) : 0);
@@ -140,6 +144,17 @@ class GpuViterbiRunner {
       HHG_CHECK(hhg_hhm_scan(rec.data(), (int64_t)rec.size(), &L, &has_ss));
       if (!has_ss) all_have_ss_ = false;
       L_.push_back(L);
+      {
+        // Neff_HMM of the record (NEFF line) through the library's tokeniser; ss_dssp lines do not occur in the test sets
+        std::vector<int32_t> f((size_t)L * 20), trn((size_t)(L + 1) * 10), nul(20);
+        std::vector<uint8_t> ssb(L);
+        float neff = 0; int32_t has_pc = 0;
+        HHG_CHECK(hhg_hhm_parse(rec.data(), (int64_t)rec.size(), L, f.data(), trn.data(), ssb.data(), nul.data(), &neff, &has_pc));
+        neff_.push_back(neff);
+      }
+      has_pred_.push_back(has_ss ? 1 : 0);
+      has_dssp_.push_back(0);
+      seqlen_.push_back(seqlen_override_.empty() ? par.maxres : seqlen_override_[has_pred_.size() - 1]);
       data += rec;
     }
     hhg_prep_params pp = {par.gapb, par.gapd, par.gape, par.gapf, par.gapg, par.gaph, par.gapi,
@@ -158,10 +173,10 @@ class GpuViterbiRunner {
       if (q->nss_pred >= 0) qss[i] = (uint8_t)(q->ss_pred[i] * MAXCF + q->ss_conf[i]);
     }
     for (int i = 0; i <= q->L; ++i) memcpy(&qtr[(size_t)i * 7], q->tr[i], 28);
-    // Viterbi::Align dispatch (src/hhviterbi.cpp:177) + the batch consensus of the runner (:14-22) for a
-    // homogeneous template list: PRED_PRED iff query and all templates carry a predicted ss
-    const int use_ss = (par.ssm == 2 && q->nss_pred >= 0 && all_have_ss_) ? 1 : 0;
-    hhg_params hp = {par.loc, par.egq, par.egt, par.shift, par.ssw, use_ss, par.corr, par.ssm};
+    // the query is sent once with the ss term armed if it could ever be used; per batch the runner decides
+    const bool q_pred = q->nss_pred >= 0, q_dssp = q->nss_dssp >= 0;
+    const int can_ss = (par.ssm == 2 && q_pred) ? 1 : 0;
+    hhg_params hp = {par.loc, par.egq, par.egt, par.shift, par.ssw, can_ss, par.corr, par.ssm};
     HHG_CHECK(hhg_query_set(ctx_, q->L, qp.data(), qtr.data(), qss.data(), &S33[0][0][0][0], &hp));
     HHG_CHECK(hhg_db_apply_null_model(ctx_, db_, q->pav, pb, par.columnscore));
 
@@ -170,62 +185,108 @@ class GpuViterbiRunner {
     std::map<int, std::pair<std::vector<int32_t>, std::vector<int32_t>>> excl;   // accumulated paths per target
     std::vector<GpuHit> ret;
     for (int alignment = 0; alignment < par.altali && !ids.empty(); alignment++) {
-      std::vector<hhg_hit> hits(ids.size());
-      size_t cap = 0;
-      for (int id : ids) cap += (size_t)q->L + L_[id] + 2;
-      std::vector<uint8_t> paths(cap);
-      std::vector<int64_t> eoff(ids.size() + 1, 0);
-      std::vector<int32_t> ei, ej;
-      if (alignment > 0) {
-        for (size_t k = 0; k < ids.size(); ++k) {
-          auto& e = excl[ids[k]];
-          ei.insert(ei.end(), e.first.begin(), e.first.end());
-          ej.insert(ej.end(), e.second.begin(), e.second.end());
-          eoff[k + 1] = (int64_t)ei.size();
-        }
-      }
-      HHG_CHECK(hhg_viterbi_search(ctx_, db_, (int)ids.size(), ids.data(), hits.data(), paths.data(), paths.size(),
-                                   alignment ? eoff.data() : nullptr, ei.data(), ej.data()));
-      if (comm_ && alignment == 0) {
-        // merged hit list of the first alignment round over all GPUs (collective: every rank calls it)
-        merged.resize(n_total_);
-        int m = 0;
-        HHG_CHECK(hhg_plan_topk(ctx_, hhg_ctx_last_plan(ctx_), comm_, n_total_, 1, 0, gids_.data(), merged.data(), &m));
-        merged.resize(m);
-        merged_width = 1;
-        for (const hhg_topk_rec& r : merged) merged_width = std::max(merged_width, (int)r.hit.nsteps);
-        merged_paths.assign((size_t)m * merged_width, 0);
-        HHG_CHECK(hhg_plan_topk_paths(ctx_, hhg_ctx_last_plan(ctx_), comm_, m, merged.data(), merged_width,
-                                      merged_paths.data()));
-      }
+      const unsigned all = (unsigned)ids.size();
+      unsigned block = all;
+      if (alignment == 0 && par.early_stopping_filter) block = 2000;          // src/hhviterbirunner.cpp:109-111
       std::vector<int32_t> next;
-      for (size_t k = 0; k < ids.size(); ++k) {
-        const hhg_hit& h = hits[k];
-        GpuHit g;
-        g.target = gids_.empty() ? ids[k] : gids_[ids[k]]; g.irep = alignment + 1;   // :257 (global template index)
-        g.lastrep = (h.hit_score <= par.smin) ? 1 : 0;                    // :36
-        g.score = h.hit_score; g.score_ss = h.score_ss;
-        g.i1 = h.i1; g.i2 = h.i2; g.j1 = h.j1; g.j2 = h.j2; g.nsteps = h.nsteps; g.matched_cols = h.matched_cols;
-        g.i.assign(h.nsteps + 1, 0); g.j.assign(h.nsteps + 1, 0); g.states.assign(h.nsteps + 1, 0);
-        int i = h.i2, j = h.j2;                                           // replay of Viterbi::Backtrace
-        for (int s = 1; s <= h.nsteps; ++s) {
-          const char st = (char)paths[h.path_off + s - 1];
-          g.i[s] = i; g.j[s] = j; g.states[s] = st;
-          if (s < h.nsteps) {
-            if (st == 2) { --i; --j; } else if (st == 3 || st == 4) { --j; } else { --i; }
+      for (unsigned start = 0; start < all; start += block) {
+        const unsigned cnt = std::min(all - start, block);
+        // the chunk is sorted by HHEntry::sequence_length, descending, with std::sort exactly like the reference
+        // (:117-119; same comparison sequence => same permutation, also among equal keys), then cut into batches of
+        // VECSIZE_FLOAT = 8 lanes; the ss mode of a batch is the consensus over its lanes (:14-22)
+        std::sort(ids.begin() + start, ids.begin() + start + cnt,
+                  [&](int32_t a, int32_t b) { return seqlen_[a] > seqlen_[b]; });
+        std::vector<int32_t> grp[2];                                             // [0]: plain kernels, [1]: *AndSS
+        for (unsigned b0 = start; b0 < start + cnt; b0 += 8) {
+          int consensus = 0xFF;
+          const unsigned b1 = std::min(b0 + 8, start + cnt);
+          for (unsigned k = b0; k < b1; ++k) {
+            const int t = ids[k];
+            int mode = 0;                                                        // HMM::computeScoreSSMode
+            if (q_pred && has_dssp_[t]) mode |= HMM::PRED_DSSP;
+            if (q_dssp && has_pred_[t]) mode |= HMM::DSSP_PRED;
+            if (q_pred && has_pred_[t]) mode |= HMM::PRED_PRED;
+            consensus &= mode;
+          }
+          int ss_mode = consensus & HMM::PRED_DSSP;
+          ss_mode = (ss_mode == 0) ? consensus & HMM::DSSP_PRED : 0;
+          ss_mode = (ss_mode == 0) ? consensus & HMM::PRED_PRED : 0;
+          const int use_ss = (par.ssm == 2 && ss_mode != HMM::NO_SS_INFORMATION) ? 1 : 0;   // Viterbi::Align, src/hhviterbi.cpp:177
+          for (unsigned k = b0; k < b1; ++k) grp[use_ss].push_back(ids[k]);
+        }
+        std::vector<float> chunk_score; std::vector<int32_t> chunk_L; std::vector<float> chunk_neff;
+        for (int g = 0; g < 2; ++g) {
+          const std::vector<int32_t>& gi = grp[g];
+          if (gi.empty()) continue;
+          if (can_ss) HHG_CHECK(hhg_set_use_ss(ctx_, g));
+          std::vector<hhg_hit> hits(gi.size());
+          size_t cap = 0;
+          for (int id : gi) cap += (size_t)q->L + L_[id] + 2;
+          std::vector<uint8_t> paths(cap);
+          std::vector<int64_t> eoff(gi.size() + 1, 0);
+          std::vector<int32_t> ei, ej;
+          if (alignment > 0) {
+            for (size_t k = 0; k < gi.size(); ++k) {
+              auto& e = excl[gi[k]];
+              ei.insert(ei.end(), e.first.begin(), e.first.end());
+              ej.insert(ej.end(), e.second.begin(), e.second.end());
+              eoff[k + 1] = (int64_t)ei.size();
+            }
+          }
+          HHG_CHECK(hhg_viterbi_search(ctx_, db_, (int)gi.size(), gi.data(), hits.data(), paths.data(), paths.size(),
+                                       alignment ? eoff.data() : nullptr, ei.data(), ej.data()));
+          if (comm_ && alignment == 0 && g == (grp[1].empty() ? 0 : 1) && grp[g == 0 ? 1 : 0].empty()) {
+            // merged hit list of the first alignment round over all GPUs (collective: every rank calls it); only
+            // formed when the round is one search (homogeneous ss mode, one chunk)
+            merged.resize(n_total_);
+            int m = 0;
+            std::vector<int32_t> gg(gi.size());
+            for (size_t k = 0; k < gi.size(); ++k) gg[k] = gids_[gi[k]];
+            HHG_CHECK(hhg_plan_topk(ctx_, hhg_ctx_last_plan(ctx_), comm_, n_total_, 1, 0, gg.data(), merged.data(), &m));
+            merged.resize(m);
+            merged_width = 1;
+            for (const hhg_topk_rec& r : merged) merged_width = std::max(merged_width, (int)r.hit.nsteps);
+            merged_paths.assign((size_t)m * merged_width, 0);
+            HHG_CHECK(hhg_plan_topk_paths(ctx_, hhg_ctx_last_plan(ctx_), comm_, m, merged.data(), merged_width,
+                                          merged_paths.data()));
+          }
+          for (size_t k = 0; k < gi.size(); ++k) {
+            const hhg_hit& h = hits[k];
+            GpuHit gh;
+            gh.target = gids_.empty() ? gi[k] : gids_[gi[k]]; gh.irep = alignment + 1;   // :257 (global template index)
+            gh.lastrep = (h.hit_score <= par.smin) ? 1 : 0;                  // :36
+            gh.score = h.hit_score; gh.score_ss = h.score_ss;
+            gh.i1 = h.i1; gh.i2 = h.i2; gh.j1 = h.j1; gh.j2 = h.j2; gh.nsteps = h.nsteps; gh.matched_cols = h.matched_cols;
+            gh.i.assign(h.nsteps + 1, 0); gh.j.assign(h.nsteps + 1, 0); gh.states.assign(h.nsteps + 1, 0);
+            int i = h.i2, j = h.j2;                                           // replay of Viterbi::Backtrace
+            for (int st = 1; st <= h.nsteps; ++st) {
+              const char c = (char)paths[h.path_off + st - 1];
+              gh.i[st] = i; gh.j[st] = j; gh.states[st] = c;
+              if (st < h.nsteps) {
+                if (c == 2) { --i; --j; } else if (c == 3 || c == 4) { --j; } else { --i; }
+              }
+            }
+            ret.push_back(gh);
+            chunk_score.push_back(h.hit_score); chunk_L.push_back(L_[gi[k]]); chunk_neff.push_back(neff_[gi[k]]);
+            if (h.hit_score > par.smin) {                                     // :260-268
+              next.push_back(gi[k]);
+              auto& e = excl[gi[k]];
+              for (int st = 1; st < h.nsteps; ++st) { e.first.push_back(gh.i[st]); e.second.push_back(gh.j[st]); }
+            }
           }
         }
-        ret.push_back(g);
-        if (h.hit_score > par.smin) {                                     // :260-268
-          next.push_back(ids[k]);
-          auto& e = excl[ids[k]];
-          for (int s = 1; s < h.nsteps; ++s) { e.first.push_back(g.i[s]); e.second.push_back(g.j[s]); }
+        if (alignment == 0 && par.early_stopping_filter) {                     // :178-188
+          const float sum = hhg_early_stop_sum((int)chunk_score.size(), chunk_score.data(), chunk_L.data(), chunk_neff.data(),
+                                               q->L, q->Neff_HMM, par.prefilter, par.dbsize, par.alphaa, par.alphab,
+                                               par.alphac, par.prefilter_evalue_thresh);
+          if (sum < cnt * par.filter_thresh) { early_stopped_at = (int)(start + cnt); break; }
         }
       }
       ids.swap(next);
     }
     return ret;
   }
+  int early_stopped_at = -1;   // number of database entries after which the first round stopped (-1: it did not)
 
   // The adapter of INTEGRATION.md section 2b: PosteriorDecoderRunner::executeComputation on the C-ABI.  `vit` are the
   // Viterbi hits to realign; q is the query AFTER the reference put it into linear transition space.
@@ -295,7 +356,11 @@ class GpuViterbiRunner {
   std::vector<int32_t> gids_;
   int n_total_ = 0;
   std::vector<int32_t> L_;
+  std::vector<int> seqlen_, has_pred_, has_dssp_;   // HHEntry::sequence_length, nss_pred >= 0, nss_dssp >= 0 per template
+  std::vector<float> neff_;                         // Neff_HMM per template
   bool all_have_ss_ = false;
+ public:
+  std::vector<int> seqlen_override_;                // UploadText: the sequence_length the reference's entries carry
 };
 
 uint32_t bits(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
@@ -303,12 +368,14 @@ uint32_t bits(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 }  // namespace
 
 int main(int argc, char** argv) {
-  bool text_loader = false, with_mac = false;
-  int gpus = 1;
+  bool text_loader = false, with_mac = false, real_lengths = false;
+  int gpus = 1, hhblits_dbsize = 0;
   while (argc > 1 && argv[1][0] == '-' && argv[1][1] == '-') {
     if (!strcmp(argv[1], "--hhm-loader")) text_loader = true;
     else if (!strcmp(argv[1], "--mac")) with_mac = true;
     else if (!strcmp(argv[1], "--gpus") && argc > 2) { gpus = atoi(argv[2]); --argc; ++argv; }
+    else if (!strcmp(argv[1], "--real-lengths")) real_lengths = true;
+    else if (!strcmp(argv[1], "--hhblits") && argc > 2) { hhblits_dbsize = atoi(argv[2]); --argc; ++argv; }
     else break;
     --argc; ++argv;
   }
@@ -320,6 +387,12 @@ int main(int argc, char** argv) {
   par.nocontxt = 1;
   par.maxres = 4096;
   par.threads = 2;
+  if (hhblits_dbsize > 0) {               // what hhblits sets on top of hhsearch (src/hhblits.cpp:87-88): early stopping
+    par.early_stopping_filter = true;
+    par.filter_thresh = 0.01;
+    par.prefilter = 1;
+    par.dbsize = hhblits_dbsize;
+  }
   float pb[21] __attribute__((aligned(32)));
   float P[20][20] __attribute__((aligned(32))), R[20][20] __attribute__((aligned(32)));
   float S[20][20] __attribute__((aligned(32))), Sim[20][20] __attribute__((aligned(32)));
@@ -342,8 +415,25 @@ int main(int argc, char** argv) {
   PrepareQueryHMM(par, input_format, q, nullptr, nullptr, pb, R);
   q_vec.MapOneHMM(q);
 
+  // entries carry a sequence_length like the ffindex entries of a real database (the runner sorts each chunk by it);
+  // --real-lengths: the template's own length, otherwise the same value for all
   std::vector<HHEntry*> entries;
-  for (int a = 2; a < argc; ++a) entries.push_back(new HHFileEntry(argv[a], par.maxres));
+  std::vector<int> seqlens;
+  for (int a = 2; a < argc; ++a) {
+    int len = par.maxres;
+    if (real_lengths) {
+      FILE* fp = fopen(argv[a], "rb");
+      if (!fp) { perror(argv[a]); return 2; }
+      std::string rec; char buf[65536]; size_t n;
+      while ((n = fread(buf, 1, sizeof(buf), fp)) > 0) rec.append(buf, n);
+      fclose(fp);
+      int32_t L = 0, has_ss = 0;
+      HHG_CHECK(hhg_hhm_scan(rec.c_str(), (int64_t)rec.size() + 1, &L, &has_ss));
+      len = L;
+    }
+    seqlens.push_back(len);
+    entries.push_back(new HHFileEntry(argv[a], len));
+  }
 
   // ---- (1) the reference runner
   std::vector<ViterbiMatrix*> mats(par.threads);
@@ -361,6 +451,7 @@ int main(int argc, char** argv) {
   if (gpus <= 1) {
     if (text_loader) {
       std::vector<std::string> files(argv + 2, argv + argc);
+      gpu_runner.seqlen_override_ = seqlens;
       gpu_runner.UploadText(par, files, R);
     } else {
       gpu_runner.Upload(par, entries, pb, S, Sim, R);
@@ -379,6 +470,7 @@ int main(int argc, char** argv) {
       std::vector<std::string> files;
       for (size_t k = r; k < entries.size(); k += gpus) { gid[r].push_back((int32_t)k); mine.push_back(entries[k]); files.push_back(argv[2 + k]); }
       if (mine.empty()) { fprintf(stderr, "--gpus %d needs at least %d templates\n", gpus, gpus); return 2; }
+      for (size_t k = r; k < entries.size(); k += gpus) runners[r]->seqlen_override_.push_back(seqlens[k]);
       if (text_loader) runners[r]->UploadText(par, files, R); else runners[r]->Upload(par, mine, pb, S, Sim, R);
     }
     std::vector<std::vector<GpuHit>> part(gpus);
@@ -478,6 +570,9 @@ int main(int argc, char** argv) {
     printf("hh_dropin_check --mac: %zu hits realigned: %s\n", hit_ptrs.size(), mbad ? "MISMATCH" : "all MAC alignments identical");
     bad += mbad;
   }
+  if (hhblits_dbsize > 0)
+    printf("hh_dropin_check --hhblits: early stop after %d of %zu database entries (reference aligned %zu first-round hits)\n",
+           gpu_runner.early_stopped_at, entries.size(), (size_t)std::count_if(ref.begin(), ref.end(), [](const Hit& h) { return h.irep == 1; }));
   printf("hh_dropin_check: query L=%d, %zu templates, %zu hits (up to irep %d): %s\n", q->L, entries.size(), ref.size(),
          maxrep, bad ? "MISMATCH" : "all hits identical");
   return bad ? 1 : 0;

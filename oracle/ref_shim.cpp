@@ -45,6 +45,7 @@
 #include "hhprefilter.h"
 #include "hhhit.h"
 #include "hhhitlist.h"
+#include "hhviterbirunner.h"
 #include "hhposteriordecoder.h"
 #include "hhposteriordecoderrunner.h"
 #include "hhposteriormatrix.h"
@@ -615,4 +616,20 @@ extern "C" int hhref_hitlist_stats(int n, const float* score, const float* score
   for (char* p : names) free(p);
   delete hl;
   return pos;
+}
+
+
+// ViterbiRunner::calculateEarlyStop (src/hhviterbirunner.cpp:213) on synthetic hits
+extern "C" float hhref_early_stop(int n, const float* score, const int* L, const float* neff, int qL, float qneff,
+                                  int prefilter, int dbsize, float alphaa, float alphab, float alphac, double thresh) {
+  Parameters par = *g->par;
+  par.prefilter = prefilter; par.dbsize = dbsize; par.alphaa = alphaa; par.alphab = alphab; par.alphac = alphac;
+  par.prefilter_evalue_thresh = thresh;
+  HMM q(2, qL + 2);
+  q.L = qL; q.Neff_HMM = qneff;
+  std::vector<Hit> hits(n);
+  for (int k = 0; k < n; ++k) { hits[k].score = score[k]; hits[k].L = L[k]; hits[k].Neff_HMM = neff[k]; }
+  std::vector<HHblitsDatabase*> nodb;
+  ViterbiRunner r(nullptr, nodb, 1);
+  return r.calculateEarlyStop(par, &q, hits, 0);
 }

@@ -5,6 +5,8 @@ oracle/ref_gpu_adapter.cpp against the unmodified reference; shipped prebuilt to
 import os
 import subprocess
 
+import numpy as np
+
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -88,3 +90,46 @@ def test_two_gpus_behind_the_c_abi(tmp_path):
     r = _run(["--gpus", "2", QUERY, QUERY] + files + [files[3]])                    # files[3] twice: an exact score tie
     assert r.returncode == 0 and "all hits identical" in r.stdout and "identical to the reference's sorted" in r.stdout, \
         r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+def test_ss_mode_is_the_batch_consensus_of_the_reference(tmp_path):
+    """ViterbiConsumerThread::align takes the *AndSS kernels only when ALL 8 lanes of a batch carry a predicted
+    secondary structure (src/hhviterbirunner.cpp:14-22); batches are formed after the length sort of the chunk.  Mixed
+    template list, entries with their real lengths: the adapter has to reproduce the reference's per-batch choice."""
+    from hhsuite_b200 import synth
+    q = tmp_path / "q.hhm"
+    q.write_text(synth.hhm_text(160, 7, "qss", with_ss=True))
+    files = []
+    lens = [160, 90, 140, 260, 45, 160, 75, 200, 66, 120, 33, 300, 180, 95, 210, 150, 58, 170, 240]
+    for k, L in enumerate(lens):
+        f = tmp_path / f"x{k}.hhm"
+        f.write_text(synth.hhm_text(L, 7 if k in (0, 5) else 400 + k, f"x{k}", with_ss=(k % 3 != 1)))
+        files.append(str(f))
+    r = _run(["--real-lengths", str(q)] + files)
+    assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+@pytest.mark.parametrize("homologs", [0, 40], ids=["stops", "continues"])
+def test_hhblits_early_stopping(tmp_path, homologs):
+    """hhblits aligns the prefilter's list in chunks of 2000 and stops after a chunk whose hits sum to less than
+    2000 * 0.01 in 1/(1+Eval) (src/hhviterbirunner.cpp:109-111,178-188,213-247).  2100 templates: without homologs
+    the first chunk ends the round (the last 100 are never aligned), with 40 copies of the query it goes on."""
+    from hhsuite_b200 import synth
+    rng = np.random.default_rng(5)
+    qtext = open(QUERY).read()
+    files = []
+    for k in range(2100):
+        f = tmp_path / f"e{k}.hhm"
+        if k < homologs:
+            f.write_text(qtext)
+        else:
+            f.write_text(synth.hhm_text(int(rng.integers(30, 70)), 9000 + k, f"e{k}"))
+        files.append(str(f))
+    r = _run(["--hhblits", "2100", "--real-lengths", QUERY] + files)
+    assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    if homologs:
+        assert "early stop after -1 of 2100" in r.stdout and "reference aligned 2100 first-round hits" in r.stdout
+    else:
+        assert "early stop after 2000 of 2100" in r.stdout and "reference aligned 2000 first-round hits" in r.stdout

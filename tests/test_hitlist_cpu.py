@@ -90,3 +90,17 @@ def test_hitlist_stats_match_goldens():
                                   c["ssm"], c["ssw"], c["ssm2"], c["files"], c["hb"])
         ref = {f: G[f"c{i}_{f}"] for f in ("Pval", "logPval", "Eval", "logEval", "score_aass", "Probab", "order")}
         _check(st, order, ref, c["files"])
+
+
+def test_early_stop_sum_matches_compiled_reference(refshim):
+    """ViterbiRunner::calculateEarlyStop (float arithmetic, src/hhviterbirunner.cpp:213-247): same float bits."""
+    import hhsuite_b200 as hh
+    rng = np.random.default_rng(3)
+    for n, qL, qneff, pf, dbsize in [(2000, 400, 7.3, True, 1000000), (2000, 60, 1.0, False, 52000), (137, 1500, 12.0, True, 20000)]:
+        score = rng.uniform(-5, 40, n).astype(np.float32)
+        score[:5] = rng.uniform(100, 900, 5)
+        L = rng.integers(20, 2000, n).astype(np.int32)
+        neff = rng.uniform(1, 13, n).astype(np.float32)
+        a = hh.capi.early_stop_sum(score, L, neff, qL, qneff, pf, dbsize)
+        b = refshim.early_stop(score, L, neff, qL, qneff, pf, dbsize)
+        assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), (a, b)

@@ -58,3 +58,36 @@ def test_alternative_alignments_loop(hhg, gpu_ctx, oracle):
     assert all(got[(t, 2)].score > 20.0 for t in range(0, 12, 3))
     assert max(h.irep for h in hits) >= 3
     db.close()
+
+
+def test_early_stopping_and_ss_consensus_mirror(hhg, gpu_ctx):
+    """The Python mirror of the two order-dependent runner behaviours (the exact check against the reference's own
+    runner is tests/test_dropin_gpu.py): chunks of 2000 with hhg_early_stop_sum, ss term by batch consensus."""
+    from hhsuite_b200 import synth
+    from tests.util import golden
+    rng = np.random.default_rng(3)
+    qp, qtr, qss, qpav, qcols = synth.query_profile(80, 5)
+    n = 2100
+    tg = [synth.prepared_profile(int(L), rng, None, 0.3) for L in rng.integers(20, 60, n)]
+    gpu_ctx.set_query(qp, qtr, qss, golden()["S33"], use_ss=True)
+    db = hhg.TargetDB.from_profiles(gpu_ctx, tg)
+    neff = rng.uniform(2, 9, n).astype(np.float32)
+    t_pred = rng.random(n) < 0.7
+    r = hhg.runner.ViterbiRunner(gpu_ctx, db, altali=2, early_stopping=dict(dbsize=n, q_neff=6.0, t_neff=neff),
+                                 ss=dict(q_pred=True, t_pred=t_pred, seqlen=db.Lh))
+    hits = r.alignment()
+    assert r.early_stopped_at == 2000                       # random targets: the first chunk ends the round
+    assert sorted({h.target for h in hits}) == list(range(2000))
+    # every hit equals a direct search of its target with the ss choice of its batch
+    order = np.argsort(-db.Lh[:2000], kind="stable")
+    use = np.zeros(2000, bool)
+    for b in range(0, 2000, 8):
+        use[order[b:b + 8]] = t_pred[order[b:b + 8]].all()
+    for flag in (0, 1):
+        ids = np.nonzero(use == bool(flag))[0].astype(np.int32)
+        hhg.capi._ck(gpu_ctx.L.hhg_set_use_ss(gpu_ctx.h, flag))
+        ref, _ = hhg.viterbi_search(gpu_ctx, db, ids=ids)
+        got = {h.target: h for h in hits if h.irep == 1}
+        for k, t in enumerate(ids):
+            assert bits(np.float32(got[int(t)].score)) == bits(ref[k]["hit_score"])
+    db.close()
