@@ -27,6 +27,7 @@
 #include <cstring>
 #include <iostream>
 #include <map>
+#include <set>
 #include <memory>
 #include <sstream>
 #include <string>
@@ -48,6 +49,10 @@
 #include "hhposteriordecoder.h"
 #include "hhposteriordecoderrunner.h"
 #include "hhposteriormatrix.h"
+#include "hhprefilter.h"
+#include "ffindexdatabase.h"
+#include "hash.h"
+#include "cs219.lib.h"
 #undef private
 #undef protected
 
@@ -363,24 +368,134 @@ class GpuViterbiRunner {
   std::vector<int> seqlen_override_;                // UploadText: the sequence_length the reference's entries carry
 };
 
+
+// The adapter of INTEGRATION.md section 3: Prefilter::prefilter_db (src/hhprefilter.h:80-85, .cpp:430-606) with the same
+// signature, both scoring stages on the C-ABI, the selection logic in between restated: stage-1 list chosen on the
+// device (hhg_prefilter_select = length correction :477, sort, keep rule :489-506), stage-2 E-values (:529), coarse cut
+// (:530), ascending sort by (E-value, index) (:545), keep rule (:547-558), de-duplication by name, split into
+// new / old hits by previous_hits (name without extension + "__1", :561-588), maxnumdb cap (:590).
+class GpuPrefilter {
+ public:
+  GpuPrefilter(hhg_ctx* ctx, FFindexDatabase* cs219_database) : ctx_(ctx) {
+    // init_prefilter (:314-335): one entry per ffindex record, length = entry->length - 1 (the record's NUL)
+    ffindex_index_t* idx = cs219_database->db_index;
+    n_ = (int)idx->n_entries;
+    std::vector<int32_t> L(n_);
+    std::vector<int64_t> off(n_);
+    std::vector<uint8_t> seq;
+    for (int k = 0; k < n_; ++k) {
+      ffindex_entry_t* e = ffindex_get_entry_by_index(idx, k);
+      const unsigned char* d = (const unsigned char*)ffindex_get_data_by_entry(cs219_database->db_data, e);
+      L[k] = (int32_t)e->length - 1;
+      off[k] = (int64_t)seq.size();
+      seq.insert(seq.end(), d, d + L[k]);
+      names_.push_back(e->name);
+    }
+    L_ = L;
+    HHG_CHECK(hhg_csdb_create(ctx_, n_, L.data(), off.data(), seq.data(), &db_));
+    // the 219 column states in linear space (Prefilter ctor :28-47: cs219.lib + TransformToLin)
+    FILE* fin = fmemopen((void*)cs219_lib, cs219_lib_len, "r");
+    cs::ContextLibrary<cs::AA> lib(fin);
+    fclose(fin);
+    cs::TransformToLin(lib);
+    lib219_.resize(219 * 20);
+    for (int k = 0; k < 219; ++k)
+      for (int a = 0; a < 20; ++a) lib219_[k * 20 + a] = lib[k].probs[0][a];
+  }
+  ~GpuPrefilter() { hhg_csdb_destroy(db_); }
+
+  void prefilter_db(HMM* q_tmp, Hash<Hit>* previous_hits, const int threads, const int prefilter_gap_open,
+                    const int prefilter_gap_extend, const int prefilter_score_offset, const int prefilter_bit_factor,
+                    const double prefilter_evalue_thresh, const double prefilter_evalue_coarse_thresh,
+                    const int preprefilter_smax_thresh, const int min_prefilter_hits, const int maxnumdb,
+                    const float R[20][20], std::vector<std::pair<int, std::string> >& new_prefilter_hits,
+                    std::vector<std::pair<int, std::string> >& old_prefilter_hits) {
+    (void)threads; (void)R;
+    const int LQ = q_tmp->L;
+    std::vector<float> qp((size_t)(LQ + 2) * 20);
+    for (int i = 0; i <= LQ + 1; ++i) memcpy(&qp[(size_t)i * 20], q_tmp->p[i], 80);
+    std::vector<uint8_t> prof((size_t)220 * LQ);
+    HHG_CHECK(hhg_prefilter_build_profile(LQ, qp.data(), q_tmp->pav, lib219_.data(), prefilter_score_offset,
+                                          prefilter_bit_factor, prof.data()));
+    // stage 1 on the whole shard, list chosen on the device
+    HHG_CHECK(hhg_prefilter_ungapped_run(ctx_, db_, LQ, prof.data(), prefilter_score_offset, 1));
+    std::vector<int32_t> first(n_), first_score(n_);
+    int nfirst = 0;
+    HHG_CHECK(hhg_prefilter_select(ctx_, db_, LQ, prefilter_bit_factor, preprefilter_smax_thresh, min_prefilter_hits,
+                                   first.data(), first_score.data(), n_, &nfirst));
+    first.resize(nfirst);
+    // stage 2: gapped byte SW on the stage-1 list, E-values with the database size
+    std::vector<int32_t> sw(nfirst), len(nfirst);
+    if (nfirst)
+      HHG_CHECK(hhg_prefilter_sw(ctx_, db_, nfirst, first.data(), LQ, prof.data(), prefilter_gap_open + prefilter_gap_extend,
+                                 prefilter_gap_extend, prefilter_score_offset, sw.data()));
+    for (int k = 0; k < nfirst; ++k) len[k] = L_[first[k]];
+    std::vector<double> ev(nfirst);
+    if (nfirst) HHG_CHECK(hhg_prefilter_evalues(nfirst, sw.data(), len.data(), n_, LQ, prefilter_bit_factor, ev.data()));
+    std::vector<std::pair<double, int> > hits;
+    for (int k = 0; k < nfirst; ++k)
+      if (ev[k] < prefilter_evalue_coarse_thresh) hits.push_back(std::make_pair(ev[k], (int)first[k]));
+    std::sort(hits.begin(), hits.end());                                      // ascending (evalue, index), :545
+    size_t keep = 0;
+    for (; keep < hits.size(); ++keep)                                         // :547-558
+      if (!((int)keep < min_prefilter_hits || hits[keep].first <= prefilter_evalue_thresh)) break;
+    hits.resize(keep);
+    std::set<std::string> doubled;
+    int count_dbs = 0;
+    for (const auto& h : hits) {
+      ++count_dbs;
+      const std::string& db_name = names_[h.second];
+      if (!doubled.count(db_name)) {
+        doubled.insert(db_name);
+        std::string name = db_name;                                            // RemoveExtension
+        const size_t dot = name.rfind('.');
+        if (dot != std::string::npos) name.resize(dot);
+        const std::string key = name + "__1";
+        std::pair<int, std::string> result(L_[h.second], db_name);
+        if (previous_hits->Contains(key.c_str())) old_prefilter_hits.push_back(result);
+        else new_prefilter_hits.push_back(result);
+      }
+      if (count_dbs >= maxnumdb) break;
+    }
+  }
+
+ private:
+  hhg_ctx* ctx_;
+  hhg_csdb* db_ = nullptr;
+  int n_ = 0;
+  std::vector<int32_t> L_;
+  std::vector<std::string> names_;
+  std::vector<float> lib219_;
+};
+
 uint32_t bits(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
 
 }  // namespace
 
 int main(int argc, char** argv) {
   bool text_loader = false, with_mac = false, real_lengths = false;
-  int gpus = 1, hhblits_dbsize = 0;
+  int gpus = 1, hhblits_dbsize = 0, maxnumdb = 20000;
+  const char* prefilter_db_base = nullptr;
+  std::vector<std::string> previous;
   while (argc > 1 && argv[1][0] == '-' && argv[1][1] == '-') {
     if (!strcmp(argv[1], "--hhm-loader")) text_loader = true;
     else if (!strcmp(argv[1], "--mac")) with_mac = true;
     else if (!strcmp(argv[1], "--gpus") && argc > 2) { gpus = atoi(argv[2]); --argc; ++argv; }
     else if (!strcmp(argv[1], "--real-lengths")) real_lengths = true;
+    else if (!strcmp(argv[1], "--prefilter") && argc > 2) { prefilter_db_base = argv[2]; --argc; ++argv; }
+    else if (!strcmp(argv[1], "--maxnumdb") && argc > 2) { maxnumdb = atoi(argv[2]); --argc; ++argv; }
+    else if (!strcmp(argv[1], "--previous") && argc > 2) {
+      std::stringstream ss(argv[2]); std::string item;
+      while (std::getline(ss, item, ',')) previous.push_back(item);
+      --argc; ++argv;
+    }
     else if (!strcmp(argv[1], "--hhblits") && argc > 2) { hhblits_dbsize = atoi(argv[2]); --argc; ++argv; }
     else break;
     --argc; ++argv;
   }
   if (gpus > 1 && with_mac) { fprintf(stderr, "--mac is checked on one GPU\n"); return 2; }
-  if (argc < 3) { fprintf(stderr, "usage: %s [--hhm-loader] [--mac] query.hhm template.hhm [...]\n", argv[0]); return 2; }
+  if (prefilter_db_base && argc < 2) { fprintf(stderr, "usage: %s --prefilter <db>_cs219 query.hhm\n", argv[0]); return 2; }
+  if (!prefilter_db_base && argc < 3) { fprintf(stderr, "usage: %s [--hhm-loader] [--mac] query.hhm template.hhm [...]\n", argv[0]); return 2; }
   Log::reporting_level() = WARNING;
   const char* pargv[] = {"hhalign"};
   Parameters par(1, pargv);
@@ -414,6 +529,40 @@ int main(int argc, char** argv) {
   char input_format = 0;
   PrepareQueryHMM(par, input_format, q, nullptr, nullptr, pb, R);
   q_vec.MapOneHMM(q);
+
+  if (prefilter_db_base) {
+    // ---- seam 2: Prefilter::prefilter_db of the reference vs GpuPrefilter::prefilter_db on the same cs219 ffindex
+    const std::string data = std::string(prefilter_db_base) + ".ffdata", index = std::string(prefilter_db_base) + ".ffindex";
+    FFindexDatabase csdb(data.c_str(), index.c_str(), false);
+    Hash<Hit> previous_hits;
+    previous_hits.New(1631, Hit());
+    for (const std::string& nm : previous) { std::string key = nm + "__1"; Hit h; previous_hits.Add((char*)key.c_str(), h); }
+    std::vector<std::pair<int, std::string> > rn, ro, gn, go;
+    Prefilter ref_pf("", &csdb);
+    ref_pf.prefilter_db(q, &previous_hits, par.threads, par.prefilter_gap_open, par.prefilter_gap_extend,
+                        par.prefilter_score_offset, par.prefilter_bit_factor, par.prefilter_evalue_thresh,
+                        par.prefilter_evalue_coarse_thresh, par.preprefilter_smax_thresh, par.min_prefilter_hits, maxnumdb, R,
+                        rn, ro);
+    hhg_ctx* pctx = nullptr;
+    HHG_CHECK(hhg_ctx_create(0, nullptr, &pctx));
+    {
+      GpuPrefilter gpu_pf(pctx, &csdb);
+      gpu_pf.prefilter_db(q, &previous_hits, par.threads, par.prefilter_gap_open, par.prefilter_gap_extend,
+                          par.prefilter_score_offset, par.prefilter_bit_factor, par.prefilter_evalue_thresh,
+                          par.prefilter_evalue_coarse_thresh, par.preprefilter_smax_thresh, par.min_prefilter_hits, maxnumdb,
+                          R, gn, go);
+    }
+    hhg_ctx_destroy(pctx);
+    const bool same = rn == gn && ro == go;
+    if (!same) {
+      printf("PREFILTER MISMATCH: reference %zu new / %zu old, gpu %zu new / %zu old\n", rn.size(), ro.size(), gn.size(), go.size());
+      for (size_t k = 0; k < std::min(rn.size(), gn.size()); ++k)
+        if (rn[k] != gn[k]) { printf("  first difference at new[%zu]: ref (%d,%s) gpu (%d,%s)\n", k, rn[k].first, rn[k].second.c_str(), gn[k].first, gn[k].second.c_str()); break; }
+    }
+    printf("hh_dropin_check --prefilter: %zu sequences, query L=%d: %zu new + %zu old prefilter hits: %s\n",
+           (size_t)csdb.db_index->n_entries, q->L, rn.size(), ro.size(), same ? "identical lists" : "MISMATCH");
+    return same ? 0 : 1;
+  }
 
   // entries carry a sequence_length like the ffindex entries of a real database (the runner sorts each chunk by it);
   // --real-lengths: the template's own length, otherwise the same value for all

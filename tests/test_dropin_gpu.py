@@ -133,3 +133,45 @@ def test_hhblits_early_stopping(tmp_path, homologs):
         assert "early stop after -1 of 2100" in r.stdout and "reference aligned 2100 first-round hits" in r.stdout
     else:
         assert "early stop after 2000 of 2100" in r.stdout and "reference aligned 2000 first-round hits" in r.stdout
+
+
+def _write_cs219_ffindex(base, names, seqs):
+    """<base>.ffdata / .ffindex like cstranslate writes them: entry = state bytes + NUL, index sorted by name."""
+    order = sorted(range(len(names)), key=lambda k: names[k])
+    off = 0
+    with open(base + ".ffdata", "wb") as fd, open(base + ".ffindex", "w") as fi:
+        for k in order:
+            b = bytes(seqs[k]) + b"\0"
+            fd.write(b)
+            fi.write(f"{names[k]}\t{off}\t{len(b)}\n")
+            off += len(b)
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+@pytest.mark.parametrize("maxnumdb", [20000, 40])
+def test_prefilter_db_seam(tmp_path, refshim, maxnumdb):
+    """Seam 2: the reference's Prefilter::prefilter_db (AVX2, OpenMP) vs GpuPrefilter::prefilter_db (same signature,
+    C-ABI underneath) on one synthetic cs219 ffindex: new_prefilter_hits / old_prefilter_hits must be equal element by
+    element (lengths, names, order), including the previous_hits split and the maxnumdb cap."""
+    from tests.util import golden
+    G = golden()
+    q = refshim.load_query_hhm(QUERY)
+    import hhsuite_b200 as hh
+    prof = hh.capi.build_prefilter_profile(q["p"], q["pav"], G["cs219_lin"], 50, 4)
+    best = prof[:219].argmax(axis=0).astype(np.uint8)
+    rng = np.random.default_rng(17)
+    n = 3000
+    seqs = [rng.integers(0, 219, int(L), dtype=np.uint8) for L in rng.integers(30, 500, n)]
+    for k in range(0, n, 12):                      # planted homologs with substitutions and an indel
+        a = int(rng.integers(0, 200)); ln = int(rng.integers(60, 230))
+        seg = best[a:a + ln].copy()
+        seg[rng.random(ln) < 0.2] = rng.integers(0, 219)
+        cut = int(rng.integers(10, ln - 10))
+        seqs[k] = np.concatenate([seg[:cut], rng.integers(0, 219, int(rng.integers(0, 6)), dtype=np.uint8), seg[cut:]])
+    names = [f"T{k:05d}.a3m" for k in range(n)]
+    base = str(tmp_path / "db_cs219")
+    _write_cs219_ffindex(base, names, seqs)
+    prev = ",".join(f"T{k:05d}" for k in range(0, n, 36))
+    r = _run(["--prefilter", base, "--maxnumdb", str(maxnumdb), "--previous", prev, QUERY])
+    assert r.returncode == 0 and "identical lists" in r.stdout, r.stdout + r.stderr
+    assert " 0 new + 0 old" not in r.stdout
