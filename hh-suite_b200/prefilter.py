@@ -6,7 +6,8 @@ over the survivors); the selection logic between and after them is the reference
            (comparePair + reverse, :489-490); keep entries while count < min_prefilter_hits or
            score > smax_thresh (:494-506)
   stage 2: evalue = N*Lq*Lt*fpow2(-score/bit_factor) (integer division, :529); keep evalue < coarse
-           threshold (:530); sort ascending by (evalue, n) (:545); keep while count < min_prefilter_hits or
+           threshold (:530); sort ascending by ((int)evalue, n) (:545: comparePair takes std::pair<int,int>, so the
+           double E-value is truncated to int by the implicit conversion); keep while count < min_prefilter_hits or
            evalue <= evalue_thresh (:547-558); cap at maxnumdb (:590)
 
 Returned: sequence ids in the reference's output order.  Name de-duplication and the old/new split by
@@ -57,7 +58,7 @@ def prefilter_db(csdb: capi.CsDB, prof: np.ndarray, gap_open=20, gap_extend=4, s
         capi._ck(L.hhg_prefilter_evalues(len(first), capi._p(sw32, capi.c_i32p), capi._p(fl, capi.c_i32p), n, Lq,
                                         bit_factor, ev.ctypes.data_as(C.POINTER(C.c_double))))
     sel = [k for k in range(len(first)) if ev[k] < evalue_coarse_thresh]
-    sel.sort(key=lambda k: (ev[k], int(first[k])))
+    sel.sort(key=lambda k: (int(ev[k]), int(first[k])))      # comparePair on std::pair<int,int>: E-value truncated
     out = []
     for k in sel:
         if len(out) >= min_prefilter_hits and ev[k] > evalue_thresh:

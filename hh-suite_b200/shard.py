@@ -134,10 +134,10 @@ def stage1_merge(cand: np.ndarray, min_hits: int, smax_thresh: int) -> np.ndarra
 def stage2_merge(cand: np.ndarray, ev: np.ndarray, min_hits: int, evalue_thresh: float, evalue_coarse: float,
                  maxnumdb: int) -> np.ndarray:
     """cand: global ids [m]; ev: their E-values (computed with the GLOBAL database size).  Keep ev < coarse
-    (:530), sort ascending by (ev, id) (:545), keep while count < min_hits or ev <= evalue_thresh (:547-558),
+    (:530), sort ascending by ((int)ev, id) (:545; the reference's comparator truncates the E-value to int), keep while count < min_hits or ev <= evalue_thresh (:547-558),
     cap at maxnumdb (:590).  Returns global ids in the reference's output order."""
     keep = np.nonzero(ev < evalue_coarse)[0]
-    order = keep[np.lexsort((cand[keep], ev[keep]))]
+    order = keep[np.lexsort((cand[keep], ev[keep].astype(np.int64)))]   # (int)evalue: comparePair takes pair<int,int>
     # keep while count < min_hits or ev <= evalue_thresh: the first position >= min_hits with ev > thresh ends the list
     tail = np.nonzero(ev[order[min_hits:]] > evalue_thresh)[0]
     ncut = min_hits + int(tail[0]) if len(tail) else len(order)

@@ -435,7 +435,13 @@ class GpuPrefilter {
     std::vector<std::pair<double, int> > hits;
     for (int k = 0; k < nfirst; ++k)
       if (ev[k] < prefilter_evalue_coarse_thresh) hits.push_back(std::make_pair(ev[k], (int)first[k]));
-    std::sort(hits.begin(), hits.end());                                      // ascending (evalue, index), :545
+    // :545 sorts with comparePair, whose arguments are std::pair<int,int>: the E-value of a std::pair<double,int>
+    // is TRUNCATED TO int by the implicit conversion, so the order is ascending ((int)evalue, index)
+    std::sort(hits.begin(), hits.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
+      const int ea = (int)a.first, eb = (int)b.first;
+      if (ea != eb) return ea < eb;
+      return a.second < b.second;
+    });
     size_t keep = 0;
     for (; keep < hits.size(); ++keep)                                         // :547-558
       if (!((int)keep < min_prefilter_hits || hits[keep].first <= prefilter_evalue_thresh)) break;

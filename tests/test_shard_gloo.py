@@ -137,7 +137,7 @@ def test_sharded_prefilter_equals_single_process():
         first.append(k)
     sw = [O.sw_byte(prof, seqs[k], 24, 4, 50) for k in first]
     ev = [float(n) * Lq * len(seqs[k]) * O.fpow2(float(int(-s / 4))) for k, s in zip(first, sw)]
-    sel = sorted([x for x in range(len(first)) if ev[x] < kw["evalue_coarse"]], key=lambda x: (ev[x], first[x]))
+    sel = sorted([x for x in range(len(first)) if ev[x] < kw["evalue_coarse"]], key=lambda x: (int(ev[x]), first[x]))   # the reference sorts with the E-value truncated to int
     want = []
     for x in sel:
         if len(want) >= kw["min_hits"] and ev[x] > kw["evalue_thresh"]:
