@@ -214,7 +214,7 @@ __device__ __forceinline__ float4 ld_jc(const float4* p) { return __ldcg(p); }
 // CELLOFF: cell-off bit input (alternative alignments / excluded regions).
 // ---------------------------------------------------------------------------------------------
 template <int R, bool LOCAL, bool SS, bool CELLOFF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)   // 168 / 255 registers; 4 CTAs (128 registers) spill and lose 8%
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)   // 168 / 255 registers; more resident warps = spills: 9 warps at 224 registers 164 GCUPS, 10 at 200: 122
     k_viterbi(const VitParams P) {
   static_assert(R % 4 == 0, "R must be a multiple of 4");
   extern __shared__ __align__(128) unsigned char smem_raw[];
