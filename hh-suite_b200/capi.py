@@ -41,7 +41,8 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_prefilter_sw", "hhg_prefilter_evalue", "hhg_prefilter_corrected_scores", "hhg_prefilter_evalues",
            "hhg_comm_unique_id", "hhg_comm_create", "hhg_comm_destroy", "hhg_comm_rank", "hhg_comm_world",
            "hhg_plan_topk", "hhg_plan_topk_by_key", "hhg_plan_topk_paths", "hhg_ctx_last_plan",
-           "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order", "hhg_early_stop_sum", "hhg_set_use_ss"]
+           "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order", "hhg_early_stop_sum", "hhg_set_use_ss",
+           "hhg_query_set_batch", "hhg_viterbi_search_batch"]
 
 
 class PrepParams(C.Structure):
@@ -180,6 +181,10 @@ def load():
                                      C.c_float, C.c_float, C.c_double]
     L.hhg_early_stop_sum.restype = C.c_float
     L.hhg_set_use_ss.argtypes = [C.c_void_p, C.c_int]
+    L.hhg_query_set_batch.argtypes = [C.c_void_p, C.c_int, c_i32p, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_f32p,
+                                      C.POINTER(Params)]
+    L.hhg_viterbi_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, c_i32p, C.c_int, c_f32p, C.c_void_p,
+                                           c_u8p, C.c_size_t]
     L.hhg_plan_topk_paths.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, c_u8p]
     L.hhg_ctx_last_plan.argtypes = [C.c_void_p]
     L.hhg_ctx_last_plan.restype = C.c_void_p
@@ -586,6 +591,40 @@ def viterbi_search(ctx: Context, db: TargetDB, ids=None, exclusions=None, want_p
     _ck(ctx.L.hhg_viterbi_search(ctx.h, db.h, n, _p(ids, c_i32p), hits.ctypes.data_as(C.c_void_p),
                                  _p(paths, c_u8p), cap if want_paths else 0, _p(eo, c_i64p), _p(ei, c_i32p),
                                  _p(ej, c_i32p)))
+    return hits, paths
+
+
+def query_set_batch(ctx: Context, queries, S33=None, q_pav=None, local=True, egq=0.0, egt=0.0, shift=-0.03, ssw=0.11,
+                    use_ss=False, corr=0.1, ssm=2):
+    """hhg_query_set_batch: queries = list of (p, tr[, ss]) prepared profiles; q_pav [nq, 20] for raw shards."""
+    nq = len(queries)
+    ps = [np.ascontiguousarray(q[0], np.float32) for q in queries]
+    trs = [np.ascontiguousarray(q[1], np.float32) for q in queries]
+    has_ss = all(len(q) > 2 and q[2] is not None for q in queries)
+    sss = [np.ascontiguousarray(q[2], np.uint8) for q in queries] if has_ss else None
+    Lq = np.array([p.shape[0] - 2 for p in ps], np.int32)
+    pp = (C.c_void_p * nq)(*[p.ctypes.data for p in ps])
+    tp = (C.c_void_p * nq)(*[t.ctypes.data for t in trs])
+    sp = (C.c_void_p * nq)(*[x.ctypes.data for x in sss]) if has_ss else None
+    S33 = None if S33 is None else np.ascontiguousarray(S33, np.float32)
+    qv = None if q_pav is None else np.ascontiguousarray(q_pav, np.float32)
+    par = Params(1 if local else 0, egq, egt, shift, ssw, 1 if use_ss else 0, corr, ssm)
+    _ck(ctx.L.hhg_query_set_batch(ctx.h, nq, _p(Lq, c_i32p), pp, tp, sp, _p(qv, c_f32p), _p(S33, c_f32p), C.byref(par)))
+    ctx.Lq = int(Lq[0])
+    ctx.batch_Lq = Lq
+
+
+def viterbi_search_batch(ctx: Context, db: TargetDB, req_query, ids, columnscore=1, pb=None, want_paths=True):
+    """hhg_viterbi_search_batch: request k aligns query req_query[k] of the current batch with target ids[k]."""
+    rq = np.ascontiguousarray(req_query, np.int32); ids = np.ascontiguousarray(ids, np.int32)
+    n = len(ids)
+    hits = np.zeros(n, HIT_DTYPE)
+    cap = int(np.sum(ctx.batch_Lq[np.clip(rq, 0, len(ctx.batch_Lq) - 1)].astype(np.int64) +
+                     db.Lh[np.clip(ids, 0, db.n - 1)].astype(np.int64) + 2))
+    paths = np.zeros(cap, np.uint8) if want_paths else None
+    pbv = None if pb is None else np.ascontiguousarray(pb, np.float32)
+    _ck(ctx.L.hhg_viterbi_search_batch(ctx.h, db.h, n, _p(rq, c_i32p), _p(ids, c_i32p), columnscore, _p(pbv, c_f32p),
+                                       hits.ctypes.data_as(C.c_void_p), _p(paths, c_u8p), cap if want_paths else 0))
     return hits, paths
 
 

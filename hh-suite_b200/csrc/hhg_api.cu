@@ -91,7 +91,15 @@ struct hhg_ctx {
   int sm_count = 0;
   long long launches = 0;
   // query
-  int Lq = 0, R = 0;     // R: forced strip height (HHG_STRIP_ROWS) or 0 = per plan
+  int Lq = 0, R = 0;     // Lq: length of query 0; R: forced strip height (HHG_STRIP_ROWS) or 0 = per plan
+  // query batch (hhg_query_set = a batch of one): lengths, first row record of each query in qrec, average aa
+  // frequencies (for the fused null model of batch searches over a raw shard)
+  int nq = 0;
+  std::vector<int> q_L, q_row0;
+  std::vector<float> h_q_pav;
+  bool has_q_pav = false;
+  DevBuf<float> d_q_pav, d_pb;
+  unsigned long long query_serial = 0;   // bumped by every hhg_query_set*: plans built for an older batch are rebuilt
   int group_jobs = 16;   // work-item interleave (see k_viterbi): 16 jobs x nstrips items keep the group L2-resident
   uint32_t epoch = 0;    // run counter feeding the boundary-slot tags
   uint32_t epoch_window = 1;   // number of times the 20-bit epoch has wrapped (+1)
@@ -156,7 +164,7 @@ struct hhg_csdb {
 
 struct Wave {
   int job_begin = 0, job_end = 0;
-  int req_begin = 0, req_end = 0;   // requests (in sorted order) covered by the wave
+  long long item_begin = 0, item_end = 0;   // slice of the plan's work-item table (job index relative to job_begin)
 };
 
 struct hhg_plan {
@@ -164,20 +172,31 @@ struct hhg_plan {
   unsigned long long db_serial = 0;
   int device = 0;
   int n = 0;            // requests
-  int Lq = 0, R = 16, nstrips = 0;
+  int Lq = 0, R = 16;   // Lq: length of query 0 (single-query callers)
+  std::vector<int> q_L, q_row0;          // query batch geometry the plan was built for
+  std::vector<int> req_query;            // request -> query index
   int njobs = 0;
+  long long ss_total = 0, co_total = 0;  // per-strip maxima blocks / cell-off words over all jobs
   double cells = 0, padded_cells = 0, alg_bytes = 0;
   std::vector<int> ids;          // request -> target id
   std::vector<int> order;        // sorted position -> request index
   std::vector<int> req_job, req_lane;   // per request
-  std::vector<int> job_Lmax;
+  std::vector<int> job_Lmax, job_query, job_nstrips, job_Lq, job_qrow0;
+  std::vector<long long> job_ss_off;
+  std::vector<int2> items;
   std::vector<long long> job_bt_off, job_bnd_off, job_co_off, job_jc_off, path_off;
   long long jc_total = 0;                 // float4 in the job-interleaved operand stream
   unsigned long long jc_version = 0;      // db->cols_version the stream was built from (0 = never)
+  int nm_mode = -1;                       // >= 0: columnscore of the null model fused into the stream (raw shard)
+  int jc_nm_mode = -2;                    // nm_mode / query batch the stream was built with
+  unsigned long long jc_query_serial = 0;
   std::vector<Wave> waves;
   long long path_total = 0;
   // device
-  DevBuf<int> d_job_target, d_job_Lmax, d_req_job, d_req_lane, d_req_Lt, d_req_target;
+  DevBuf<int> d_job_target, d_job_Lmax, d_req_job, d_req_lane, d_req_Lt, d_req_Lq, d_req_target;
+  DevBuf<int> d_job_query, d_job_nstrips, d_job_Lq, d_job_qrow0;
+  DevBuf<long long> d_job_ss_off;
+  DevBuf<int2> d_items;
   DevBuf<float> d_S;
   DevBuf<long long> d_job_bt_off, d_job_bnd_off, d_job_co_off, d_job_jc_off, d_path_off;
   DevBuf<float4> d_jcols;
@@ -644,31 +663,65 @@ int hhg_db_lengths(const hhg_db* db, int32_t* out) {
 }
 
 // --------------------------------------------------------------------------------------- query
-int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const uint8_t* ss,
-                  const float* S33, const hhg_params* par) {
-  if (!ctx || Lq < 1 || Lq > 32767 || !p || !tr || !par) return fail(HHG_EINVAL, "hhg_query_set: bad argument");
-  if (par->use_ss && (!ss || !S33)) return fail(HHG_EINVAL, "hhg_query_set: use_ss needs ss and S33");
+static int query_set_impl(hhg_ctx* ctx, int nq, const int32_t* Lq, const float* const* p, const float* const* tr,
+                          const uint8_t* const* ss, const float* q_pav, const float* S33, const hhg_params* par) {
+  if (!ctx || nq < 1 || !Lq || !p || !tr || !par) return fail(HHG_EINVAL, "hhg_query_set: bad argument");
+  bool all_ss = ss != nullptr;
+  for (int q = 0; q < nq; ++q) {
+    if (Lq[q] < 1 || Lq[q] > 32767 || !p[q] || !tr[q]) return fail(HHG_EINVAL, "hhg_query_set: bad query %d", q);
+    if (ss && !ss[q]) all_ss = false;
+  }
+  if (par->use_ss && (!all_ss || !S33)) return fail(HHG_EINVAL, "hhg_query_set: use_ss needs ss and S33");
   CK(cudaSetDevice(ctx->device));
   ctx->par = *par;
-  ctx->Lq = Lq;
-  const int rows = (Lq + 47) / 48 * 48;   // zero padded to a multiple of every strip height (8, 12, 16)
+  ctx->nq = nq;
+  ctx->q_L.assign(Lq, Lq + nq);
+  ctx->q_row0.resize(nq);
+  long long rows = 0;
+  for (int q = 0; q < nq; ++q) {
+    ctx->q_row0[q] = (int)rows;
+    rows += (Lq[q] + 47) / 48 * 48;     // each query zero padded to a multiple of every strip height (8, 12, 16)
+  }
+  if (rows > 0x7fffffffLL / 7) return fail(HHG_EINVAL, "hhg_query_set: query batch too large");
+  ctx->Lq = Lq[0];
   CK(ctx->qrec.ensure((size_t)rows * 7));
   CK(cudaMemsetAsync(ctx->qrec.p, 0, (size_t)rows * 112, ctx->stream));
-  // pack with the same kernel as the DB (a one-profile shard)
-  std::vector<long long> col_off(1, 0);
-  const int32_t L1 = Lq;
-  const int64_t zero = 0;
-  int rc = pack_profiles(ctx, 1, &L1, &zero, &zero, &zero, p, tr, ss, col_off, Lq, ctx->qrec.p);
-  if (rc != HHG_OK) return rc;
-  ctx->has_ss = ss != nullptr;
+  // pack with the same kernel as the DB (one-profile shards)
+  for (int q = 0; q < nq; ++q) {
+    std::vector<long long> col_off(1, 0);
+    const int32_t L1 = Lq[q];
+    const int64_t zero = 0;
+    int rc = pack_profiles(ctx, 1, &L1, &zero, &zero, &zero, p[q], tr[q], ss ? ss[q] : nullptr, col_off, L1,
+                           ctx->qrec.p + (size_t)ctx->q_row0[q] * 7);
+    if (rc != HHG_OK) return rc;
+  }
+  ctx->has_ss = all_ss;
   ctx->has_S33 = false;
   if (S33) {
     CK(ctx->S33.ensure(44 * 44));
     CK(cudaMemcpyAsync(ctx->S33.p, S33, 44 * 44 * 4, cudaMemcpyHostToDevice, ctx->stream));
     ctx->has_S33 = true;
   }
+  ctx->has_q_pav = q_pav != nullptr;
+  if (q_pav) {
+    ctx->h_q_pav.assign(q_pav, q_pav + (size_t)nq * 20);
+    CK(ctx->d_q_pav.ensure((size_t)nq * 20));
+    CK(cudaMemcpyAsync(ctx->d_q_pav.p, q_pav, (size_t)nq * 80, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->query_serial++;
   CK(cudaStreamSynchronize(ctx->stream));
   return HHG_OK;
+}
+
+int hhg_query_set(hhg_ctx* ctx, int Lq, const float* p, const float* tr, const uint8_t* ss,
+                  const float* S33, const hhg_params* par) {
+  const int32_t L1 = Lq;
+  return query_set_impl(ctx, 1, &L1, &p, &tr, ss ? &ss : nullptr, nullptr, S33, par);
+}
+
+int hhg_query_set_batch(hhg_ctx* ctx, int nq, const int32_t* Lq, const float* const* p, const float* const* tr,
+                        const uint8_t* const* ss, const float* q_pav, const float* S33, const hhg_params* par) {
+  return query_set_impl(ctx, nq, Lq, p, tr, ss, q_pav, S33, par);
 }
 
 // Switch the PRED_PRED secondary-structure term on/off for the following searches without re-sending the query
@@ -685,26 +738,40 @@ int hhg_set_use_ss(hhg_ctx* ctx, int use_ss) {
 // 253 GCUPS).  A small request (the few thousand survivors of the prefilter) is latency bound: its longest job is one
 // serial sweep over Lmax columns per strip, so halving the strip height halves that critical path and doubles the
 // number of work items that can run side by side.
-static int plan_strip_rows(const hhg_ctx* ctx, int n) {
+static int plan_strip_rows(const hhg_ctx* ctx, const int32_t* req_query, int n) {
   if (ctx->R) return ctx->R;
-  const long long items16 = (long long)((n + 31) / 32) * ((ctx->Lq + 15) / 16);
+  long long items16 = 0;
+  if (!req_query) items16 = (long long)((n + 31) / 32) * ((ctx->q_L[0] + 15) / 16);
+  else {
+    std::vector<long long> cnt(ctx->nq, 0);
+    for (int k = 0; k < n; ++k) if (req_query[k] >= 0 && req_query[k] < ctx->nq) cnt[req_query[k]]++;
+    for (int q = 0; q < ctx->nq; ++q) items16 += (cnt[q] + 31) / 32 * ((ctx->q_L[q] + 15) / 16);
+  }
   return items16 >= 4LL * ctx->sm_count * 8 ? 16 : 8;
 }
 
 // (Re)build a plan in place; device buffers only ever grow, so a plan object that is reused across
 // searches (hhg_viterbi_search keeps one per context) does not touch cudaMalloc in steady state.
-static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const int32_t* ids) {
+// req_query[k] = index (into the context's query batch) of the query request k is aligned with; NULL = query 0.
+// Jobs never mix queries: the requests of each query are length-sorted and cut into 32-target jobs separately.
+static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const int32_t* ids,
+                      const int32_t* req_query = nullptr) {
   if (!ctx || !db || n <= 0) return fail(HHG_EINVAL, "hhg_plan_create: bad argument");
-  if (ctx->Lq <= 0) return fail(HHG_EINVAL, "hhg_plan_create: no query set");
+  if (ctx->nq <= 0) return fail(HHG_EINVAL, "hhg_plan_create: no query set");
   if (db->device != ctx->device) return fail(HHG_EINVAL, "db lives on device %d, ctx on %d", db->device, ctx->device);
   CK(cudaSetDevice(ctx->device));
-  // the common case of a repeated request (same shard, same target list, same query geometry, e.g. every
-  // query of a batch against the whole shard) reuses the plan: no host sort, no uploads
-  if (pl->db == db && pl->db_serial == db->serial && pl->n == n && pl->Lq == ctx->Lq && pl->R == plan_strip_rows(ctx, n) &&
-      !pl->ids.empty() && pl->max_bt_bytes == ctx->max_bt_bytes) {
+  const int R = plan_strip_rows(ctx, req_query, n);
+  // the common case of a repeated request (same shard, same target list, same query batch geometry, e.g. every
+  // query of a series against the whole shard) reuses the plan: no host sort, no uploads
+  if (pl->db == db && pl->db_serial == db->serial && pl->n == n && pl->R == R && pl->q_L == ctx->q_L &&
+      pl->q_row0 == ctx->q_row0 && !pl->ids.empty() && pl->max_bt_bytes == ctx->max_bt_bytes) {
     bool same = true;
     if (ids) same = memcmp(ids, pl->ids.data(), (size_t)n * 4) == 0;
     else for (int k = 0; k < n && same; ++k) same = pl->ids[k] == k;
+    if (same) {
+      if (req_query) same = memcmp(req_query, pl->req_query.data(), (size_t)n * 4) == 0;
+      else for (int k = 0; k < n && same; ++k) same = pl->req_query[k] == 0;
+    }
     if (same) { pl->celloff = false; return HHG_OK; }
   }
   pl->db = db;
@@ -715,46 +782,64 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   pl->waves.clear();
   pl->celloff = false;
   pl->n = n;
-  pl->Lq = ctx->Lq; pl->R = plan_strip_rows(ctx, n); pl->nstrips = (pl->Lq + pl->R - 1) / pl->R;
-  pl->ids.resize(n);
+  pl->R = R;
+  pl->q_L = ctx->q_L; pl->q_row0 = ctx->q_row0;
+  pl->Lq = ctx->q_L[0];
+  pl->ids.resize(n); pl->req_query.resize(n);
   for (int k = 0; k < n; ++k) {
     const int id = ids ? ids[k] : k;
     if (id < 0 || id >= db->n) return fail(HHG_EINVAL, "request %d: target id %d out of range", k, id);
-    pl->ids[k] = id;
+    const int q = req_query ? req_query[k] : 0;
+    if (q < 0 || q >= ctx->nq) return fail(HHG_EINVAL, "request %d: query index %d out of range (batch of %d)", k, q, ctx->nq);
+    pl->ids[k] = id; pl->req_query[k] = q;
   }
-  // sort requests by target length, longest first (as ViterbiRunner does per chunk,
+  // sort requests by (query, target length descending) (the length sort is what ViterbiRunner does per chunk,
   // src/hhviterbirunner.cpp:117-119; here it also makes LPT scheduling of the work queue)
   pl->order.resize(n);
   std::iota(pl->order.begin(), pl->order.end(), 0);
-  std::stable_sort(pl->order.begin(), pl->order.end(),
-                   [&](int a, int b) { return db->L[pl->ids[a]] > db->L[pl->ids[b]]; });
-  pl->njobs = (n + 31) / 32;
+  std::stable_sort(pl->order.begin(), pl->order.end(), [&](int a, int b) {
+    if (pl->req_query[a] != pl->req_query[b]) return pl->req_query[a] < pl->req_query[b];
+    return db->L[pl->ids[a]] > db->L[pl->ids[b]];
+  });
+  // jobs: runs of up to 32 consecutive sorted requests of the same query
+  std::vector<int> job_first, job_cnt;
+  for (int k = 0; k < n;) {
+    const int q = pl->req_query[pl->order[k]];
+    int e = k;
+    while (e < n && e - k < 32 && pl->req_query[pl->order[e]] == q) ++e;
+    job_first.push_back(k); job_cnt.push_back(e - k);
+    k = e;
+  }
+  pl->njobs = (int)job_first.size();
   pl->req_job.resize(n); pl->req_lane.resize(n);
-  pl->job_Lmax.resize(pl->njobs);
+  pl->job_Lmax.resize(pl->njobs); pl->job_query.resize(pl->njobs); pl->job_nstrips.resize(pl->njobs);
+  pl->job_Lq.resize(pl->njobs); pl->job_qrow0.resize(pl->njobs); pl->job_ss_off.resize(pl->njobs);
   pl->job_bt_off.resize(pl->njobs); pl->job_bnd_off.resize(pl->njobs); pl->job_co_off.resize(pl->njobs);
   pl->job_jc_off.resize(pl->njobs);
   pl->jc_version = 0;
   std::vector<int> job_target((size_t)pl->njobs * 32);
-  std::vector<int> req_Lt(n);
-  const int rowgroups = pl->nstrips * pl->R / 4;
-  long long bnd = 0, co = 0, jc = 0;
-  size_t wave_bt = 0;   // words in the current wave
+  std::vector<int> req_Lt(n), req_Lq(n);
+  long long bnd = 0, co = 0, jc = 0, ss = 0;
+  size_t wave_bt = 0, max_wave_words = 0;   // words in the current wave
   Wave w;
   for (int jb = 0; jb < pl->njobs; ++jb) {
-    const int first = jb * 32;
-    const int cnt = std::min(32, n - first);
-    int Lmax = db->L[pl->ids[pl->order[first]]];
-    pl->job_Lmax[jb] = Lmax;
+    const int first = job_first[jb], cnt = job_cnt[jb];
+    const int q = pl->req_query[pl->order[first]];
+    const int Lmax = db->L[pl->ids[pl->order[first]]];
+    const int ns = (ctx->q_L[q] + R - 1) / R;
+    pl->job_Lmax[jb] = Lmax; pl->job_query[jb] = q; pl->job_nstrips[jb] = ns;
+    pl->job_Lq[jb] = ctx->q_L[q]; pl->job_qrow0[jb] = ctx->q_row0[q];
     for (int l = 0; l < 32; ++l) {
       const int rq = pl->order[first + std::min(l, cnt - 1)];   // padded lanes repeat the last target
       job_target[(size_t)jb * 32 + l] = pl->ids[rq];
       if (l < cnt) { pl->req_job[rq] = jb; pl->req_lane[rq] = l; }
     }
-    const size_t words = (size_t)rowgroups * (Lmax + 1) * 32;
+    const size_t words = (size_t)(ns * R / 4) * (Lmax + 1) * 32;
     if (wave_bt > 0 && (wave_bt + words) * 4 > ctx->max_bt_bytes) {
-      w.job_end = jb; w.req_end = first;
+      w.job_end = jb;
       pl->waves.push_back(w);
-      w.job_begin = jb; w.req_begin = first;
+      max_wave_words = std::max(max_wave_words, wave_bt);
+      w.job_begin = jb;
       wave_bt = 0;
     }
     pl->job_bt_off[jb] = (long long)wave_bt;
@@ -763,27 +848,42 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
     bnd += (long long)(Lmax + 1) * 32;
     pl->job_co_off[jb] = co;
     pl->job_jc_off[jb] = jc;
+    pl->job_ss_off[jb] = ss;
     jc += (long long)Lmax * 224;
-    co += (long long)pl->nstrips * (Lmax + 1) * 32;
-    pl->padded_cells += (double)pl->nstrips * pl->R * (double)Lmax * 32.0;
+    co += (long long)ns * (Lmax + 1) * 32;
+    ss += ns;
+    pl->padded_cells += (double)ns * R * (double)Lmax * 32.0;
   }
-  w.job_end = pl->njobs; w.req_end = n;
+  w.job_end = pl->njobs;
   pl->waves.push_back(w);
-  size_t max_wave_words = 0;
-  for (const Wave& wv : pl->waves) {
-    size_t words = 0;
-    for (int jb = wv.job_begin; jb < wv.job_end; ++jb) words += (size_t)rowgroups * (pl->job_Lmax[jb] + 1) * 32;
-    max_wave_words = std::max(max_wave_words, words);
+  max_wave_words = std::max(max_wave_words, wave_bt);
+  pl->ss_total = ss;
+  pl->co_total = co;
+  // work items (job, strip) of every wave in dispatch order: groups of G consecutive jobs, strip-major inside a group
+  // (strip s of all the group's jobs, then strip s+1, ...), so consecutive strips of a job are G items apart
+  pl->items.clear();
+  for (Wave& wv : pl->waves) {
+    wv.item_begin = (long long)pl->items.size();
+    for (int g0 = wv.job_begin; g0 < wv.job_end; g0 += ctx->group_jobs) {
+      const int g1 = std::min(g0 + ctx->group_jobs, wv.job_end);
+      int maxns = 0;
+      for (int jb = g0; jb < g1; ++jb) maxns = std::max(maxns, pl->job_nstrips[jb]);
+      for (int sidx = 0; sidx < maxns; ++sidx)
+        for (int jb = g0; jb < g1; ++jb)
+          if (sidx < pl->job_nstrips[jb]) pl->items.push_back(make_int2(jb - wv.job_begin, sidx));
+    }
+    wv.item_end = (long long)pl->items.size();
   }
   pl->path_off.resize(n);
   long long po = 0;
   double cols_sum = 0;
   for (int k = 0; k < n; ++k) {
     const int Lt = db->L[pl->ids[k]];
-    req_Lt[k] = Lt;
+    const int Lqk = ctx->q_L[pl->req_query[k]];
+    req_Lt[k] = Lt; req_Lq[k] = Lqk;
     pl->path_off[k] = po;
-    po += pl->Lq + Lt + 2;
-    pl->cells += (double)pl->Lq * Lt;
+    po += Lqk + Lt + 2;
+    pl->cells += (double)Lqk * Lt;
     cols_sum += Lt;
   }
   if (po > 0x7fffffffLL) return fail(HHG_EINVAL, "plan too large: %lld path bytes (> 2^31-1); split the request", po);
@@ -796,31 +896,42 @@ static int plan_build(hhg_ctx* ctx, hhg_plan* pl, const hhg_db* db, int n, const
   A(pl->d_job_target.ensure(job_target.size())); A(pl->d_job_Lmax.ensure(pl->njobs));
   A(pl->d_job_bt_off.ensure(pl->njobs)); A(pl->d_job_bnd_off.ensure(pl->njobs)); A(pl->d_job_co_off.ensure(pl->njobs));
   A(pl->d_job_jc_off.ensure(pl->njobs)); A(pl->d_jcols.ensure((size_t)jc));
-  A(pl->d_req_job.ensure(n)); A(pl->d_req_lane.ensure(n)); A(pl->d_req_Lt.ensure(n)); A(pl->d_path_off.ensure(n));
+  A(pl->d_job_query.ensure(pl->njobs)); A(pl->d_job_nstrips.ensure(pl->njobs)); A(pl->d_job_Lq.ensure(pl->njobs));
+  A(pl->d_job_qrow0.ensure(pl->njobs)); A(pl->d_job_ss_off.ensure(pl->njobs)); A(pl->d_items.ensure(pl->items.size()));
+  A(pl->d_req_job.ensure(n)); A(pl->d_req_lane.ensure(n)); A(pl->d_req_Lt.ensure(n)); A(pl->d_req_Lq.ensure(n));
+  A(pl->d_path_off.ensure(n));
   A(pl->d_req_target.ensure(n)); A(pl->d_S.ensure((size_t)po));
   A(pl->d_bt.ensure(max_wave_words));
   { BndSlot* before = pl->d_bnd.p; A(pl->d_bnd.ensure((size_t)bnd));
     // fresh slots must not carry a bit pattern that looks like a valid tag (epochs start at 1)
     if (e == cudaSuccess && pl->d_bnd.p != before) A(cudaMemsetAsync(pl->d_bnd.p, 0, pl->d_bnd.n * sizeof(BndSlot), ctx->stream)); }
-  A(pl->d_strip_score.ensure((size_t)pl->njobs * pl->nstrips * 32));
-  A(pl->d_strip_ij.ensure((size_t)pl->njobs * pl->nstrips * 32));
+  A(pl->d_strip_score.ensure((size_t)ss * 32));
+  A(pl->d_strip_ij.ensure((size_t)ss * 32));
   A(pl->d_counter.ensure(pl->waves.size()));
   A(pl->d_hits.ensure(n));
   A(pl->d_paths.ensure((size_t)po));
   if (e != cudaSuccess) return fail(HHG_ENOMEM, "hhg_plan_create: %s", cudaGetErrorString(e));
 
   cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(pl->d_job_target.p, job_target.data(), job_target.size() * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_job_Lmax.p, pl->job_Lmax.data(), (size_t)pl->njobs * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_job_bt_off.p, pl->job_bt_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_job_bnd_off.p, pl->job_bnd_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_job_co_off.p, pl->job_co_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_job_jc_off.p, pl->job_jc_off.data(), (size_t)pl->njobs * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_req_job.p, pl->req_job.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_req_lane.p, pl->req_lane.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_req_Lt.p, req_Lt.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_req_target.p, pl->ids.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(pl->d_path_off.p, pl->path_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  auto H2D = [&](void* d, const void* h, size_t bytes) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st); };
+  CK(H2D(pl->d_job_target.p, job_target.data(), job_target.size() * 4));
+  CK(H2D(pl->d_job_Lmax.p, pl->job_Lmax.data(), (size_t)pl->njobs * 4));
+  CK(H2D(pl->d_job_bt_off.p, pl->job_bt_off.data(), (size_t)pl->njobs * 8));
+  CK(H2D(pl->d_job_bnd_off.p, pl->job_bnd_off.data(), (size_t)pl->njobs * 8));
+  CK(H2D(pl->d_job_co_off.p, pl->job_co_off.data(), (size_t)pl->njobs * 8));
+  CK(H2D(pl->d_job_jc_off.p, pl->job_jc_off.data(), (size_t)pl->njobs * 8));
+  CK(H2D(pl->d_job_query.p, pl->job_query.data(), (size_t)pl->njobs * 4));
+  CK(H2D(pl->d_job_nstrips.p, pl->job_nstrips.data(), (size_t)pl->njobs * 4));
+  CK(H2D(pl->d_job_Lq.p, pl->job_Lq.data(), (size_t)pl->njobs * 4));
+  CK(H2D(pl->d_job_qrow0.p, pl->job_qrow0.data(), (size_t)pl->njobs * 4));
+  CK(H2D(pl->d_job_ss_off.p, pl->job_ss_off.data(), (size_t)pl->njobs * 8));
+  CK(H2D(pl->d_items.p, pl->items.data(), pl->items.size() * sizeof(int2)));
+  CK(H2D(pl->d_req_job.p, pl->req_job.data(), (size_t)n * 4));
+  CK(H2D(pl->d_req_lane.p, pl->req_lane.data(), (size_t)n * 4));
+  CK(H2D(pl->d_req_Lt.p, req_Lt.data(), (size_t)n * 4));
+  CK(H2D(pl->d_req_Lq.p, req_Lq.data(), (size_t)n * 4));
+  CK(H2D(pl->d_req_target.p, pl->ids.data(), (size_t)n * 4));
+  CK(H2D(pl->d_path_off.p, pl->path_off.data(), (size_t)n * 8));
   CK(cudaStreamSynchronize(st));
   return HHG_OK;
 }
@@ -857,14 +968,14 @@ static int set_exclusions(hhg_ctx* ctx, hhg_plan* pl, const int64_t* excl_off, c
     if (excl_off[k + 1] < excl_off[k]) return fail(HHG_EINVAL, "excl_off is not monotonic at request %d", k);
     const int Lt = pl->db->L[pl->ids[k]];
     for (long long s = excl_off[k]; s < excl_off[k + 1]; ++s) {
-      if (excl_i[s] < 1 || excl_i[s] > pl->Lq || excl_j[s] < 1 || excl_j[s] > Lt)
+      const int Lqk = pl->q_L[pl->req_query[k]];
+      if (excl_i[s] < 1 || excl_i[s] > Lqk || excl_j[s] < 1 || excl_j[s] > Lt)
         return fail(HHG_EINVAL, "excluded step %lld of request %d is (%d,%d), outside 1..%d x 1..%d", s - excl_off[k], k,
-                    excl_i[s], excl_j[s], pl->Lq, Lt);
+                    excl_i[s], excl_j[s], Lqk, Lt);
       sreq[(size_t)s] = k;
     }
   }
-  size_t co_words = 0;
-  for (int jb = 0; jb < pl->njobs; ++jb) co_words += (size_t)pl->nstrips * (pl->job_Lmax[jb] + 1) * 32;
+  const size_t co_words = (size_t)pl->co_total;
   CK(pl->d_co.ensure(co_words));
   CK(pl->d_step_req.ensure((size_t)total)); CK(pl->d_step_i.ensure((size_t)total)); CK(pl->d_step_j.ensure((size_t)total));
   CK(cudaMemcpyAsync(pl->d_step_req.p, sreq.data(), (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -874,7 +985,7 @@ static int set_exclusions(hhg_ctx* ctx, hhg_plan* pl, const int64_t* excl_off, c
   const int threads = 128;
   k_celloff_raster<<<(unsigned)((total + threads - 1) / threads), threads, 0, ctx->stream>>>(
       (int)total, pl->d_step_req.p, pl->d_step_i.p, pl->d_step_j.p, pl->d_req_job.p, pl->d_req_lane.p,
-      pl->d_req_Lt.p, pl->d_job_Lmax.p, pl->d_job_co_off.p, pl->Lq, pl->R, pl->d_co.p);
+      pl->d_req_Lt.p, pl->d_req_Lq.p, pl->d_job_Lmax.p, pl->d_job_co_off.p, pl->R, pl->d_co.p);
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));   // sreq is a host temporary
@@ -913,9 +1024,11 @@ extern "C" {
 
 static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
   if (!ctx || !pl) return fail(HHG_EINVAL, "hhg_plan_run: bad argument");
-  if (pl->Lq != ctx->Lq) return fail(HHG_EINVAL, "plan was made for another query length");
+  if (pl->q_L != ctx->q_L || pl->q_row0 != ctx->q_row0) return fail(HHG_EINVAL, "plan was made for another query (batch) geometry");
   const hhg_db* db = pl->db;
-  if (!db->prepared) return fail(HHG_EINVAL, "raw db: call hhg_db_apply_null_model for the current query first");
+  const bool fused = pl->nm_mode >= 0;     // null model factored in per job while the operand stream is built
+  if (fused && (!db->raw || !ctx->has_q_pav)) return fail(HHG_EINVAL, "fused null model needs a raw shard and query pav");
+  if (!fused && !db->prepared) return fail(HHG_EINVAL, "raw db: call hhg_db_apply_null_model for the current query first");
   if (ctx->par.use_ss && (!db->has_ss || !ctx->has_ss || !ctx->has_S33))
     return fail(HHG_EINVAL, "use_ss requested but query/db/S33 carry no ss information");
   CK(cudaSetDevice(ctx->device));
@@ -930,23 +1043,30 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
     pl->bnd_epoch_window = ctx->epoch_window;
   }
   CK(cudaMemsetAsync(pl->d_counter.p, 0, pl->waves.size() * 4, st));
-  if (pl->jc_version != db->cols_version) {
-    // (re)build the job-interleaved operand stream: once per plan, and again after every
-    // hhg_db_apply_null_model (the prepared emissions changed)
+  if (pl->jc_version != db->cols_version || pl->jc_nm_mode != pl->nm_mode ||
+      (fused && pl->jc_query_serial != ctx->query_serial)) {
+    // (re)build the job-interleaved operand stream: once per plan, again after every hhg_db_apply_null_model (the
+    // prepared emissions changed) and, with the fused null model, for every new query batch
     int maxL = 0;
     for (int jb = 0; jb < pl->njobs; ++jb) maxL = std::max(maxL, pl->job_Lmax[jb]);
     dim3 grid((unsigned)pl->njobs, (unsigned)std::min(64, (maxL + 7) / 8), 1);
     k_interleave_cols<<<grid, 256, 0, st>>>(pl->njobs, pl->d_job_target.p, pl->d_job_Lmax.p, pl->d_job_jc_off.p,
-                                            db->cols.p, db->dcol_off.p, db->dL.p, pl->d_jcols.p);
+                                            fused ? db->cols_raw.p : db->cols.p, db->dcol_off.p, db->dL.p, pl->d_jcols.p,
+                                            pl->nm_mode, pl->d_job_query.p, ctx->d_q_pav.p, db->pav.p, ctx->d_pb.p);
     ctx->launches++;
     CK(cudaGetLastError());
     pl->jc_version = db->cols_version;
+    pl->jc_nm_mode = pl->nm_mode;
+    pl->jc_query_serial = ctx->query_serial;
   }
   for (size_t wi = 0; wi < pl->waves.size(); ++wi) {
     const Wave& w = pl->waves[wi];
     const int nj = w.job_end - w.job_begin;
     VitParams P{};
-    P.qrec = ctx->qrec.p; P.Lq = pl->Lq; P.nstrips = pl->nstrips;
+    P.qrec = ctx->qrec.p;
+    P.job_Lq = pl->d_job_Lq.p + w.job_begin; P.job_nstrips = pl->d_job_nstrips.p + w.job_begin;
+    P.job_qrow0 = pl->d_job_qrow0.p + w.job_begin; P.job_ss_off = pl->d_job_ss_off.p + w.job_begin;
+    P.items = pl->d_items.p + w.item_begin; P.n_items = (int)(w.item_end - w.item_begin);
     P.Lt = db->dL.p;
     P.jcols = pl->d_jcols.p;
     P.job_jc_off = pl->d_job_jc_off.p + w.job_begin;
@@ -959,16 +1079,15 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
     P.bt = pl->d_bt.p; P.bnd = pl->d_bnd.p;
     P.tag_base = ctx->epoch << 12;
     P.counter = pl->d_counter.p + wi;
-    P.strip_score = pl->d_strip_score.p + (size_t)w.job_begin * pl->nstrips * 32;
-    P.strip_ij = pl->d_strip_ij.p + (size_t)w.job_begin * pl->nstrips * 32;
+    P.strip_score = pl->d_strip_score.p;     // job_ss_off is absolute
+    P.strip_ij = pl->d_strip_ij.p;
     P.celloff = pl->celloff ? pl->d_co.p : nullptr;
     P.S33 = ctx->has_S33 ? ctx->S33.p : nullptr;
     P.egq = ctx->par.egq; P.egt = ctx->par.egt; P.shift = ctx->par.shift; P.ssw = ctx->par.ssw;
     P.one2 = 0x3F8000003F800000ull;
-    P.group_jobs = ctx->group_jobs;
     P.zero = 0u;
 
-    const int items = nj * pl->nstrips;
+    const int items = P.n_items;
     int rc;
     if (timed) CK(cudaEventRecord(ctx->ev[0], st));
     if (pl->R == 8) rc = launch_viterbi<8>(ctx, P, ctx->par.local != 0, ctx->par.use_ss != 0, pl->celloff, items);
@@ -980,13 +1099,15 @@ static int plan_run_impl(hhg_ctx* ctx, hhg_plan* pl, bool timed) {
     // wave covers sorted positions [req_begin, req_end); req_job/req_lane are per original request.
     BtParams B{};
     B.n_req = pl->n;   // filtered by job range inside: simpler to launch per wave over all requests
-    B.nstrips = pl->nstrips;
+    B.job_nstrips = pl->d_job_nstrips.p; B.job_ss_off = pl->d_job_ss_off.p; B.job_qrow0 = pl->d_job_qrow0.p;
+    B.nm_mode = pl->nm_mode; B.job_query = pl->d_job_query.p; B.q_pav = ctx->d_q_pav.p; B.t_pav = db->pav.p;
+    B.pb = ctx->d_pb.p;
     B.req_job = pl->d_req_job.p; B.req_lane = pl->d_req_lane.p;
     B.job_Lmax = pl->d_job_Lmax.p; B.job_bt_off = pl->d_job_bt_off.p;
     B.bt = pl->d_bt.p; B.strip_score = pl->d_strip_score.p; B.strip_ij = pl->d_strip_ij.p;
     B.path_off = pl->d_path_off.p; B.hits = pl->d_hits.p; B.paths = pl->d_paths.p;
     B.job_begin = w.job_begin; B.job_end = w.job_end;
-    B.req_target = pl->d_req_target.p; B.qrec = ctx->qrec.p; B.cols = db->cols.p; B.col_off = db->dcol_off.p;
+    B.req_target = pl->d_req_target.p; B.qrec = ctx->qrec.p; B.cols = fused ? db->cols_raw.p : db->cols.p; B.col_off = db->dcol_off.p;
     B.lg2 = ctx->lg2.p; B.diff = ctx->diff.p; B.S33 = ctx->has_S33 ? ctx->S33.p : nullptr; B.S = pl->d_S.p;
     B.corr = ctx->par.corr; B.ssw = ctx->par.ssw; B.use_ss = ctx->par.use_ss; B.ss_score_mode = (ctx->par.ssm == 2);
     const int threads = 128;
@@ -1059,11 +1180,12 @@ int hhg_plan_debug_bt(hhg_ctx* ctx, hhg_plan* pl, int k, uint8_t* bt) {
   CK(cudaSetDevice(ctx->device));
   const int job = pl->req_job[k], lane = pl->req_lane[k];
   const int Lt = pl->db->L[pl->ids[k]];
-  const int total = (pl->Lq + 1) * (Lt + 1);
+  const int Lqk = pl->q_L[pl->req_query[k]];
+  const int total = (Lqk + 1) * (Lt + 1);
   DevBuf<uint8_t> tmp;
   CK(tmp.alloc(total));
   k_debug_bt<<<(total + 255) / 256, 256, 0, ctx->stream>>>(pl->d_bt.p, pl->job_bt_off[job], lane,
-                                                            pl->job_Lmax[job], pl->Lq, Lt, tmp.p);
+                                                            pl->job_Lmax[job], Lqk, Lt, tmp.p);
   ctx->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(bt, tmp.p, total, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1082,6 +1204,7 @@ int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids
   auto t0 = now();
   int rc = plan_build(ctx, pl, db, n, ids);
   if (rc != HHG_OK) return rc;
+  pl->nm_mode = -1;
   auto t1 = now();
   rc = set_exclusions(ctx, pl, excl_off, excl_i, excl_j);
   if (rc == HHG_OK) rc = hhg_plan_run(ctx, pl);
@@ -1092,6 +1215,34 @@ int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids
     auto ms = [](decltype(t0) a, decltype(t0) b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     fprintf(stderr, "[hhg] viterbi_search n=%d: plan %.3f ms, run (device) %.3f ms, fetch %.3f ms\n", n, ms(t0, t1), ms(t1, t2), ms(t2, now()));
   }
+  return rc;
+}
+
+
+// Query-batch search: nq queries set by hhg_query_set_batch, request k aligns query req_query[k] with
+// target ids[k]; ONE plan, one forward launch per memory wave with the work items of all queries in it.
+int hhg_viterbi_search_batch(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* req_query, const int32_t* ids,
+                             int columnscore, const float* pb, hhg_hit* hits, uint8_t* paths, size_t paths_cap) {
+  if (!ctx || !db || !req_query || !ids) return fail(HHG_EINVAL, "hhg_viterbi_search_batch: bad argument");
+  if (!ctx->scratch_plan) ctx->scratch_plan = new hhg_plan();
+  hhg_plan* pl = ctx->scratch_plan;
+  int rc = plan_build(ctx, pl, db, n, ids, req_query);
+  if (rc != HHG_OK) return rc;
+  pl->nm_mode = -1;
+  if (db->raw) {
+    // every query needs its own null model: factor it in while the plan's operand stream is built
+    if (columnscore < 0 || columnscore > 3) return fail(HHG_EINVAL, "hhg_viterbi_search_batch: columnscore %d", columnscore);
+    if (!ctx->has_q_pav) return fail(HHG_EINVAL, "hhg_viterbi_search_batch: raw shard needs q_pav in hhg_query_set_batch");
+    if (columnscore == 0 && !pb) return fail(HHG_EINVAL, "hhg_viterbi_search_batch: columnscore 0 needs pb");
+    float h[20] = {0};
+    if (pb) memcpy(h, pb, 80);
+    CK(ctx->d_pb.ensure(20));
+    CK(cudaMemcpyAsync(ctx->d_pb.p, h, 80, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    pl->nm_mode = columnscore;
+  }
+  rc = hhg_plan_run(ctx, pl);
+  if (rc == HHG_OK) rc = hhg_plan_fetch(ctx, pl, hits, paths, paths_cap);
   return rc;
 }
 

@@ -83,10 +83,14 @@ __device__ __forceinline__ bool slot_ok(uint32_t tag, uint32_t pad0, uint32_t pa
 }
 
 struct VitParams {
-  // query
-  const float4* qrec;        // [nstrips*R] records (rows 1..), zero padded
-  int Lq;
-  int nstrips;
+  // queries: a plan may hold several (query-batch mode, hhblits_omp semantics); every job belongs to one of them
+  const float4* qrec;        // query row records (rows 1..Lq of every query, each block zero padded to a multiple of 48)
+  const int* job_Lq;         // [njobs] length of the job's query
+  const int* job_nstrips;    // [njobs] ceil(Lq / R)
+  const int* job_qrow0;      // [njobs] first row record of the job's query in qrec
+  const long long* job_ss_off;   // [njobs] offset (in 32-lane blocks) of the job's per-strip maxima
+  const int2* items;         // [n_items] work items (job, strip) in dispatch order (see plan_build)
+  int n_items;
   // database shard
   const int* Lt;             // [n_targets]
   // plan: the job-interleaved operand stream, [job][column 1..Lmax][k 0..6][lane] float4 (lanes shorter than
@@ -111,7 +115,6 @@ struct VitParams {
   // scoring
   float egq, egt, shift, ssw;
   unsigned long long one2;   // bit pattern of (1.0f, 1.0f); see add2()
-  int group_jobs;            // work-item interleave: jobs per group
   uint32_t zero;             // always 0, opaque to the compiler (register-liveness anchor)
 };
 
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)   // 168
   __syncthreads();
 
   const float smin = LOCAL ? 0.0f : HHG_NEG;
-  const int total_items = P.njobs * P.nstrips;
+  const int total_items = P.n_items;
   uint32_t parity = 0;
 
   for (;;) {
@@ -243,20 +246,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)   // 168
     if (lane == 0) item = (int)atomicAdd(P.counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= total_items) break;
-    // items are ordered group by group; inside a group of G jobs strip-major, so the strips s and s+1
-    // of one job are dispatched G items apart (natural skew) while the group's targets stay L2-resident
-    const int gsz = P.group_jobs * P.nstrips;
-    const int g = item / gsz;
-    const int rem = item - g * gsz;
-    const int gjobs = min(P.group_jobs, P.njobs - g * P.group_jobs);
-    const int s = rem / gjobs;
-    const int job = g * P.group_jobs + (rem - s * gjobs);
+    // the item table is ordered group by group; inside a group of G jobs strip-major, so the strips s and s+1 of
+    // one job are dispatched G items apart (natural skew) while the group's targets stay L2-resident
+    const int2 it = __ldg(P.items + item);
+    const int job = it.x, s = it.y;
+    const int Lq = P.job_Lq[job];
+    const int nstrips = P.job_nstrips[job];
     const int i0 = s * R;
 
     // ---- stage this strip's query rows with one TMA bulk copy
     if (lane == 0) {
       mbar_expect_tx(bar, R * 112);
-      tma_bulk_g2s(qs, P.qrec + (size_t)i0 * 7, R * 112, bar);
+      tma_bulk_g2s(qs, P.qrec + (size_t)(P.job_qrow0[job] + i0) * 7, R * 112, bar);
     }
 
     const int t = P.job_target[job * 32 + lane];
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)   // 168
     BndSlot* bnd = P.bnd + P.job_bnd_off[job] + lane;
     const uint32_t tag_in = P.tag_base + (uint32_t)s;        // written by strip s-1
     const uint32_t tag_out = P.tag_base + (uint32_t)s + 1u;  // what this strip writes
-    const bool last_strip = (s == P.nstrips - 1);
+    const bool last_strip = (s == nstrips - 1);
     const uint32_t* co = nullptr;
     if (CELLOFF) co = P.celloff + P.job_co_off[job] + (size_t)s * (Lmax + 1) * 32 + lane;
 
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)   // 168
             const float mm = MM[r];
             if (mm >= bc) {
               const int i = i0 + 1 + r;
-              const bool cand = (i <= P.Lq) && (LOCAL || i == P.Lq || j == Lt);
+              const bool cand = (i <= Lq) && (LOCAL || i == Lq || j == Lt);
               if (cand && (mm > best || i < bi)) { best = mm; bi = i; bj = j; bc = mm; }
             }
           }
@@ -445,11 +446,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (R <= 12) ? 3 : 2)   // 168
       if (!last_strip)
         st_slot(bnd + (size_t)j * 32, MM[R - 1], DG[R - 1], MI[R - 1], GD[R - 1], IM[R - 1], tag_out);
     }
-    const size_t o = ((size_t)job * P.nstrips + s) * 32 + lane;
+    const size_t o = ((size_t)P.job_ss_off[job] + s) * 32 + lane;
     P.strip_score[o] = best;
     P.strip_ij[o] = (bi << 16) | bj;
     __syncwarp();   // all lanes done with the smem slice before the next TMA overwrites it
   }
+}
+
+// pnul[a] of HMM::IncludeNullModelInHMM (src/hhhmm.cpp:2059-2088) for one (query, template) pair.
+// columnscore: 0 = pb, 1 = 0.5(q.pav + t.pav) (default), 2 = t.pav, 3 = q.pav.
+__device__ __forceinline__ void null_model_vec(int columnscore, const float* __restrict__ q_pav,
+                                               const float* __restrict__ t_pav, const float* __restrict__ pb,
+                                               float (&pn)[20]) {
+#pragma unroll
+  for (int a = 0; a < 20; ++a) {
+    switch (columnscore) {
+      case 0: pn[a] = pb[a]; break;
+      case 2: pn[a] = t_pav[a]; break;
+      case 3: pn[a] = q_pav[a]; break;
+      default: pn[a] = __fmul_rn(0.5f, __fadd_rn(q_pav[a], t_pav[a])); break;
+    }
+  }
+}
+__device__ __forceinline__ float4 div4(float4 v, const float* pn) {
+  v.x = __fdiv_rn(v.x, pn[0]); v.y = __fdiv_rn(v.y, pn[1]); v.z = __fdiv_rn(v.z, pn[2]); v.w = __fdiv_rn(v.w, pn[3]);
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -465,7 +486,16 @@ struct HitRec {
 
 struct BtParams {
   int n_req;
-  int nstrips;
+  const int* job_nstrips;    // [njobs]
+  const long long* job_ss_off;
+  const int* job_qrow0;      // [njobs] first row record of the job's query
+  // fused null model (query-batch plans over a raw shard): cols = emissions BEFORE the null model and the division
+  // t.p[j][a] / pnul[a] is applied on the fly exactly like HMM::IncludeNullModelInHMM; nm_mode < 0: cols are prepared
+  int nm_mode;
+  const int* job_query;      // [njobs]
+  const float* q_pav;        // [nq*20]
+  const float* t_pav;        // [n_targets*20]
+  const float* pb;           // [20]
   int job_begin, job_end;    // only requests whose job lies in [job_begin, job_end) are traced
   const int* req_job;        // [n_req]
   const int* req_lane;       // [n_req]
@@ -506,11 +536,12 @@ __device__ __forceinline__ float fast_log2_dev(float x, const float* lg2, const 
 // plain left-to-right sum  t0*q0 + t1*q1 + ... + t19*q19  (verified against the compiled reference:
 // 300/300 random vectors bit-identical; the SSE shuffle tree matches only ~70%).
 __device__ __forceinline__ float score_cols_dev(const float4* q, const float4* t, const float* lg2,
-                                                const float* diff) {
+                                                const float* diff, const float* pn = nullptr) {
   float sum = 0.0f;
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    const float4 a = q[k], b = t[k];
+    const float4 a = q[k];
+    const float4 b = pn ? div4(t[k], pn + 4 * k) : t[k];
     if (k == 0) sum = __fmul_rn(b.x, a.x); else sum = __fadd_rn(sum, __fmul_rn(b.x, a.x));
     sum = __fadd_rn(sum, __fmul_rn(b.y, a.y));
     sum = __fadd_rn(sum, __fmul_rn(b.z, a.z));
@@ -531,8 +562,9 @@ __global__ void k_backtrace(const BtParams P) {
   if (job < P.job_begin || job >= P.job_end) return;
   float best = HHG_NEG;
   int ij = 0;
-  for (int s = 0; s < P.nstrips; ++s) {
-    const size_t o = ((size_t)job * P.nstrips + s) * 32 + lane;
+  const int nstrips = P.job_nstrips[job];
+  for (int s = 0; s < nstrips; ++s) {
+    const size_t o = ((size_t)P.job_ss_off[job] + s) * 32 + lane;
     const float v = P.strip_score[o];
     if (v > best) { best = v; ij = P.strip_ij[o]; }
   }
@@ -543,6 +575,13 @@ __global__ void k_backtrace(const BtParams P) {
   uint8_t* path = P.paths ? P.paths + P.path_off[k] : nullptr;
 
   const float4* tcol = P.cols + (size_t)P.col_off[P.req_target[k]] * 7;
+  const float4* qrec = P.qrec + (size_t)P.job_qrow0[job] * 7;
+  float pnv[20];
+  const float* pn = nullptr;
+  if (P.nm_mode >= 0) {
+    null_model_vec(P.nm_mode, P.q_pav + (size_t)P.job_query[job] * 20, P.t_pav + (size_t)P.req_target[k] * 20, P.pb, pnv);
+    pn = pnv;
+  }
   float* S = P.S + P.path_off[k];
   float score_ss = 0.0f;
 
@@ -554,9 +593,9 @@ __global__ void k_backtrace(const BtParams P) {
     // be the last one is re-scored below because the reference forces states[nsteps] = MM first
     float Sv = 0.0f;
     if (state == 2 && i >= 1 && j >= 1) {
-      Sv = score_cols_dev(P.qrec + (size_t)(i - 1) * 7, tcol + (size_t)(j - 1) * 7, P.lg2, P.diff);
+      Sv = score_cols_dev(qrec + (size_t)(i - 1) * 7, tcol + (size_t)(j - 1) * 7, P.lg2, P.diff, pn);
       if (P.use_ss) {
-        const uint32_t qs = __float_as_uint(P.qrec[(size_t)(i - 1) * 7 + 6].w);
+        const uint32_t qs = __float_as_uint(qrec[(size_t)(i - 1) * 7 + 6].w);
         const uint32_t ts = __float_as_uint(tcol[(size_t)(j - 1) * 7 + 6].w);
         score_ss = __fadd_rn(score_ss, __fmul_rn(P.ssw, P.S33[qs * 44 + ts]));
       }
@@ -576,9 +615,9 @@ __global__ void k_backtrace(const BtParams P) {
     }
     if (state == 0 && prev_state != 2 && li >= 1 && lj >= 1) {
       // last step ended in a gap state: the reference relabels it MM (src/hhviterbi.cpp:147) and scores it
-      S[step - 1] = score_cols_dev(P.qrec + (size_t)(li - 1) * 7, tcol + (size_t)(lj - 1) * 7, P.lg2, P.diff);
+      S[step - 1] = score_cols_dev(qrec + (size_t)(li - 1) * 7, tcol + (size_t)(lj - 1) * 7, P.lg2, P.diff, pn);
       if (P.use_ss) {
-        const uint32_t qs = __float_as_uint(P.qrec[(size_t)(li - 1) * 7 + 6].w);
+        const uint32_t qs = __float_as_uint(qrec[(size_t)(li - 1) * 7 + 6].w);
         const uint32_t ts = __float_as_uint(tcol[(size_t)(lj - 1) * 7 + 6].w);
         score_ss = __fadd_rn(score_ss, __fmul_rn(P.ssw, P.S33[qs * 44 + ts]));
       }
@@ -614,26 +653,12 @@ __global__ void k_null_model(long long total_cols, int n, const long long* col_o
     const int mid = (lo + hi + 1) >> 1;
     if (col_off[mid] <= c) lo = mid; else hi = mid - 1;
   }
-  const float* tp = t_pav + (size_t)lo * 20;
   float pn[20];
-#pragma unroll
-  for (int a = 0; a < 20; ++a) {
-    switch (columnscore) {
-      case 0: pn[a] = pb[a]; break;
-      case 2: pn[a] = tp[a]; break;
-      case 3: pn[a] = q_pav[a]; break;
-      default: pn[a] = __fmul_rn(0.5f, __fadd_rn(q_pav[a], tp[a])); break;
-    }
-  }
+  null_model_vec(columnscore, q_pav, t_pav + (size_t)lo * 20, pb, pn);
   const float4* src = raw + (size_t)c * 7;
   float4* dst = out + (size_t)c * 7;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    float4 v = src[k];
-    v.x = __fdiv_rn(v.x, pn[4 * k + 0]); v.y = __fdiv_rn(v.y, pn[4 * k + 1]);
-    v.z = __fdiv_rn(v.z, pn[4 * k + 2]); v.w = __fdiv_rn(v.w, pn[4 * k + 3]);
-    dst[k] = v;
-  }
+  for (int k = 0; k < 5; ++k) dst[k] = div4(src[k], pn + 4 * k);
   dst[5] = src[5];
   dst[6] = src[6];
 }
@@ -694,7 +719,9 @@ __global__ void k_pack_cols(int n, const int* L, const long long* col_off, const
 __global__ void __launch_bounds__(256)
 k_interleave_cols(int njobs, const int* __restrict__ job_target, const int* __restrict__ job_Lmax,
                   const long long* __restrict__ job_jc_off, const float4* __restrict__ cols,
-                  const long long* __restrict__ col_off, const int* __restrict__ Lt, float4* __restrict__ out) {
+                  const long long* __restrict__ col_off, const int* __restrict__ Lt, float4* __restrict__ out,
+                  int nm_mode, const int* __restrict__ job_query, const float* __restrict__ q_pav,
+                  const float* __restrict__ t_pav, const float* __restrict__ pb) {
   const int job = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int Lmax = job_Lmax[job];
@@ -702,24 +729,31 @@ k_interleave_cols(int njobs, const int* __restrict__ job_target, const int* __re
   const int L = Lt[t];
   const float4* src0 = cols + (size_t)col_off[t] * 7;
   float4* dst0 = out + job_jc_off[job] + lane;
+  // nm_mode >= 0: `cols` holds the emissions before the null model; factor it in for this job's query on the way
+  // (HMM::IncludeNullModelInHMM, the query-dependent step of PrepareTemplateHMM), so a batch of queries can share one
+  // resident raw shard
+  float pn[20];
+  if (nm_mode >= 0) null_model_vec(nm_mode, q_pav + (size_t)job_query[job] * 20, t_pav + (size_t)t * 20, pb, pn);
   for (int j = blockIdx.y * 8 + (threadIdx.x >> 5) + 1; j <= Lmax; j += gridDim.y * 8) {
     const float4* src = src0 + (size_t)(min(j, L) - 1) * 7;
     float4* dst = dst0 + (size_t)(j - 1) * 224;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) dst[k * 32] = __ldg(src + k);
+    for (int k = 0; k < 5; ++k) dst[k * 32] = nm_mode >= 0 ? div4(__ldg(src + k), pn + 4 * k) : __ldg(src + k);
+    dst[5 * 32] = __ldg(src + 5);
+    dst[6 * 32] = __ldg(src + 6);
   }
 }
 
 // Rasterise excluded alignments into the cell-off bit words (Viterbi::ExcludeAlignment,
 // src/hhviterbi.cpp:61-77): one thread per excluded path step.
 __global__ void k_celloff_raster(int n_steps, const int* step_req, const int* step_i, const int* step_j,
-                                 const int* req_job, const int* req_lane, const int* req_Lt,
-                                 const int* job_Lmax, const long long* job_co_off, int Lq, int R,
+                                 const int* req_job, const int* req_lane, const int* req_Lt, const int* req_Lq,
+                                 const int* job_Lmax, const long long* job_co_off, int R,
                                  uint32_t* co) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_steps) return;
   const int rq = step_req[k];
-  const int job = req_job[rq], lane = req_lane[rq], Lt = req_Lt[rq];
+  const int job = req_job[rq], lane = req_lane[rq], Lt = req_Lt[rq], Lq = req_Lq[rq];
   const int Lmax = job_Lmax[job];
   uint32_t* base = co + job_co_off[job] + lane;
   const int i = step_i[k], j = step_j[k];

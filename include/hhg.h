@@ -181,6 +181,24 @@ int hhg_viterbi_search(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids
                        uint8_t* paths, size_t paths_cap, const int64_t* excl_off,
                        const int32_t* excl_i, const int32_t* excl_j);
 
+/* ---- query-batch mode ---------------------------------------------------------------------------
+ * hhblits_omp (src/hhblits_omp.cpp:119-160) runs one full HHblits per OpenMP thread, i.e. many independent queries
+ * against the same mmap'd database at once.  Here a batch of queries shares ONE resident shard and ONE launch: the
+ * work items (query, 32-target job, strip) of all queries feed the same persistent grid, which is what keeps the GPU
+ * busy when each query only aligns the few thousand survivors of its prefilter (a single such request is latency
+ * bound at ~100 GCUPS).
+ *   hhg_query_set_batch : the queries (prepared like hhg_query_set; ss / S33 as there, ss may be NULL); q_pav[nq*20]
+ *                         = HMM::pav of each query, needed when the shard is raw.  hhg_query_set == a batch of one.
+ *   hhg_viterbi_search_batch : request k = (query req_query[k], target ids[k]); hits[k] / paths as in
+ *                         hhg_viterbi_search (paths_cap >= sum(Lq_of_request + Lt + 2)).  Raw shard
+ *                         (hhg_db_create_raw / _hhm / _packed): the query-dependent null model
+ *                         (HMM::IncludeNullModelInHMM, columnscore / pb as in hhg_db_apply_null_model) is applied per
+ *                         query while the plan's operand stream is built -- no per-query pass over the whole shard. */
+int hhg_query_set_batch(hhg_ctx* ctx, int nq, const int32_t* Lq, const float* const* p, const float* const* tr,
+                        const uint8_t* const* ss, const float* q_pav, const float* S33, const hhg_params* par);
+int hhg_viterbi_search_batch(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* req_query, const int32_t* ids,
+                             int columnscore, const float* pb, hhg_hit* hits, uint8_t* paths, size_t paths_cap);
+
 /* Device-resident variant used for kernel-only timing: plan once, run many times, fetch at the end. */
 typedef struct hhg_plan hhg_plan;
 int hhg_plan_create(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* ids, hhg_plan** out);
