@@ -265,14 +265,14 @@ def run_reference(args, host):
     val = cells / t / 1e9
     cb = dict(cb, value=val)
     cb.pop("seconds", None)
-    print(json.dumps({
+    args.emit({
         "impl": "reference", "metric": "Viterbi GCUPS (query_L x sum target_L / s)", "value": val, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world, len(db["L"]), int(db["L"].sum())),
         "cpu_baseline": cb, "host": host,
         "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
     return 0
 
 
@@ -453,14 +453,24 @@ def extras(args, hh, ctx, comm, rank, world, dev, qprof, base, dist):
 # ----------------------------------------------------------------------------------------------- main
 def main():
     args = parse_args()
+    # stdout carries exactly ONE line, the JSON record: anything a library prints there (NCCL's version banner, ...)
+    # goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+    args.emit = emit
     if args.no_prefilter:
         args.no_extras = True
-    # read the CPU budget BEFORE anything loads libgomp: with OMP_PROC_BIND set, libgomp pins the initial thread to
-    # its first place at load time (torch pulls libgomp in), after which sched_getaffinity() reports one core
     host = host_threads()
-    # must be set before libgomp is loaded by the reference shim
-    os.environ.setdefault("OMP_PROC_BIND", "close")
-    os.environ.setdefault("OMP_PLACES", "cores")
+    if args.impl == "reference":
+        # pin the reference's OpenMP team; must be in the environment before libgomp is loaded by the reference shim.
+        # Only for this arm: with OMP_PROC_BIND set libgomp also pins the INITIAL thread of every process that loads it
+        # (torch does), which would put the host threads of all ranks of a multi-GPU run on the same core.
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        os.environ.setdefault("OMP_PLACES", "cores")
     if args.impl == "reference":
         return run_reference(args, host)
 
@@ -619,14 +629,23 @@ def main():
     }
     if not args.no_extras:
         out["configs"] = extras(args, hh, ctx, comm, rank, world, dev, qprof, db_h if rank == 0 and world == 1 else
-                                headline_shard(argparse.Namespace(**{**vars(args)}), 0, 1)[1], dist)
+                                headline_shard(args, 0, 1)[1], dist)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_baseline(args, qprof, db_h, args.cpu_sample, host)
-        cb.pop("seconds", None)
-        out["cpu_baseline"] = cb
-        out["host"] = host
+        # the CPU figure comes from the reference arm itself, run as a child process on a bounded sample of the same
+        # shard (own environment: OpenMP pinning must be set before libgomp loads, and must not leak into this process)
+        env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                            "--ref-sample", str(args.cpu_sample), "--targets", str(args.targets), "--lq", str(args.lq)],
+                           capture_output=True, text=True, env=env, timeout=600)
+        try:
+            ref = json.loads(r.stdout.strip().splitlines()[-1])
+            out["cpu_baseline"] = ref["cpu_baseline"]
+            out["host"] = ref["host"]
+        except Exception:
+            out["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": host["used"], "kind": "reference",
+                                   "sample": "reference arm failed: " + (r.stderr or r.stdout)[-300:]}
     if rank == 0:
-        print(json.dumps(out))
+        args.emit(out)
     plan.close(); db.close()
     if comm is not None:
         comm.close()
