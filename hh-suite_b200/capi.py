@@ -42,7 +42,7 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_comm_unique_id", "hhg_comm_create", "hhg_comm_destroy", "hhg_comm_rank", "hhg_comm_world",
            "hhg_plan_topk", "hhg_plan_topk_by_key", "hhg_plan_topk_paths", "hhg_ctx_last_plan",
            "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order", "hhg_early_stop_sum", "hhg_set_use_ss",
-           "hhg_query_set_batch", "hhg_viterbi_search_batch"]
+           "hhg_query_set_batch", "hhg_viterbi_search_batch", "hhg_query_from_hhm"]
 
 
 class PrepParams(C.Structure):
@@ -181,6 +181,8 @@ def load():
                                      C.c_float, C.c_float, C.c_double]
     L.hhg_early_stop_sum.restype = C.c_float
     L.hhg_set_use_ss.argtypes = [C.c_void_p, C.c_int]
+    L.hhg_query_from_hhm.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(PrepParams), c_f32p, C.c_int32, c_i32p,
+                                     c_f32p, c_f32p, c_u8p, c_f32p, c_f32p]
     L.hhg_query_set_batch.argtypes = [C.c_void_p, C.c_int, c_i32p, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_f32p,
                                       C.POINTER(Params)]
     L.hhg_viterbi_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, c_i32p, C.c_int, c_f32p, C.c_void_p,
@@ -297,6 +299,19 @@ def mac_debug_posterior(ctx, request, Lt):
     out = np.zeros((ctx.mac_Lq + 1, Lt + 1), np.float32)
     _ck(ctx.L.hhg_mac_debug_posterior(ctx.h, request, _p(out, c_f32p)))
     return out
+
+
+def query_from_hhm(ctx: "Context", record: bytes, R, params: "PrepParams | None" = None):
+    """hhg_query_from_hhm: PrepareQueryHMM (nocontxt) of one HHM record -> dict(L, p, tr, ss, pav, neff)."""
+    L, has_ss = hhm_scan(record)
+    p = np.zeros((L + 2, 20), np.float32); tr = np.zeros((L + 1, 7), np.float32)
+    ss = np.zeros(L + 2, np.uint8); pav = np.zeros(20, np.float32)
+    neff = np.zeros(1, np.float32); Lo = np.zeros(1, np.int32)
+    R = np.ascontiguousarray(R, np.float32)
+    pp = params or PrepParams.defaults()
+    _ck(ctx.L.hhg_query_from_hhm(ctx.h, record, len(record), C.byref(pp), _p(R, c_f32p), L, _p(Lo, c_i32p), _p(p, c_f32p),
+                                 _p(tr, c_f32p), _p(ss, c_u8p), _p(pav, c_f32p), _p(neff, c_f32p)))
+    return dict(L=L, p=p, tr=tr, ss=ss, pav=pav, neff=float(neff[0]), has_ss=has_ss)
 
 
 def hhm_scan(record: bytes):

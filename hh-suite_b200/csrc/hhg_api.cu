@@ -468,8 +468,8 @@ int hhg_hhm_parse(const char* rec, int64_t len, int32_t L, int32_t* f_mb, int32_
   return HHG_OK;
 }
 
-int hhg_db_create_hhm(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
-                      const hhg_prep_params* pp, const float* R, hhg_db** out) {
+static int db_create_hhm_impl(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
+                              const hhg_prep_params* pp, const float* R, hhg_db** out, float* d_tr_full) {
   if (!ctx || !out || n <= 0 || !data || !off || !len || !pp || !R)
     return fail(HHG_EINVAL, "hhg_db_create_hhm: bad argument");
   if (pp->pcm < 0 || pp->pcm > 2 || (pp->pcm == 2 && pp->pcc != 1.0f))
@@ -569,7 +569,7 @@ int hhg_db_create_hhm(hhg_ctx* ctx, int n, const char* data, const int64_t* off,
     const int threads = 128;
     k_hhm_prepare<<<(unsigned)((cols + threads - 1) / threads), threads, 0, ctx->stream>>>(
         m, db->dL.p + t0, d_coff.p, d_f.p, d_trn.p, any_ss ? d_ss.p : nullptr, d_haspc.p, A, ctx->lg2.p,
-        ctx->diff.p, dst, cols);
+        ctx->diff.p, dst, cols, d_tr_full);   // d_tr_full only with a single chunk (hhg_query_from_hhm: one record)
     k_hhm_pav<<<(unsigned)(((long long)m * 32 + threads - 1) / threads), threads, 0, ctx->stream>>>(
         m, db->dL.p + t0, d_coff.p, dst, d_null.p, d_neff.p, A, db->pav.p + (size_t)t0 * 20);
     ctx->launches += 2;
@@ -582,6 +582,52 @@ int hhg_db_create_hhm(hhg_ctx* ctx, int n, const char* data, const int64_t* off,
   db->raw = true;
   db->prepared = false;
   *out = holder.release();
+  return HHG_OK;
+}
+
+int hhg_db_create_hhm(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
+                      const hhg_prep_params* pp, const float* R, hhg_db** out) {
+  return db_create_hhm_impl(ctx, n, data, off, len, pp, R, out, nullptr);
+}
+
+// PrepareQueryHMM for an HHM query without context-specific pseudocounts (par.nocontxt; src/hhfunc.cpp:121-160): the
+// same three steps a template gets -- AddTransitionPseudocounts, PreparePseudocounts + AddAminoAcidPseudocounts,
+// CalculateAminoAcidBackground -- so the record runs through the database loader's kernels and comes back as the host
+// arrays hhg_query_set / hhg_prefilter_build_profile take.
+int hhg_query_from_hhm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_prep_params* pp, const float* R,
+                       int32_t L_cap, int32_t* L_out, float* p, float* tr, uint8_t* ss, float* pav, float* neff) {
+  if (!ctx || !rec || len <= 0 || !pp || !R || !L_out || !p || !tr || !pav) return fail(HHG_EINVAL, "hhg_query_from_hhm: bad argument");
+  int32_t L = 0, has_ss = 0;
+  { HhmScanner sc(rec, len); if (!sc.peek(&L, &has_ss)) return fail(HHG_EINVAL, "hhg_query_from_hhm: not an HHM record"); }
+  if (L < 1 || L > L_cap) return fail(HHG_EINVAL, "hhg_query_from_hhm: query length %d exceeds the caller's capacity %d", L, L_cap);
+  CK(cudaSetDevice(ctx->device));
+  DevBuf<float> d_tr;
+  CK(d_tr.alloc((size_t)(L + 1) * 7));
+  hhg_db* db = nullptr;
+  const int64_t zero = 0;
+  int rc = db_create_hhm_impl(ctx, 1, rec, &zero, &len, pp, R, &db, d_tr.p);
+  if (rc != HHG_OK) return rc;
+  std::unique_ptr<hhg_db> holder(db);
+  std::vector<ColRec> cols((size_t)L);
+  CK(cudaMemcpyAsync(cols.data(), db->cols_raw.p, (size_t)L * sizeof(ColRec), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(tr, d_tr.p, (size_t)(L + 1) * 28, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(pav, db->pav.p, 80, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 1; i <= L; ++i) {
+    memcpy(p + (size_t)i * 20, cols[i - 1].p, 80);
+    if (ss) ss[i] = (uint8_t)cols[i - 1].ss;
+  }
+  memcpy(p, pav, 80);                               // CalculateAminoAcidBackground: p[0] = p[L+1] = pav (:1866)
+  memcpy(p + (size_t)(L + 1) * 20, pav, 80);
+  if (ss) ss[0] = ss[L + 1] = 0;
+  if (neff) {
+    std::vector<int32_t> f((size_t)L * 20), trn((size_t)(L + 1) * 10), nul(20);
+    std::vector<uint8_t> ssb(L);
+    int32_t has_pc = 0;
+    rc = hhg_hhm_parse(rec, len, L, f.data(), trn.data(), ssb.data(), nul.data(), neff, &has_pc);
+    if (rc != HHG_OK) return rc;
+  }
+  *L_out = L;
   return HHG_OK;
 }
 

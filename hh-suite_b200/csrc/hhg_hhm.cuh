@@ -247,7 +247,11 @@ k_hhm_prepare(int m, const int* __restrict__ L, const long long* __restrict__ co
               const int32_t* __restrict__ f_mb, const int32_t* __restrict__ trn_mb,
               const uint8_t* __restrict__ ss, const int32_t* __restrict__ has_pc,
               const __grid_constant__ HhmPrepArgs A, const float* __restrict__ lg2,
-              const float* __restrict__ diff, ColRec* __restrict__ out, long long total_cols) {
+              const float* __restrict__ diff, ColRec* __restrict__ out, long long total_cols,
+              float* __restrict__ tr_full) {
+  // tr_full (optional): the complete transition rows tr[i][M2M,M2I,M2D,I2M,I2I,D2M,D2D], i = 0..L, of every record at
+  // float offset (col_off[t] + t + i) * 7 -- what a QUERY needs (hhg_query_from_hhm); column records only keep the
+  // entries the DP reads from a template
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= total_cols) return;
   int lo = 0, hi = m - 1;
@@ -261,6 +265,15 @@ k_hhm_prepare(int m, const int* __restrict__ L, const long long* __restrict__ co
   float tr_prev[7], tr_here[7];
   hhm_transitions(rows + (size_t)(j - 1) * 10, j - 1, Lt, A, lg2, diff, tr_prev);
   hhm_transitions(rows + (size_t)j * 10, j, Lt, A, lg2, diff, tr_here);
+  if (tr_full) {
+    float* dst = tr_full + (size_t)(col_off[t] + t) * 7;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) dst[(size_t)j * 7 + k] = tr_here[k];
+    if (j == 1) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) dst[k] = tr_prev[k];
+    }
+  }
 
   float f[20];
   const int32_t* fm = f_mb + (size_t)c * 20;

@@ -130,6 +130,14 @@ typedef struct hhg_prep_params {
 } hhg_prep_params;
 int hhg_db_create_hhm(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
                       const hhg_prep_params* pp, const float* R, hhg_db** out);
+/* PrepareQueryHMM for an HHM-format query without context-specific pseudocounts (the par.nocontxt
+ * branch of src/hhfunc.cpp:121-160: AddTransitionPseudocounts, PreparePseudocounts + AddAminoAcidPseudocounts,
+ * CalculateAminoAcidBackground -- the same steps a template gets, run by the same kernels).  Fills the host arrays that
+ * hhg_query_set / hhg_prefilter_build_profile take: p[(L+2)*20] (rows 0 and L+1 = pav like the reference), tr[(L+1)*7]
+ * in HMM::tr order, ss[L+2] (may be NULL), pav[20], *neff = Neff_HMM.  L_cap = capacity of the caller's arrays in
+ * columns.  The context-specific (CRF) pseudocounts of default hhblits stay in the reference's host code. */
+int hhg_query_from_hhm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_prep_params* pp, const float* R,
+                       int32_t L_cap, int32_t* L_out, float* p, float* tr, uint8_t* ss, float* pav, float* neff);
 /* Host only: LENG and whether the record carries an ss_pred sequence (no numbers are parsed). */
 int hhg_hhm_scan(const char* rec, int64_t len, int32_t* L, int32_t* has_ss);
 /* Host only: the tokeniser hhg_db_create_hhm runs per record, exposed for inspection and CPU-side tests.

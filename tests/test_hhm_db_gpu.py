@@ -199,3 +199,26 @@ def test_dropin_with_text_loader(tmp_path):
         files.append(str(f))
     r = subprocess.run([binp, "--hhm-loader", str(q)] + files, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr
+
+
+def test_query_from_hhm_equals_reference_prepare_query(hhg, gpu_ctx, refshim, tmp_path):
+    """hhg_query_from_hhm = HMM::Read + PrepareQueryHMM with par.nocontxt (src/hhfunc.cpp:121-160): p (all rows incl. 0
+    and L+1), the complete transition rows, ss, pav and Neff_HMM bit-identical to the reference's query."""
+    from hhsuite_b200 import synth
+    import os
+    cases = [os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "data", "query.hhm")]
+    for k, (L, ss) in enumerate([(1, False), (57, True), (300, False)]):
+        f = tmp_path / f"q{k}.hhm"
+        f.write_text(synth.hhm_text(L, 70 + k, f"q{k}", with_ss=ss))
+        cases.append(str(f))
+    for path in cases:
+        ref = refshim.load_query_hhm(path)
+        rec = open(path, "rb").read() + b"\0"
+        got = hhg.capi.query_from_hhm(gpu_ctx, rec, refshim.R())
+        assert got["L"] == ref["L"]
+        assert np.array_equal(got["p"].view(np.uint32), ref["p"].view(np.uint32)), path
+        assert np.array_equal(got["tr"].view(np.uint32), ref["tr"].view(np.uint32)), path
+        assert np.array_equal(got["pav"].view(np.uint32), ref["pav"].view(np.uint32))
+        if got["has_ss"]:
+            assert np.array_equal(got["ss"][1:-1], ref["ss"][1:-1])
+        assert np.float32(got["neff"]).view(np.uint32) == np.float32(ref["neff"]).view(np.uint32)
