@@ -57,14 +57,12 @@ def prefilter_db(csdb: capi.CsDB, prof: np.ndarray, gap_open=20, gap_extend=4, s
         fl = np.ascontiguousarray(lens32[first])
         capi._ck(L.hhg_prefilter_evalues(len(first), capi._p(sw32, capi.c_i32p), capi._p(fl, capi.c_i32p), n, Lq,
                                         bit_factor, ev.ctypes.data_as(C.POINTER(C.c_double))))
-    sel = [k for k in range(len(first)) if ev[k] < evalue_coarse_thresh]
-    sel.sort(key=lambda k: (int(ev[k]), int(first[k])))      # comparePair on std::pair<int,int>: E-value truncated
-    out = []
-    for k in sel:
-        if len(out) >= min_prefilter_hits and ev[k] > evalue_thresh:
-            break
-        out.append(k)
-    out = out[:maxnumdb]
+    # coarse cut (:530), sort ascending by ((int)evalue, index) (:545), keep rule (:547-558), maxnumdb (:590) -- vectorised
+    keep = np.nonzero(ev < evalue_coarse_thresh)[0]
+    order = keep[np.lexsort((first[keep], ev[keep].astype(np.int64)))]
+    tail = np.nonzero(ev[order[min_prefilter_hits:]] > evalue_thresh)[0]
+    ncut = min_prefilter_hits + int(tail[0]) if len(tail) else len(order)
+    out = order[:min(ncut, maxnumdb)]
     ids = first[out] if len(out) else np.zeros(0, np.int32)
     if return_details:
         return ids, dict(raw=raw, corrected=corr, first=first, first_scores=first_scores, sw=sw, evalue=ev)
