@@ -42,7 +42,8 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_comm_unique_id", "hhg_comm_create", "hhg_comm_destroy", "hhg_comm_rank", "hhg_comm_world",
            "hhg_plan_topk", "hhg_plan_topk_by_key", "hhg_plan_topk_paths", "hhg_ctx_last_plan",
            "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order", "hhg_early_stop_sum", "hhg_set_use_ss",
-           "hhg_query_set_batch", "hhg_viterbi_search_batch", "hhg_query_from_hhm"]
+           "hhg_query_set_batch", "hhg_viterbi_search_batch", "hhg_query_from_hhm",
+           "hhg_cs219_parse", "hhg_csdb_create_ffindex"]
 
 
 class PrepParams(C.Structure):
@@ -183,6 +184,8 @@ def load():
     L.hhg_set_use_ss.argtypes = [C.c_void_p, C.c_int]
     L.hhg_query_from_hhm.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(PrepParams), c_f32p, C.c_int32, c_i32p,
                                      c_f32p, c_f32p, c_u8p, c_f32p, c_f32p]
+    L.hhg_cs219_parse.argtypes = [C.c_char_p, C.c_int64, c_f32p, C.c_int, c_i32p]
+    L.hhg_csdb_create_ffindex.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_i64p, c_i64p, C.POINTER(C.c_void_p)]
     L.hhg_query_set_batch.argtypes = [C.c_void_p, C.c_int, c_i32p, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_f32p,
                                       C.POINTER(Params)]
     L.hhg_viterbi_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_i32p, c_i32p, C.c_int, c_f32p, C.c_void_p,
@@ -312,6 +315,14 @@ def query_from_hhm(ctx: "Context", record: bytes, R, params: "PrepParams | None"
     _ck(ctx.L.hhg_query_from_hhm(ctx.h, record, len(record), C.byref(pp), _p(R, c_f32p), L, _p(Lo, c_i32p), _p(p, c_f32p),
                                  _p(tr, c_f32p), _p(ss, c_u8p), _p(pav, c_f32p), _p(neff, c_f32p)))
     return dict(L=L, p=p, tr=tr, ss=ss, pav=pav, neff=float(neff[0]), has_ss=has_ss)
+
+
+def cs219_parse(text: bytes, n_cap: int = 256):
+    """hhg_cs219_parse: the column-state library text (cs219.lib) -> float[n_states, 20] linear probabilities."""
+    lib = np.zeros((n_cap, 20), np.float32)
+    n = np.zeros(1, np.int32)
+    _ck(load().hhg_cs219_parse(text, len(text), _p(lib, c_f32p), n_cap, _p(n, c_i32p)))
+    return lib[:int(n[0])].copy()
 
 
 def hhm_scan(record: bytes):
@@ -684,6 +695,19 @@ class CsDB:
                                   C.byref(h)))
         self.h = h
         self.n = len(self.Lh)
+
+    @classmethod
+    def from_ffindex(cls, ctx, data: bytes, offsets, lengths):
+        """The shard from <db>_cs219.ffdata + the (offset, length) columns of its .ffindex (init_prefilter)."""
+        off = np.ascontiguousarray(offsets, np.int64); ln = np.ascontiguousarray(lengths, np.int64)
+        h = C.c_void_p()
+        buf = np.frombuffer(data, np.uint8)
+        _ck(ctx.L.hhg_csdb_create_ffindex(ctx.h, len(off), buf.ctypes.data_as(C.c_char_p), _p(off, c_i64p), _p(ln, c_i64p),
+                                          C.byref(h)))
+        self = cls.__new__(cls)
+        self.ctx, self.h, self.n = ctx, h, len(off)
+        self.Lh = (ln - 1).astype(np.int32)
+        return self
 
     def ungapped(self, prof, offset=50):
         prof = np.ascontiguousarray(prof, np.uint8)

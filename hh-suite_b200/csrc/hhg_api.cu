@@ -1814,6 +1814,78 @@ int hhg_prefilter_ungapped_run(hhg_ctx* ctx, const hhg_csdb* db, int Lq, const u
   return HHG_OK;
 }
 
+// Prefilter::Prefilter + init_prefilter (src/hhprefilter.cpp:28-47,314-335), the two set-up steps of the prefilter:
+// (1) the column-state library: parse the text of cs219.lib (cs::ContextLibrary / ContextProfile::Read,
+//     src/cs/context_profile-inl.h:81-141) and put it in linear space (cs::TransformToLin; the shipped file has
+//     ISLOG F, i.e. probs = pow(2, -value/1000) in double, already linear) -> lib[k*20+a], a in the library's own
+//     alphabet order A R N D C Q E G H I L K M F P S T W Y V (= the internal amino-acid order of HH-suite);
+// (2) the sequences: one per ffindex entry of <db>_cs219, length = entry length - 1 (the NUL terminator).
+int hhg_cs219_parse(const char* text, int64_t len, float* lib, int n_cap, int* n_states) {
+  if (!text || len <= 0 || !lib || !n_states) return fail(HHG_EINVAL, "hhg_cs219_parse: bad argument");
+  const char* p = text;
+  const char* end = text + len;
+  auto next_line = [&](const char*& b, const char*& e) {
+    if (p >= end) return false;
+    b = p;
+    while (p < end && *p != '\n') ++p;
+    e = p;
+    if (p < end) ++p;
+    return true;
+  };
+  int k = 0;
+  bool is_log = false;
+  const char *b, *e;
+  while (next_line(b, e)) {
+    if (e - b >= 5 && !strncmp(b, "ISLOG", 5)) { const char* q = b + 5; while (q < e && (*q == ' ' || *q == '\t')) ++q; is_log = (q < e && *q == 'T'); }
+    if (e - b >= 5 && !strncmp(b, "PROBS", 5)) {
+      if (!next_line(b, e)) break;                       // the row of the central (only) column: index + 20 values
+      if (k >= n_cap) return fail(HHG_EINVAL, "hhg_cs219_parse: more than %d states", n_cap);
+      const char* q = b;
+      while (q < e && (*q == ' ' || *q == '\t')) ++q;
+      while (q < e && *q >= '0' && *q <= '9') ++q;         // column index
+      for (int a = 0; a < 20; ++a) {
+        while (q < e && (*q == ' ' || *q == '\t')) ++q;
+        if (q >= e) return fail(HHG_EINVAL, "hhg_cs219_parse: state %d has fewer than 20 values", k);
+        double prob;
+        if (*q == '*') { prob = 0.0; ++q; }
+        else {
+          long v = 0; bool neg = false;
+          if (*q == '-') { neg = true; ++q; }
+          if (q >= e || *q < '0' || *q > '9') return fail(HHG_EINVAL, "hhg_cs219_parse: state %d: not a number", k);
+          while (q < e && *q >= '0' && *q <= '9') v = v * 10 + (*q++ - '0');
+          if (neg) v = -v;
+          prob = pow(2, static_cast<double>(-v) / 1000.0);      // ContextProfile::Read, kScale = 1000
+          if (is_log) prob = exp(log(prob));                       // read as log, then TransformToLin
+        }
+        lib[(size_t)k * 20 + a] = (float)prob;
+      }
+      ++k;
+    }
+  }
+  if (k == 0) return fail(HHG_EINVAL, "hhg_cs219_parse: no ContextProfile found");
+  *n_states = k;
+  return HHG_OK;
+}
+
+int hhg_csdb_create_ffindex(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len, hhg_csdb** out) {
+  if (!ctx || n <= 0 || !data || !off || !len || !out) return fail(HHG_EINVAL, "hhg_csdb_create_ffindex: bad argument");
+  std::vector<int32_t> L(n);
+  std::vector<int64_t> o(n);
+  std::vector<uint8_t> seq;
+  size_t tot = 0;
+  for (int k = 0; k < n; ++k) {
+    if (len[k] < 1 || off[k] < 0) return fail(HHG_EINVAL, "hhg_csdb_create_ffindex: entry %d has length %lld", k, (long long)len[k]);
+    tot += (size_t)len[k] - 1;
+  }
+  seq.reserve(tot);
+  for (int k = 0; k < n; ++k) {
+    L[k] = (int32_t)(len[k] - 1);                        // length[n] = entry->length - 1, :328
+    o[k] = (int64_t)seq.size();
+    seq.insert(seq.end(), (const uint8_t*)data + off[k], (const uint8_t*)data + off[k] + L[k]);
+  }
+  return hhg_csdb_create(ctx, n, L.data(), o.data(), seq.data(), out);
+}
+
 // Host-side query profile of the prefilter (once per query; Prefilter::stripe_query_profile,
 // src/hhprefilter.cpp:356-424) in the LINEAR layout prof[k*Lq+pos]: 219 column states + the ANY state.
 // q_p is HMM::p of the (prefilter-pseudocount) query, i.e. float[(Lq+2)*20]; note the reference indexes

@@ -343,6 +343,15 @@ int hhg_mac_debug_posterior(hhg_ctx* ctx, int request, float* out);
 int hhg_csdb_create(hhg_ctx* ctx, int n, const int32_t* L, const int64_t* off, const uint8_t* seq,
                     hhg_csdb** out);
 int hhg_csdb_destroy(hhg_csdb* db);
+/* The two set-up steps of the reference's Prefilter (ctor src/hhprefilter.cpp:28-47, init_prefilter
+ * :314-335).  hhg_cs219_parse (host only): the text of the column-state library cs219.lib (the caller reads the file
+ * that ships with HH-suite; cs::ContextLibrary / ContextProfile::Read) -> lib[k*20+a] linear probabilities, the
+ * `lib219` argument of hhg_prefilter_build_profile; *n_states = 219.  hhg_csdb_create_ffindex: the shard straight
+ * from <db>_cs219.ffdata and the (offset, length) columns of its .ffindex (length includes the NUL, like
+ * ffindex_entry_t::length; sequence length = length - 1). */
+int hhg_cs219_parse(const char* text, int64_t len, float* lib, int n_cap, int* n_states);
+int hhg_csdb_create_ffindex(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
+                            hhg_csdb** out);
 /* prof: uint8[220*Lq] linear query profile prof[k*Lq+pos] (the un-striped content of
  * Prefilter::stripe_query_profile, src/hhprefilter.cpp:356-424).  scores[n] receives the raw maximum
  * ungapped score per sequence (0..255), before the length correction of :477. */

@@ -104,3 +104,17 @@ def test_early_stop_sum_matches_compiled_reference(refshim):
         a = hh.capi.early_stop_sum(score, L, neff, qL, qneff, pf, dbsize)
         b = refshim.early_stop(score, L, neff, qL, qneff, pf, dbsize)
         assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), (a, b)
+
+
+def test_cs219_library_parser_matches_reference(refshim):
+    """hhg_cs219_parse (Prefilter ctor: ContextLibrary read + TransformToLin, src/hhprefilter.cpp:28-47) on the
+    reference's own cs219.lib: every float equal to what the compiled reference holds and to the golden copy."""
+    import hhsuite_b200 as hh
+    from tests.util import golden
+    path = "/root/reference/data/cs219.lib"
+    if not os.path.exists(path):
+        pytest.skip("the reference's data/cs219.lib is only present in the authoring container")
+    lib = hh.capi.cs219_parse(open(path, "rb").read())
+    assert lib.shape == (219, 20)
+    assert np.array_equal(lib.view(np.uint32), refshim.cs219().view(np.uint32))
+    assert np.array_equal(lib.view(np.uint32), np.ascontiguousarray(golden()["cs219_lin"], np.float32).view(np.uint32))

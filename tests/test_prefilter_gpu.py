@@ -235,3 +235,20 @@ def test_stage1_selection_on_device(hhg, gpu_ctx, oracle, case):
     if case == "few_above_ties":
         assert len(want) == min_hits and corr[want[-1]] <= thresh       # the tie class really was cut by index
     db.close()
+
+
+def test_shard_from_cs219_ffindex(hhg, gpu_ctx, tmp_path):
+    """hhg_csdb_create_ffindex = init_prefilter (src/hhprefilter.cpp:314-335): entries of <db>_cs219.ffdata with
+    their index (offset, length incl. the NUL); same scores as the shard built from arrays."""
+    rng = np.random.default_rng(4)
+    seqs = [rng.integers(0, 219, int(L), dtype=np.uint8) for L in rng.integers(1, 300, 50)]
+    data, off, ln = b"", [], []
+    for s in seqs:
+        off.append(len(data)); ln.append(len(s) + 1)
+        data += bytes(s) + b"\0"
+    prof = rng.integers(30, 75, (220, 130), dtype=np.uint8)
+    a = _db(hhg, gpu_ctx, seqs)
+    b = hhg.CsDB.from_ffindex(gpu_ctx, data, off, ln)
+    assert np.array_equal(a.ungapped(prof, 50), b.ungapped(prof, 50))
+    assert np.array_equal(b.Lh, [len(s) for s in seqs])
+    a.close(); b.close()
