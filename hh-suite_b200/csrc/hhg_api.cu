@@ -472,9 +472,9 @@ static int db_create_hhm_impl(hhg_ctx* ctx, int n, const char* data, const int64
                               const hhg_prep_params* pp, const float* R, hhg_db** out, float* d_tr_full) {
   if (!ctx || !out || n <= 0 || !data || !off || !len || !pp || !R)
     return fail(HHG_EINVAL, "hhg_db_create_hhm: bad argument");
-  if (pp->pcm < 0 || pp->pcm > 2 || (pp->pcm == 2 && pp->pcc != 1.0f))
-    return fail(HHG_EINVAL, "hhg_db_create_hhm: pseudocount mode %d with pcc=%g not supported (modes 0,1 and 2 "
-                "with pcc=1, i.e. no pow(); src/hhhmm.cpp:1896-1911)", pp->pcm, (double)pp->pcc);
+  if (pp->pcm < 0 || pp->pcm > 3)
+    return fail(HHG_EINVAL, "hhg_db_create_hhm: pseudocount mode %d does not exist (src/hhhmm.cpp:1885-1918: 0..3)", pp->pcm);
+  const bool tau_on_host = pp->pcm == 2 && pp->pcc != 1.0f;   // needs the C library's powf: computed per column below
   CK(cudaSetDevice(ctx->device));
   std::unique_ptr<hhg_db> holder(new hhg_db());
   hhg_db* db = holder.get();
@@ -514,14 +514,15 @@ static int db_create_hhm_impl(hhg_ctx* ctx, int n, const char* data, const int64
   A.pI2M = 1 - A.pI2I;
   A.pD2D = (float)(1.0 * pp->gape / (pp->gape - 1 + 1.0 / 0.75));
   A.pD2M = 1 - A.pD2D;
-  A.pcm = pp->pcm; A.pca = pp->pca; A.pcb = pp->pcb;
+  A.pcm = pp->pcm; A.pca = pp->pca; A.pcb = pp->pcb; A.pcc = pp->pcc;
 
   // pass 2: chunks of records -> host staging (parsed by a few threads) -> device -> k_hhm_prepare / k_hhm_pav
   const long long kChunkCols = 2000000;
   DevBuf<int32_t> d_f, d_trn, d_null, d_haspc;
   DevBuf<uint8_t> d_ss;
-  DevBuf<float> d_neff;
+  DevBuf<float> d_neff, d_tau;
   DevBuf<long long> d_coff;
+  std::vector<float> tau_h;
   HhmStaging st;
   std::vector<long long> coff;
   const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -565,11 +566,26 @@ static int db_create_hhm_impl(hhg_ctx* ctx, int n, const char* data, const int64
     CK(cudaMemcpyAsync(d_haspc.p, st.has_pc.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_neff.p, st.neff_hmm.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_coff.p, coff.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (tau_on_host) {
+      // AddAminoAcidPseudocounts mode 2 with pcc != 1 (src/hhhmm.cpp:1905-1909): tau = fmin(1.0, pca / (1. + pow(Neff_M/pcb, pcc)))
+      // with float arguments, i.e. the C library's powf; one value per column, computed here with the same libm
+      tau_h.resize((size_t)cols);
+      for (int k = 0; k < m; ++k) {
+        const int32_t* rows = st.trn_mb.data() + (size_t)(coff[k] + k) * 10;
+        for (int j = 1; j <= db->L[t0 + k]; ++j) {
+          const float nM = (float)rows[(size_t)j * 10 + 7] / 1000.0f;
+          tau_h[(size_t)coff[k] + j - 1] = (float)fmin(1.0, pp->pca / (1. + powf(nM / pp->pcb, pp->pcc)));
+        }
+      }
+      CK(d_tau.ensure((size_t)cols));
+      CK(cudaMemcpyAsync(d_tau.p, tau_h.data(), (size_t)cols * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
     ColRec* dst = reinterpret_cast<ColRec*>(db->cols_raw.p) + db->col_off[t0];
     const int threads = 128;
     k_hhm_prepare<<<(unsigned)((cols + threads - 1) / threads), threads, 0, ctx->stream>>>(
         m, db->dL.p + t0, d_coff.p, d_f.p, d_trn.p, any_ss ? d_ss.p : nullptr, d_haspc.p, A, ctx->lg2.p,
-        ctx->diff.p, dst, cols, d_tr_full);   // d_tr_full only with a single chunk (hhg_query_from_hhm: one record)
+        ctx->diff.p, dst, cols, d_tr_full,    // d_tr_full only with a single chunk (hhg_query_from_hhm: one record)
+        tau_on_host ? d_tau.p : nullptr);
     k_hhm_pav<<<(unsigned)(((long long)m * 32 + threads - 1) / threads), threads, 0, ctx->stream>>>(
         m, db->dL.p + t0, d_coff.p, dst, d_null.p, d_neff.p, A, db->pav.p + (size_t)t0 * 20);
     ctx->launches += 2;

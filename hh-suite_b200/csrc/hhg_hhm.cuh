@@ -186,7 +186,7 @@ struct HhmPrepArgs {
   float gapb, gapf, gapg, gaph, gapi;
   float pM2M, pM2I, pM2D, pI2I, pI2M, pD2D, pD2M;   // a-priori transition pseudocounts (:1744-1752), host-computed
   int pcm;
-  float pca, pcb;
+  float pca, pcb, pcc;
 };
 
 // alphabetical file order (ACDEFGHIKLMNPQRSTVWY) -> internal amino-acid index (s2a, src/hhdecl.h:61) and back
@@ -248,7 +248,7 @@ k_hhm_prepare(int m, const int* __restrict__ L, const long long* __restrict__ co
               const uint8_t* __restrict__ ss, const int32_t* __restrict__ has_pc,
               const __grid_constant__ HhmPrepArgs A, const float* __restrict__ lg2,
               const float* __restrict__ diff, ColRec* __restrict__ out, long long total_cols,
-              float* __restrict__ tr_full) {
+              float* __restrict__ tr_full, const float* __restrict__ tau_host) {
   // tr_full (optional): the complete transition rows tr[i][M2M,M2I,M2D,I2M,I2I,D2M,D2D], i = 0..L, of every record at
   // float offset (col_off[t] + t + i) * 7 -- what a QUERY needs (hhg_query_from_hhm); column records only keep the
   // entries the DP reads from a template
@@ -286,10 +286,21 @@ k_hhm_prepare(int m, const int* __restrict__ L, const long long* __restrict__ co
     for (int a = 0; a < 20; ++a) r.p[a] = f[a];
   } else {
     float tau = A.pca;                                              // mode 1
-    if (pcm == 2) {                                                 // tau = fmin(1.0, pca / (1. + Neff_M[i]/pcb))
+    if (pcm == 2 && tau_host) {
+      // pcc != 1: tau = fmin(1.0, pca / (1. + pow(Neff_M[i]/pcb, pcc))) -- the reference's pow is the C library's powf;
+      // only the host's libm reproduces its bits, so tau comes precomputed per column (db_create_hhm_impl)
+      tau = tau_host[c];
+    } else if (pcm == 2) {                                          // tau = fmin(1.0, pca / (1. + Neff_M[i]/pcb))
       const float nM = __fdiv_rn((float)rows[(size_t)j * 10 + 7], 1000.0f);
       const double den = __dadd_rn(1.0, (double)__fdiv_rn(nM, A.pcb));
       tau = __double2float_rn(fmin(1.0, __ddiv_rn((double)A.pca, den)));
+    } else if (pcm == 3) {                                          // constant-diversity pseudocounts, :1911-1918
+      const float nM = __fdiv_rn((float)rows[(size_t)j * 10 + 7], 1000.0f);
+      const float x = __fdiv_rn(nM, A.pcb);
+      const float pca3 = __double2float_rn(__dadd_rn(0.793, __dmul_rn(0.048, __dsub_rn((double)A.pcb, 10.0))));
+      const float one_m_x = __fsub_rn(1.0f, x);
+      const float inner = __fadd_rn(one_m_x, __fmul_rn(__fmul_rn(A.pcc, x), one_m_x));   // 1 - x + pcc*x*(1-x)
+      tau = __double2float_rn(fmax(0.0, (double)__fmul_rn(pca3, inner)));
     }
     const double one_minus_tau = __dsub_rn(1.0, (double)tau);
 #pragma unroll

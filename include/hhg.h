@@ -120,8 +120,9 @@ int hhg_db_apply_null_model(hhg_ctx* ctx, hhg_db* db, const float* q_pav, const 
  * data/off/len: the `_hhm.ffdata` bytes and the (offset, length) columns of its `.ffindex` (lib/ffindex/src/ffindex.h:
  * ffindex_entry_t), n records.  Each record must be in HHM format with a NULL line (every record's own NULL line
  * is its background, as HMM::Read sets pb before using it, src/hhhmm.cpp:540-543,666-668).  R = the 20x20
- * pseudocount matrix of SetSubstitutionMatrix (R[a][b], src/hhfunc.cpp).  Supported pseudocount modes: 0, 1 and
- * 2 with pcc == 1 (the default; other settings need pow() and are refused with HHG_EINVAL).
+ * pseudocount matrix of SetSubstitutionMatrix (R[a][b], src/hhfunc.cpp).  All pseudocount modes 0..3 of
+ * HMM::AddAminoAcidPseudocounts; for mode 2 with pcc != 1 the admixture tau = f(powf(Neff/pcb, pcc)) is computed per
+ * column on the host with the C library's powf (the call the reference makes), everything else on the device.
  * Errors (malformed record, LENG/column mismatch) name the record; the reference would warn and skip. */
 typedef struct hhg_prep_params {
   float gapb, gapd, gape, gapf, gapg, gaph, gapi; /* Parameters::gap*, defaults 1, .15, 1, .6, .6, .6, .6       */

@@ -317,6 +317,11 @@ class RefShim:
         return PrepParams(*[float(x) for x in v[:7]], int(v[7]), *[float(x) for x in v[8:]])
 
     # -- query
+    def set_pc(self, mode, a, b, c):
+        """par.pc_hhm_nocontext_mode/_a/_b/_c (-pcm -pca -pcb -pcc) for the following template / query preparations."""
+        self.lib.hhref_set_pc.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+        self.lib.hhref_set_pc(mode, a, b, c)
+
     def load_query_hhm(self, path):
         L = self.lib.hhref_load_query_hhm(path.encode())
         if L < 0:

@@ -512,7 +512,7 @@ typedef struct {
 } hho_prep_params;
 
 /* HMM::Read's number conversion + AddTransitionPseudocounts (src/hhhmm.cpp:1722-1785) + PreparePseudocounts
- * (:1811-1815) + AddAminoAcidPseudocounts (:1874-1921, modes 0,1,2 with pcc == 1) + CalculateAminoAcidBackground
+ * (:1811-1815) + AddAminoAcidPseudocounts (:1874-1921, modes 0..3) + CalculateAminoAcidBackground
  * (:1854-1868).  pb[20] = the background in INTERNAL order that HMM::Read leaves in the global pb after this
  * record's NULL line.  Outputs p[(L+2)*20] (pre-null-model), tr[(L+1)*7], pav[20]. */
 int hho_hhm_prepare(int L, const int* f_mb, const int* tr_mb, const int* neff_mb, const float* pb,
@@ -563,13 +563,18 @@ int hho_hhm_prepare(int L, const int* f_mb, const int* tr_mb, const int* neff_mb
     }
   }
   int pcm = has_pc ? 0 : pp->pcm;
-  if (pcm == 2 && pp->pcc != 1.0f) { free(f); free(NM); return -2; }
-  if (pcm < 0 || pcm > 2) { free(f); free(NM); return -2; }
+  if (pcm < 0 || pcm > 3) { free(f); free(NM); return -2; }
   for (int i = 1; i <= L; ++i) {
     const float* fi = f + i * 20;
     float tau = 0;
     if (pcm == 1) tau = pp->pca;
-    else if (pcm == 2) tau = (float)fmin(1.0, pp->pca / (1. + NM[i * 3] / pp->pcb));
+    else if (pcm == 2 && pp->pcc == 1.0f) tau = (float)fmin(1.0, pp->pca / (1. + NM[i * 3] / pp->pcb));
+    else if (pcm == 2) tau = (float)fmin(1.0, pp->pca / (1. + powf(NM[i * 3] / pp->pcb, pp->pcc)));   /* pow(float,float) */
+    else if (pcm == 3) {                                                                              /* :1911-1918 */
+      float x = NM[i * 3] / pp->pcb;
+      float pca3 = (float)(0.793 + 0.048 * (pp->pcb - 10.0));
+      tau = (float)fmax(0.0, pca3 * (1 - x + pp->pcc * x * (1 - x)));
+    }
     for (int a = 0; a < 20; ++a) {
       if (pcm == 0) { p[i * 20 + a] = fi[a]; continue; }
       /* g[i][a] = ScalarProd20(R[a], f[i]): plain left-to-right sum (SSE undefined, src/hhhit-inl.h:117) */

@@ -171,6 +171,12 @@ void hhref_get_prep_params(float* out11) {
   memcpy(out11, v, sizeof(v));
 }
 
+// override par.pc_hhm_nocontext_mode / _a / _b / _c (the -pcm/-pca/-pcb/-pcc options) for the following preparations
+extern "C" void hhref_set_pc(int mode, float a, float b, float c) {
+  g->par->pc_hhm_nocontext_mode = mode; g->par->pc_hhm_nocontext_a = a; g->par->pc_hhm_nocontext_b = b;
+  g->par->pc_hhm_nocontext_c = c;
+}
+
 // Read query HHM, add pseudocounts exactly like HHalign::run (src/hhalign.cpp:615-626), map to SIMD.
 int hhref_load_query_hhm(const char* path) {
   FILE* f = fopen(path, "r");

@@ -167,9 +167,9 @@ def test_loader_errors(hhg, gpu_ctx):
     with pytest.raises(hhg.HhgError, match="record 1"):
         hhg.TargetDB.from_hhm(gpu_ctx, data, off, ln, G["R"], _pp(G))
     pp = PrepParams.defaults()
-    pp.pcc = 0.5                                          # would need pow(): refused, not approximated
+    pp.pcm = 4                                            # there is no such mode (src/hhhmm.cpp:1885-1918: 0..3)
     data, off, ln = _pack([good])
-    with pytest.raises(hhg.HhgError, match="pcc"):
+    with pytest.raises(hhg.HhgError, match="mode 4"):
         hhg.TargetDB.from_hhm(gpu_ctx, data, off, ln, G["R"], pp)
 
 
@@ -222,3 +222,36 @@ def test_query_from_hhm_equals_reference_prepare_query(hhg, gpu_ctx, refshim, tm
         if got["has_ss"]:
             assert np.array_equal(got["ss"][1:-1], ref["ss"][1:-1])
         assert np.float32(got["neff"]).view(np.uint32) == np.float32(ref["neff"]).view(np.uint32)
+
+
+@pytest.mark.parametrize("pc", [(2, 1.0, 1.5, 0.5), (2, 0.9, 2.0, 1.7), (3, 1.0, 12.0, 0.3), (1, 0.35, 1.5, 1.0), (0, 1.0, 1.5, 1.0)],
+                         ids=["pcm2-pcc0.5", "pcm2-pcc1.7", "pcm3", "pcm1", "pcm0"])
+def test_every_pseudocount_mode_equals_compiled_reference(hhg, gpu_ctx, refshim, tmp_path, pc):
+    """HMM::AddAminoAcidPseudocounts modes 0..3 (src/hhhmm.cpp:1874-1921) incl. mode 2 with pcc != 1, whose pow() is the C
+    library's powf (tau computed per column on the host with the same libm) and the constant-diversity mode 3."""
+    G = golden()
+    qpath = os.path.join(ROOT, "oracle", "_ref", "data", "query.hhm")
+    if not os.path.exists(qpath):
+        pytest.skip("oracle/_ref/data/query.hhm not shipped")
+    refshim.load_query_hhm(qpath)
+    texts = _texts(G, extra_seed=2, n_extra=4)
+    data, off, ln = _pack(texts)
+    pp = hhg.capi.PrepParams.defaults()
+    pp.pcm, pp.pca, pp.pcb, pp.pcc = pc
+    refshim.set_pc(*pc)
+    try:
+        db = hhg.TargetDB.from_hhm(gpu_ctx, data, off, ln, refshim.R(), pp)
+        cols, pav = db.read_cols(0), db.read_pav()
+        pos = 0
+        for k, t in enumerate(texts):
+            f = tmp_path / f"t{k}.hhm"
+            f.write_bytes(t)
+            ref = refshim.prepare_template_hhm_raw(str(f))
+            L = ref["L"]
+            got_p = np.stack([cols["p"][pos + j] for j in range(L)])
+            assert np.array_equal(got_p.view(np.uint32), ref["p_raw"][1:L + 1].view(np.uint32)), (k, pc)
+            assert np.array_equal(bits(pav[k]), bits(ref["pav"])), k
+            pos += L
+        db.close()
+    finally:
+        refshim.set_pc(2, 1.0, 1.5, 1.0)
