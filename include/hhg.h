@@ -306,7 +306,9 @@ int hhg_plan_debug_bt(hhg_ctx* ctx, hhg_plan* plan, int k, uint8_t* bt);
  * (src/hhforwardalgorithm.cpp, src/hhbackwardalgorithm.cpp), the MAC dynamic programme over posterior - mact
  * (src/hhmacalgorithm.cpp) and its backtrace (src/hhbacktracemac.cpp:112-210).  One warp per hit; every value is
  * computed with the reference's operation order and types, so posteriors, Pforward and paths are bit-identical.
- * Not covered: the secondary-structure term (hit.ssm2 != 0), self-alignment (hit.self), exclstr regions.
+ * The secondary-structure term: for predicted-vs-predicted structure (hit.ssm2 = 3) the reference's ScoreSS switch has
+ * no such case (HMM::PRED_PRED = 4) and contributes exactly 0, so those hits are exact; not covered: DSSP-annotated
+ * templates (hit.ssm2 = 1 or 2), self-alignment (hit.self), exclstr regions.
  *
  * hhg_mac_query_set: q_p = HMM::p of the query, q_tr_lin = HMM::tr after Log2LinTransitionProbs(1.0)
  *   (src/hhposteriordecoderrunner.cpp:48); the boundary rows are reset here like initializeQueryHMMTransitions.

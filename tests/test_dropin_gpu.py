@@ -76,6 +76,25 @@ def test_mac_realignment_in_the_dropin_check(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+def test_mac_realignment_with_predicted_secondary_structure(tmp_path):
+    """Query and templates carry ss_pred: Viterbi runs the *AndSS kernels (hit.ssm2 = 3), and the reference's MAC calls
+    Viterbi::ScoreSS(..., hit.ssm2, ...) whose switch knows HMM::PRED_PRED = 4 but not 3 (src/hhhit.cpp:303-308 vs
+    src/hhviterbi.h:199-209, src/hhhmm.h:58-61): the SS term of the realignment is identically 0 for predicted-vs-
+    predicted structure, so hhg_mac_realign (no SS term) must still match bit for bit."""
+    from hhsuite_b200 import synth
+    q = tmp_path / "q.hhm"
+    q.write_text(synth.hhm_text(170, 7, "qss", with_ss=True))
+    files = []
+    for k, L in enumerate([170, 90, 140, 260, 170, 75]):
+        f = tmp_path / f"s{k}.hhm"
+        f.write_text(synth.hhm_text(L, 7 if k in (0, 4) else 600 + k, f"s{k}", with_ss=True))
+        files.append(str(f))
+    r = _run(["--mac", str(q)] + files)
+    assert r.returncode == 0 and "all MAC alignments identical" in r.stdout and "all hits identical" in r.stdout, \
+        r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_two_gpus_behind_the_c_abi(tmp_path):
     """--gpus 2: C++ only (no torch): templates sharded over two GPUs, one host thread + hhg_ctx + hhg_comm each;
