@@ -43,7 +43,7 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_plan_topk", "hhg_plan_topk_by_key", "hhg_plan_topk_paths", "hhg_ctx_last_plan",
            "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order", "hhg_early_stop_sum", "hhg_set_use_ss",
            "hhg_query_set_batch", "hhg_viterbi_search_batch", "hhg_query_from_hhm",
-           "hhg_cs219_parse", "hhg_csdb_create_ffindex"]
+           "hhg_cs219_parse", "hhg_csdb_create_ffindex", "hhg_set_excluded_regions"]
 
 
 class PrepParams(C.Structure):
@@ -184,6 +184,7 @@ def load():
     L.hhg_set_use_ss.argtypes = [C.c_void_p, C.c_int]
     L.hhg_query_from_hhm.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(PrepParams), c_f32p, C.c_int32, c_i32p,
                                      c_f32p, c_f32p, c_u8p, c_f32p, c_f32p]
+    L.hhg_set_excluded_regions.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i32p, C.c_int, c_i32p, c_i32p]
     L.hhg_cs219_parse.argtypes = [C.c_char_p, C.c_int64, c_f32p, C.c_int, c_i32p]
     L.hhg_csdb_create_ffindex.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_i64p, c_i64p, C.POINTER(C.c_void_p)]
     L.hhg_query_set_batch.argtypes = [C.c_void_p, C.c_int, c_i32p, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_f32p,
@@ -226,6 +227,14 @@ class Context:
         out = np.zeros(1025, np.float32)
         _ck(self.L.hhg_debug_fastlog2_table(self.h, _p(out, c_f32p)))
         return out
+
+    def set_excluded_regions(self, query_ranges=(), template_ranges=()):
+        """-excl / -template_excl: lists of (lo, hi) 1-based inclusive ranges; empty lists clear."""
+        q = np.array(query_ranges, np.int32).reshape(-1, 2); t = np.array(template_ranges, np.int32).reshape(-1, 2)
+        ql, qh = np.ascontiguousarray(q[:, 0]), np.ascontiguousarray(q[:, 1])
+        tl, th = np.ascontiguousarray(t[:, 0]), np.ascontiguousarray(t[:, 1])
+        _ck(self.L.hhg_set_excluded_regions(self.h, len(q), _p(ql, c_i32p), _p(qh, c_i32p), len(t), _p(tl, c_i32p),
+                                            _p(th, c_i32p)))
 
     def set_query(self, p, tr, ss=None, S33=None, local=True, egq=0.0, egt=0.0, shift=-0.03, ssw=0.11,
                   use_ss=False, corr=0.1, ssm=2):

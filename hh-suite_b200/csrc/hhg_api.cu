@@ -99,6 +99,9 @@ struct hhg_ctx {
   std::vector<float> h_q_pav;
   bool has_q_pav = false;
   DevBuf<float> d_q_pav, d_pb;
+  // excluded regions (-excl / -template_excl), applied to every search until cleared
+  std::vector<int> ex_q_lo, ex_q_hi, ex_t_lo, ex_t_hi;
+  DevBuf<int> d_ex;
   unsigned long long query_serial = 0;   // bumped by every hhg_query_set*: plans built for an older batch are rebuilt
   int group_jobs = 16;   // work-item interleave (see k_viterbi): 16 jobs x nstrips items keep the group L2-resident
   uint32_t epoch = 0;    // run counter feeding the boundary-slot tags
@@ -1019,40 +1022,69 @@ static int set_exclusions(hhg_ctx* ctx, hhg_plan* pl, const int64_t* excl_off, c
                           const int32_t* excl_j) {
   pl->celloff = false;
   pl->n_excl_steps = 0;
-  if (!excl_off) return HHG_OK;
-  const long long total = excl_off[pl->n];
-  if (total <= 0) return HHG_OK;
-  // validate like hhg_mac_realign does: k_celloff_raster indexes the mask with these values
-  if (excl_off[0] != 0) return fail(HHG_EINVAL, "excl_off[0] must be 0");
-  if (!excl_i || !excl_j) return fail(HHG_EINVAL, "excl_i / excl_j are NULL");
-  std::vector<int> sreq((size_t)total);
-  for (int k = 0; k < pl->n; ++k) {
-    if (excl_off[k + 1] < excl_off[k]) return fail(HHG_EINVAL, "excl_off is not monotonic at request %d", k);
-    const int Lt = pl->db->L[pl->ids[k]];
-    for (long long s = excl_off[k]; s < excl_off[k + 1]; ++s) {
-      const int Lqk = pl->q_L[pl->req_query[k]];
-      if (excl_i[s] < 1 || excl_i[s] > Lqk || excl_j[s] < 1 || excl_j[s] > Lt)
-        return fail(HHG_EINVAL, "excluded step %lld of request %d is (%d,%d), outside 1..%d x 1..%d", s - excl_off[k], k,
-                    excl_i[s], excl_j[s], Lqk, Lt);
-      sreq[(size_t)s] = k;
-    }
-  }
+  const long long total = excl_off ? excl_off[pl->n] : 0;
+  const bool regions = !ctx->ex_q_lo.empty() || !ctx->ex_t_lo.empty();
+  if (total <= 0 && !regions) return HHG_OK;
   const size_t co_words = (size_t)pl->co_total;
   CK(pl->d_co.ensure(co_words));
-  CK(pl->d_step_req.ensure((size_t)total)); CK(pl->d_step_i.ensure((size_t)total)); CK(pl->d_step_j.ensure((size_t)total));
-  CK(cudaMemcpyAsync(pl->d_step_req.p, sreq.data(), (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(pl->d_step_i.p, excl_i, (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(pl->d_step_j.p, excl_j, (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(pl->d_co.p, 0, co_words * 4, ctx->stream));
-  const int threads = 128;
-  k_celloff_raster<<<(unsigned)((total + threads - 1) / threads), threads, 0, ctx->stream>>>(
-      (int)total, pl->d_step_req.p, pl->d_step_i.p, pl->d_step_j.p, pl->d_req_job.p, pl->d_req_lane.p,
-      pl->d_req_Lt.p, pl->d_req_Lq.p, pl->d_job_Lmax.p, pl->d_job_co_off.p, pl->R, pl->d_co.p);
-  ctx->launches++;
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(ctx->stream));   // sreq is a host temporary
+  if (total > 0) {
+    // validate like hhg_mac_realign does: k_celloff_raster indexes the mask with these values
+    if (excl_off[0] != 0) return fail(HHG_EINVAL, "excl_off[0] must be 0");
+    if (!excl_i || !excl_j) return fail(HHG_EINVAL, "excl_i / excl_j are NULL");
+    std::vector<int> sreq((size_t)total);
+    for (int k = 0; k < pl->n; ++k) {
+      if (excl_off[k + 1] < excl_off[k]) return fail(HHG_EINVAL, "excl_off is not monotonic at request %d", k);
+      const int Lt = pl->db->L[pl->ids[k]];
+      for (long long s = excl_off[k]; s < excl_off[k + 1]; ++s) {
+        const int Lqk = pl->q_L[pl->req_query[k]];
+        if (excl_i[s] < 1 || excl_i[s] > Lqk || excl_j[s] < 1 || excl_j[s] > Lt)
+          return fail(HHG_EINVAL, "excluded step %lld of request %d is (%d,%d), outside 1..%d x 1..%d", s - excl_off[k], k,
+                      excl_i[s], excl_j[s], Lqk, Lt);
+        sreq[(size_t)s] = k;
+      }
+    }
+    CK(pl->d_step_req.ensure((size_t)total)); CK(pl->d_step_i.ensure((size_t)total)); CK(pl->d_step_j.ensure((size_t)total));
+    CK(cudaMemcpyAsync(pl->d_step_req.p, sreq.data(), (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(pl->d_step_i.p, excl_i, (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(pl->d_step_j.p, excl_j, (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 128;
+    k_celloff_raster<<<(unsigned)((total + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        (int)total, pl->d_step_req.p, pl->d_step_i.p, pl->d_step_j.p, pl->d_req_job.p, pl->d_req_lane.p,
+        pl->d_req_Lt.p, pl->d_req_Lq.p, pl->d_job_Lmax.p, pl->d_job_co_off.p, pl->R, pl->d_co.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));   // sreq is a host temporary
+  }
+  if (regions) {
+    const int nq = (int)ctx->ex_q_lo.size(), nt = (int)ctx->ex_t_lo.size();
+    std::vector<int> h;
+    h.insert(h.end(), ctx->ex_q_lo.begin(), ctx->ex_q_lo.end()); h.insert(h.end(), ctx->ex_q_hi.begin(), ctx->ex_q_hi.end());
+    h.insert(h.end(), ctx->ex_t_lo.begin(), ctx->ex_t_lo.end()); h.insert(h.end(), ctx->ex_t_hi.begin(), ctx->ex_t_hi.end());
+    CK(ctx->d_ex.ensure(h.size()));
+    CK(cudaMemcpyAsync(ctx->d_ex.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int* d = ctx->d_ex.p;
+    k_celloff_regions<<<(unsigned)((co_words + 255) / 256), 256, 0, ctx->stream>>>(
+        (long long)co_words, pl->njobs, pl->d_job_co_off.p, pl->d_job_Lmax.p, pl->d_job_nstrips.p, pl->R, nq, d, d + nq,
+        nt, d + 2 * nq, d + 2 * nq + nt, pl->d_co.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   pl->celloff = true;
   pl->n_excl_steps = (int)total;
+  return HHG_OK;
+}
+
+// -excl / -template_excl (par.exclstr / par.template_exclstr): ranges of query rows / template columns that are switched
+// off in every following search of this context (ViterbiRunner::exclude_regions, src/hhviterbirunner.cpp:291-330);
+// n = 0 clears.  Ranges are 1-based and inclusive like the option strings.
+int hhg_set_excluded_regions(hhg_ctx* ctx, int nq, const int32_t* q_lo, const int32_t* q_hi, int nt, const int32_t* t_lo,
+                             const int32_t* t_hi) {
+  if (!ctx || nq < 0 || nt < 0 || (nq && (!q_lo || !q_hi)) || (nt && (!t_lo || !t_hi)))
+    return fail(HHG_EINVAL, "hhg_set_excluded_regions: bad argument");
+  ctx->ex_q_lo.assign(q_lo, q_lo + nq); ctx->ex_q_hi.assign(q_hi, q_hi + nq);
+  ctx->ex_t_lo.assign(t_lo, t_lo + nt); ctx->ex_t_hi.assign(t_hi, t_hi + nt);
   return HHG_OK;
 }
 
@@ -1303,7 +1335,8 @@ int hhg_viterbi_search_batch(hhg_ctx* ctx, const hhg_db* db, int n, const int32_
     CK(cudaStreamSynchronize(ctx->stream));
     pl->nm_mode = columnscore;
   }
-  rc = hhg_plan_run(ctx, pl);
+  rc = set_exclusions(ctx, pl, nullptr, nullptr, nullptr);     // excluded regions of the context, if any
+  if (rc == HHG_OK) rc = hhg_plan_run(ctx, pl);
   if (rc == HHG_OK) rc = hhg_plan_fetch(ctx, pl, hits, paths, paths_cap);
   return rc;
 }

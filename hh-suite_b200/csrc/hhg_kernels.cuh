@@ -768,6 +768,35 @@ __global__ void k_celloff_raster(int n_steps, const int* step_req, const int* st
   }
 }
 
+// Excluded regions (ViterbiRunner::exclude_regions / exclude_template_regions, src/hhviterbirunner.cpp:291-330; the
+// -excl / -template_excl options): query rows i0..i1 are switched off for every template column, template columns
+// j0..j1 for every query row.  One thread per cell-off word (job, strip, column, lane).
+__global__ void __launch_bounds__(256)
+k_celloff_regions(long long n_words, int njobs, const long long* __restrict__ job_co_off, const int* __restrict__ job_Lmax,
+                  const int* __restrict__ job_nstrips, int R, int nqr, const int* __restrict__ q_lo,
+                  const int* __restrict__ q_hi, int ntr, const int* __restrict__ t_lo, const int* __restrict__ t_hi,
+                  uint32_t* __restrict__ co) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  int lo = 0, hi = njobs - 1;                       // job owning word w
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (job_co_off[mid] <= w) lo = mid; else hi = mid - 1;
+  }
+  const long long rel = w - job_co_off[lo];
+  const int cols1 = job_Lmax[lo] + 1;
+  const int s = (int)(rel / ((long long)cols1 * 32));
+  const int j = (int)((rel / 32) % cols1);
+  if (s >= job_nstrips[lo] || j < 1) return;
+  uint32_t m = 0;
+  for (int k = 0; k < ntr; ++k) if (j >= t_lo[k] && j <= t_hi[k]) m = 0xFFFFFFFFu;
+  for (int k = 0; k < nqr && m != 0xFFFFFFFFu; ++k) {
+    const int a = max(q_lo[k], s * R + 1), b = min(q_hi[k], s * R + R);   // rows of this strip inside the range
+    if (a <= b) m |= (b - a + 1 >= 32 ? 0xFFFFFFFFu : ((1u << (b - a + 1)) - 1u)) << (a - 1 - s * R);
+  }
+  if (m) co[w] |= m;
+}
+
 // ---------------------------------------------------------------------------------------------
 // cs219 ungapped prefilter (Prefilter::ungapped_sse_score, src/hhprefilter.cpp:214-275).
 //   S(i,j) = max(0, min(255, S(i-1,j-1) + prof[x_j][i]) - offset);  score = max over all cells.

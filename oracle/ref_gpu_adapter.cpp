@@ -184,6 +184,21 @@ class GpuViterbiRunner {
     hhg_params hp = {par.loc, par.egq, par.egt, par.shift, par.ssw, can_ss, par.corr, par.ssm};
     HHG_CHECK(hhg_query_set(ctx_, q->L, qp.data(), qtr.data(), qss.data(), &S33[0][0][0][0], &hp));
     HHG_CHECK(hhg_db_apply_null_model(ctx_, db_, q->pav, pb, par.columnscore));
+    {
+      // par.exclstr / par.template_exclstr: "a-b,c-d" -> ranges, read like the reference does (pairs of integers)
+      auto parse = [](const char* str, std::vector<int32_t>& lo, std::vector<int32_t>& hi) {
+        std::vector<int> v;
+        for (const char* c = str; c && *c;) {
+          if (*c >= '0' && *c <= '9') { int x = 0; while (*c >= '0' && *c <= '9') x = x * 10 + (*c++ - '0'); v.push_back(x); }
+          else ++c;
+        }
+        for (size_t k = 0; k + 1 < v.size(); k += 2) { lo.push_back(v[k]); hi.push_back(v[k + 1]); }
+      };
+      std::vector<int32_t> ql, qh, tl, th;
+      parse(par.exclstr, ql, qh);
+      parse(par.template_exclstr, tl, th);
+      HHG_CHECK(hhg_set_excluded_regions(ctx_, (int)ql.size(), ql.data(), qh.data(), (int)tl.size(), tl.data(), th.data()));
+    }
 
     std::vector<int32_t> ids(n_targets);
     for (int k = 0; k < n_targets; ++k) ids[k] = k;
@@ -482,12 +497,16 @@ int main(int argc, char** argv) {
   bool text_loader = false, with_mac = false, real_lengths = false;
   int gpus = 1, hhblits_dbsize = 0, maxnumdb = 20000;
   const char* prefilter_db_base = nullptr;
+  char* exclstr = nullptr;
+  char* template_exclstr = nullptr;
   std::vector<std::string> previous;
   while (argc > 1 && argv[1][0] == '-' && argv[1][1] == '-') {
     if (!strcmp(argv[1], "--hhm-loader")) text_loader = true;
     else if (!strcmp(argv[1], "--mac")) with_mac = true;
     else if (!strcmp(argv[1], "--gpus") && argc > 2) { gpus = atoi(argv[2]); --argc; ++argv; }
     else if (!strcmp(argv[1], "--real-lengths")) real_lengths = true;
+    else if (!strcmp(argv[1], "--excl") && argc > 2) { exclstr = argv[2]; --argc; ++argv; }
+    else if (!strcmp(argv[1], "--template-excl") && argc > 2) { template_exclstr = argv[2]; --argc; ++argv; }
     else if (!strcmp(argv[1], "--prefilter") && argc > 2) { prefilter_db_base = argv[2]; --argc; ++argv; }
     else if (!strcmp(argv[1], "--maxnumdb") && argc > 2) { maxnumdb = atoi(argv[2]); --argc; ++argv; }
     else if (!strcmp(argv[1], "--previous") && argc > 2) {
@@ -508,6 +527,8 @@ int main(int argc, char** argv) {
   par.nocontxt = 1;
   par.maxres = 4096;
   par.threads = 2;
+  par.exclstr = exclstr;                  // -excl / -template_excl (src/hhdecl.h; ViterbiRunner::exclude_regions)
+  par.template_exclstr = template_exclstr;
   if (hhblits_dbsize > 0) {               // what hhblits sets on top of hhsearch (src/hhblits.cpp:87-88): early stopping
     par.early_stopping_filter = true;
     par.filter_thresh = 0.01;

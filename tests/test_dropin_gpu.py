@@ -194,3 +194,17 @@ def test_prefilter_db_seam(tmp_path, refshim, maxnumdb):
     r = _run(["--prefilter", base, "--maxnumdb", str(maxnumdb), "--previous", prev, QUERY])
     assert r.returncode == 0 and "identical lists" in r.stdout, r.stdout + r.stderr
     assert " 0 new + 0 old" not in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+def test_excluded_regions_in_the_dropin_check(tmp_path):
+    """par.exclstr / par.template_exclstr: the reference's runner masks the regions itself; the adapter passes the
+    same ranges to hhg_set_excluded_regions; all Hits of all alternative alignments identical."""
+    from hhsuite_b200 import synth
+    files = []
+    for k, L in enumerate([150, 431, 300, 97, 200, 60]):
+        f = tmp_path / f"x{k}.hhm"
+        f.write_text(synth.hhm_text(L, 800 + k, f"x{k}"))
+        files.append(str(f))
+    r = _run(["--excl", "1-33,200-260", "--template-excl", "10-20,400-500", QUERY, QUERY] + files)
+    assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr
