@@ -149,28 +149,87 @@ def captured_traffic(key):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+    NVML in a thread (5 ms period) is the sampler; if NVML cannot be loaded, `nvidia-smi -lms 20` is, and start()
+    then waits for its first line (a fresh box can take seconds to deliver it -- longer than the timed region)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                    ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
-        self.lines = []
+        self.nvml = None
+        self.samples = []          # (time, sm_mhz, max_mhz, set(reasons))
+        self.stop_flag = False
+        self.source = None
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.idx < len(ids) and ids[self.idx].isdigit():
+                return int(ids[self.idx])
+        return self.idx
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self._sample_nvml()                      # fail here, not in the thread
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._loop_nvml, daemon=True)
             self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+            self.samples = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "20", "-i", str(self._nvml_index())],
+                                         stdout=subprocess.PIPE, text=True)
+            self.source = "nvidia-smi"
+            self.t = threading.Thread(target=self._loop_smi, daemon=True)
+            self.t.start()
+            t0 = time.time()
+            while not self.samples and time.time() - t0 < 20.0 and self.proc.poll() is None:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _sample_nvml(self):
+        nv = self.nvml
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.samples.append((time.time(), sm, self.max_mhz, {n for n, bit in self.NVML_REASONS if mask & bit}))
+
+    def _loop_nvml(self):
+        while not self.stop_flag:
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _loop_smi(self):
         for ln in self.proc.stdout:
-            self.lines.append((time.time(), ln))
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm = float(f[1]); mx = float(f[2])
+            except ValueError:
+                continue
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.samples.append((time.time(), sm, mx, {n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")}))
 
     def mark_begin(self):
         self.t_begin = time.time()
@@ -179,30 +238,25 @@ class ClockSampler:
         self.t_end = time.time()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
-        sm, mx, reasons = [], None, set()
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        if self.nvml:
+            self.t.join(timeout=1)
         t0 = getattr(self, "t_begin", 0.0)
         t1 = getattr(self, "t_end", float("inf"))
-        inside = [(ts, ln) for ts, ln in self.lines if t0 <= ts <= t1 + 0.02]
-        for ts, ln in (inside or self.lines[-3:]):      # a very short region may fall between two samples
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); mx = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1 + 0.02]
+        use = inside or self.samples[-3:]            # a very short region may fall between two samples
+        sm = [s[1] for s in use]
+        reasons = set().union(*[s[3] for s in use]) if use else set()
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": use[-1][2] if use else None,
+                "reasons": sorted(reasons), "samples": len(inside), "source": self.source}
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -511,29 +565,43 @@ def main():
         plan.run()
         return plan.topk(TOPK, comm=comm, by_hit_score=True, global_ids=gids)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()                      # before the warm-up: nvidia-smi takes a moment to deliver its first sample
-    for _ in range(max(args.warmup, 1)):
-        step()
-    torch.cuda.synchronize()
+    def timed_region(warm):
+        sampler = ClockSampler(local_rank)
+        sampler.start()                  # before the warm-up, so that samples exist when the timed region starts
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler.mark_begin()
+        l0 = ctx.launches
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler.mark_end()
+        return e0.elapsed_time(e1), sampler.stop(), ctx.launches - l0, out
+
+    def bad_clocks(c):                   # the contract's rejection rule; sw_power_cap is kept and noted
+        if {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]):
+            return True
+        return bool(c["sm_mhz"] and c["sm_max_mhz"] and c["sm_mhz"] < 0.85 * c["sm_max_mhz"] and not c["reasons"])
+
+    el_ms, clocks, launches, merged = timed_region(max(args.warmup, 3))
+    flag = torch.tensor([1.0 if bad_clocks(clocks) else 0.0], device=dev)
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.mark_begin()
-    l0 = ctx.launches
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        merged = step()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.mark_end()
-    clocks = sampler.stop()
-    launches = ctx.launches - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if flag.item() > 0:                  # throttled or clock-locked run: rejected and measured once more
+        first = clocks
+        el_ms, clocks, launches, merged = timed_region(1)
+        clocks["remeasured_after"] = first
+    ms = torch.tensor([el_ms], device=dev, dtype=torch.float64)
     cells_all = torch.tensor([cells_rank], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
