@@ -43,7 +43,8 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_plan_topk", "hhg_plan_topk_by_key", "hhg_plan_topk_paths", "hhg_ctx_last_plan",
            "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order", "hhg_early_stop_sum", "hhg_set_use_ss",
            "hhg_query_set_batch", "hhg_viterbi_search_batch", "hhg_query_from_hhm",
-           "hhg_cs219_parse", "hhg_csdb_create_ffindex", "hhg_set_excluded_regions"]
+           "hhg_cs219_parse", "hhg_csdb_create_ffindex", "hhg_set_excluded_regions",
+           "hhg_msa_params_default", "hhg_a3m_scan", "hhg_a3m_parse", "hhg_msa_to_hmm", "hhg_db_create_a3m"]
 
 
 class PrepParams(C.Structure):
@@ -56,6 +57,22 @@ class PrepParams(C.Structure):
     @classmethod
     def defaults(cls):
         return cls(1.0, 0.15, 1.0, 0.6, 0.6, 0.6, 0.6, 2, 1.0, 1.5, 1.0)
+
+
+class MsaParams(C.Structure):
+    """hhg_msa_params: the Parameters the A3M branch of HHEntry::getTemplateHMM reads (src/hhdatabase.cpp:441-449;
+    defaults src/hhdecl.cpp:10-14,45,117-135)."""
+    _fields_ = [("maxseq", C.c_int32), ("maxcol", C.c_int32), ("maxres", C.c_int32), ("M", C.c_int32), ("mark", C.c_int32),
+                ("max_seqid", C.c_int32), ("coverage", C.c_int32), ("qid", C.c_int32), ("Ndiff", C.c_int32),
+                ("qsc", C.c_float), ("wg", C.c_int32)]
+
+    @classmethod
+    def defaults(cls, **kw):
+        mp = cls()
+        load().hhg_msa_params_default(C.byref(mp))
+        for k, v in kw.items():
+            setattr(mp, k, v)
+        return mp
 
 
 # one 112-byte column record of the resident database (include/hhg.h, hhg_db_read_cols)
@@ -184,6 +201,15 @@ def load():
     L.hhg_set_use_ss.argtypes = [C.c_void_p, C.c_int]
     L.hhg_query_from_hhm.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(PrepParams), c_f32p, C.c_int32, c_i32p,
                                      c_f32p, c_f32p, c_u8p, c_f32p, c_f32p]
+    L.hhg_msa_params_default.argtypes = [C.c_void_p]
+    L.hhg_msa_params_default.restype = None
+    L.hhg_a3m_scan.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, c_i32p, c_i32p, c_i32p]
+    L.hhg_a3m_parse.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, c_i32p, c_u8p, C.c_void_p,
+                                C.c_void_p, c_i32p, c_i32p]
+    L.hhg_msa_to_hmm.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, c_f32p, c_f32p, C.c_int32, C.c_int32,
+                                 c_i32p, C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_u8p]
+    L.hhg_db_create_a3m.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_i64p, c_i64p, C.c_void_p, c_f32p, c_f32p,
+                                    C.POINTER(PrepParams), c_f32p, C.POINTER(C.c_void_p)]
     L.hhg_set_excluded_regions.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i32p, C.c_int, c_i32p, c_i32p]
     L.hhg_cs219_parse.argtypes = [C.c_char_p, C.c_int64, c_f32p, C.c_int, c_i32p]
     L.hhg_csdb_create_ffindex.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_i64p, c_i64p, C.POINTER(C.c_void_p)]
@@ -326,6 +352,44 @@ def query_from_hhm(ctx: "Context", record: bytes, R, params: "PrepParams | None"
     return dict(L=L, p=p, tr=tr, ss=ss, pav=pav, neff=float(neff[0]), has_ss=has_ss)
 
 
+def a3m_scan(record: bytes, mp: "MsaParams | None" = None):
+    """(match columns, sequences, has ss_pred) of one A3M record; host only."""
+    mp = mp or MsaParams.defaults()
+    L = np.zeros(1, np.int32); N = np.zeros(1, np.int32); ss = np.zeros(1, np.int32)
+    _ck(load().hhg_a3m_scan(record, len(record), C.byref(mp), _p(L, c_i32p), _p(N, c_i32p), _p(ss, c_i32p)))
+    return int(L[0]), int(N[0]), bool(ss[0])
+
+
+def a3m_parse(record: bytes, mp: "MsaParams | None" = None):
+    """hhg_a3m_parse (host only): what Alignment::Read + Compress + the first steps of Filter2 hold for one record."""
+    mp = mp or MsaParams.defaults()
+    L, N, _ = a3m_scan(record, mp)
+    dims = np.zeros(6, np.int32)
+    X = np.zeros((N, L + 2), np.uint8); I = np.zeros((N, L + 2), np.uint16); keep = np.zeros(N, np.int8)
+    nres = np.zeros(N, np.int32); ksort = np.zeros(N, np.int32)
+    _ck(load().hhg_a3m_parse(record, len(record), C.byref(mp), L, N, _p(dims, c_i32p), _p(X, c_u8p), I.ctypes.data,
+                             keep.ctypes.data, _p(nres, c_i32p), _p(ksort, c_i32p)))
+    return dict(L=L, N_in=N, kfirst=int(dims[3]), kss_pred=int(dims[4]), kss_conf=int(dims[5]), X=X, I=I, keep=keep,
+                nres=nres, ksort=ksort)
+
+
+def msa_to_hmm(ctx: "Context", record: bytes, pb, S=None, mp: "MsaParams | None" = None):
+    """hhg_msa_to_hmm: one A3M record -> the HMM Alignment::FrequenciesAndTransitions computes (no pseudocounts)."""
+    mp = mp or MsaParams.defaults()
+    L, N, _ = a3m_scan(record, mp)
+    dims = np.zeros(6, np.int32)
+    keep = np.zeros(N, np.int8); wg = np.zeros(N, np.float32)
+    f = np.zeros((L + 2, 20), np.float32); tr = np.zeros((L + 1, 7), np.float32); neff = np.zeros((3, L + 1), np.float32)
+    nh = np.zeros(1, np.float32); ss = np.zeros(L + 2, np.uint8)
+    pb = np.ascontiguousarray(pb, np.float32)
+    Sm = None if S is None else np.ascontiguousarray(S, np.float32)
+    _ck(ctx.L.hhg_msa_to_hmm(ctx.h, record, len(record), C.byref(mp), _p(Sm, c_f32p), _p(pb, c_f32p), L, N,
+                             _p(dims, c_i32p), keep.ctypes.data, _p(wg, c_f32p), _p(f, c_f32p), _p(tr, c_f32p),
+                             _p(neff, c_f32p), _p(nh, c_f32p), _p(ss, c_u8p)))
+    return dict(L=L, N_in=N, N_filtered=int(dims[2]), kfirst=int(dims[3]), keep=keep, wg=wg, f=f, tr=tr, neff_m=neff[0],
+                neff_i=neff[1], neff_d=neff[2], neff_hmm=float(nh[0]), ss=ss)
+
+
 def cs219_parse(text: bytes, n_cap: int = 256):
     """hhg_cs219_parse: the column-state library text (cs219.lib) -> float[n_states, 20] linear probabilities."""
     lib = np.zeros((n_cap, 20), np.float32)
@@ -400,6 +464,29 @@ class TargetDB:
         buf = np.frombuffer(data, np.uint8)        # bytes or a (read-only) mmap of the ffdata file
         _ck(ctx.L.hhg_db_create_hhm(ctx.h, n, buf.ctypes.data_as(C.c_char_p), _p(off, c_i64p), _p(ln, c_i64p),
                                     C.byref(pp), _p(R, c_f32p), C.byref(h)))
+        self = cls._wrap(ctx, h, n)
+        self.Lh = np.zeros(n, np.int32)
+        _ck(ctx.L.hhg_db_lengths(h, _p(self.Lh, c_i32p)))
+        return self
+
+    @classmethod
+    def from_a3m(cls, ctx, data: bytes, offsets, lengths, R, pb, S=None, params: "PrepParams | None" = None,
+                 mp: "MsaParams | None" = None):
+        """Build the shard from A3M alignments (`_a3m.ffdata` bytes + offset/length columns): the alignment branch of
+        getTemplateHMM (Read, Compress, Filter, FrequenciesAndTransitions) + the query-independent part of
+        PrepareTemplateHMM, once per database.  pb: background frequencies, S: substitution matrix in bits (qsc only)."""
+        off = np.ascontiguousarray(offsets, np.int64); ln = np.ascontiguousarray(lengths, np.int64)
+        n = len(off)
+        if n == 0 or len(ln) != n or off.min() < 0 or int((off + ln).max()) > len(data):
+            raise ValueError("offsets/lengths do not fit the data buffer")
+        R = np.ascontiguousarray(R, np.float32); pb = np.ascontiguousarray(pb, np.float32)
+        Sm = None if S is None else np.ascontiguousarray(S, np.float32)
+        pp = params or PrepParams.defaults()
+        mp = mp or MsaParams.defaults()
+        h = C.c_void_p()
+        buf = np.frombuffer(data, np.uint8)
+        _ck(ctx.L.hhg_db_create_a3m(ctx.h, n, buf.ctypes.data_as(C.c_char_p), _p(off, c_i64p), _p(ln, c_i64p),
+                                    C.byref(mp), _p(Sm, c_f32p), _p(pb, c_f32p), C.byref(pp), _p(R, c_f32p), C.byref(h)))
         self = cls._wrap(ctx, h, n)
         self.Lh = np.zeros(n, np.int32)
         _ck(ctx.L.hhg_db_lengths(h, _p(self.Lh, c_i32p)))

@@ -4,11 +4,13 @@
 #include "../../include/hhg.h"
 #include "hhg_kernels.cuh"
 #include "hhg_hhm.cuh"
+#include "hhg_msa.cuh"
 #include "hhg_mac.cuh"
 #include "hhg_topk.cuh"
 #include "hhg_hitlist.h"
 
 #include <dlfcn.h>
+#include <xmmintrin.h>
 
 #include <algorithm>
 #include <chrono>
@@ -454,6 +456,385 @@ int hhg_db_apply_null_model(hhg_ctx* ctx, hhg_db* db, const float* q_pav, const 
 
 // ------------------------------------------------------------------------------ DB from HHM text records
 // HHEntry::getTemplateHMM + the query-independent part of PrepareTemplateHMM, once per database load.
+// ---------------------------------------------------------------------------------------------------------------
+// A3M alignments -> HMMs (hhg_msa.cuh).  One chunk of parsed alignments goes through filter, weights, M state and
+// finish; the callers either export the raw HMM (hhg_msa_to_hmm) or continue into the pseudocount step and the shard.
+}  // extern "C"
+namespace {
+
+struct MsaChunk {
+  std::vector<MsaHost> host;
+  std::vector<MsaDesc> desc;
+  long long seq_total = 0, col_total = 0, x_total = 0, ins_total = 0;
+  int Lmax = 0, Nmax = 0;
+  DevBuf<MsaDesc> d_desc;
+  DevBuf<uint8_t> X, member;
+  DevBuf<int8_t> keep, display;
+  DevBuf<int> first, last, nres, ksort, in_, inkk, seqid_prev, acc, Ncnt, Nmaxv, idw, ins_k, nfil, status, ni, counter, cnt;
+  DevBuf<uint16_t> ins_cnt;
+  DevBuf<uint32_t> ins_off;
+  DevBuf<float> wg, f, tr, nm, ni_f, nd, nseg, nhmm, wc, wi, pb, rcp;
+  DevBuf<long long> item_off;
+  MsaArrays A{};
+};
+
+const float* msa_rcp_table(hhg_ctx* ctx, MsaChunk& C) {
+  // RCPPS of this host for every integer argument the weighting can produce (src/hhalignment.cpp:2531)
+  static std::vector<float> table;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    table.resize(MSA_RCP_N);
+    for (int m = 0; m < MSA_RCP_N; m += 4) {
+      const __m128 v = _mm_set_ps((float)(m + 3), (float)(m + 2), (float)(m + 1), (float)m);
+      _mm_storeu_ps(&table[m], _mm_rcp_ps(v));
+    }
+  });
+  if (C.rcp.n != (size_t)MSA_RCP_N) {
+    if (C.rcp.alloc(MSA_RCP_N) != cudaSuccess) return nullptr;
+    if (cudaMemcpyAsync(C.rcp.p, table.data(), (size_t)MSA_RCP_N * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return nullptr;
+  }
+  return C.rcp.p;
+}
+
+#define MSA_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(HHG_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
+
+template <typename T, typename V>
+int msa_upload(hhg_ctx* ctx, DevBuf<T>& d, const std::vector<V>& h) {
+  static_assert(sizeof(T) == sizeof(V), "element size");
+  MSA_CK(d.ensure(h.size() ? h.size() : 1));
+  if (!h.empty()) MSA_CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return HHG_OK;
+}
+
+// C.host is filled (parsed); runs the four kernels and leaves f / tr / Neff / keep / wg on the device.
+int msa_chunk_run(hhg_ctx* ctx, MsaChunk& C, const hhg_msa_params& mp, const float* S, const float* pb, int first_record) {
+  const int m = (int)C.host.size();
+  C.desc.resize(m);
+  C.seq_total = C.col_total = C.x_total = C.ins_total = 0;
+  C.Lmax = C.Nmax = 0;
+  std::vector<long long> item_off(m);
+  long long items = 0;
+  for (int k = 0; k < m; ++k) {
+    const MsaHost& H = C.host[k];
+    MsaDesc& d = C.desc[k];
+    d.N = H.N_in; d.L = H.L; d.stride = H.stride; d.kfirst = H.kfirst;
+    d.x_off = C.x_total; d.seq_off = C.seq_total; d.col_off = C.col_total; d.ins_base = C.ins_total;
+    C.x_total += (long long)H.N_in * H.stride;
+    C.seq_total += H.N_in;
+    C.col_total += H.L + 2;
+    C.ins_total += (long long)H.ins_k.size();
+    C.Lmax = std::max(C.Lmax, H.L); C.Nmax = std::max(C.Nmax, H.N_in);
+    item_off[k] = items;
+    items += H.L;
+  }
+  std::vector<uint8_t> X((size_t)C.x_total);
+  std::vector<int8_t> keep((size_t)C.seq_total), display((size_t)C.seq_total);
+  std::vector<int> first((size_t)C.seq_total), last((size_t)C.seq_total), nres((size_t)C.seq_total), ksort((size_t)C.seq_total);
+  std::vector<uint32_t> ins_off((size_t)C.col_total);
+  std::vector<int> ins_k((size_t)C.ins_total);
+  std::vector<uint16_t> ins_cnt((size_t)C.ins_total);
+  for (int k = 0; k < m; ++k) {
+    const MsaHost& H = C.host[k];
+    const MsaDesc& d = C.desc[k];
+    memcpy(X.data() + d.x_off, H.X.data(), H.X.size());
+    memcpy(keep.data() + d.seq_off, H.keep.data(), H.N_in);
+    memcpy(display.data() + d.seq_off, H.display.data(), H.N_in);
+    memcpy(first.data() + d.seq_off, H.first.data(), (size_t)H.N_in * 4);
+    memcpy(last.data() + d.seq_off, H.last.data(), (size_t)H.N_in * 4);
+    memcpy(nres.data() + d.seq_off, H.nres.data(), (size_t)H.N_in * 4);
+    memcpy(ksort.data() + d.seq_off, H.ksort.data(), (size_t)H.N_in * 4);
+    memcpy(ins_off.data() + d.col_off, H.ins_off.data(), (size_t)(H.L + 2) * 4);
+    if (!H.ins_k.empty()) {
+      memcpy(ins_k.data() + d.ins_base, H.ins_k.data(), H.ins_k.size() * 4);
+      memcpy(ins_cnt.data() + d.ins_base, H.ins_cnt.data(), H.ins_cnt.size() * 2);
+    }
+  }
+  int rc;
+  if ((rc = msa_upload(ctx, C.d_desc, C.desc)) || (rc = msa_upload(ctx, C.X, X)) || (rc = msa_upload(ctx, C.keep, keep)) ||
+      (rc = msa_upload(ctx, C.display, display)) || (rc = msa_upload(ctx, C.first, first)) || (rc = msa_upload(ctx, C.last, last)) ||
+      (rc = msa_upload(ctx, C.nres, nres)) || (rc = msa_upload(ctx, C.ksort, ksort)) || (rc = msa_upload(ctx, C.ins_off, ins_off)) ||
+      (rc = msa_upload(ctx, C.ins_k, ins_k)) || (rc = msa_upload(ctx, C.ins_cnt, ins_cnt)) || (rc = msa_upload(ctx, C.item_off, item_off)))
+    return rc;
+  const size_t ns = (size_t)C.seq_total, nc = (size_t)C.col_total;
+  MSA_CK(C.in_.ensure(ns)); MSA_CK(C.inkk.ensure(ns)); MSA_CK(C.seqid_prev.ensure(ns)); MSA_CK(C.acc.ensure(ns)); MSA_CK(C.wg.ensure(ns));
+  MSA_CK(C.Ncnt.ensure(nc)); MSA_CK(C.Nmaxv.ensure(nc)); MSA_CK(C.idw.ensure(nc)); MSA_CK(C.ni.ensure(nc * 21));
+  MSA_CK(C.f.ensure(nc * 20)); MSA_CK(C.tr.ensure(nc * 7)); MSA_CK(C.nm.ensure(nc)); MSA_CK(C.ni_f.ensure(nc)); MSA_CK(C.nd.ensure(nc));
+  MSA_CK(C.nseg.ensure(nc)); MSA_CK(C.nhmm.ensure(m)); MSA_CK(C.nfil.ensure(m)); MSA_CK(C.status.ensure(m)); MSA_CK(C.counter.ensure(1));
+  MSA_CK(C.pb.ensure(20));
+  MSA_CK(cudaMemcpyAsync(C.pb.p, pb, 80, cudaMemcpyHostToDevice, ctx->stream));
+  MSA_CK(cudaMemsetAsync(C.status.p, 0, (size_t)m * 4, ctx->stream));
+  MSA_CK(cudaMemsetAsync(C.counter.p, 0, 4, ctx->stream));
+  MSA_CK(cudaMemsetAsync(C.nseg.p, 0, nc * 4, ctx->stream));
+  MSA_CK(cudaMemsetAsync(C.tr.p, 0, nc * 7 * 4, ctx->stream));
+  const float* rcp = msa_rcp_table(ctx, C);
+  if (!rcp) return fail(HHG_ECUDA, "reciprocal table upload failed");
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int nblk = (int)std::min<long long>((long long)sms * 3, std::max<long long>(items, 1));
+  MSA_CK(C.cnt.ensure((size_t)nblk * (C.Lmax + 2) * 24)); MSA_CK(C.wc.ensure((size_t)nblk * (C.Lmax + 2) * 24));
+  MSA_CK(C.wi.ensure((size_t)nblk * C.Nmax)); MSA_CK(C.member.ensure((size_t)nblk * C.Nmax));
+
+  MsaArrays& A = C.A;
+  A.desc = C.d_desc.p; A.X = C.X.p; A.keep = C.keep.p; A.display = C.display.p;
+  A.first = C.first.p; A.last = C.last.p; A.nres = C.nres.p; A.ksort = C.ksort.p;
+  A.in_ = C.in_.p; A.inkk = C.inkk.p; A.seqid_prev = C.seqid_prev.p; A.acc = C.acc.p;
+  A.Ncnt = C.Ncnt.p; A.Nmax = C.Nmaxv.p; A.idmaxwin = C.idw.p; A.wg = C.wg.p;
+  A.ins_off = C.ins_off.p; A.ins_k = C.ins_k.p; A.ins_cnt = C.ins_cnt.p;
+  A.n_filtered = C.nfil.p; A.status = C.status.p;
+  A.f = C.f.p; A.tr = C.tr.p; A.neff_m = C.nm.p; A.neff_i = C.ni_f.p; A.neff_d = C.nd.p; A.neff_seg = C.nseg.p; A.neff_hmm = C.nhmm.p;
+
+  MsaFilterParams FP;
+  FP.max_seqid = mp.max_seqid; FP.coverage = mp.coverage; FP.qid = mp.qid; FP.Ndiff = mp.Ndiff; FP.qsc = mp.qsc;
+  if (S) memcpy(FP.S, S, sizeof(FP.S)); else memset(FP.S, 0, sizeof(FP.S));
+  k_msa_filter<<<m, 256, 0, ctx->stream>>>(A, FP);
+  k_msa_weights<<<m, 256, 0, ctx->stream>>>(A, C.ni.p);
+  k_msa_mstate<<<nblk, 256, 0, ctx->stream>>>(A, m, C.item_off.p, items, C.counter.p, C.cnt.p, C.wc.p, C.wi.p, C.member.p,
+                                              C.Lmax, C.Nmax, rcp, C.pb.p, mp.wg ? 1 : 0, ctx->lg2.p, ctx->diff.p);
+  k_msa_finish<<<m, 256, 0, ctx->stream>>>(A, C.pb.p, mp.wg ? 1 : 0, ctx->lg2.p, ctx->diff.p);
+  ctx->launches += 4;
+  MSA_CK(cudaGetLastError());
+  std::vector<int> status(m);
+  MSA_CK(cudaMemcpyAsync(status.data(), C.status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MSA_CK(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < m; ++k)
+    if (status[k])
+      return fail(HHG_EINVAL, "alignment %d: %s", first_record + k,
+                  status[k] == 1 ? "contains no sequences after filtering (the reference exits here)"
+                  : status[k] == 2 ? "the position-dependent identity schedule divides by zero (as in the reference)"
+                                   : "no sequence left for the profile");
+  return HHG_OK;
+}
+
+int msa_params_check(const hhg_msa_params* mp) {
+  if (!mp) return fail(HHG_EINVAL, "alignment parameters are NULL");
+  if (mp->maxseq < 2 || mp->maxseq > 65535) return fail(HHG_EINVAL, "maxseq %d outside [2, 65535]", mp->maxseq);
+  if (mp->maxres < 8 || mp->maxcol < mp->maxres) return fail(HHG_EINVAL, "maxres %d / maxcol %d", mp->maxres, mp->maxcol);
+  if (mp->M != 1) return fail(HHG_EINVAL, "match-state assignment %d: only 1 (A2M/A3M, upper case = match; par.M_template) is built", mp->M);
+  if (mp->mark != 0) return fail(HHG_EINVAL, "the -mark option is not built");
+  return HHG_OK;
+}
+
+// ss byte of column j (1..L) the DP reads: ss_pred * MAXCF + ss_conf (src/hhhmmsimd.cpp:133); ss_conf = 5 without an
+// ss_conf row (FrequenciesAndTransitions :2313-2319)
+void msa_ss_bytes(const MsaHost& H, uint8_t* out) {
+  if (H.kss_pred < 0) { memset(out, 0, (size_t)H.L); return; }
+  const uint8_t* pr = H.X.data() + (size_t)H.kss_pred * H.stride;
+  const uint8_t* cf = H.kss_conf >= 0 ? H.X.data() + (size_t)H.kss_conf * H.stride : nullptr;
+  for (int j = 1; j <= H.L; ++j) out[j - 1] = (uint8_t)((pr[j] & 0x7f) * 11 + (cf ? (cf[j] & 0x7f) : 5));
+}
+
+}  // namespace
+extern "C" {
+
+void hhg_msa_params_default(hhg_msa_params* mp) {
+  if (!mp) return;
+  mp->maxseq = 65535; mp->maxcol = 32765; mp->maxres = 20001;       // src/hhdecl.cpp:10-14
+  mp->M = 1; mp->mark = 0;
+  mp->max_seqid = 90; mp->coverage = 0; mp->qid = 0; mp->Ndiff = 100; mp->qsc = -20.0f;   // :35-39, :131-135
+  mp->wg = 0;
+}
+
+int hhg_a3m_scan(const char* rec, int64_t len, const hhg_msa_params* mp, int32_t* L, int32_t* N_in, int32_t* has_ss) {
+  if (!rec || len <= 0 || !L || !N_in) return fail(HHG_EINVAL, "hhg_a3m_scan: bad argument");
+  int rc = msa_params_check(mp);
+  if (rc != HHG_OK) return rc;
+  MsaHost H;
+  const std::string msg = MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, &H);
+  if (!msg.empty()) return fail(HHG_EINVAL, "hhg_a3m_scan: %s", msg.c_str());
+  *L = H.L; *N_in = H.N_in;
+  if (has_ss) *has_ss = H.kss_pred >= 0;
+  return HHG_OK;
+}
+
+int hhg_a3m_parse(const char* rec, int64_t len, const hhg_msa_params* mp, int32_t L_cap, int32_t N_cap, int32_t* dims,
+                  uint8_t* X, uint16_t* I, int8_t* keep, int32_t* nres, int32_t* ksort) {
+  if (!rec || len <= 0 || !dims || !X) return fail(HHG_EINVAL, "hhg_a3m_parse: bad argument");
+  int rc = msa_params_check(mp);
+  if (rc != HHG_OK) return rc;
+  MsaHost H;
+  const std::string msg = MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, &H);
+  if (!msg.empty()) return fail(HHG_EINVAL, "hhg_a3m_parse: %s", msg.c_str());
+  dims[0] = H.L; dims[1] = H.N_in; dims[2] = 0; dims[3] = H.kfirst; dims[4] = H.kss_pred; dims[5] = H.kss_conf;
+  if (H.L > L_cap || H.N_in > N_cap) return fail(HHG_EINVAL, "hhg_a3m_parse: %d columns / %d sequences exceed the caller's capacity", H.L, H.N_in);
+  const int L = H.L, N = H.N_in;
+  for (int k = 0; k < N; ++k) {
+    for (int i = 0; i <= L + 1; ++i) X[(size_t)k * (L + 2) + i] = H.X[(size_t)k * H.stride + i] & 0x7f;
+    if (I) for (int i = 0; i <= L + 1; ++i) I[(size_t)k * (L + 2) + i] = 0;
+    if (keep) keep[k] = H.keep[k];
+    if (nres) nres[k] = H.nres[k];
+    if (ksort) ksort[k] = H.ksort[k];
+  }
+  if (I)
+    for (int i = 0; i <= L; ++i)
+      for (uint32_t e = H.ins_off[i]; e < H.ins_off[i + 1]; ++e) I[(size_t)H.ins_k[e] * (L + 2) + i] = H.ins_cnt[e];
+  return HHG_OK;
+}
+
+int hhg_msa_to_hmm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa_params* mp, const float* S, const float* pb,
+                   int32_t L_cap, int32_t N_cap, int32_t* dims, int8_t* keep, float* wg, float* f, float* tr,
+                   float* neff, float* neff_hmm, uint8_t* ss) {
+  if (!ctx || !rec || len <= 0 || !pb || !dims || !f || !tr || !neff || !neff_hmm)
+    return fail(HHG_EINVAL, "hhg_msa_to_hmm: bad argument");
+  int rc = msa_params_check(mp);
+  if (rc != HHG_OK) return rc;
+  if (mp->qsc > -10.f && !S) return fail(HHG_EINVAL, "hhg_msa_to_hmm: the qsc filter needs the substitution matrix S");
+  CK(cudaSetDevice(ctx->device));
+  MsaChunk C;
+  C.host.resize(1);
+  const std::string msg = MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, &C.host[0]);
+  if (!msg.empty()) return fail(HHG_EINVAL, "hhg_msa_to_hmm: %s", msg.c_str());
+  const MsaHost& H = C.host[0];
+  dims[0] = H.L; dims[1] = H.N_in; dims[2] = 0; dims[3] = H.kfirst; dims[4] = H.kss_pred; dims[5] = H.kss_conf;
+  if (H.L > L_cap || H.N_in > N_cap) return fail(HHG_EINVAL, "hhg_msa_to_hmm: %d columns / %d sequences exceed the caller's capacity %d / %d", H.L, H.N_in, L_cap, N_cap);
+  rc = msa_chunk_run(ctx, C, *mp, S, pb, 0);
+  if (rc != HHG_OK) return rc;
+  const int L = H.L, N = H.N_in;
+  int nf = 0;
+  CK(cudaMemcpyAsync(&nf, C.nfil.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (keep) CK(cudaMemcpyAsync(keep, C.keep.p, (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+  if (wg) CK(cudaMemcpyAsync(wg, C.wg.p, (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(f, C.f.p, (size_t)(L + 2) * 80, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(tr, C.tr.p, (size_t)(L + 1) * 28, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(neff, C.nm.p, (size_t)(L + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(neff + (L + 1), C.ni_f.p, (size_t)(L + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(neff + 2 * (L + 1), C.nd.p, (size_t)(L + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(neff_hmm, C.nhmm.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  dims[2] = nf;
+  if (ss) { ss[0] = 0; msa_ss_bytes(H, ss + 1); ss[L + 1] = 0; }
+  return HHG_OK;
+}
+
+static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
+                              const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
+                              const float* R, hhg_db** out, float* d_tr_full, float* neff_hmm_out) {
+  if (!ctx || !out || n <= 0 || !data || !off || !len || !pp || !R || !pb)
+    return fail(HHG_EINVAL, "hhg_db_create_a3m: bad argument");
+  int rc = msa_params_check(mp);
+  if (rc != HHG_OK) return rc;
+  if (mp->qsc > -10.f && !S) return fail(HHG_EINVAL, "hhg_db_create_a3m: the qsc filter needs the substitution matrix S");
+  if (pp->pcm < 0 || pp->pcm > 3) return fail(HHG_EINVAL, "hhg_db_create_a3m: pseudocount mode %d does not exist", pp->pcm);
+  const bool tau_on_host = pp->pcm == 2 && pp->pcc != 1.0f;
+  CK(cudaSetDevice(ctx->device));
+  // pass 1: parse everything (host threads); the parsed alignments of one chunk are kept, the rest re-parsed later
+  // would double the work, so all are kept: 1 byte per residue
+  std::vector<MsaHost> all((size_t)n);
+  {
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::string> errs(hw);
+    std::vector<int> err_rec(hw, -1);
+    auto work = [&](unsigned w) {
+      for (int k = (int)w; k < n; k += (int)hw) {
+        if (len[k] <= 0) { if (err_rec[w] < 0) { errs[w] = "empty record"; err_rec[w] = k; } continue; }
+        std::string msg = MsaScanner::parse(data + off[k], len[k], mp->maxseq, mp->maxcol, mp->maxres, &all[k]);
+        if (!msg.empty() && err_rec[w] < 0) { errs[w] = msg; err_rec[w] = k; }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < hw; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (unsigned w = 0; w < hw; ++w)
+      if (err_rec[w] >= 0) return fail(HHG_EINVAL, "record %d: %s", err_rec[w], errs[w].c_str());
+  }
+  std::unique_ptr<hhg_db> holder(new hhg_db());
+  hhg_db* db = holder.get();
+  db->device = ctx->device;
+  db->n = n;
+  db->L.resize(n);
+  db->col_off.resize(n);
+  long long tot = 0;
+  bool any_ss = false;
+  for (int k = 0; k < n; ++k) {
+    if (all[k].L > 32767) return fail(HHG_EINVAL, "record %d: length %d out of [1,32767]", k, all[k].L);
+    db->L[k] = all[k].L;
+    db->col_off[k] = tot;
+    tot += all[k].L;
+    any_ss |= all[k].kss_pred >= 0;
+  }
+  db->total_cols = tot;
+  db->has_ss = any_ss;
+  cudaError_t e;
+  if ((e = db->cols.alloc((size_t)tot * 7)) != cudaSuccess || (e = db->cols_raw.alloc((size_t)tot * 7)) != cudaSuccess ||
+      (e = db->dL.alloc(n)) != cudaSuccess || (e = db->dcol_off.alloc(n)) != cudaSuccess ||
+      (e = db->pav.alloc((size_t)n * 20)) != cudaSuccess)
+    return fail(HHG_ENOMEM, "hhg_db_create_a3m: %s", cudaGetErrorString(e));
+  CK(cudaMemcpyAsync(db->dL.p, db->L.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->dcol_off.p, db->col_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  HhmPrepArgs A;
+  memcpy(A.R, R, sizeof(A.R));
+  A.gapb = pp->gapb; A.gapf = pp->gapf; A.gapg = pp->gapg; A.gaph = pp->gaph; A.gapi = pp->gapi;
+  A.pM2D = A.pM2I = (float)(pp->gapd * 0.0286);
+  A.pM2M = 1 - A.pM2D - A.pM2I;
+  A.pI2I = (float)(1.0 * pp->gape / (pp->gape - 1 + 1.0 / 0.75));
+  A.pI2M = 1 - A.pI2I;
+  A.pD2D = (float)(1.0 * pp->gape / (pp->gape - 1 + 1.0 / 0.75));
+  A.pD2M = 1 - A.pD2D;
+  A.pcm = pp->pcm; A.pca = pp->pca; A.pcb = pp->pcb; A.pcc = pp->pcc;
+
+  const long long kChunkBytes = 256ll << 20;
+  MsaChunk C;
+  DevBuf<long long> d_rec_off;
+  DevBuf<uint8_t> d_ss;
+  DevBuf<float> d_tau;
+  int t0 = 0;
+  while (t0 < n) {
+    int t1 = t0;
+    long long bytes = 0;
+    while (t1 < n && t1 - t0 < 8192 && (bytes == 0 || bytes + (long long)all[t1].X.size() <= kChunkBytes)) bytes += (long long)all[t1++].X.size();
+    const int m = t1 - t0;
+    C.host.clear();
+    for (int k = t0; k < t1; ++k) C.host.push_back(std::move(all[k]));
+    rc = msa_chunk_run(ctx, C, *mp, S, pb, t0);
+    if (rc != HHG_OK) return rc;
+    std::vector<long long> rec_off(m);
+    long long cols = 0;
+    for (int k = 0; k < m; ++k) { rec_off[k] = cols; cols += C.host[k].L; }
+    std::vector<uint8_t> ssb((size_t)cols, 0);
+    if (any_ss) for (int k = 0; k < m; ++k) msa_ss_bytes(C.host[k], ssb.data() + rec_off[k]);
+    CK(d_rec_off.ensure(m)); CK(d_ss.ensure((size_t)cols));
+    CK(cudaMemcpyAsync(d_rec_off.p, rec_off.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_ss.p, ssb.data(), (size_t)cols, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<float> tau_h;
+    if (tau_on_host) {
+      std::vector<float> nm((size_t)C.col_total);
+      CK(cudaMemcpyAsync(nm.data(), C.nm.p, nm.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      tau_h.resize((size_t)cols);
+      for (int k = 0; k < m; ++k)
+        for (int j = 1; j <= C.host[k].L; ++j)
+          tau_h[(size_t)rec_off[k] + j - 1] = (float)fmin(1.0, pp->pca / (1. + powf(nm[(size_t)C.desc[k].col_off + j] / pp->pcb, pp->pcc)));
+      CK(d_tau.ensure((size_t)cols));
+      CK(cudaMemcpyAsync(d_tau.p, tau_h.data(), (size_t)cols * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ColRec* dst = reinterpret_cast<ColRec*>(db->cols_raw.p) + db->col_off[t0];
+    const int threads = 128;
+    k_msa_prepare<<<(unsigned)((cols + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        m, C.d_desc.p, d_rec_off.p, C.A, any_ss ? d_ss.p : nullptr, A, ctx->lg2.p, ctx->diff.p, dst, cols, d_tr_full,
+        tau_on_host ? d_tau.p : nullptr);
+    k_hhm_pav<<<(unsigned)(((long long)m * 32 + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        m, db->dL.p + t0, d_rec_off.p, dst, nullptr, C.nhmm.p, A, db->pav.p + (size_t)t0 * 20, C.pb.p);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    if (neff_hmm_out) CK(cudaMemcpyAsync(neff_hmm_out + t0, C.nhmm.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    t0 = t1;
+  }
+  CK(cudaMemcpyAsync(db->cols.p, db->cols_raw.p, db->cols.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  db->raw = true;
+  db->prepared = false;
+  *out = holder.release();
+  return HHG_OK;
+}
+
+int hhg_db_create_a3m(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
+                      const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
+                      const float* R, hhg_db** out) {
+  return db_create_a3m_impl(ctx, n, data, off, len, mp, S, pb, pp, R, out, nullptr, nullptr);
+}
+
 int hhg_hhm_scan(const char* rec, int64_t len, int32_t* L, int32_t* has_ss) {
   if (!rec || len <= 0 || !L || !has_ss) return fail(HHG_EINVAL, "hhg_hhm_scan: bad argument");
   HhmScanner sc(rec, len);

@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include "hhg_math.cuh"
+
 namespace hhg {
 
 // ------------------------------------------------------------------------------------------ host: scanner
@@ -195,29 +197,11 @@ struct HhmPrepArgs {
 #define HHG_A2S(i) ((i)==0?0:(i)==4?1:(i)==3?2:(i)==6?3:(i)==13?4:(i)==7?5:(i)==8?6:(i)==9?7:(i)==11?8:(i)==10?9: \
                     (i)==12?10:(i)==2?11:(i)==14?12:(i)==5?13:(i)==1?14:(i)==15?15:(i)==16?16:(i)==19?17:(i)==17?18:19)
 
-// fpow2, src/util-inl.h:190-214
-__device__ __forceinline__ float fpow2_dev(float x) {
-  if (x >= 128.0f) return FLT_MAX;
-  if (x <= -125.0f) return 0.0f;
-  const float tx = __fadd_rn(__fsub_rn(x, 0.5f), 12582912.0f);
-  const int lx = __float_as_int(tx) - 0x4b400000;
-  const float dx = __fsub_rn(x, (float)lx);
-  float y = __fadd_rn(0.0520749f, __fmul_rn(dx, 0.0134929f));
-  y = __fadd_rn(0.241404f, __fmul_rn(dx, y));
-  y = __fadd_rn(0.693019f, __fmul_rn(dx, y));
-  y = __fadd_rn(1.0f, __fmul_rn(dx, y));
-  return __int_as_float(__float_as_int(y) + (lx << 23));
-}
-
-// One row of HMM::AddTransitionPseudocounts (:1755-1783): row i of target with L columns -> tr[7] (enum order).
-__device__ __forceinline__ void hhm_transitions(const int32_t* __restrict__ row, int i, int L,
-                                                const HhmPrepArgs& A, const float* lg2, const float* diff,
-                                                float* tr) {
-#pragma unroll
-  for (int k = 0; k < 7; ++k) tr[k] = __fdiv_rn((float)(-row[k]), 1000.0f);
+// One row of HMM::AddTransitionPseudocounts (:1755-1783): tr[7] (enum order, log2) of row i of a template with L
+// columns and its Neff_M / Neff_I / Neff_D, in place.
+__device__ __forceinline__ void hhm_transitions_core(float* tr, float nM, float nI, float nD, int i, int L,
+                                                     const HhmPrepArgs& A, const float* lg2, const float* diff) {
   if (!(A.gapb > 0.f)) return;
-  const float nM = __fdiv_rn((float)row[7], 1000.0f), nI = __fdiv_rn((float)row[8], 1000.0f),
-              nD = __fdiv_rn((float)row[9], 1000.0f);
   const float nm1 = __fsub_rn(nM, 1.0f);
   float p0 = __fadd_rn(__fmul_rn(nm1, fpow2_dev(tr[0])), __fmul_rn(A.gapb, A.pM2M));
   float p1 = __fadd_rn(__fmul_rn(nm1, fpow2_dev(tr[2])), __fmul_rn(A.gapb, A.pM2D));
@@ -238,6 +222,50 @@ __device__ __forceinline__ void hhm_transitions(const int32_t* __restrict__ row,
   sum = __fadd_rn(__fadd_rn(p0, p1), FLT_MIN);
   tr[5] = fast_log2_dev(__fdiv_rn(p0, sum), lg2, diff);
   tr[6] = __fmul_rn(fast_log2_dev(__fdiv_rn(p1, sum), lg2, diff), A.gaph);
+}
+
+// the same from the integers of an HHM file (1/1000 bits; Neff * 1000)
+__device__ __forceinline__ void hhm_transitions(const int32_t* __restrict__ row, int i, int L,
+                                                const HhmPrepArgs& A, const float* lg2, const float* diff,
+                                                float* tr) {
+#pragma unroll
+  for (int k = 0; k < 7; ++k) tr[k] = __fdiv_rn((float)(-row[k]), 1000.0f);
+  if (!(A.gapb > 0.f)) return;
+  hhm_transitions_core(tr, __fdiv_rn((float)row[7], 1000.0f), __fdiv_rn((float)row[8], 1000.0f),
+                       __fdiv_rn((float)row[9], 1000.0f), i, L, A, lg2, diff);
+}
+
+// HMM::PreparePseudocounts + AddAminoAcidPseudocounts (:1811-1815, :1874-1921) of one column: f[20] -> p[20].
+// tau_pre: mode 2 with pcc != 1 needs the C library's powf; the caller passes the per-column tau computed on the host.
+__device__ __forceinline__ void hhm_emissions(const float* f, float nM, int pcm, const HhmPrepArgs& A, bool have_tau,
+                                              float tau_pre, float* p) {
+  if (pcm == 0) {
+#pragma unroll
+    for (int a = 0; a < 20; ++a) p[a] = f[a];
+    return;
+  }
+  float tau = A.pca;                                                // mode 1
+  if (pcm == 2 && have_tau) {
+    tau = tau_pre;
+  } else if (pcm == 2) {                                            // tau = fmin(1.0, pca / (1. + Neff_M[i]/pcb))
+    const double den = __dadd_rn(1.0, (double)__fdiv_rn(nM, A.pcb));
+    tau = __double2float_rn(fmin(1.0, __ddiv_rn((double)A.pca, den)));
+  } else if (pcm == 3) {                                            // constant-diversity pseudocounts, :1911-1918
+    const float x = __fdiv_rn(nM, A.pcb);
+    const float pca3 = __double2float_rn(__dadd_rn(0.793, __dmul_rn(0.048, __dsub_rn((double)A.pcb, 10.0))));
+    const float one_m_x = __fsub_rn(1.0f, x);
+    const float inner = __fadd_rn(one_m_x, __fmul_rn(__fmul_rn(A.pcc, x), one_m_x));   // 1 - x + pcc*x*(1-x)
+    tau = __double2float_rn(fmax(0.0, (double)__fmul_rn(pca3, inner)));
+  }
+  const double one_minus_tau = __dsub_rn(1.0, (double)tau);
+#pragma unroll
+  for (int a = 0; a < 20; ++a) {
+    const float* Ra = A.R + a * 20;
+    float g = __fmul_rn(f[0], Ra[0]);                               // ScalarProd20(R[a], f[i]), left to right
+#pragma unroll
+    for (int b = 1; b < 20; ++b) g = __fadd_rn(g, __fmul_rn(f[b], Ra[b]));
+    p[a] = __double2float_rn(__dadd_rn(__dmul_rn(one_minus_tau, (double)f[a]), (double)__fmul_rn(tau, g)));
+  }
 }
 
 // Thread per column j = 1..L of every record in the chunk.  col_off[m] are chunk-local column offsets;
@@ -281,37 +309,10 @@ k_hhm_prepare(int m, const int* __restrict__ L, const long long* __restrict__ co
   for (int a = 0; a < 20; ++a) f[HHG_S2A(a)] = fpow2_dev(__fdiv_rn((float)(-fm[a]), 1000.0f));   // :608
   const int pcm = has_pc[t] ? 0 : A.pcm;
   ColRec r;
-  if (pcm == 0) {
-#pragma unroll
-    for (int a = 0; a < 20; ++a) r.p[a] = f[a];
-  } else {
-    float tau = A.pca;                                              // mode 1
-    if (pcm == 2 && tau_host) {
-      // pcc != 1: tau = fmin(1.0, pca / (1. + pow(Neff_M[i]/pcb, pcc))) -- the reference's pow is the C library's powf;
-      // only the host's libm reproduces its bits, so tau comes precomputed per column (db_create_hhm_impl)
-      tau = tau_host[c];
-    } else if (pcm == 2) {                                          // tau = fmin(1.0, pca / (1. + Neff_M[i]/pcb))
-      const float nM = __fdiv_rn((float)rows[(size_t)j * 10 + 7], 1000.0f);
-      const double den = __dadd_rn(1.0, (double)__fdiv_rn(nM, A.pcb));
-      tau = __double2float_rn(fmin(1.0, __ddiv_rn((double)A.pca, den)));
-    } else if (pcm == 3) {                                          // constant-diversity pseudocounts, :1911-1918
-      const float nM = __fdiv_rn((float)rows[(size_t)j * 10 + 7], 1000.0f);
-      const float x = __fdiv_rn(nM, A.pcb);
-      const float pca3 = __double2float_rn(__dadd_rn(0.793, __dmul_rn(0.048, __dsub_rn((double)A.pcb, 10.0))));
-      const float one_m_x = __fsub_rn(1.0f, x);
-      const float inner = __fadd_rn(one_m_x, __fmul_rn(__fmul_rn(A.pcc, x), one_m_x));   // 1 - x + pcc*x*(1-x)
-      tau = __double2float_rn(fmax(0.0, (double)__fmul_rn(pca3, inner)));
-    }
-    const double one_minus_tau = __dsub_rn(1.0, (double)tau);
-#pragma unroll
-    for (int a = 0; a < 20; ++a) {
-      const float* Ra = A.R + a * 20;
-      float g = __fmul_rn(f[0], Ra[0]);                             // ScalarProd20(R[a], f[i]), left to right
-#pragma unroll
-      for (int b = 1; b < 20; ++b) g = __fadd_rn(g, __fmul_rn(f[b], Ra[b]));
-      r.p[a] = __double2float_rn(__dadd_rn(__dmul_rn(one_minus_tau, (double)f[a]), (double)__fmul_rn(tau, g)));
-    }
-  }
+  // pcc != 1: tau = fmin(1.0, pca / (1. + pow(Neff_M[i]/pcb, pcc))) -- the reference's pow is the C library's powf;
+  // only the host's libm reproduces its bits, so tau comes precomputed per column (db_create_hhm_impl)
+  hhm_emissions(f, __fdiv_rn((float)rows[(size_t)j * 10 + 7], 1000.0f), pcm, A, tau_host != nullptr,
+                tau_host ? tau_host[c] : 0.f, r.p);
   r.m2m = tr_prev[0]; r.m2d = tr_prev[2]; r.d2m = tr_prev[5]; r.d2d = tr_prev[6]; r.i2m = tr_prev[3];
   r.i2i = tr_here[4]; r.m2i = tr_here[1];
   r.ss = ss ? (uint32_t)ss[c] : 0u;
@@ -323,7 +324,8 @@ k_hhm_prepare(int m, const int* __restrict__ L, const long long* __restrict__ co
 __global__ void __launch_bounds__(128)
 k_hhm_pav(int m, const int* __restrict__ L, const long long* __restrict__ col_off,
           const ColRec* __restrict__ cols, const int32_t* __restrict__ null_mb,
-          const float* __restrict__ neff_hmm, const __grid_constant__ HhmPrepArgs A, float* __restrict__ pav) {
+          const float* __restrict__ neff_hmm, const __grid_constant__ HhmPrepArgs A, float* __restrict__ pav,
+          const float* __restrict__ pb_glob = nullptr) {
   const int t = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= m) return;
@@ -331,7 +333,8 @@ k_hhm_pav(int m, const int* __restrict__ L, const long long* __restrict__ col_of
   float acc = 0.f;
   if (lane < 20) {
     const int src = HHG_A2S(lane);
-    const float pb = fpow2_dev(__fdiv_rn((float)(-null_mb[t * 20 + src]), 1000.0f));   // :543
+    // HHM records: HMM::Read overwrites pb[] from the file's NULL line (:543); alignments: the caller's pb
+    const float pb = pb_glob ? pb_glob[lane] : fpow2_dev(__fdiv_rn((float)(-null_mb[t * 20 + src]), 1000.0f));
     acc = __fdiv_rn(__fmul_rn(pb, 100.0f), neff_hmm[t]);
     const ColRec* col = cols + col_off[t];
     const int Lt = L[t];

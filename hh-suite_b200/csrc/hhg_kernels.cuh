@@ -31,6 +31,8 @@
 #define HHG_MAX3 1   // MM-state maximum as 3-input maxima + equality selects (same bits, fewer ALU-pipe instructions)
 #endif
 
+#include "hhg_math.cuh"
+
 namespace hhg {
 
 constexpr int kWarpsPerCta = 4;
@@ -521,16 +523,6 @@ struct BtParams {
   int ss_score_mode;         // par.ssm == 2: subtract the ss score again (SCORE_ALIGNMENT)
 };
 
-// fast_log2 (src/util-inl.h:108-128): table lookup + linear interpolation, x > 0 else -100000
-__device__ __forceinline__ float fast_log2_dev(float x, const float* lg2, const float* diff) {
-  if (!(x > 0.0f)) return -100000.0f;
-  const uint32_t u = __float_as_uint(x);
-  const int a = (int)((u & 0x7F800000u) >> 23) - 0x7f;
-  const int b = (int)((u & 0x007FE000u) >> 13);
-  const int c = (int)(u & 0x00001FFFu);
-  return __fadd_rn(__fadd_rn((float)a, lg2[b]), __fmul_rn(diff[b], (float)c));
-}
-
 // Score(q.p[i], t.p[j]) = fast_log2(ScalarProd20(q, t)), src/hhhit-inl.h:61-134.  In the AVX2 build of the
 // reference (the pinned oracle) the macro SSE is not defined in that header, so ScalarProd20 is the
 // plain left-to-right sum  t0*q0 + t1*q1 + ... + t19*q19  (verified against the compiled reference:
@@ -990,22 +982,6 @@ __global__ void __launch_bounds__(256) k_prefilter_sw(const SwParams P) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kPfHistBins = 1024;   // bin = corrected score + 512, clamped
 constexpr int kPfHistBias = 512;
-
-// flog2, src/util-inl.h:83-93 (the polynomial is evaluated in double, as the C++ expression promotes)
-__device__ __forceinline__ float flog2_dev(float x) {
-  if (x <= 0.f) return -128.f;
-  uint32_t u = __float_as_uint(x);
-  const float e = (float)((int)((u & 0x7F800000u) >> 23) - 0x7f);
-  x = __uint_as_float((u & 0x007FFFFFu) | 0x3f800000u);
-  x = __double2float_rn(__dsub_rn((double)x, 1.0));
-  const double xd = (double)x;
-  double y = __dadd_rn(-0.1903190, __dmul_rn(xd, 0.0440047));
-  y = __dadd_rn(0.4123442, __dmul_rn(xd, y));
-  y = __dadd_rn(-0.7077702, __dmul_rn(xd, y));
-  y = __dadd_rn(1.441740, __dmul_rn(xd, y));
-  x = __double2float_rn(__dmul_rn(xd, y));
-  return __fadd_rn(x, e);
-}
 
 __global__ void __launch_bounds__(256)
 k_pf_correct_hist(int n, const int* __restrict__ L, const int* __restrict__ raw, float flog2_Lq, int bit_factor,

@@ -199,3 +199,71 @@ def cs219_db(n: int, seed: int, lens: np.ndarray | None = None, median: int = 20
     off = np.concatenate([[0], np.cumsum(L.astype(np.int64))[:-1]]).astype(np.int64)
     seq = rng.integers(0, 219, int(L.sum()), dtype=np.uint8)
     return dict(L=L, seq=seq, off=off)
+
+
+AA = "ARNDCQEGHILKMFPSTWYV"
+
+
+def a3m_text(L: int, nseq: int, seed: int, name: str = "msa", with_ss: bool = False, with_comment: bool = False,
+             consensus_first: bool = False, ident: float = 0.5, dup_frac: float = 0.3, x_frac: float = 0.01) -> str:
+    """A synthetic A3M alignment with L match columns (upper case / '-') and `nseq` sequences after the master:
+    point mutations at rate 1-ident, a fraction of near-duplicates (> 90 % identical: removed by the filter), runs
+    of deletions, lower-case insert runs, N-/C-terminal truncation (end gaps), a few 'X', optional >ss_pred / >ss_conf
+    rows, a '#' name line and a '_consensus' first sequence (what compressed databases produce)."""
+    rng = np.random.default_rng(seed)
+    master = rng.integers(0, 20, L)
+    out = []
+    if with_comment:
+        out.append(f"#{name} synthetic alignment")
+    if with_ss:
+        out.append(">ss_pred PSIPRED predicted secondary structure")
+        out.append("".join("CHE"[int(v)] for v in rng.integers(0, 3, L)))
+        out.append(">ss_conf PSIPRED confidence values")
+        out.append("".join(str(int(v)) for v in rng.integers(0, 10, L)))
+    mseq = "".join(AA[a] for a in master)
+    out.append(f">{name}_consensus" if consensus_first else f">{name} master")
+    out.append(mseq)
+    prev = master
+    for k in range(nseq):
+        base = prev if (k > 0 and rng.random() < dup_frac) else master
+        rate = 0.03 if base is prev else (1.0 - ident) * rng.uniform(0.3, 1.4)
+        seq = base.copy()
+        mut = rng.random(L) < rate
+        seq[mut] = rng.integers(0, 20, int(mut.sum()))
+        prev = seq
+        chars = [AA[a] for a in seq]
+        for i in np.nonzero(rng.random(L) < x_frac)[0]:
+            chars[i] = "X"
+        # deletions
+        for _ in range(int(rng.integers(0, 4))):
+            a = int(rng.integers(0, L)); b = min(L, a + int(rng.integers(1, 8)))
+            for i in range(a, b):
+                chars[i] = "-"
+        # end gaps
+        if rng.random() < 0.5:
+            a = int(rng.integers(0, max(1, L // 3)))
+            for i in range(a):
+                chars[i] = "-"
+        if rng.random() < 0.5:
+            b = int(rng.integers(0, max(1, L // 3)))
+            for i in range(L - b, L):
+                chars[i] = "-"
+        if all(c == "-" for c in chars):
+            chars[L // 2] = "A"
+        # inserts (lower case) between match columns
+        pieces = []
+        for i, c in enumerate(chars):
+            pieces.append(c)
+            if rng.random() < 0.03:
+                pieces.append("".join(AA[a].lower() for a in rng.integers(0, 20, int(rng.integers(1, 6)))))
+        if rng.random() < 0.2:
+            pieces.insert(0, "".join(AA[a].lower() for a in rng.integers(0, 20, int(rng.integers(1, 4)))))
+        out.append(f">seq{k} synthetic")
+        s = "".join(pieces)
+        # a3m files wrap nothing, but the reader joins lines: split some sequences over two lines
+        if rng.random() < 0.3 and len(s) > 10:
+            cut = int(rng.integers(1, len(s) - 1))
+            out.append(s[:cut]); out.append(s[cut:])
+        else:
+            out.append(s)
+    return "\n".join(out) + "\n"

@@ -139,6 +139,54 @@ int hhg_db_create_hhm(hhg_ctx* ctx, int n, const char* data, const int64_t* off,
  * columns.  The context-specific (CRF) pseudocounts of default hhblits stay in the reference's host code. */
 int hhg_query_from_hhm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_prep_params* pp, const float* R,
                        int32_t L_cap, int32_t* L_out, float* p, float* tr, uint8_t* ss, float* pav, float* neff);
+/* ---- A3M multiple alignments -> HMMs (the alignment branch of the database reader) ----------
+ * Replaces, once per database instead of once per (query, target),
+ *   HHEntry::getTemplateHMM, A3M branch          src/hhdatabase.cpp:441-449
+ *     Alignment::Read                            src/hhalignment.cpp:181-544
+ *     Alignment::Compress (par.M_template = 1)   :822-990
+ *     Alignment::Filter -> Filter2               :1470-1473, :1598-1968
+ *     Alignment::FrequenciesAndTransitions       :2047-2400  (global weights :2083-2108,
+ *       Amino_acid_frequencies_and_transitions_from_M_state :2408-2683, Transitions_from_I_state :2957-3157,
+ *       Transitions_from_D_state :3165-3382)
+ * followed by the same PrepareTemplateHMM steps as hhg_db_create_hhm.  The text is scanned on the host (residue codes,
+ * insert counts, the reference's own length sort); filter, sequence weights, frequencies, transitions and Neff run in
+ * CUDA kernels with the reference's operation types and order.
+ * One step of the reference is a hardware approximation: the position-specific weights use simdf32_rcp = RCPPS
+ * (:2531), whose bits differ between CPU vendors.  The library samples the host's RCPPS for every possible integer
+ * argument once and the kernel looks the values up: the HMM equals the one the reference computes ON THE SAME HOST,
+ * bit for bit.
+ * Not built: match-state assignment other than by case (-M first / -M <percent>), the -mark option. */
+typedef struct hhg_msa_params {
+  int32_t maxseq, maxcol, maxres;   /* par.maxseq 65535, par.maxcol 32765, par.maxres 20001 (src/hhdecl.cpp:10-14)       */
+  int32_t M, mark;                  /* par.M_template 1, par.mark 0: the only values built                              */
+  int32_t max_seqid, coverage, qid, Ndiff;   /* par.max_seqid_db 90, coverage_db 0, qid_db 0, Ndiff_db 100 (Filter)      */
+  float qsc;                        /* par.qsc_db -20 (off); > -10 needs the substitution matrix S                      */
+  int32_t wg;                       /* par.wg 0: position-specific weights; 1: global weights                           */
+} hhg_msa_params;
+void hhg_msa_params_default(hhg_msa_params* mp);
+/* Host only: number of match columns and of sequences of one A3M record, and whether it carries >ss_pred. */
+int hhg_a3m_scan(const char* rec, int64_t len, const hhg_msa_params* mp, int32_t* L, int32_t* N_in, int32_t* has_ss);
+/* Host only: the scanner hhg_db_create_a3m / hhg_msa_to_hmm run per record, exposed for inspection and CPU-side tests:
+ * X[N_in*(L+2)] residue codes of columns 0..L+1 (0..19 amino acids, 20 ANY, 21 GAP, 22 ENDGAP; column 0 = ANY and
+ * column L+1 = ENDGAP), I[N_in*(L+2)] insert counts after each column (may be NULL), keep[N_in] as Alignment::Read and
+ * the "no residues" rule of Filter2 leave it, nres[N_in], ksort[N_in] the length order the filter walks (QSortInt). */
+int hhg_a3m_parse(const char* rec, int64_t len, const hhg_msa_params* mp, int32_t L_cap, int32_t N_cap, int32_t* dims,
+                  uint8_t* X, uint16_t* I, int8_t* keep, int32_t* nres, int32_t* ksort);
+/* One alignment -> the HMM as Alignment::FrequenciesAndTransitions leaves it (no pseudocounts): what a QUERY alignment
+ * becomes in hhblits (src/hhblits.cpp:1438-1453) and what the parity tests compare.
+ *   S[400] substitution matrix in bits (only read by the qsc test, may be NULL), pb[20] background frequencies
+ *   dims[6] = {L, N_in, N_filtered, kfirst, kss_pred, kss_conf};  keep[N_in] (may be NULL): 0 / 1 / 2 after the filter;
+ *   wg[N_in] (may be NULL) global weights;  f[(L+2)*20];  tr[(L+1)*7] log2, HMM::tr order;
+ *   neff[3*(L+1)] = Neff_M, Neff_I, Neff_D;  *neff_hmm;  ss[L+2] (may be NULL) = ss_pred*11 + ss_conf per column */
+int hhg_msa_to_hmm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa_params* mp, const float* S, const float* pb,
+                   int32_t L_cap, int32_t N_cap, int32_t* dims, int8_t* keep, float* wg, float* f, float* tr,
+                   float* neff, float* neff_hmm, uint8_t* ss);
+/* The shard straight from the `_a3m.ffdata` records (uncompressed A3M text): same result object as hhg_db_create_hhm.
+ * pb[20]: the background the reference holds when it reads the alignments (SetSubstitutionMatrix's, unless an HHM file
+ * read earlier overwrote it -- HMM::Read does, src/hhhmm.cpp:543). */
+int hhg_db_create_a3m(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
+                      const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
+                      const float* R, hhg_db** out);
 /* Host only: LENG and whether the record carries an ss_pred sequence (no numbers are parsed). */
 int hhg_hhm_scan(const char* rec, int64_t len, int32_t* L, int32_t* has_ss);
 /* Host only: the tokeniser hhg_db_create_hhm runs per record, exposed for inspection and CPU-side tests.

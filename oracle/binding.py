@@ -306,6 +306,11 @@ class RefShim:
         self.lib.hhref_get_R(_p(out, c_f32p))
         return out.reshape(20, 20)
 
+    def S(self):
+        out = np.zeros(400, np.float32)
+        self.lib.hhref_get_S(_p(out, c_f32p))
+        return out.reshape(20, 20)
+
     def pb(self):
         out = np.zeros(20, np.float32)
         self.lib.hhref_get_pb(_p(out, c_f32p))
@@ -512,6 +517,48 @@ class RefShim:
                                          out["Eval"].ctypes.data_as(dp), out["logEval"].ctypes.data_as(dp),
                                          _p(out["score_aass"], c_f32p), _p(out["Probab"], c_f32p), _p(out["order"], c_i32p))
         assert m == n
+        return out
+
+    def msa_to_hmm(self, path, filt=None, wg=0, prep=False, capL=4000, capN=20000):
+        """The A3M template branch of HHEntry::getTemplateHMM (src/hhdatabase.cpp:441-449) run by the compiled reference:
+        Read, Compress, Filter, FrequenciesAndTransitions (+ PrepareTemplateHMM's query-independent steps with prep).
+        filt = (max_seqid, coverage, qid, qsc, Ndiff) or None for the reference defaults."""
+        dims = np.zeros(8, np.int32)
+        X = np.zeros(capN * (capL + 2), np.uint8); I = np.zeros(capN * (capL + 2), np.uint16)
+        keep = np.zeros(capN, np.int8); wgv = np.zeros(capN, np.float32)
+        nres = np.zeros(capN, np.int32); ksort = np.zeros(capN, np.int32)
+        f = np.zeros((capL + 2) * 20, np.float32); tr = np.zeros((capL + 1) * 7, np.float32)
+        neff = np.zeros(3 * (capL + 1), np.float32); nh = np.zeros(1, np.float32)
+        ssp = np.zeros(capL + 2, np.uint8); ssc = np.zeros(capL + 2, np.uint8)
+        p = np.zeros((capL + 2) * 20, np.float32); trp = np.zeros((capL + 1) * 7, np.float32); pav = np.zeros(20, np.float32)
+        fl = None if filt is None else np.asarray(filt, np.float32)
+        fn = self.lib.hhref_msa_to_hmm
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_char_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, c_u8p, C.POINTER(C.c_uint16),
+                       C.POINTER(C.c_int8), c_f32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p,
+                       c_f32p, c_f32p, c_f32p]
+        L = fn(path.encode(), _p(fl, c_f32p), int(wg), int(bool(prep)), capL, capN, _p(dims, c_i32p), _p(X, c_u8p),
+               I.ctypes.data_as(C.POINTER(C.c_uint16)), keep.ctypes.data_as(C.POINTER(C.c_int8)), _p(wgv, c_f32p),
+               _p(nres, c_i32p), _p(ksort, c_i32p), _p(f, c_f32p), _p(tr, c_f32p), _p(neff, c_f32p), _p(nh, c_f32p),
+               _p(ssp, c_u8p), _p(ssc, c_u8p), _p(p, c_f32p), _p(trp, c_f32p), _p(pav, c_f32p))
+        if L < 0:
+            raise IOError(f"hhref_msa_to_hmm({path}) = {L} (dims {dims.tolist()})")
+        N = int(dims[1])
+        out = dict(L=L, N_in=N, N_filtered=int(dims[2]), kfirst=int(dims[3]), kss_pred=int(dims[4]), kss_conf=int(dims[5]),
+                   X=X[:N * (L + 2)].reshape(N, L + 2).copy(), I=I[:N * (L + 2)].reshape(N, L + 2).copy(),
+                   keep=keep[:N].copy(), wg=wgv[:N].copy(), nres=nres[:N].copy(), ksort=ksort[:N].copy(),
+                   f=f[:(L + 2) * 20].reshape(L + 2, 20).copy(), tr=tr[:(L + 1) * 7].reshape(L + 1, 7).copy(),
+                   neff_m=neff[:L + 1].copy(), neff_i=neff[L + 1:2 * (L + 1)].copy(), neff_d=neff[2 * (L + 1):3 * (L + 1)].copy(),
+                   neff_hmm=float(nh[0]), ss_pred=ssp[:L + 2].copy(), ss_conf=ssc[:L + 2].copy())
+        if prep:
+            out.update(p=p[:(L + 2) * 20].reshape(L + 2, 20).copy(), tr_prep=trp[:(L + 1) * 7].reshape(L + 1, 7).copy(),
+                       pav=pav.copy())
+        return out
+
+    def rcp_table(self, n):
+        out = np.zeros(n, np.float32)
+        self.lib.hhref_rcp_table.argtypes = [C.c_int, c_f32p]
+        self.lib.hhref_rcp_table(n, _p(out, c_f32p))
         return out
 
     def early_stop(self, score, L, neff, qL, qneff, prefilter=True, dbsize=1, alphaa=0.4, alphab=0.02, alphac=0.1,

@@ -76,6 +76,6 @@ $(OUT)/libhhref_shim.so: oracle/ref_shim.cpp $(OUT)/libhhref.a
 # The drop-in check: reference front half + reference ViterbiRunner vs the C-ABI adapter (needs libhhg.so).
 dropin: $(OUT)/hh_dropin_check
 $(OUT)/hh_dropin_check: oracle/ref_gpu_adapter.cpp $(OUT)/libhhref.a hh-suite_b200/libhhg.so include/hhg.h
-	mkdir -p $(OUT)/data && cp -f $(REF)/data/query.hhm $(OUT)/data/query.hhm && chmod u+w $(OUT)/data/query.hhm
+	mkdir -p $(OUT)/data && cp -f $(REF)/data/query.hhm $(REF)/data/query.a3m $(OUT)/data/ && chmod u+w $(OUT)/data/query.hhm $(OUT)/data/query.a3m
 	$(CXX) $(CXXFLAGS) $(INC) -o $@ oracle/ref_gpu_adapter.cpp -Wl,--whole-archive $(OUT)/libhhref.a -Wl,--no-whole-archive \
 	    -Lhh-suite_b200 -lhhg -Wl,-rpath,'$$ORIGIN/../../hh-suite_b200' -lgomp

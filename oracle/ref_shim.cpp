@@ -49,6 +49,7 @@
 #include "hhposteriordecoder.h"
 #include "hhposteriordecoderrunner.h"
 #include "hhposteriormatrix.h"
+#include "hhalignment.h"
 #include "cs219.lib.h"
 #undef private
 #undef protected
@@ -162,6 +163,8 @@ void hhref_get_S33(float* out) { memcpy(out, g->S33, sizeof(g->S33)); }
 void hhref_get_pb(float* out) { memcpy(out, g->pb, 20 * sizeof(float)); }
 // R[a][b] = P(a|b), the pseudocount matrix of SetSubstitutionMatrix (src/hhfunc.cpp), out[400]
 void hhref_get_R(float* out) { memcpy(out, g->R, 400 * sizeof(float)); }
+// S[a][b]: substitution matrix in bits (Alignment::Filter2 qsc test)
+void hhref_get_S(float* out) { memcpy(out, g->S, 400 * sizeof(float)); }
 // the transition / aa pseudocount parameters PrepareTemplateHMM passes on (src/hhfunc.cpp:170-178)
 void hhref_get_prep_params(float* out11) {
   Parameters& par = *g->par;
@@ -638,4 +641,82 @@ extern "C" float hhref_early_stop(int n, const float* score, const int* L, const
   std::vector<HHblitsDatabase*> nodb;
   ViterbiRunner r(nullptr, nodb, 1);
   return r.calculateEarlyStop(par, &q, hits, 0);
+}
+
+
+// ---------------------------------------------------------------- A3M -> HMM (rows a10 / f1)
+// The template branch of HHEntry::getTemplateHMM for an A3M record (src/hhdatabase.cpp:441-449): Alignment::Read,
+// Compress (par.M_template), Filter (par.max_seqid_db / coverage_db / qid_db / qsc / Ndiff_db), FrequenciesAndTransitions.
+// Exports the alignment as the reference holds it after filtering (X, I, keep, wg, nres, ksort) and the raw HMM
+// (f, tr, Neff_M/I/D, Neff_HMM, ss); with prep != 0 PrepareTemplateHMM's query-independent steps are run as well and
+// p / tr / pav exported like hhref_prepare_template_hhm_raw's p_raw.
+// filt[5] = {max_seqid, coverage, qid, qsc, Ndiff} (NULL: the reference defaults); wg_mode = par.wg.
+// dims[8] = {L, N_in, N_filtered, kfirst, kss_pred, kss_conf, kss_dssp, N_ss}
+extern "C" int hhref_msa_to_hmm(const char* path, const float* filt, int wg_mode, int prep, int capL, int capN, int* dims,
+                                unsigned char* X, unsigned short* I, signed char* keep, float* wg, int* nres, int* ksort,
+                                float* f, float* tr, float* neff, float* neff_hmm, unsigned char* ss_pred,
+                                unsigned char* ss_conf, float* p, float* tr_prep, float* pav) {
+  FILE* fh = fopen(path, "r");
+  if (!fh) return -1;
+  Parameters& par = *g->par;
+  Alignment* ali = new Alignment(par.maxseq, g->maxres);
+  char name[NAMELEN];
+  strncpy(name, path, NAMELEN - 1); name[NAMELEN - 1] = 0;
+  ali->Read(fh, name, par.mark, par.maxcol, par.nseqdis);
+  fclose(fh);
+  ali->Compress(name, par.cons, par.maxcol, par.M_template, par.Mgaps);
+  const int max_seqid = filt ? (int)filt[0] : par.max_seqid_db;
+  const int coverage = filt ? (int)filt[1] : par.coverage_db;
+  const int qid = filt ? (int)filt[2] : par.qid_db;
+  const float qsc = filt ? filt[3] : par.qsc_db;
+  const int Ndiff = filt ? (int)filt[4] : par.Ndiff_db;
+  ali->N_filtered = ali->Filter(max_seqid, g->S, coverage, qid, qsc, Ndiff);
+  HMM* t = new HMM(MAXSEQDIS, g->maxres);
+  t->name[0] = t->longname[0] = t->fam[0] = 0;
+  ali->FrequenciesAndTransitions(t, (char)wg_mode, par.mark, par.cons, par.showcons, g->pb, g->Sim);
+  const int L = ali->L, N = ali->N_in;
+  dims[0] = L; dims[1] = N; dims[2] = ali->N_filtered; dims[3] = ali->kfirst; dims[4] = ali->kss_pred;
+  dims[5] = ali->kss_conf; dims[6] = ali->kss_dssp; dims[7] = ali->N_ss;
+  if (L > capL || N > capN) { delete t; delete ali; return -2; }
+  for (int k = 0; k < N; ++k) {
+    for (int i = 0; i <= L + 1; ++i) X[(size_t)k * (L + 2) + i] = (unsigned char)ali->X[k][i];
+    for (int i = 0; i <= L; ++i) I[(size_t)k * (L + 2) + i] = (ali->keep[k] || k == ali->kfirst) ? ali->I[k][i] : 0;
+    keep[k] = ali->keep[k];
+    wg[k] = ali->wg[k];
+    nres[k] = ali->nres ? ali->nres[k] : -1;
+    ksort[k] = ali->ksort ? ali->ksort[k] : -1;
+  }
+  for (int i = 0; i <= L + 1; ++i)
+    for (int a = 0; a < 20; ++a) f[(size_t)i * 20 + a] = t->f[i][a];
+  for (int i = 0; i <= L; ++i) {
+    for (int k = 0; k < 7; ++k) tr[(size_t)i * 7 + k] = t->tr[i][k];
+    neff[i] = t->Neff_M[i]; neff[(L + 1) + i] = t->Neff_I[i]; neff[2 * (L + 1) + i] = t->Neff_D[i];
+  }
+  *neff_hmm = t->Neff_HMM;
+  for (int i = 0; i <= L + 1; ++i) {
+    ss_pred[i] = (t->nss_pred >= 0 && i >= 1 && i <= L) ? (unsigned char)t->ss_pred[i] : 0;
+    ss_conf[i] = (t->nss_pred >= 0 && i >= 1 && i <= L) ? (unsigned char)t->ss_conf[i] : 0;
+  }
+  if (prep) {
+    t->AddTransitionPseudocounts(par.gapd, par.gape, par.gapf, par.gapg, par.gaph, par.gapi, par.gapb, par.gapb);
+    t->PreparePseudocounts(g->R);
+    t->AddAminoAcidPseudocounts(par.pc_hhm_nocontext_mode, par.pc_hhm_nocontext_a, par.pc_hhm_nocontext_b,
+                                par.pc_hhm_nocontext_c);
+    t->CalculateAminoAcidBackground(g->pb);
+    export_hmm(t, p, tr_prep, pav, nullptr, nullptr, nullptr, nullptr);
+  }
+  delete t;
+  delete ali;
+  return L;
+}
+
+// _mm_rcp_ps of this host (Alignment::Amino_acid_frequencies_and_transitions_from_M_state uses simdf32_rcp,
+// src/hhalignment.cpp:2531): lets a test compare the product's own sampled table with the reference build's view.
+extern "C" void hhref_rcp_table(int n, float* out) {
+  for (int m = 0; m < n; m += VECSIZE_FLOAT) {
+    float in[VECSIZE_FLOAT] __attribute__((aligned(32))), res[VECSIZE_FLOAT] __attribute__((aligned(32)));
+    for (int v = 0; v < VECSIZE_FLOAT; ++v) in[v] = (float)(m + v);
+    simdf32_store(res, simdf32_rcp(simdf32_load(in)));
+    for (int v = 0; v < VECSIZE_FLOAT && m + v < n; ++v) out[m + v] = res[v];
+  }
 }

@@ -1,0 +1,40 @@
+"""CPU tests of the A3M scanner (hhg_a3m_parse: Alignment::Read + Compress + the first steps of Filter2 restated on the
+host side of the library) against the compiled reference: residue codes, insert counts, residue counts and the
+length order the identity filter walks."""
+import numpy as np
+import pytest
+
+from tests import msa_cases
+
+
+def test_scanner_equals_reference(refshim, tmp_path):
+    from hhsuite_b200 import capi
+    for k, t in enumerate(msa_cases.texts()):
+        path = tmp_path / f"m{k}.a3m"
+        path.write_bytes(t)
+        ref = refshim.msa_to_hmm(str(path))
+        got = capi.a3m_parse(t)
+        assert (got["L"], got["N_in"], got["kfirst"], got["kss_pred"], got["kss_conf"]) == \
+               (ref["L"], ref["N_in"], ref["kfirst"], ref["kss_pred"], ref["kss_conf"]), k
+        assert np.array_equal(got["X"][:, 1:-1], ref["X"][:, 1:-1]), k      # columns 0 / L+1 are set later by the reference
+        rows = ref["keep"] > 0                                              # the shim exports inserts of profile rows
+        assert np.array_equal(got["I"][rows][:, :-1], ref["I"][rows][:, :-1]), k
+        assert np.array_equal(got["nres"], ref["nres"]) and np.array_equal(got["ksort"], ref["ksort"]), k
+
+
+def test_scanner_errors_and_limits():
+    from hhsuite_b200 import capi
+    with pytest.raises(capi.HhgError):
+        capi.a3m_parse(b"no header line\nACDE\n")
+    with pytest.raises(capi.HhgError):
+        capi.a3m_parse(b">a\nACDEFGHIKL\n>b\nACDEFGH\n")                    # unequal number of match columns
+    with pytest.raises(capi.HhgError):
+        capi.a3m_parse(b">a\n>b\nACDE\n")                                   # a sequence without residues
+    with pytest.raises(capi.HhgError):
+        capi.a3m_parse(b">a\nACDEFGHIKL\n", capi.MsaParams.defaults(M=2))   # only match states by case are built
+    # maxseq: rows beyond the limit are ignored like the reference does (with a warning)
+    t = b">m\nACDEFGHIKL\n" + b"".join(b">s%d\nACDEFGHIKL\n" % i for i in range(10))
+    assert capi.a3m_parse(t, capi.MsaParams.defaults(maxseq=4))["N_in"] == 4
+    # lower case = insert, '.' dropped, inserts before the first match column belong to column 0
+    a = capi.a3m_parse(b">m\nACDE\n>s\nab.A-cdDE\n")
+    assert a["L"] == 4 and a["I"][1].tolist() == [2, 0, 2, 0, 0, 0] and a["X"][1, 1:5].tolist() == [0, 22, 3, 6][:0] + [0, 21, 3, 6]

@@ -1,0 +1,86 @@
+"""The product's alignment -> HMM kernels (hh-suite_b200/csrc/hhg_msa.cuh, unmodified source) executed on the CPU by
+the multi-warp host emulation in tests/emul/cuda_emul_mw.h and compared bit for bit with the compiled reference's
+Alignment::Filter + FrequenciesAndTransitions.  This is how the kernels are checked in the authoring container before
+GPU minutes are spent (it caught a warp-divergent early exit ahead of a shuffle that hangs real hardware)."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import msa_cases
+from tests.util import ROOT, bits
+
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+LIB = os.path.join(EMUL_DIR, "libmsaemul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    srcs = [os.path.join(EMUL_DIR, "msa_emul.cpp"), os.path.join(EMUL_DIR, "cuda_emul_mw.h"),
+            os.path.join(ROOT, "hh-suite_b200", "csrc", "hhg_msa.cuh"), os.path.join(ROOT, "hh-suite_b200", "csrc", "hhg_math.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-DHHG_EMUL",
+                               "-o", LIB, srcs[0]])
+    L = C.CDLL(LIB)
+    L.emul_msa_to_hmm.argtypes = [C.c_char_p, C.c_longlong, C.c_void_p, C.c_float] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 7
+    return L
+
+
+def _tables():
+    """fast_log2's lg2 / diff tables as the library builds them (double log, src/util-inl.h:117-123)."""
+    lg2 = np.zeros(1025, np.float32); dif = np.zeros(1025, np.float32)
+    prev = np.float32(0)
+    for i in range(1, 1025):
+        lg2[i] = np.float32(math.log(1024 + i) * 1.442695041 - 10.0)
+        dif[i - 1] = np.float32(float(np.float32(lg2[i] - prev)) * 1.2352E-4)
+        prev = lg2[i]
+    return lg2, dif
+
+
+def _run(L, refshim, t, filt=(90, 0, 0, -20.0, 100), wg=0, threads=64):
+    lg2, dif = _tables()
+    ip = np.array([65535, 32765, 20001, filt[0], filt[1], filt[2], filt[4], wg], np.int32)
+    Lc, Nc = 1000, 1000
+    dims = np.zeros(4, np.int32); keep = np.zeros(Nc, np.int8); wgv = np.zeros(Nc, np.float32)
+    f = np.zeros((Lc + 2) * 20, np.float32); tr = np.zeros((Lc + 1) * 7, np.float32)
+    neff = np.zeros(3 * (Lc + 1), np.float32); nh = np.zeros(1, np.float32)
+    S = np.ascontiguousarray(refshim.S(), np.float32); pb = refshim.pb()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = L.emul_msa_to_hmm(t, len(t), p(ip), C.c_float(filt[3]), p(S), p(pb), p(lg2), p(dif), threads, p(dims), p(keep),
+                           p(wgv), p(f), p(tr), p(neff), p(nh))
+    assert rc == 0 and dims[3] == 0
+    Lm, N = int(dims[0]), int(dims[1])
+    return dict(L=Lm, N_in=N, N_filtered=int(dims[2]), keep=keep[:N], wg=wgv[:N], f=f[:(Lm + 2) * 20].reshape(Lm + 2, 20),
+                tr=tr[:(Lm + 1) * 7].reshape(Lm + 1, 7), neff_m=neff[:Lm + 1], neff_i=neff[Lm + 1:2 * (Lm + 1)],
+                neff_d=neff[2 * (Lm + 1):3 * (Lm + 1)], neff_hmm=float(nh[0]))
+
+
+def _cmp(got, ref, tag):
+    assert (got["L"], got["N_in"], got["N_filtered"]) == (ref["L"], ref["N_in"], ref["N_filtered"]), tag
+    assert np.array_equal(got["keep"], ref["keep"]), tag
+    if ref["N_filtered"] > 1:
+        assert np.array_equal(bits(got["wg"]), bits(ref["wg"])), tag
+    for key in ("f", "tr", "neff_m", "neff_i", "neff_d"):
+        assert np.array_equal(bits(got[key]), bits(ref[key])), (tag, key)
+    assert bits(np.float32(got["neff_hmm"])) == bits(np.float32(ref["neff_hmm"])), tag
+
+
+@pytest.mark.parametrize("case", [0, 1, 4, 5, 7, 8])
+def test_emulated_kernels_equal_compiled_reference(emul, refshim, tmp_path, case):
+    t = msa_cases.texts()[case]
+    path = tmp_path / "m.a3m"
+    path.write_bytes(t)
+    _cmp(_run(emul, refshim, t), refshim.msa_to_hmm(str(path)), f"case {case}")
+
+
+@pytest.mark.parametrize("filt,wg", [((70, 0, 30, -20.0, 0), 0), ((90, 0, 0, 0.2, 0), 0), ((50, 30, 20, 0.0, 20), 0),
+                                     ((15, 0, 0, -20.0, 5), 0), ((90, 0, 0, -20.0, 100), 1)])
+def test_emulated_filter_options_and_global_weights(emul, refshim, tmp_path, filt, wg):
+    for case in (0, 4):
+        t = msa_cases.texts()[case]
+        path = tmp_path / "m.a3m"
+        path.write_bytes(t)
+        _cmp(_run(emul, refshim, t, filt=filt, wg=wg), refshim.msa_to_hmm(str(path), filt=filt, wg=wg), f"case {case} {filt} wg={wg}")
