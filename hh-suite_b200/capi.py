@@ -44,7 +44,8 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_hitlist_pvalues", "hhg_hitlist_hhblits_evalues", "hhg_hitlist_order", "hhg_early_stop_sum", "hhg_set_use_ss",
            "hhg_query_set_batch", "hhg_viterbi_search_batch", "hhg_query_from_hhm",
            "hhg_cs219_parse", "hhg_csdb_create_ffindex", "hhg_set_excluded_regions",
-           "hhg_msa_params_default", "hhg_a3m_scan", "hhg_a3m_parse", "hhg_msa_to_hmm", "hhg_db_create_a3m"]
+           "hhg_msa_params_default", "hhg_a3m_scan", "hhg_a3m_parse", "hhg_msa_to_hmm", "hhg_db_create_a3m", "hhg_query_from_a3m",
+           "hhg_ca3m_scan", "hhg_ca3m_parse", "hhg_ca3m_to_hmm", "hhg_db_create_ca3m"]
 
 
 class PrepParams(C.Structure):
@@ -73,6 +74,19 @@ class MsaParams(C.Structure):
         for k, v in kw.items():
             setattr(mp, k, v)
         return mp
+
+
+class SeqDb(C.Structure):
+    """hhg_seqdb: `<db>_sequence.ffdata` + the offset / length columns of its `.ffindex` in index-file order."""
+    _fields_ = [("n", C.c_int64), ("data", C.c_void_p), ("off", C.c_void_p), ("len", C.c_void_p)]
+
+    @classmethod
+    def make(cls, data: bytes, offsets, lengths):
+        self = cls()
+        self._buf = np.frombuffer(data, np.uint8)
+        self._off = np.ascontiguousarray(offsets, np.int64); self._len = np.ascontiguousarray(lengths, np.int64)
+        self.n = len(self._off); self.data = self._buf.ctypes.data; self.off = self._off.ctypes.data; self.len = self._len.ctypes.data
+        return self
 
 
 # one 112-byte column record of the resident database (include/hhg.h, hhg_db_read_cols)
@@ -208,6 +222,15 @@ def load():
                                 C.c_void_p, c_i32p, c_i32p]
     L.hhg_msa_to_hmm.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, c_f32p, c_f32p, C.c_int32, C.c_int32,
                                  c_i32p, C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_u8p]
+    L.hhg_ca3m_scan.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, c_i32p, c_i32p]
+    L.hhg_ca3m_parse.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_i32p, c_u8p,
+                                 C.c_void_p, C.c_void_p, c_i32p, c_i32p]
+    L.hhg_ca3m_to_hmm.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, c_f32p, c_f32p, C.c_int32,
+                                  C.c_int32, c_i32p, C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]
+    L.hhg_db_create_ca3m.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_i64p, c_i64p, C.c_void_p, C.c_void_p, c_f32p, c_f32p,
+                                     C.POINTER(PrepParams), c_f32p, C.POINTER(C.c_void_p)]
+    L.hhg_query_from_a3m.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, c_f32p, c_f32p, C.POINTER(PrepParams),
+                                     c_f32p, C.c_int32, c_i32p, c_f32p, c_f32p, c_u8p, c_f32p, c_f32p]
     L.hhg_db_create_a3m.argtypes = [C.c_void_p, C.c_int, C.c_char_p, c_i64p, c_i64p, C.c_void_p, c_f32p, c_f32p,
                                     C.POINTER(PrepParams), c_f32p, C.POINTER(C.c_void_p)]
     L.hhg_set_excluded_regions.argtypes = [C.c_void_p, C.c_int, c_i32p, c_i32p, C.c_int, c_i32p, c_i32p]
@@ -373,6 +396,39 @@ def a3m_parse(record: bytes, mp: "MsaParams | None" = None):
                 nres=nres, ksort=ksort)
 
 
+def ca3m_parse(record: bytes, seqs: "SeqDb", mp: "MsaParams | None" = None):
+    """hhg_ca3m_parse (host only): a compressed-alignment record as Alignment::ReadCompressed + Compress hold it."""
+    mp = mp or MsaParams.defaults()
+    Lh = np.zeros(1, np.int32); Nh = np.zeros(1, np.int32)
+    _ck(load().hhg_ca3m_scan(record, len(record), C.byref(seqs), C.byref(mp), _p(Lh, c_i32p), _p(Nh, c_i32p)))
+    L, N = int(Lh[0]), int(Nh[0])
+    dims = np.zeros(6, np.int32)
+    X = np.zeros((N, L + 2), np.uint8); I = np.zeros((N, L + 2), np.uint16); keep = np.zeros(N, np.int8)
+    nres = np.zeros(N, np.int32); ksort = np.zeros(N, np.int32)
+    _ck(load().hhg_ca3m_parse(record, len(record), C.byref(seqs), C.byref(mp), L, N, _p(dims, c_i32p), _p(X, c_u8p),
+                              I.ctypes.data, keep.ctypes.data, _p(nres, c_i32p), _p(ksort, c_i32p)))
+    return dict(L=L, N_in=N, kfirst=int(dims[3]), X=X, I=I, keep=keep, nres=nres, ksort=ksort)
+
+
+def ca3m_to_hmm(ctx: "Context", record: bytes, seqs: "SeqDb", pb, S=None, mp: "MsaParams | None" = None):
+    """hhg_ca3m_to_hmm: one compressed-alignment record -> the raw HMM (see msa_to_hmm)."""
+    mp = mp or MsaParams.defaults()
+    Lh = np.zeros(1, np.int32); Nh = np.zeros(1, np.int32)
+    _ck(load().hhg_ca3m_scan(record, len(record), C.byref(seqs), C.byref(mp), _p(Lh, c_i32p), _p(Nh, c_i32p)))
+    L, N = int(Lh[0]), int(Nh[0])
+    dims = np.zeros(6, np.int32)
+    keep = np.zeros(N, np.int8); wg = np.zeros(N, np.float32)
+    f = np.zeros((L + 2, 20), np.float32); tr = np.zeros((L + 1, 7), np.float32); neff = np.zeros((3, L + 1), np.float32)
+    nh = np.zeros(1, np.float32)
+    pb = np.ascontiguousarray(pb, np.float32)
+    Sm = None if S is None else np.ascontiguousarray(S, np.float32)
+    _ck(ctx.L.hhg_ca3m_to_hmm(ctx.h, record, len(record), C.byref(seqs), C.byref(mp), _p(Sm, c_f32p), _p(pb, c_f32p), L, N,
+                              _p(dims, c_i32p), keep.ctypes.data, _p(wg, c_f32p), _p(f, c_f32p), _p(tr, c_f32p),
+                              _p(neff, c_f32p), _p(nh, c_f32p)))
+    return dict(L=L, N_in=N, N_filtered=int(dims[2]), kfirst=int(dims[3]), keep=keep, wg=wg, f=f, tr=tr, neff_m=neff[0],
+                neff_i=neff[1], neff_d=neff[2], neff_hmm=float(nh[0]), ss=np.zeros(L + 2, np.uint8))
+
+
 def msa_to_hmm(ctx: "Context", record: bytes, pb, S=None, mp: "MsaParams | None" = None):
     """hhg_msa_to_hmm: one A3M record -> the HMM Alignment::FrequenciesAndTransitions computes (no pseudocounts)."""
     mp = mp or MsaParams.defaults()
@@ -388,6 +444,23 @@ def msa_to_hmm(ctx: "Context", record: bytes, pb, S=None, mp: "MsaParams | None"
                              _p(neff, c_f32p), _p(nh, c_f32p), _p(ss, c_u8p)))
     return dict(L=L, N_in=N, N_filtered=int(dims[2]), kfirst=int(dims[3]), keep=keep, wg=wg, f=f, tr=tr, neff_m=neff[0],
                 neff_i=neff[1], neff_d=neff[2], neff_hmm=float(nh[0]), ss=ss)
+
+
+def query_from_a3m(ctx: "Context", record: bytes, R, pb, S=None, params: "PrepParams | None" = None,
+                   mp: "MsaParams | None" = None):
+    """hhg_query_from_a3m: query alignment -> HMM -> PrepareQueryHMM (nocontxt) -> dict(L, p, tr, ss, pav, neff)."""
+    mp = mp or MsaParams.defaults()
+    L, _, has_ss = a3m_scan(record, mp)
+    p = np.zeros((L + 2, 20), np.float32); tr = np.zeros((L + 1, 7), np.float32)
+    ss = np.zeros(L + 2, np.uint8); pav = np.zeros(20, np.float32)
+    neff = np.zeros(1, np.float32); Lo = np.zeros(1, np.int32)
+    R = np.ascontiguousarray(R, np.float32); pb = np.ascontiguousarray(pb, np.float32)
+    Sm = None if S is None else np.ascontiguousarray(S, np.float32)
+    pp = params or PrepParams.defaults()
+    _ck(ctx.L.hhg_query_from_a3m(ctx.h, record, len(record), C.byref(mp), _p(Sm, c_f32p), _p(pb, c_f32p), C.byref(pp),
+                                 _p(R, c_f32p), L, _p(Lo, c_i32p), _p(p, c_f32p), _p(tr, c_f32p), _p(ss, c_u8p),
+                                 _p(pav, c_f32p), _p(neff, c_f32p)))
+    return dict(L=L, p=p, tr=tr, ss=ss, pav=pav, neff=float(neff[0]), has_ss=has_ss)
 
 
 def cs219_parse(text: bytes, n_cap: int = 256):
@@ -487,6 +560,28 @@ class TargetDB:
         buf = np.frombuffer(data, np.uint8)
         _ck(ctx.L.hhg_db_create_a3m(ctx.h, n, buf.ctypes.data_as(C.c_char_p), _p(off, c_i64p), _p(ln, c_i64p),
                                     C.byref(mp), _p(Sm, c_f32p), _p(pb, c_f32p), C.byref(pp), _p(R, c_f32p), C.byref(h)))
+        self = cls._wrap(ctx, h, n)
+        self.Lh = np.zeros(n, np.int32)
+        _ck(ctx.L.hhg_db_lengths(h, _p(self.Lh, c_i32p)))
+        return self
+
+    @classmethod
+    def from_ca3m(cls, ctx, data: bytes, offsets, lengths, seqs: "SeqDb", R, pb, S=None, params: "PrepParams | None" = None,
+                  mp: "MsaParams | None" = None):
+        """Build the shard from a compressed alignment database (`_ca3m.ffdata` + `_sequence.ffdata`, see SeqDb)."""
+        off = np.ascontiguousarray(offsets, np.int64); ln = np.ascontiguousarray(lengths, np.int64)
+        n = len(off)
+        if n == 0 or len(ln) != n or off.min() < 0 or int((off + ln).max()) > len(data):
+            raise ValueError("offsets/lengths do not fit the data buffer")
+        R = np.ascontiguousarray(R, np.float32); pb = np.ascontiguousarray(pb, np.float32)
+        Sm = None if S is None else np.ascontiguousarray(S, np.float32)
+        pp = params or PrepParams.defaults()
+        mp = mp or MsaParams.defaults()
+        h = C.c_void_p()
+        buf = np.frombuffer(data, np.uint8)
+        _ck(ctx.L.hhg_db_create_ca3m(ctx.h, n, buf.ctypes.data_as(C.c_char_p), _p(off, c_i64p), _p(ln, c_i64p),
+                                     C.byref(seqs), C.byref(mp), _p(Sm, c_f32p), _p(pb, c_f32p), C.byref(pp),
+                                     _p(R, c_f32p), C.byref(h)))
         self = cls._wrap(ctx, h, n)
         self.Lh = np.zeros(n, np.int32)
         _ck(ctx.L.hhg_db_lengths(h, _p(self.Lh, c_i32p)))

@@ -646,13 +646,26 @@ int hhg_a3m_scan(const char* rec, int64_t len, const hhg_msa_params* mp, int32_t
   return HHG_OK;
 }
 
-int hhg_a3m_parse(const char* rec, int64_t len, const hhg_msa_params* mp, int32_t L_cap, int32_t N_cap, int32_t* dims,
-                  uint8_t* X, uint16_t* I, int8_t* keep, int32_t* nres, int32_t* ksort) {
+static int seqdb_check(const hhg_seqdb* sq) {
+  if (!sq) return HHG_OK;
+  if (sq->n <= 0 || !sq->data || !sq->off || !sq->len) return fail(HHG_EINVAL, "sequence database: bad argument");
+  return HHG_OK;
+}
+
+static std::string msa_parse_any(const char* rec, int64_t len, const hhg_seqdb* sq, const hhg_msa_params* mp, MsaHost* H) {
+  if (!sq) return MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, H);
+  const MsaScanner::SeqDb db{sq->n, sq->data, sq->off, sq->len};
+  return MsaScanner::parse_ca3m(rec, len, db, mp->maxseq, mp->maxcol, mp->maxres, H);
+}
+
+static int msa_parse_impl(const char* rec, int64_t len, const hhg_seqdb* sq, const hhg_msa_params* mp, int32_t L_cap,
+                          int32_t N_cap, int32_t* dims, uint8_t* X, uint16_t* I, int8_t* keep, int32_t* nres, int32_t* ksort) {
   if (!rec || len <= 0 || !dims || !X) return fail(HHG_EINVAL, "hhg_a3m_parse: bad argument");
   int rc = msa_params_check(mp);
   if (rc != HHG_OK) return rc;
+  if ((rc = seqdb_check(sq)) != HHG_OK) return rc;
   MsaHost H;
-  const std::string msg = MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, &H);
+  const std::string msg = msa_parse_any(rec, len, sq, mp, &H);
   if (!msg.empty()) return fail(HHG_EINVAL, "hhg_a3m_parse: %s", msg.c_str());
   dims[0] = H.L; dims[1] = H.N_in; dims[2] = 0; dims[3] = H.kfirst; dims[4] = H.kss_pred; dims[5] = H.kss_conf;
   if (H.L > L_cap || H.N_in > N_cap) return fail(HHG_EINVAL, "hhg_a3m_parse: %d columns / %d sequences exceed the caller's capacity", H.L, H.N_in);
@@ -670,18 +683,30 @@ int hhg_a3m_parse(const char* rec, int64_t len, const hhg_msa_params* mp, int32_
   return HHG_OK;
 }
 
-int hhg_msa_to_hmm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa_params* mp, const float* S, const float* pb,
-                   int32_t L_cap, int32_t N_cap, int32_t* dims, int8_t* keep, float* wg, float* f, float* tr,
-                   float* neff, float* neff_hmm, uint8_t* ss) {
+int hhg_a3m_parse(const char* rec, int64_t len, const hhg_msa_params* mp, int32_t L_cap, int32_t N_cap, int32_t* dims,
+                  uint8_t* X, uint16_t* I, int8_t* keep, int32_t* nres, int32_t* ksort) {
+  return msa_parse_impl(rec, len, nullptr, mp, L_cap, N_cap, dims, X, I, keep, nres, ksort);
+}
+
+int hhg_ca3m_parse(const char* rec, int64_t len, const hhg_seqdb* seqs, const hhg_msa_params* mp, int32_t L_cap, int32_t N_cap,
+                   int32_t* dims, uint8_t* X, uint16_t* I, int8_t* keep, int32_t* nres, int32_t* ksort) {
+  if (!seqs) return fail(HHG_EINVAL, "hhg_ca3m_parse: the sequence database is NULL");
+  return msa_parse_impl(rec, len, seqs, mp, L_cap, N_cap, dims, X, I, keep, nres, ksort);
+}
+
+static int msa_to_hmm_impl(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_seqdb* sq, const hhg_msa_params* mp,
+                           const float* S, const float* pb, int32_t L_cap, int32_t N_cap, int32_t* dims, int8_t* keep,
+                           float* wg, float* f, float* tr, float* neff, float* neff_hmm, uint8_t* ss) {
   if (!ctx || !rec || len <= 0 || !pb || !dims || !f || !tr || !neff || !neff_hmm)
     return fail(HHG_EINVAL, "hhg_msa_to_hmm: bad argument");
   int rc = msa_params_check(mp);
   if (rc != HHG_OK) return rc;
+  if ((rc = seqdb_check(sq)) != HHG_OK) return rc;
   if (mp->qsc > -10.f && !S) return fail(HHG_EINVAL, "hhg_msa_to_hmm: the qsc filter needs the substitution matrix S");
   CK(cudaSetDevice(ctx->device));
   MsaChunk C;
   C.host.resize(1);
-  const std::string msg = MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, &C.host[0]);
+  const std::string msg = msa_parse_any(rec, len, sq, mp, &C.host[0]);
   if (!msg.empty()) return fail(HHG_EINVAL, "hhg_msa_to_hmm: %s", msg.c_str());
   const MsaHost& H = C.host[0];
   dims[0] = H.L; dims[1] = H.N_in; dims[2] = 0; dims[3] = H.kfirst; dims[4] = H.kss_pred; dims[5] = H.kss_conf;
@@ -705,13 +730,39 @@ int hhg_msa_to_hmm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa_par
   return HHG_OK;
 }
 
+int hhg_msa_to_hmm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa_params* mp, const float* S, const float* pb,
+                   int32_t L_cap, int32_t N_cap, int32_t* dims, int8_t* keep, float* wg, float* f, float* tr,
+                   float* neff, float* neff_hmm, uint8_t* ss) {
+  return msa_to_hmm_impl(ctx, rec, len, nullptr, mp, S, pb, L_cap, N_cap, dims, keep, wg, f, tr, neff, neff_hmm, ss);
+}
+
+int hhg_ca3m_to_hmm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_seqdb* seqs, const hhg_msa_params* mp,
+                    const float* S, const float* pb, int32_t L_cap, int32_t N_cap, int32_t* dims, int8_t* keep, float* wg,
+                    float* f, float* tr, float* neff, float* neff_hmm) {
+  if (!seqs) return fail(HHG_EINVAL, "hhg_ca3m_to_hmm: the sequence database is NULL");
+  return msa_to_hmm_impl(ctx, rec, len, seqs, mp, S, pb, L_cap, N_cap, dims, keep, wg, f, tr, neff, neff_hmm, nullptr);
+}
+
+int hhg_ca3m_scan(const char* rec, int64_t len, const hhg_seqdb* seqs, const hhg_msa_params* mp, int32_t* L, int32_t* N_in) {
+  if (!rec || len <= 0 || !L || !N_in || !seqs) return fail(HHG_EINVAL, "hhg_ca3m_scan: bad argument");
+  int rc = msa_params_check(mp);
+  if (rc != HHG_OK) return rc;
+  if ((rc = seqdb_check(seqs)) != HHG_OK) return rc;
+  MsaHost H;
+  const std::string msg = msa_parse_any(rec, len, seqs, mp, &H);
+  if (!msg.empty()) return fail(HHG_EINVAL, "hhg_ca3m_scan: %s", msg.c_str());
+  *L = H.L; *N_in = H.N_in;
+  return HHG_OK;
+}
+
 static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
-                              const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
+                              const hhg_seqdb* sq, const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
                               const float* R, hhg_db** out, float* d_tr_full, float* neff_hmm_out) {
   if (!ctx || !out || n <= 0 || !data || !off || !len || !pp || !R || !pb)
     return fail(HHG_EINVAL, "hhg_db_create_a3m: bad argument");
   int rc = msa_params_check(mp);
   if (rc != HHG_OK) return rc;
+  if ((rc = seqdb_check(sq)) != HHG_OK) return rc;
   if (mp->qsc > -10.f && !S) return fail(HHG_EINVAL, "hhg_db_create_a3m: the qsc filter needs the substitution matrix S");
   if (pp->pcm < 0 || pp->pcm > 3) return fail(HHG_EINVAL, "hhg_db_create_a3m: pseudocount mode %d does not exist", pp->pcm);
   const bool tau_on_host = pp->pcm == 2 && pp->pcc != 1.0f;
@@ -726,7 +777,7 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
     auto work = [&](unsigned w) {
       for (int k = (int)w; k < n; k += (int)hw) {
         if (len[k] <= 0) { if (err_rec[w] < 0) { errs[w] = "empty record"; err_rec[w] = k; } continue; }
-        std::string msg = MsaScanner::parse(data + off[k], len[k], mp->maxseq, mp->maxcol, mp->maxres, &all[k]);
+        std::string msg = msa_parse_any(data + off[k], len[k], sq, mp, &all[k]);
         if (!msg.empty() && err_rec[w] < 0) { errs[w] = msg; err_rec[w] = k; }
       }
     };
@@ -832,7 +883,14 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
 int hhg_db_create_a3m(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
                       const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
                       const float* R, hhg_db** out) {
-  return db_create_a3m_impl(ctx, n, data, off, len, mp, S, pb, pp, R, out, nullptr, nullptr);
+  return db_create_a3m_impl(ctx, n, data, off, len, nullptr, mp, S, pb, pp, R, out, nullptr, nullptr);
+}
+
+int hhg_db_create_ca3m(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len, const hhg_seqdb* seqs,
+                       const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
+                       const float* R, hhg_db** out) {
+  if (!seqs) return fail(HHG_EINVAL, "hhg_db_create_ca3m: the sequence database is NULL");
+  return db_create_a3m_impl(ctx, n, data, off, len, seqs, mp, S, pb, pp, R, out, nullptr, nullptr);
 }
 
 int hhg_hhm_scan(const char* rec, int64_t len, int32_t* L, int32_t* has_ss) {
@@ -1027,6 +1085,42 @@ int hhg_query_from_hhm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_pre
     rc = hhg_hhm_parse(rec, len, L, f.data(), trn.data(), ssb.data(), nul.data(), neff, &has_pc);
     if (rc != HHG_OK) return rc;
   }
+  *L_out = L;
+  return HHG_OK;
+}
+
+// The same for a query ALIGNMENT (hhblits: ReadQueryFile -> Alignment::Read / Compress / Filter /
+// FrequenciesAndTransitions, src/hhblits.cpp:1424-1453, then PrepareQueryHMM's nocontxt branch).
+int hhg_query_from_a3m(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa_params* mp, const float* S, const float* pb,
+                       const hhg_prep_params* pp, const float* R, int32_t L_cap, int32_t* L_out, float* p, float* tr,
+                       uint8_t* ss, float* pav, float* neff) {
+  if (!ctx || !rec || len <= 0 || !pp || !R || !pb || !L_out || !p || !tr || !pav) return fail(HHG_EINVAL, "hhg_query_from_a3m: bad argument");
+  int32_t L = 0, N = 0, has_ss = 0;
+  int rc = hhg_a3m_scan(rec, len, mp, &L, &N, &has_ss);
+  if (rc != HHG_OK) return rc;
+  if (L < 1 || L > L_cap) return fail(HHG_EINVAL, "hhg_query_from_a3m: query length %d exceeds the caller's capacity %d", L, L_cap);
+  CK(cudaSetDevice(ctx->device));
+  DevBuf<float> d_tr;
+  CK(d_tr.alloc((size_t)(L + 1) * 7));
+  hhg_db* db = nullptr;
+  const int64_t zero = 0;
+  float nh = 0.f;
+  rc = db_create_a3m_impl(ctx, 1, rec, &zero, &len, nullptr, mp, S, pb, pp, R, &db, d_tr.p, &nh);
+  if (rc != HHG_OK) return rc;
+  std::unique_ptr<hhg_db> holder(db);
+  std::vector<ColRec> cols((size_t)L);
+  CK(cudaMemcpyAsync(cols.data(), db->cols_raw.p, (size_t)L * sizeof(ColRec), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(tr, d_tr.p, (size_t)(L + 1) * 28, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(pav, db->pav.p, 80, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 1; i <= L; ++i) {
+    memcpy(p + (size_t)i * 20, cols[i - 1].p, 80);
+    if (ss) ss[i] = (uint8_t)cols[i - 1].ss;
+  }
+  memcpy(p, pav, 80);                               // CalculateAminoAcidBackground: p[0] = p[L+1] = pav (:1866)
+  memcpy(p + (size_t)(L + 1) * 20, pav, 80);
+  if (ss) ss[0] = ss[L + 1] = 0;
+  if (neff) *neff = nh;
   *L_out = L;
   return HHG_OK;
 }

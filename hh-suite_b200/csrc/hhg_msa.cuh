@@ -18,6 +18,7 @@
 // host's own RCPPS for every possible argument (n*naa <= 65535*20, integers) at first use and the kernel looks the
 // value up, so the result is bit-identical to the reference running on the same host.
 #pragma once
+#include <cctype>
 #include <cfloat>
 #include <cstdint>
 #include <cstring>
@@ -100,12 +101,110 @@ class MsaScanner {
   // Alignment::Read with mark == 0, then Compress with M == 1.  Returns "" or an error description (the cases in
   // which the reference exits).  maxseq / maxcol / maxres: Parameters of the same names (src/hhdecl.cpp:10-14).
   static std::string parse(const char* rec, int64_t len, int maxseq, int maxcol, int maxres, MsaHost* out) {
+    std::vector<std::string> seq;
+    std::string msg = read_a3m(rec, len, maxseq, maxcol, out, &seq);
+    if (!msg.empty()) return msg;
+    return compress(seq, maxres, out);
+  }
+
+  // The sequence database of a compressed alignment database (`<db>_sequence.ffdata` + the offset / length columns of
+  // its `.ffindex`, IN INDEX-FILE ORDER: ReadCompressed addresses entries with ffindex_get_entry_by_index).
+  struct SeqDb { int64_t n; const char* data; const int64_t* off; const int64_t* len; };
+
+  // Alignment::ReadCompressed (src/hhalignment.cpp:546-815) with mark == 0, then Compress with M == 1.
+  static std::string parse_ca3m(const char* rec, int64_t len, const SeqDb& db, int maxseq, int maxcol, int maxres, MsaHost* out) {
+    std::vector<std::string> seq;
+    std::string msg = read_ca3m(rec, len, db, maxseq, maxcol, out, &seq);
+    if (!msg.empty()) return msg;
+    return compress(seq, maxres, out);
+  }
+
+ private:
+  static std::string read_ca3m(const char* rec, int64_t len, const SeqDb& db, int maxseq, int maxcol, MsaHost* out,
+                               std::vector<std::string>* seq_out) {
     MsaHost& A = *out;
     A = MsaHost();
+    std::vector<std::string>& seq = *seq_out;
+    const int64_t data_size = len - 1;            // entry->length - 1: the ffindex entry ends with NUL
+    int64_t ix = 0;
+    const char* d = rec;
+    if (data_size <= 0) return "empty record";
+    if (d[0] == '#') {                            // name line
+      ++ix;
+      while (ix < data_size && isspace((unsigned char)d[ix])) ++ix;
+      while (ix < data_size && d[ix] != '\n') ++ix;
+      ++ix;
+    }
+    std::string header, cons;
+    char last = '\0';
+    int in_cons = 0;
+    while (ix < data_size && !(last == '\n' && d[ix] == ';')) {
+      if (d[ix] == '\n') ++in_cons;
+      else if (in_cons == 0) header.push_back(d[ix]);
+      else if (in_cons == 1) cons.push_back(d[ix]);
+      last = d[ix];
+      ++ix;
+    }
+    ++ix;                                         // past ';'
+    if ((int)cons.size() > maxcol - 2) return "consensus longer than maxcol-2";
+    const size_t consensus_length = cons.size();
+    std::string s0;
+    for (char c : cons) if (aa_code(c) >= 0) s0.push_back(c);
+    if (s0.empty()) return "the consensus sequence contains no residues";
+    seq.push_back(s0);
+    A.keep.push_back(0); A.display.push_back(2);  // the consensus row is shown, not part of the profile
+    A.kfirst = 0;
+    while (ix < data_size) {
+      if (ix + 8 > data_size) return "truncated sequence record";
+      const unsigned char* u = (const unsigned char*)d + ix;
+      const uint32_t entry = u[0] | (u[1] << 8) | (u[2] << 16) | ((uint32_t)u[3] << 24);
+      const unsigned start_pos = u[4] | (u[5] << 8), nr_blocks = u[6] | (u[7] << 8);
+      ix += 8;
+      if ((int64_t)entry >= db.n) return "sequence entry " + std::to_string(entry) + " is not in the sequence database";
+      const char* sd = db.data + db.off[entry];
+      const int64_t sl = db.len[entry];
+      std::string cur;
+      size_t pos = start_pos, ali_len = 0;
+      for (unsigned b = 0; b < nr_blocks; ++b) {
+        if (ix + 2 > data_size) return "truncated block list";
+        const unsigned nm = (unsigned char)d[ix];
+        const int nid = (signed char)d[ix + 1];
+        ix += 2;
+        for (unsigned i = 0; i < nm; ++i) {
+          if (pos < 1 || (int64_t)pos > sl) return "block list runs past the end of sequence entry " + std::to_string(entry);
+          cur.push_back(sd[pos - 1]); ++pos; ++ali_len;
+        }
+        if (nid > 0) {
+          for (int i = 0; i < nid; ++i) {
+            if (pos < 1 || (int64_t)pos > sl) return "block list runs past the end of sequence entry " + std::to_string(entry);
+            cur.push_back((char)tolower((unsigned char)sd[pos - 1])); ++pos;
+          }
+        } else {
+          for (int i = 0; i < -nid; ++i) { cur.push_back('-'); ++ali_len; }
+        }
+        if ((int)cur.size() > maxcol - 2) return "sequence longer than maxcol-2";
+      }
+      while (ali_len < consensus_length) { cur.push_back('-'); ++ali_len; }
+      if ((int)cur.size() > maxcol - 2) return "sequence longer than maxcol-2";
+      std::string s;
+      for (char c : cur) if (aa_code(c) >= 0) s.push_back(c);
+      if ((int)seq.size() >= maxseq) return "more than maxseq sequences";
+      seq.push_back(s);
+      A.keep.push_back(1); A.display.push_back(1);
+    }
+    A.N_in = (int)seq.size();
+    if (A.N_in - (A.keep[A.kfirst] == 0 ? 1 : 0) == 0) return "the alignment contains no master sequence";
+    return "";
+  }
+
+  static std::string read_a3m(const char* rec, int64_t len, int maxseq, int maxcol, MsaHost* out,
+                              std::vector<std::string>* seq_out) {
+    MsaHost& A = *out;
+    A = MsaHost();
+    std::vector<std::string>& seq = *seq_out;
     const char* p = rec;
     const char* end = rec + len;
     { const void* z = memchr(rec, '\0', (size_t)len); if (z) end = (const char*)z; }   // ffindex entries end with NUL
-    std::vector<std::string> seq;        // cur_seq of each stored sequence, residues from index 0
     std::string cur;
     int k = -1;
     bool skip = false;
@@ -172,6 +271,11 @@ class MsaScanner {
     A.N_in = k + 1;
     if ((int)seq.size() != A.N_in) return "internal: sequence count";
     if (A.kfirst < 0 || (A.N_in - A.N_ss - (A.keep[A.kfirst] == 0 ? 1 : 0)) == 0) return "the alignment contains no master sequence";
+    return "";
+  }
+
+  static std::string compress(const std::vector<std::string>& seq, int maxres, MsaHost* out) {
+    MsaHost& A = *out;
 
     // ---- Compress, case M == 1 (:889-990)
     const int N = A.N_in;
@@ -260,7 +364,6 @@ class MsaScanner {
     return "";
   }
 
- private:
   // QSortInt(v, k, left, right, -1), src/util.cpp:247-274, with an explicit stack (same swap sequence)
   static void qsort_desc(const int* v, int* k, int left, int right) {
     std::vector<std::pair<int, int>> st;

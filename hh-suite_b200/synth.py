@@ -267,3 +267,66 @@ def a3m_text(L: int, nseq: int, seed: int, name: str = "msa", with_ss: bool = Fa
         else:
             out.append(s)
     return "\n".join(out) + "\n"
+
+
+def a3m_to_ca3m(a3m: str, seq_index_base: int = 0):
+    """Compress an A3M alignment (master first, no ss rows) the way a compressed HH-suite database stores it
+    (what Alignment::ReadCompressed, src/hhalignment.cpp:546-815, decodes): returns (ca3m record bytes,
+    [unaligned sequences for the sequence database], [headers for the header database]).  Sequence k (k >= 1) of the
+    alignment refers to entry seq_index_base + k - 1 of the sequence database."""
+    import struct
+    names, rows = [], []
+    for ln in a3m.splitlines():
+        if ln.startswith("#"):
+            continue
+        if ln.startswith(">"):
+            names.append(ln[1:]); rows.append("")
+        elif names:
+            rows[-1] += ln.strip()
+    cons = "".join(c for c in rows[0] if not c.islower())
+    out = bytearray()
+    out += (">" + names[0].split()[0] + "_consensus\n").encode()
+    out += (cons + "\n;").encode()
+    seqs, heads = [], []
+    for k in range(1, len(rows)):
+        row = rows[k]
+        full = "".join(c.upper() for c in row if c not in "-.")
+        seqs.append(full.encode() + b"\n")
+        heads.append((">" + names[k] + "\n").encode())
+        blocks = []
+        i, n = 0, len(row)
+        m = 0
+        while i < n:
+            c = row[i]
+            if c == "-":
+                j = i
+                while j < n and row[j] == "-":
+                    j += 1
+                g = j - i
+                if j == n:                       # trailing gaps are implied by the consensus length
+                    i = j
+                    break
+                while g > 0:
+                    t = min(g, 127)
+                    blocks.append((m, -t)); m = 0; g -= t
+                i = j
+            elif c.islower():
+                j = i
+                while j < n and row[j].islower():
+                    j += 1
+                g = j - i
+                while g > 0:
+                    t = min(g, 127)
+                    blocks.append((m, t)); m = 0; g -= t
+                i = j
+            else:
+                m += 1
+                if m == 255:
+                    blocks.append((255, 0)); m = 0
+                i += 1
+        if m:
+            blocks.append((m, 0))
+        out += struct.pack("<IHH", seq_index_base + k - 1, 1, len(blocks))
+        for (nm, nid) in blocks:
+            out += struct.pack("<Bb", nm, nid)
+    return bytes(out), seqs, heads

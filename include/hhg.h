@@ -181,6 +181,28 @@ int hhg_a3m_parse(const char* rec, int64_t len, const hhg_msa_params* mp, int32_
 int hhg_msa_to_hmm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa_params* mp, const float* S, const float* pb,
                    int32_t L_cap, int32_t N_cap, int32_t* dims, int8_t* keep, float* wg, float* f, float* tr,
                    float* neff, float* neff_hmm, uint8_t* ss);
+/* Compressed alignment databases (`<db>_ca3m.ffdata`, what UniClust ships): Alignment::ReadCompressed
+ * (src/hhalignment.cpp:546-815; HHDatabaseEntry::getTemplateHMM, src/hhdatabase.cpp:303-326) -- a consensus row that is
+ * shown but stays outside the profile, then one record per sequence {u32 entry in the sequence database, u16 start, u16
+ * blocks, blocks x (u8 matches, s8 inserts (+) or gaps (-))} -- followed by the steps of the A3M path.  seqs = the
+ * `<db>_sequence.ffdata` bytes and the offset / length columns of its `.ffindex` in index-file order (the reference
+ * addresses entries by position, ffindex_get_entry_by_index); the header database only names rows and is not needed. */
+typedef struct hhg_seqdb { int64_t n; const char* data; const int64_t* off; const int64_t* len; } hhg_seqdb;
+int hhg_ca3m_scan(const char* rec, int64_t len, const hhg_seqdb* seqs, const hhg_msa_params* mp, int32_t* L, int32_t* N_in);
+int hhg_ca3m_parse(const char* rec, int64_t len, const hhg_seqdb* seqs, const hhg_msa_params* mp, int32_t L_cap, int32_t N_cap,
+                   int32_t* dims, uint8_t* X, uint16_t* I, int8_t* keep, int32_t* nres, int32_t* ksort);   /* host only */
+int hhg_ca3m_to_hmm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_seqdb* seqs, const hhg_msa_params* mp,
+                    const float* S, const float* pb, int32_t L_cap, int32_t N_cap, int32_t* dims, int8_t* keep, float* wg,
+                    float* f, float* tr, float* neff, float* neff_hmm);
+int hhg_db_create_ca3m(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len, const hhg_seqdb* seqs,
+                       const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
+                       const float* R, hhg_db** out);
+/* PrepareQueryHMM (nocontxt branch) for a query ALIGNMENT: the alignment -> HMM steps above with the caller's filter
+ * parameters (hhblits: par.max_seqid / coverage / qid / qsc / Ndiff, src/hhblits.cpp:1438-1453), then the pseudocount
+ * steps of hhg_query_from_hhm.  Outputs as hhg_query_from_hhm. */
+int hhg_query_from_a3m(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa_params* mp, const float* S, const float* pb,
+                       const hhg_prep_params* pp, const float* R, int32_t L_cap, int32_t* L_out, float* p, float* tr,
+                       uint8_t* ss, float* pav, float* neff);
 /* The shard straight from the `_a3m.ffdata` records (uncompressed A3M text): same result object as hhg_db_create_hhm.
  * pb[20]: the background the reference holds when it reads the alignments (SetSubstitutionMatrix's, unless an HHM file
  * read earlier overwrote it -- HMM::Read does, src/hhhmm.cpp:543). */

@@ -519,10 +519,7 @@ class RefShim:
         assert m == n
         return out
 
-    def msa_to_hmm(self, path, filt=None, wg=0, prep=False, capL=4000, capN=20000):
-        """The A3M template branch of HHEntry::getTemplateHMM (src/hhdatabase.cpp:441-449) run by the compiled reference:
-        Read, Compress, Filter, FrequenciesAndTransitions (+ PrepareTemplateHMM's query-independent steps with prep).
-        filt = (max_seqid, coverage, qid, qsc, Ndiff) or None for the reference defaults."""
+    def _msa_call(self, fn, lead_args, filt, wg, prep, capL, capN):
         dims = np.zeros(8, np.int32)
         X = np.zeros(capN * (capL + 2), np.uint8); I = np.zeros(capN * (capL + 2), np.uint16)
         keep = np.zeros(capN, np.int8); wgv = np.zeros(capN, np.float32)
@@ -532,17 +529,16 @@ class RefShim:
         ssp = np.zeros(capL + 2, np.uint8); ssc = np.zeros(capL + 2, np.uint8)
         p = np.zeros((capL + 2) * 20, np.float32); trp = np.zeros((capL + 1) * 7, np.float32); pav = np.zeros(20, np.float32)
         fl = None if filt is None else np.asarray(filt, np.float32)
-        fn = self.lib.hhref_msa_to_hmm
         fn.restype = C.c_int
-        fn.argtypes = [C.c_char_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, c_u8p, C.POINTER(C.c_uint16),
-                       C.POINTER(C.c_int8), c_f32p, c_i32p, c_i32p, c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p,
-                       c_f32p, c_f32p, c_f32p]
-        L = fn(path.encode(), _p(fl, c_f32p), int(wg), int(bool(prep)), capL, capN, _p(dims, c_i32p), _p(X, c_u8p),
-               I.ctypes.data_as(C.POINTER(C.c_uint16)), keep.ctypes.data_as(C.POINTER(C.c_int8)), _p(wgv, c_f32p),
-               _p(nres, c_i32p), _p(ksort, c_i32p), _p(f, c_f32p), _p(tr, c_f32p), _p(neff, c_f32p), _p(nh, c_f32p),
-               _p(ssp, c_u8p), _p(ssc, c_u8p), _p(p, c_f32p), _p(trp, c_f32p), _p(pav, c_f32p))
+        fn.argtypes = [C.c_char_p] * len(lead_args) + [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, c_u8p,
+                                                        C.POINTER(C.c_uint16), C.POINTER(C.c_int8), c_f32p, c_i32p, c_i32p,
+                                                        c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_u8p, c_f32p, c_f32p, c_f32p]
+        L = fn(*[a.encode() for a in lead_args], _p(fl, c_f32p), int(wg), int(bool(prep)), capL, capN, _p(dims, c_i32p),
+               _p(X, c_u8p), I.ctypes.data_as(C.POINTER(C.c_uint16)), keep.ctypes.data_as(C.POINTER(C.c_int8)),
+               _p(wgv, c_f32p), _p(nres, c_i32p), _p(ksort, c_i32p), _p(f, c_f32p), _p(tr, c_f32p), _p(neff, c_f32p),
+               _p(nh, c_f32p), _p(ssp, c_u8p), _p(ssc, c_u8p), _p(p, c_f32p), _p(trp, c_f32p), _p(pav, c_f32p))
         if L < 0:
-            raise IOError(f"hhref_msa_to_hmm({path}) = {L} (dims {dims.tolist()})")
+            raise IOError(f"reference alignment reader {lead_args} = {L} (dims {dims.tolist()})")
         N = int(dims[1])
         out = dict(L=L, N_in=N, N_filtered=int(dims[2]), kfirst=int(dims[3]), kss_pred=int(dims[4]), kss_conf=int(dims[5]),
                    X=X[:N * (L + 2)].reshape(N, L + 2).copy(), I=I[:N * (L + 2)].reshape(N, L + 2).copy(),
@@ -554,6 +550,17 @@ class RefShim:
             out.update(p=p[:(L + 2) * 20].reshape(L + 2, 20).copy(), tr_prep=trp[:(L + 1) * 7].reshape(L + 1, 7).copy(),
                        pav=pav.copy())
         return out
+
+    def msa_to_hmm(self, path, filt=None, wg=0, prep=False, capL=4000, capN=20000):
+        """The A3M template branch of HHEntry::getTemplateHMM (src/hhdatabase.cpp:441-449) run by the compiled reference:
+        Read, Compress, Filter, FrequenciesAndTransitions (+ PrepareTemplateHMM's query-independent steps with prep).
+        filt = (max_seqid, coverage, qid, qsc, Ndiff) or None for the reference defaults."""
+        return self._msa_call(self.lib.hhref_msa_to_hmm, [path], filt, wg, prep, capL, capN)
+
+    def ca3m_to_hmm(self, prefix, entry_name, filt=None, wg=0, prep=False, capL=4000, capN=20000):
+        """The compressed branch (src/hhdatabase.cpp:303-326): entry of <prefix>_ca3m.ff*, decoded by
+        Alignment::ReadCompressed with <prefix>_sequence.ff* / <prefix>_header.ff*."""
+        return self._msa_call(self.lib.hhref_ca3m_to_hmm, [prefix, entry_name], filt, wg, prep, capL, capN)
 
     def rcp_table(self, n):
         out = np.zeros(n, np.float32)

@@ -50,6 +50,9 @@
 #include "hhposteriordecoderrunner.h"
 #include "hhposteriormatrix.h"
 #include "hhalignment.h"
+extern "C" {
+#include "ffindex.h"
+}
 #include "cs219.lib.h"
 #undef private
 #undef protected
@@ -652,19 +655,14 @@ extern "C" float hhref_early_stop(int n, const float* score, const int* L, const
 // p / tr / pav exported like hhref_prepare_template_hhm_raw's p_raw.
 // filt[5] = {max_seqid, coverage, qid, qsc, Ndiff} (NULL: the reference defaults); wg_mode = par.wg.
 // dims[8] = {L, N_in, N_filtered, kfirst, kss_pred, kss_conf, kss_dssp, N_ss}
-extern "C" int hhref_msa_to_hmm(const char* path, const float* filt, int wg_mode, int prep, int capL, int capN, int* dims,
-                                unsigned char* X, unsigned short* I, signed char* keep, float* wg, int* nres, int* ksort,
-                                float* f, float* tr, float* neff, float* neff_hmm, unsigned char* ss_pred,
-                                unsigned char* ss_conf, float* p, float* tr_prep, float* pav) {
-  FILE* fh = fopen(path, "r");
-  if (!fh) return -1;
+static int msa_export(Alignment* ali, const char* name, const float* filt, int wg_mode, int prep, int capL, int capN, int* dims,
+                      unsigned char* X, unsigned short* I, signed char* keep, float* wg, int* nres, int* ksort,
+                      float* f, float* tr, float* neff, float* neff_hmm, unsigned char* ss_pred,
+                      unsigned char* ss_conf, float* p, float* tr_prep, float* pav) {
   Parameters& par = *g->par;
-  Alignment* ali = new Alignment(par.maxseq, g->maxres);
-  char name[NAMELEN];
-  strncpy(name, path, NAMELEN - 1); name[NAMELEN - 1] = 0;
-  ali->Read(fh, name, par.mark, par.maxcol, par.nseqdis);
-  fclose(fh);
-  ali->Compress(name, par.cons, par.maxcol, par.M_template, par.Mgaps);
+  char nm[NAMELEN];
+  strncpy(nm, name, NAMELEN - 1); nm[NAMELEN - 1] = 0;
+  ali->Compress(nm, par.cons, par.maxcol, par.M_template, par.Mgaps);
   const int max_seqid = filt ? (int)filt[0] : par.max_seqid_db;
   const int coverage = filt ? (int)filt[1] : par.coverage_db;
   const int qid = filt ? (int)filt[2] : par.qid_db;
@@ -677,7 +675,7 @@ extern "C" int hhref_msa_to_hmm(const char* path, const float* filt, int wg_mode
   const int L = ali->L, N = ali->N_in;
   dims[0] = L; dims[1] = N; dims[2] = ali->N_filtered; dims[3] = ali->kfirst; dims[4] = ali->kss_pred;
   dims[5] = ali->kss_conf; dims[6] = ali->kss_dssp; dims[7] = ali->N_ss;
-  if (L > capL || N > capN) { delete t; delete ali; return -2; }
+  if (L > capL || N > capN) { delete t; return -2; }
   for (int k = 0; k < N; ++k) {
     for (int i = 0; i <= L + 1; ++i) X[(size_t)k * (L + 2) + i] = (unsigned char)ali->X[k][i];
     for (int i = 0; i <= L; ++i) I[(size_t)k * (L + 2) + i] = (ali->keep[k] || k == ali->kfirst) ? ali->I[k][i] : 0;
@@ -706,8 +704,56 @@ extern "C" int hhref_msa_to_hmm(const char* path, const float* filt, int wg_mode
     export_hmm(t, p, tr_prep, pav, nullptr, nullptr, nullptr, nullptr);
   }
   delete t;
-  delete ali;
   return L;
+}
+
+extern "C" int hhref_msa_to_hmm(const char* path, const float* filt, int wg_mode, int prep, int capL, int capN, int* dims,
+                                unsigned char* X, unsigned short* I, signed char* keep, float* wg, int* nres, int* ksort,
+                                float* f, float* tr, float* neff, float* neff_hmm, unsigned char* ss_pred,
+                                unsigned char* ss_conf, float* p, float* tr_prep, float* pav) {
+  FILE* fh = fopen(path, "r");
+  if (!fh) return -1;
+  Parameters& par = *g->par;
+  Alignment* ali = new Alignment(par.maxseq, g->maxres);
+  char name[NAMELEN];
+  strncpy(name, path, NAMELEN - 1); name[NAMELEN - 1] = 0;
+  ali->Read(fh, name, par.mark, par.maxcol, par.nseqdis);
+  fclose(fh);
+  const int rc = msa_export(ali, path, filt, wg_mode, prep, capL, capN, dims, X, I, keep, wg, nres, ksort, f, tr, neff, neff_hmm,
+                            ss_pred, ss_conf, p, tr_prep, pav);
+  delete ali;
+  return rc;
+}
+
+// The compressed branch of HHDatabaseEntry::getTemplateHMM (src/hhdatabase.cpp:303-326): entry `entry_name` of
+// <prefix>_ca3m.ff{data,index}, decoded with <prefix>_sequence.ff* and <prefix>_header.ff* by Alignment::ReadCompressed.
+extern "C" int hhref_ca3m_to_hmm(const char* prefix, const char* entry_name, const float* filt, int wg_mode, int prep, int capL,
+                                 int capN, int* dims, unsigned char* X, unsigned short* I, signed char* keep, float* wg,
+                                 int* nres, int* ksort, float* f, float* tr, float* neff, float* neff_hmm,
+                                 unsigned char* ss_pred, unsigned char* ss_conf, float* p, float* tr_prep, float* pav) {
+  struct FF { FILE* fd = nullptr; FILE* fi = nullptr; char* data = nullptr; size_t size = 0; ffindex_index_t* index = nullptr; };
+  auto open_ff = [&](const char* suffix, FF& ff) {
+    const std::string base = std::string(prefix) + suffix;
+    ff.fd = fopen((base + ".ffdata").c_str(), "r");
+    ff.fi = fopen((base + ".ffindex").c_str(), "r");
+    if (!ff.fd || !ff.fi) return false;
+    ff.data = ffindex_mmap_data(ff.fd, &ff.size);
+    ff.index = ffindex_index_parse(ff.fi, 0);
+    return ff.data && ff.index;
+  };
+  FF ca, sq, hd;
+  if (!open_ff("_ca3m", ca) || !open_ff("_sequence", sq) || !open_ff("_header", hd)) return -1;
+  ffindex_entry_t* entry = ffindex_get_entry_by_name(ca.index, const_cast<char*>(entry_name));
+  if (!entry) return -3;
+  Parameters& par = *g->par;
+  Alignment* ali = new Alignment(par.maxseq, g->maxres);
+  char* data = ffindex_get_data_by_entry(ca.data, entry);
+  ali->ReadCompressed(entry, data, sq.index, sq.data, hd.index, hd.data, par.mark, par.maxcol);
+  const int rc = msa_export(ali, entry->name, filt, wg_mode, prep, capL, capN, dims, X, I, keep, wg, nres, ksort, f, tr, neff,
+                            neff_hmm, ss_pred, ss_conf, p, tr_prep, pav);
+  delete ali;
+  for (FF* ff : {&ca, &sq, &hd}) { if (ff->fd) fclose(ff->fd); if (ff->fi) fclose(ff->fi); }
+  return rc;
 }
 
 // _mm_rcp_ps of this host (Alignment::Amino_acid_frequencies_and_transitions_from_M_state uses simdf32_rcp,

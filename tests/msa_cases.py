@@ -23,3 +23,24 @@ def texts():
     if os.path.exists(q):
         out.append(open(q, "rb").read())
     return out
+
+
+CA3M_CASES = [(50, 20, 21, {}), (120, 200, 22, dict(ident=0.8, dup_frac=0.5)), (300, 40, 23, {}),
+              (260, 30, 25, dict(ident=0.4)), (9, 6, 26, {})]
+
+
+def ca3m_database(directory):
+    """A small compressed alignment database (<dir>/db_ca3m|_sequence|_header .ffdata/.ffindex) made from synthetic
+    alignments.  Returns (prefix, names in index order)."""
+    from hhsuite_b200 import ffindex, synth
+    prefix = os.path.join(str(directory), "db")
+    recs, seqs, heads = [], [], []
+    for (L, n, seed, kw) in CA3M_CASES:
+        a = synth.a3m_text(L, n, seed, name=f"al{seed}", **kw)
+        ca, sq, hd = synth.a3m_to_ca3m(a, seq_index_base=len(seqs))
+        recs.append((f"al{seed}", ca)); seqs += sq; heads += hd
+    names = [f"s{i:06d}" for i in range(len(seqs))]
+    ffindex.write_ffindex(prefix + "_ca3m.ffdata", recs)
+    ffindex.write_ffindex(prefix + "_sequence.ffdata", list(zip(names, seqs)))
+    ffindex.write_ffindex(prefix + "_header.ffdata", list(zip(names, heads)))
+    return prefix

@@ -38,3 +38,31 @@ def test_scanner_errors_and_limits():
     # lower case = insert, '.' dropped, inserts before the first match column belong to column 0
     a = capi.a3m_parse(b">m\nACDE\n>s\nab.A-cdDE\n")
     assert a["L"] == 4 and a["I"][1].tolist() == [2, 0, 2, 0, 0, 0] and a["X"][1, 1:5].tolist() == [0, 22, 3, 6][:0] + [0, 21, 3, 6]
+
+
+def test_ca3m_scanner_equals_reference(refshim, tmp_path):
+    """Compressed alignments: hhg_ca3m_parse (Alignment::ReadCompressed + Compress restated) against the compiled
+    reference reading the same ffindex triple."""
+    from hhsuite_b200 import capi, ffindex
+    prefix = msa_cases.ca3m_database(tmp_path)
+    sq = ffindex.FFIndex(prefix + "_sequence.ffdata")
+    ca = ffindex.FFIndex(prefix + "_ca3m.ffdata")
+    seqs = capi.SeqDb.make(bytes(sq.data), sq.offsets, sq.lengths)
+    for k, name in enumerate(ca.names):
+        ref = refshim.ca3m_to_hmm(prefix, name)
+        got = capi.ca3m_parse(bytes(ca.record(k)), seqs)
+        assert (got["L"], got["N_in"], got["kfirst"]) == (ref["L"], ref["N_in"], ref["kfirst"]) and got["keep"][0] == 0, name
+        assert np.array_equal(got["X"][:, 1:-1], ref["X"][:, 1:-1]), name
+        rows = ref["keep"] > 0
+        assert np.array_equal(got["I"][rows][:, :-1], ref["I"][rows][:, :-1]), name
+        assert np.array_equal(got["nres"], ref["nres"]) and np.array_equal(got["ksort"], ref["ksort"]), name
+    # a record with the consensus row only has no master sequence (the reference exits)
+    from hhsuite_b200 import synth
+    lone, _, _ = synth.a3m_to_ca3m(synth.a3m_text(30, 0, 24))
+    with pytest.raises(capi.HhgError):
+        capi.ca3m_parse(lone + b"\0", seqs)
+    # a sequence record pointing outside the sequence database is refused
+    bad = bytearray(ca.record(0)); pos = bad.index(b";") + 1; bad[pos:pos + 4] = (10 ** 6).to_bytes(4, "little")
+    with pytest.raises(capi.HhgError):
+        capi.ca3m_parse(bytes(bad), seqs)
+    sq.close(); ca.close()

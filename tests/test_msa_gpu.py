@@ -132,3 +132,54 @@ def test_search_over_a3m_shard(hhg, gpu_ctx, refshim, tmp_path):
     assert np.array_equal(bits(h1["score"]), bits(h2["score"])) and np.array_equal(h1["nsteps"], h2["nsteps"])
     assert np.array_equal(p1, p2)
     db.close(); db2.close()
+
+
+def test_query_from_alignment(hhg, gpu_ctx, refshim, tmp_path):
+    """hhg_query_from_a3m: the query alignment of hhblits -> the arrays hhg_query_set takes, equal to the reference's
+    Read / Compress / Filter / FrequenciesAndTransitions + the nocontxt pseudocount steps; then usable as a query."""
+    qa = msa_cases.texts()[-1]
+    path = tmp_path / "q.a3m"
+    path.write_bytes(qa)
+    ref = refshim.msa_to_hmm(str(path), prep=True)
+    q = hhg.capi.query_from_a3m(gpu_ctx, qa, refshim.R(), refshim.pb())
+    L = ref["L"]
+    assert q["L"] == L
+    assert np.array_equal(bits(q["p"][1:L + 1]), bits(ref["p"][1:L + 1]))
+    assert np.array_equal(bits(q["tr"]), bits(ref["tr_prep"])) and np.array_equal(bits(q["pav"]), bits(ref["pav"]))
+    assert np.array_equal(bits(q["p"][0]), bits(ref["pav"])) and bits(np.float32(q["neff"])) == bits(np.float32(ref["neff_hmm"]))
+    gpu_ctx.set_query(q["p"], q["tr"])
+    texts = msa_cases.texts()[:4]
+    data, off, ln = _pack(texts)
+    db = hhg.TargetDB.from_a3m(gpu_ctx, data, off, ln, refshim.R(), refshim.pb())
+    db.apply_null_model(q_pav=q["pav"], pb=refshim.pb(), columnscore=1)
+    hits, _ = hhg.viterbi_search(gpu_ctx, db)
+    assert len(hits) == 4 and np.all(np.isfinite(hits["score"]))
+    db.close()
+
+
+def test_compressed_alignment_database(hhg, gpu_ctx, refshim, tmp_path):
+    """hhg_ca3m_to_hmm / hhg_db_create_ca3m (`_ca3m` + `_sequence` ffindex files, what UniClust ships) against the
+    compiled reference's Alignment::ReadCompressed branch of getTemplateHMM."""
+    from hhsuite_b200 import ffindex
+    from tests.test_hhm_db_gpu import _expected_records
+    prefix = msa_cases.ca3m_database(tmp_path)
+    sq = ffindex.FFIndex(prefix + "_sequence.ffdata")
+    ca = ffindex.FFIndex(prefix + "_ca3m.ffdata")
+    seqs = hhg.capi.SeqDb.make(bytes(sq.data), sq.offsets, sq.lengths)
+    pb = refshim.pb()
+    refs = []
+    for k, name in enumerate(ca.names):
+        ref = refshim.ca3m_to_hmm(prefix, name, prep=True)
+        got = hhg.capi.ca3m_to_hmm(gpu_ctx, bytes(ca.record(k)), seqs, pb)
+        _cmp(got, ref, name)
+        refs.append(ref)
+    db = hhg.TargetDB.from_ca3m(gpu_ctx, bytes(ca.data), ca.offsets, ca.lengths, seqs, refshim.R(), pb)
+    cols, pav = db.read_cols(0), db.read_pav()
+    pos = 0
+    for k, ref in enumerate(refs):
+        L = ref["L"]
+        want = _expected_records(ref["p"], ref["tr_prep"], np.zeros(L + 2, np.uint8), True)
+        assert cols[pos:pos + L].tobytes() == want.tobytes(), k
+        assert np.array_equal(bits(pav[k]), bits(ref["pav"])), k
+        pos += L
+    db.close(); sq.close(); ca.close()
