@@ -32,6 +32,7 @@
 #include <string>
 #include <vector>
 #include <omp.h>
+#include <sys/mman.h>
 
 #define private public
 #define protected public
@@ -50,6 +51,9 @@
 #include "hhposteriordecoderrunner.h"
 #include "hhposteriormatrix.h"
 #include "hhalignment.h"
+extern "C" {
+#include "ffutil.h"
+}
 extern "C" {
 #include "ffindex.h"
 }
@@ -738,7 +742,7 @@ extern "C" int hhref_ca3m_to_hmm(const char* prefix, const char* entry_name, con
     ff.fi = fopen((base + ".ffindex").c_str(), "r");
     if (!ff.fd || !ff.fi) return false;
     ff.data = ffindex_mmap_data(ff.fd, &ff.size);
-    ff.index = ffindex_index_parse(ff.fi, 0);
+    ff.index = ffindex_index_parse(ff.fi, ffcount_lines((base + ".ffindex").c_str()));   // 0 would reserve 200 M entries
     return ff.data && ff.index;
   };
   FF ca, sq, hd;
@@ -752,7 +756,12 @@ extern "C" int hhref_ca3m_to_hmm(const char* prefix, const char* entry_name, con
   const int rc = msa_export(ali, entry->name, filt, wg_mode, prep, capL, capN, dims, X, I, keep, wg, nres, ksort, f, tr, neff,
                             neff_hmm, ss_pred, ss_conf, p, tr_prep, pav);
   delete ali;
-  for (FF* ff : {&ca, &sq, &hd}) { if (ff->fd) fclose(ff->fd); if (ff->fi) fclose(ff->fi); }
+  for (FF* ff : {&ca, &sq, &hd}) {
+    if (ff->index) ffindex_index_free(ff->index);
+    if (ff->data) munmap(ff->data, ff->size);
+    if (ff->fd) fclose(ff->fd);
+    if (ff->fi) fclose(ff->fi);
+  }
   return rc;
 }
 
