@@ -161,7 +161,9 @@ typedef struct hhg_msa_params {
   int32_t M, mark;                  /* par.M_template 1, par.mark 0: the only values built                              */
   int32_t max_seqid, coverage, qid, Ndiff;   /* par.max_seqid_db 90, coverage_db 0, qid_db 0, Ndiff_db 100 (Filter)      */
   float qsc;                        /* par.qsc_db -20 (off); > -10 needs the substitution matrix S                      */
-  int32_t wg;                       /* par.wg 0: position-specific weights; 1: global weights                           */
+  int32_t wg;                       /* 0: position-specific weights (par.wg; what the realignment stage reads templates   */
+                                    /* with), 1: global weights -- ViterbiRunner::alignment reads alignment templates    */
+                                    /* with wg = 1 "for performance" (src/hhviterbirunner.cpp:143): use 1 for its shard   */
 } hhg_msa_params;
 void hhg_msa_params_default(hhg_msa_params* mp);
 /* Host only: number of match columns and of sequences of one A3M record, and whether it carries >ss_pred. */

@@ -16,7 +16,8 @@
 //                 per GPU; every Hit must still equal the reference's, and the hit list merged over NCCL by
 //                 hhg_plan_topk / hhg_plan_topk_paths (K = all templates, key = Hit.score) must be the reference's
 //                 first-alignment hits in (score descending, template index ascending) order, paths included
-//   --hhm-loader  templates are loaded by hhg_db_create_hhm from the HHM text instead of the reference's preparation
+//   --hhm-loader  templates are loaded by hhg_db_create_hhm from the HHM text (or, when the template files are A3M
+//                 alignments, by hhg_db_create_a3m) instead of the reference's preparation
 //   --mac         additionally realign every hit: PosteriorDecoderRunner::executeComputation vs hhg_mac_realign
 //                 (written in round 1, first exercised on a GPU in round 2; the MAC parity of round 1 is established
 //                 by tests/test_mac_gpu.py against the same reference code through oracle/ref_shim.cpp)
@@ -146,10 +147,32 @@ class GpuViterbiRunner {
       rec.push_back('\0');                                        // like an ffindex entry
       off.push_back((int64_t)data.size()); len.push_back((int64_t)rec.size());
       int32_t L = 0, has_ss = 0;
+      const bool is_msa = rec[0] == '>' || rec[0] == '#';         // the format test of HHEntry::getTemplateHMM (:441)
+      if (files.front() == f) msa_ = is_msa;
+      if (is_msa != msa_) { fprintf(stderr, "templates must be all HHM or all A3M\n"); exit(2); }
+      if (is_msa) {
+        // alignment branch: Read / Compress / Filter / FrequenciesAndTransitions run inside hhg_db_create_a3m; the
+        // Viterbi stage reads templates with GLOBAL sequence weights (char wg = 1, src/hhviterbirunner.cpp:143)
+        hhg_msa_params_default(&mp_);
+        mp_.maxseq = par.maxseq; mp_.maxcol = par.maxcol; mp_.maxres = par.maxres;
+        mp_.max_seqid = par.max_seqid_db; mp_.coverage = par.coverage_db; mp_.qid = par.qid_db; mp_.qsc = par.qsc_db;
+        mp_.Ndiff = par.Ndiff_db; mp_.wg = 1;
+        int32_t N = 0;
+        HHG_CHECK(hhg_a3m_scan(rec.data(), (int64_t)rec.size(), &mp_, &L, &N, &has_ss));
+        if (!has_ss) all_have_ss_ = false;
+        L_.push_back(L);
+        // Neff_HMM of the record for Hit.Neff_HMM: one extra pass through the alignment kernels
+        std::vector<float> f((size_t)(L + 2) * 20), tr((size_t)(L + 1) * 7), ne((size_t)3 * (L + 1));
+        int32_t dims[6]; float nh = 0;
+        HHG_CHECK(hhg_msa_to_hmm(ctx_, rec.data(), (int64_t)rec.size(), &mp_, S_, pb_, L, N, dims, nullptr, nullptr, f.data(),
+                                 tr.data(), ne.data(), &nh, nullptr));
+        neff_.push_back(nh);
+      } else {
       HHG_CHECK(hhg_hhm_scan(rec.data(), (int64_t)rec.size(), &L, &has_ss));
       if (!has_ss) all_have_ss_ = false;
       L_.push_back(L);
-      {
+      }
+      if (!is_msa) {
         // Neff_HMM of the record (NEFF line) through the library's tokeniser; ss_dssp lines do not occur in the test sets
         std::vector<int32_t> f((size_t)L * 20), trn((size_t)(L + 1) * 10), nul(20);
         std::vector<uint8_t> ssb(L);
@@ -165,8 +188,15 @@ class GpuViterbiRunner {
     hhg_prep_params pp = {par.gapb, par.gapd, par.gape, par.gapf, par.gapg, par.gaph, par.gapi,
                           par.pc_hhm_nocontext_mode, par.pc_hhm_nocontext_a, par.pc_hhm_nocontext_b,
                           par.pc_hhm_nocontext_c};
-    HHG_CHECK(hhg_db_create_hhm(ctx_, (int)files.size(), data.data(), off.data(), len.data(), &pp, &R[0][0], &db_));
+    if (msa_)
+      HHG_CHECK(hhg_db_create_a3m(ctx_, (int)files.size(), data.data(), off.data(), len.data(), &mp_, S_, pb_, &pp, &R[0][0], &db_));
+    else
+      HHG_CHECK(hhg_db_create_hhm(ctx_, (int)files.size(), data.data(), off.data(), len.data(), &pp, &R[0][0], &db_));
   }
+  bool msa_ = false;
+  hhg_msa_params mp_;
+  const float* S_ = nullptr;      // substitution matrix / background the reference holds when it reads the templates
+  const float* pb_ = nullptr;
 
   std::vector<GpuHit> alignment(Parameters& par, HMMSimd* q_simd, int n_targets, float* pb,
                                 const float S33[NSSPRED][MAXCF][NSSPRED][MAXCF]) {
@@ -604,7 +634,13 @@ int main(int argc, char** argv) {
       while ((n = fread(buf, 1, sizeof(buf), fp)) > 0) rec.append(buf, n);
       fclose(fp);
       int32_t L = 0, has_ss = 0;
-      HHG_CHECK(hhg_hhm_scan(rec.c_str(), (int64_t)rec.size() + 1, &L, &has_ss));
+      if (rec[0] == '>' || rec[0] == '#') {
+        hhg_msa_params mp; hhg_msa_params_default(&mp);
+        int32_t N = 0;
+        HHG_CHECK(hhg_a3m_scan(rec.c_str(), (int64_t)rec.size() + 1, &mp, &L, &N, &has_ss));
+      } else {
+        HHG_CHECK(hhg_hhm_scan(rec.c_str(), (int64_t)rec.size() + 1, &L, &has_ss));
+      }
       len = L;
     }
     seqlens.push_back(len);
@@ -628,6 +664,7 @@ int main(int argc, char** argv) {
     if (text_loader) {
       std::vector<std::string> files(argv + 2, argv + argc);
       gpu_runner.seqlen_override_ = seqlens;
+      gpu_runner.S_ = &S[0][0]; gpu_runner.pb_ = pb;
       gpu_runner.UploadText(par, files, R);
     } else {
       gpu_runner.Upload(par, entries, pb, S, Sim, R);

@@ -208,3 +208,21 @@ def test_excluded_regions_in_the_dropin_check(tmp_path):
         files.append(str(f))
     r = _run(["--excl", "1-33,200-260", "--template-excl", "10-20,400-500", QUERY, QUERY] + files)
     assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+def test_alignment_templates_in_the_dropin_check(tmp_path):
+    """Templates given as A3M alignments: the reference's runner takes the alignment branch of getTemplateHMM per
+    template (Read, Compress, Filter, FrequenciesAndTransitions with global weights, src/hhviterbirunner.cpp:143),
+    the adapter builds the shard with hhg_db_create_a3m; every Hit must be identical."""
+    from hhsuite_b200 import synth
+    qa = os.path.join(ROOT, "oracle", "_ref", "data", "query.a3m")
+    files = []
+    for k, (L, n) in enumerate([(150, 40), (60, 5), (300, 120), (33, 0), (200, 25), (97, 60), (120, 250), (250, 12), (75, 33)]):
+        f = tmp_path / f"t{k}.a3m"
+        f.write_text(synth.a3m_text(L, n, 400 + k, f"t{k}", with_ss=(k % 4 == 0)))
+        files.append(str(f))
+    if os.path.exists(qa):
+        files.insert(1, qa)                                  # the query's own alignment: a strong hit, alternative alignments
+    r = _run(["--hhm-loader", QUERY] + files)
+    assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr

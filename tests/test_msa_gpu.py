@@ -183,3 +183,17 @@ def test_compressed_alignment_database(hhg, gpu_ctx, refshim, tmp_path):
         assert np.array_equal(bits(pav[k]), bits(ref["pav"])), k
         pos += L
     db.close(); sq.close(); ca.close()
+
+
+@pytest.mark.parametrize("wg", [0, 1])
+def test_large_alignment(hhg, gpu_ctx, refshim, tmp_path, wg):
+    """2 500 sequences x 250 columns: many filter passes of the position-dependent schedule, sub-alignment counts
+    beyond one byte, long ordered sums."""
+    from hhsuite_b200 import synth
+    t = synth.a3m_text(250, 2500, 31, ident=0.55, dup_frac=0.2).encode()
+    path = tmp_path / "big.a3m"
+    path.write_bytes(t)
+    ref = refshim.msa_to_hmm(str(path), wg=wg, capL=300, capN=2600)
+    got = hhg.capi.msa_to_hmm(gpu_ctx, t, refshim.pb(), mp=hhg.capi.MsaParams.defaults(wg=wg))
+    assert ref["N_filtered"] > 100
+    _cmp(got, ref, f"large wg={wg}")
