@@ -533,7 +533,7 @@ k_msa_filter(MsaArrays A, const __grid_constant__ MsaFilterParams P) {
       int nm = Nmax[i];
       if (nm < mx) { nm = mx; Nmax[i] = nm; }
       if (nm < Ndiff) {
-        s_flag = 0;
+        atomicExch(&s_flag, 0);
         idw[i] = seqid;
         atomicMax(&s_max, Ndiff - nm);
       }
@@ -586,7 +586,7 @@ k_msa_filter(MsaArrays A, const __grid_constant__ MsaFilterParams P) {
       for (int a = warp; a < nacc; a += nw) {
         // early exit once another warp has found a rejecting sequence; the decision must be warp-uniform (the lanes
         // meet again in the shuffles below), so one lane reads the flag for all
-        int seen = lane == 0 ? *(volatile int*)&s_flag : 0;
+        int seen = lane == 0 ? atomicOr(&s_flag, 0) : 0;       // atomic on both sides: concurrent with the store below
         seen = __shfl_sync(0xffffffffu, seen, 0);
         if (seen) break;
         const int jj = acc[a];
@@ -608,7 +608,7 @@ k_msa_filter(MsaArrays A, const __grid_constant__ MsaFilterParams P) {
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) { diff += __shfl_xor_sync(0xffffffffu, diff, o); cov += __shfl_xor_sync(0xffffffffu, cov, o); }
-        if (lane == 0 && diff < diff_suff && (float)diff < __fmul_rn(dmf, (float)cov)) s_flag = 1;
+        if (lane == 0 && diff < diff_suff && (float)diff < __fmul_rn(dmf, (float)cov)) atomicExch(&s_flag, 1);
       }
       __syncthreads();
       const int rejected = s_flag;
@@ -735,7 +735,7 @@ k_msa_mstate(MsaArrays A, int n_msa, const long long* __restrict__ item_off, lon
         const bool prev = i > 1 && msa_x(row, i - 1) < MSA_ANY, cur = msa_x(row, i) < MSA_ANY;
         any |= prev != cur;
       }
-      if (any) s_any = 1;
+      if (any) atomicExch(&s_any, 1);
       __syncthreads();
       return s_any;
     };
