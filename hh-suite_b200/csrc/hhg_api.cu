@@ -2144,6 +2144,17 @@ int hhg_mac_realign(hhg_ctx* ctx, const hhg_db* db, int n, const int32_t* target
   }
   t_lin = ms_since(t_lin0);
   const auto t_k0 = now();
+  // -excl / -template_excl of the context apply to the realignment like they do to the Viterbi stage
+  DevBuf<int> d_reg;
+  if (!ctx->ex_q_lo.empty() || !ctx->ex_t_lo.empty()) {
+    std::vector<int> hreg;
+    hreg.insert(hreg.end(), ctx->ex_q_lo.begin(), ctx->ex_q_lo.end()); hreg.insert(hreg.end(), ctx->ex_q_hi.begin(), ctx->ex_q_hi.end());
+    hreg.insert(hreg.end(), ctx->ex_t_lo.begin(), ctx->ex_t_lo.end()); hreg.insert(hreg.end(), ctx->ex_t_hi.begin(), ctx->ex_t_hi.end());
+    CK(d_reg.alloc(hreg.size()));
+    CK(cudaMemcpyAsync(d_reg.p, hreg.data(), hreg.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));            // hreg goes out of scope
+    A.reg = d_reg.p; A.reg_nq = (int)ctx->ex_q_lo.size(); A.reg_nt = (int)ctx->ex_t_lo.size();
+  }
   k_mac_band<<<n, 256, 0, ctx->stream>>>(A);
   {
     // working set in shared memory (117 bytes per template column).  Requests whose templates fit 64 KB (Lt <= ~555)

@@ -45,6 +45,10 @@ struct MacArgs {
   const int* vit_i; const int* vit_j;
   const long long* excl_off;           // [n+1] or nullptr
   const int* excl_i; const int* excl_j;
+  // -excl / -template_excl ranges (PosteriorDecoder::exclude_regions / exclude_template_regions,
+  // src/hhposteriordecoder.cpp:120-152): nq query-row ranges then nt template-column ranges, {lo..., hi...} each
+  int reg_nq, reg_nt;
+  const int* reg;                      // [2*nq + 2*nt] = q_lo[nq], q_hi[nq], t_lo[nt], t_hi[nt] or nullptr
   // scratch / outputs
   const long long* cell_off;           // [n] offset of the request's (Lq+1)*(Lt+1) cell block
   float* post; uint8_t* off; uint8_t* bt;
@@ -122,6 +126,24 @@ __global__ void __launch_bounds__(256) k_mac_band(const MacArgs A) {
       const int i = ei[s], j = ej[s];
       if (i + d >= 1 && i + d <= Lq) off[(size_t)(i + d) * W + j] = 1;
       if (j + d >= 1 && j + d <= Lt) off[(size_t)i * W + (j + d)] = 1;
+    }
+  }
+  if (A.reg) {                                             // whole query rows / template columns switched off
+    __syncthreads();
+    for (int g = 0; g < A.reg_nq; ++g) {
+      const int lo = max(A.reg[g], 1), hi = min(A.reg[A.reg_nq + g], Lq);
+      for (long long c = threadIdx.x; c < (long long)(hi - lo + 1) * Lt; c += blockDim.x) {
+        const int i = lo + (int)(c / Lt), j = 1 + (int)(c % Lt);
+        off[(size_t)i * W + j] = 1;
+      }
+    }
+    const int* tr_ = A.reg + 2 * A.reg_nq;
+    for (int g = 0; g < A.reg_nt; ++g) {
+      const int lo = max(tr_[g], 1), hi = min(tr_[A.reg_nt + g], Lt);
+      for (long long c = threadIdx.x; c < (long long)(hi - lo + 1) * Lq; c += blockDim.x) {
+        const int j = lo + (int)(c / Lq), i = 1 + (int)(c % Lq);
+        off[(size_t)i * W + j] = 1;
+      }
     }
   }
 }

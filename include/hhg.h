@@ -246,7 +246,9 @@ int hhg_set_use_ss(hhg_ctx* ctx, int use_ss);
 /* -excl / -template_excl (par.exclstr, par.template_exclstr; ViterbiRunner::exclude_regions / exclude_template_regions,
  * src/hhviterbirunner.cpp:291-330): query rows q_lo[k]..q_hi[k] are switched off for every template column, template
  * columns t_lo[k]..t_hi[k] for every query row, in every following search of this context (1-based, inclusive; counts of
- * 0 clear the setting).  Works together with the excl_* path exclusions of hhg_viterbi_search. */
+ * 0 clear the setting).  Works together with the excl_* path exclusions of hhg_viterbi_search, and applies to
+ * hhg_mac_realign as well (PosteriorDecoder::exclude_regions / exclude_template_regions,
+ * src/hhposteriordecoder.cpp:100-152). */
 int hhg_set_excluded_regions(hhg_ctx* ctx, int nq, const int32_t* q_lo, const int32_t* q_hi, int nt, const int32_t* t_lo,
                              const int32_t* t_hi);
 

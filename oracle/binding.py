@@ -380,6 +380,11 @@ class RefShim:
             raise IOError(path)
         return dict(L=L, p_raw=p_raw[:L + 2].copy(), p=p_prep[:L + 2].copy(), tr=tr[:L + 1].copy(), pav=pav)
 
+    def set_mac_exclstr(self, q="", t=""):
+        """par.exclstr / par.template_exclstr (-excl / -template_excl) for the following mac_realign calls."""
+        self.lib.hhref_set_mac_exclstr.argtypes = [C.c_char_p, C.c_char_p]
+        self.lib.hhref_set_mac_exclstr(q.encode(), t.encode())
+
     def mac_realign(self, t_p, t_tr, vit, excl=(), local=True, shift=-0.03, mact=0.35, corr=0.1, min_overlap=0,
                     want_post=True):
         """PosteriorDecoder::realign for one hit of the loaded query.  vit = (i1, i2, j1, j2, nsteps, i_steps,

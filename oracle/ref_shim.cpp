@@ -275,6 +275,10 @@ int hhref_prepare_template_hhm_raw(const char* path, int columnscore, float* p_r
 // Outputs: MAC path out_i/out_j/out_states[1..nsteps'], P_posterior per step, res[6] = {i1,i2,j1,j2,nsteps,
 // matched_cols}, fres[2] = {sum_of_probs, forward score before restoreHitValues}, *pforward,
 // post[(Lq+1)*(Lt+1)] the posterior matrix (optional).
+// par.exclstr / par.template_exclstr for the following hhref_mac_realign calls ("" = none)
+static std::string g_mac_exclstr, g_mac_texclstr;
+void hhref_set_mac_exclstr(const char* q, const char* t) { g_mac_exclstr = q ? q : ""; g_mac_texclstr = t ? t : ""; }
+
 int hhref_mac_realign(int Lt, const float* t_p, const float* t_tr, int local, float shift, float mact, float corr,
                       int min_overlap, int i1, int i2, int j1, int j2, int nsteps, const int* vit_i,
                       const int* vit_j, int excl_n, const int* excl_off, const int* excl_i, const int* excl_j,
@@ -319,7 +323,8 @@ int hhref_mac_realign(int Lt, const float* t_p, const float* t_tr, int local, fl
     excl.push_back(PosteriorDecoder::MACBacktraceResult(ai, aj));
   }
   // realign() minus restoreHitValues' effect on what we export: run the public entry, then read the fields
-  dec.realign(*q, *t, hit, pm, vm, excl, nullptr, nullptr, min_overlap, shift, mact, corr);
+  dec.realign(*q, *t, hit, pm, vm, excl, g_mac_exclstr.empty() ? nullptr : &g_mac_exclstr[0],
+              g_mac_texclstr.empty() ? nullptr : &g_mac_texclstr[0], min_overlap, shift, mact, corr);
   res[0] = hit.i1; res[1] = hit.i2; res[2] = hit.j1; res[3] = hit.j2; res[4] = hit.nsteps; res[5] = hit.matched_cols;
   fres[0] = hit.sum_of_probs; fres[1] = 0;
   *pforward = hit.Pforward;

@@ -22,6 +22,13 @@ alignas(16) unsigned char mac_smem[256 * 1024];   // the block's dynamic shared 
 
 using namespace hhg;
 
+// -excl / -template_excl ranges for the following emul_mac_realign calls: q_lo[nq], q_hi[nq], t_lo[nt], t_hi[nt]
+static std::vector<int> g_reg;
+static int g_reg_nq = 0, g_reg_nt = 0;
+extern "C" void emul_mac_set_regions(int nq, int nt, const int* reg) {
+  g_reg.assign(reg, reg + 2 * (nq + nt)); g_reg_nq = nq; g_reg_nt = nt;
+}
+
 // One request, inputs in the reference layout (like the oracle's hho_mac_realign): prepared template p/(log2) tr,
 // query p and LINEAR tr.  t_tr_lin: linear template transitions (boundary rows are set here like the host API does).
 extern "C" int emul_mac_realign(int Lq, const float* q_p, const float* q_tr_lin, int Lt, const float* t_p,
@@ -74,6 +81,7 @@ extern "C" int emul_mac_realign(int Lq, const float* q_p, const float* q_tr_lin,
   A.path_off = path_off.data(); A.out_i = oi.data(); A.out_j = oj.data(); A.out_states = os.data(); A.out_post = op.data();
   A.smem_rows = smem_bytes;
   A.band_scan = band_scan;
+  if (g_reg_nq + g_reg_nt) { A.reg = g_reg.data(); A.reg_nq = g_reg_nq; A.reg_nt = g_reg_nt; }
   emul_launch(emul_dim3(1), 256, k_mac_band, A);
   emul_launch(emul_dim3(1), 32, k_mac_realign, A);
   res6[0] = out.i1; res6[1] = out.i2; res6[2] = out.j1; res6[3] = out.j2; res6[4] = out.nsteps; res6[5] = out.matched_cols;

@@ -226,3 +226,18 @@ def test_alignment_templates_in_the_dropin_check(tmp_path):
         files.insert(1, qa)                                  # the query's own alignment: a strong hit, alternative alignments
     r = _run(["--hhm-loader", QUERY] + files)
     assert r.returncode == 0 and "all hits identical" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/hh_dropin_check not built/shipped")
+def test_mac_realignment_with_excluded_regions(tmp_path):
+    """--mac together with -excl / -template_excl: PosteriorDecoderRunner masks the regions in the realignment as well
+    (src/hhposteriordecoder.cpp:100-108); the library applies the context's regions in k_mac_band."""
+    from hhsuite_b200 import synth
+    files = []
+    for k, L in enumerate([150, 431, 300, 97]):
+        f = tmp_path / f"y{k}.hhm"
+        f.write_text(synth.hhm_text(L, 900 + k, f"y{k}"))
+        files.append(str(f))
+    r = _run(["--mac", "--excl", "1-33,200-260", "--template-excl", "10-20,400-500", QUERY, QUERY] + files)
+    assert r.returncode == 0 and "all MAC alignments identical" in r.stdout and "all hits identical" in r.stdout, \
+        r.stdout + r.stderr

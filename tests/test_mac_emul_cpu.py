@@ -126,3 +126,30 @@ def test_emulated_kernel_on_reference_goldens(emul, oracle):
             n = got["nsteps"]
             assert np.array_equal(got["i"][1:n + 1], G[f"mac_{name}_i"][1:n + 1])
             assert np.array_equal(bits(got["P_posterior"][1:n + 1]), bits(G[f"mac_{name}_ppost"][1:n + 1]))
+
+
+def test_emulated_kernel_with_excluded_regions(emul, oracle, refshim):
+    """-excl / -template_excl ranges in the realignment against the compiled reference
+    (PosteriorDecoder::exclude_regions / exclude_template_regions), both scan modes."""
+    from hhsuite_b200 import synth
+    rng = np.random.default_rng(56)
+    qp, qtr, qss, qpav, qcols = synth.query_profile(70, 12)
+    refshim.set_query(qp, qtr, qpav, None)
+    tp, ttr, _ = synth.prepared_profile(80, rng, qcols, noise=0.2)
+    sc, i2, j2, bt = refshim.viterbi([(tp, ttr, None)])[0]
+    n, i_s, j_s, st, mc = refshim.backtrace(0)
+    vit = (int(i_s[n]), i2, int(j_s[n]), j2, n, i_s, j_s)
+    qlin = oracle.log2lin(qtr)
+    emul.emul_mac_set_regions.argtypes = [C.c_int, C.c_int, c_i32p]
+    try:
+        for (qreg, treg) in (([(20, 30)], []), ([], [(35, 50), (70, 400)]), ([(1, 3), (40, 41)], [(10, 12)])):
+            refshim.set_mac_exclstr(",".join(f"{a}-{b}" for a, b in qreg), ",".join(f"{a}-{b}" for a, b in treg))
+            reg = np.array([a for a, _ in qreg] + [b for _, b in qreg] + [a for a, _ in treg] + [b for _, b in treg], np.int32)
+            emul.emul_mac_set_regions(len(qreg), len(treg), _p(reg, c_i32p))
+            want = refshim.mac_realign(tp, ttr, vit, local=True, mact=0.35)
+            for band in (0, 1):
+                got = _run(emul, oracle, qp, qlin, tp, ttr, vit, local=True, mact=0.35, band=band)
+                _same(got, want)
+    finally:
+        refshim.set_mac_exclstr("", "")
+        emul.emul_mac_set_regions(0, 0, _p(np.zeros(1, np.int32), c_i32p))

@@ -164,6 +164,37 @@ def test_mac_against_compiled_reference(hhg, gpu_ctx, refshim):
     db.close()
 
 
+def test_mac_with_excluded_regions(hhg, gpu_ctx, refshim):
+    """-excl / -template_excl in the realignment (PosteriorDecoder::exclude_regions / exclude_template_regions,
+    src/hhposteriordecoder.cpp:120-152): the context's regions switch off whole query rows / template columns."""
+    from hhsuite_b200 import synth
+    rng = np.random.default_rng(56)
+    Lq = 120
+    qp, qtr, qss, qpav, qcols = synth.query_profile(Lq, 12)
+    refshim.set_query(qp, qtr, qpav, None)
+    tg = [synth.prepared_profile(L, rng, qcols, noise=0.2) for L in (130, 118)]
+    gpu_ctx.set_query(qp, qtr)
+    db = hhg.TargetDB.from_profiles(gpu_ctx, tg)
+    hhg.capi.mac_query_set(gpu_ctx, qp, hhg.capi.log2lin(qtr))
+    try:
+        for (qreg, treg) in (([(30, 45)], []), ([], [(50, 70), (100, 400)]), ([(1, 5), (60, 62)], [(10, 12)])):
+            refshim.set_mac_exclstr(",".join(f"{a}-{b}" for a, b in qreg), ",".join(f"{a}-{b}" for a, b in treg))
+            gpu_ctx.set_excluded_regions(qreg, treg)
+            for t, (tp, ttr, _) in enumerate(tg):
+                sc, i2, j2, bt = refshim.viterbi([(tp, ttr, None)])[0]
+                n, i_s, j_s, st, mc = refshim.backtrace(0)
+                vit = (int(i_s[n]), i2, int(j_s[n]), j2, n, i_s, j_s)
+                ref = refshim.mac_realign(tp, ttr, vit, local=True, mact=0.35)
+                mh, mp = hhg.capi.mac_realign(gpu_ctx, db, [t], [vit], local=True, mact=0.35)
+                _check(mh[0], mp[0], ref)
+                post = hhg.capi.mac_debug_posterior(gpu_ctx, 0, tp.shape[0] - 2)
+                assert np.array_equal(bits(post[1:, 1:]), bits(ref["post"][1:, 1:]))
+    finally:
+        refshim.set_mac_exclstr("", "")
+        gpu_ctx.set_excluded_regions([], [])
+    db.close()
+
+
 def test_mac_error_paths(hhg, gpu_ctx):
     from hhsuite_b200 import synth
     rng = np.random.default_rng(1)
