@@ -45,7 +45,9 @@ SYMBOLS = ["hhg_last_error", "hhg_ctx_create", "hhg_ctx_destroy", "hhg_ctx_sync"
            "hhg_query_set_batch", "hhg_viterbi_search_batch", "hhg_query_from_hhm",
            "hhg_cs219_parse", "hhg_csdb_create_ffindex", "hhg_set_excluded_regions",
            "hhg_msa_params_default", "hhg_a3m_scan", "hhg_a3m_parse", "hhg_msa_to_hmm", "hhg_db_create_a3m", "hhg_query_from_a3m",
-           "hhg_ca3m_scan", "hhg_ca3m_parse", "hhg_ca3m_to_hmm", "hhg_db_create_ca3m"]
+           "hhg_ca3m_scan", "hhg_ca3m_parse", "hhg_ca3m_to_hmm", "hhg_db_create_ca3m",
+           "hhg_crf_create", "hhg_crf_destroy", "hhg_crf_info", "hhg_query_context_pseudocounts", "hhg_crf_parse_host",
+           "hhg_crf_state", "hhg_crf_tail_host"]
 
 
 class PrepParams(C.Structure):
@@ -74,6 +76,70 @@ class MsaParams(C.Structure):
         for k, v in kw.items():
             setattr(mp, k, v)
         return mp
+
+
+class Admix(C.Structure):
+    """hhg_admix: pseudocount admixture tau(Neff) of cs::Admix (src/cs/pseudocounts.h:52-115).
+    kind 0 constant, 1 CS-BLAST (prefilter default 0.8 / 2.0), 2 HHsearch (query HMM default 0.9 / 4.0 / 1.0)."""
+    _fields_ = [("kind", C.c_int32), ("pca", C.c_double), ("pcb", C.c_double), ("pcc", C.c_double)]
+
+    @classmethod
+    def hhm(cls):
+        return cls(2, 0.90, 4.00, 1.0)        # par.pc_hhm_context_engine, src/hhdecl.cpp:52-56
+
+    @classmethod
+    def prefilter(cls):
+        return cls(1, 0.80, 2.00, 1.0)        # par.pc_prefilter_context_engine, :58-62
+
+
+class Crf:
+    """hhg_crf: the context library of the CRF pseudocounts (text of a `.crf` file, e.g. HH-suite's context_data.crf)."""
+
+    def __init__(self, ctx, text: bytes):
+        self.h = C.c_void_p()
+        self.ctx = ctx
+        if ctx is None:
+            _ck(load().hhg_crf_parse_host(text, len(text), C.byref(self.h)))
+        else:
+            _ck(ctx.L.hhg_crf_create(ctx.h, text, len(text), C.byref(self.h)))
+        n = np.zeros(1, np.int32); w = np.zeros(1, np.int32)
+        _ck(load().hhg_crf_info(self.h, _p(n, c_i32p), _p(w, c_i32p), None))
+        self.n_states, self.window = int(n[0]), int(w[0])
+
+    def pc(self):
+        out = np.zeros((self.n_states, 20), np.float64)
+        n = np.zeros(1, np.int32); w = np.zeros(1, np.int32)
+        _ck(load().hhg_crf_info(self.h, _p(n, c_i32p), _p(w, c_i32p), out.ctypes.data))
+        return out
+
+    def state(self, k):
+        w = np.zeros((self.window, 20), np.float64); b = C.c_double()
+        _ck(load().hhg_crf_state(self.h, k, w.ctypes.data, C.byref(b)))
+        return w, b.value
+
+    def tail_host(self, score, f, neff_m, admix):
+        """Host only: the per-column log-sum-exp / admixture tail on given context scores [L, n_states]."""
+        f = np.ascontiguousarray(f, np.float32); neff_m = np.ascontiguousarray(neff_m, np.float32)
+        score = np.ascontiguousarray(score, np.float64).copy()
+        L = f.shape[0] - 2
+        p = np.zeros((L + 2, 20), np.float32)
+        _ck(load().hhg_crf_tail_host(self.h, L, score.ctypes.data, _p(f, c_f32p), _p(neff_m, c_f32p), C.byref(admix), _p(p, c_f32p)))
+        return p
+
+    def pseudocounts(self, f, neff_m, neff_hmm, pb, admix):
+        """hhg_query_context_pseudocounts -> (p[(L+2),20] incl. rows 0 / L+1 = pav, pav[20])."""
+        f = np.ascontiguousarray(f, np.float32); neff_m = np.ascontiguousarray(neff_m, np.float32)
+        pb = np.ascontiguousarray(pb, np.float32)
+        L = f.shape[0] - 2
+        p = np.zeros((L + 2, 20), np.float32); pav = np.zeros(20, np.float32)
+        _ck(self.ctx.L.hhg_query_context_pseudocounts(self.ctx.h, self.h, L, _p(f, c_f32p), _p(neff_m, c_f32p), float(neff_hmm),
+                                                      _p(pb, c_f32p), C.byref(admix), _p(p, c_f32p), _p(pav, c_f32p)))
+        return p, pav
+
+    def close(self):
+        if self.h:
+            load().hhg_crf_destroy(self.h)
+            self.h = None
 
 
 class SeqDb(C.Structure):
@@ -222,6 +288,14 @@ def load():
                                 C.c_void_p, c_i32p, c_i32p]
     L.hhg_msa_to_hmm.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, c_f32p, c_f32p, C.c_int32, C.c_int32,
                                  c_i32p, C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_u8p]
+    L.hhg_crf_create.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]
+    L.hhg_crf_parse_host.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]
+    L.hhg_crf_destroy.argtypes = [C.c_void_p]
+    L.hhg_crf_info.argtypes = [C.c_void_p, c_i32p, c_i32p, C.c_void_p]
+    L.hhg_crf_state.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]
+    L.hhg_crf_tail_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, c_f32p, c_f32p, C.c_void_p, c_f32p]
+    L.hhg_query_context_pseudocounts.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, c_f32p, c_f32p, C.c_float, c_f32p,
+                                                 C.c_void_p, c_f32p, c_f32p]
     L.hhg_ca3m_scan.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, c_i32p, c_i32p]
     L.hhg_ca3m_parse.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_i32p, c_u8p,
                                  C.c_void_p, C.c_void_p, c_i32p, c_i32p]

@@ -5,6 +5,7 @@
 #include "hhg_kernels.cuh"
 #include "hhg_hhm.cuh"
 #include "hhg_msa.cuh"
+#include "hhg_crf.cuh"
 #include "hhg_mac.cuh"
 #include "hhg_topk.cuh"
 #include "hhg_hitlist.h"
@@ -1122,6 +1123,119 @@ int hhg_query_from_a3m(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa
   if (ss) ss[0] = ss[L + 1] = 0;
   if (neff) *neff = nh;
   *L_out = L;
+  return HHG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Context-specific pseudocounts of the query (hhg_crf.cuh)
+}  // extern "C"
+struct hhg_crf {
+  int device = 0;
+  hhg::CrfHost host;
+  DevBuf<double> d_w, d_bias;
+};
+extern "C" {
+
+int hhg_crf_create(hhg_ctx* ctx, const char* text, int64_t len, hhg_crf** out) {
+  if (!ctx || !text || len <= 0 || !out) return fail(HHG_EINVAL, "hhg_crf_create: bad argument");
+  std::unique_ptr<hhg_crf> c(new hhg_crf());
+  const std::string msg = crf_parse(text, len, &c->host);
+  if (!msg.empty()) return fail(HHG_EINVAL, "hhg_crf_create: %s", msg.c_str());
+  CK(cudaSetDevice(ctx->device));
+  c->device = ctx->device;
+  CK(c->d_w.alloc(c->host.w.size())); CK(c->d_bias.alloc(c->host.bias.size()));
+  CK(cudaMemcpyAsync(c->d_w.p, c->host.w.data(), c->host.w.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(c->d_bias.p, c->host.bias.data(), c->host.bias.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = c.release();
+  return HHG_OK;
+}
+
+int hhg_crf_destroy(hhg_crf* crf) { delete crf; return HHG_OK; }
+
+int hhg_crf_info(const hhg_crf* crf, int32_t* n_states, int32_t* window, double* pc /* [n_states*20] or NULL */) {
+  if (!crf || !n_states || !window) return fail(HHG_EINVAL, "hhg_crf_info: bad argument");
+  *n_states = crf->host.K; *window = crf->host.W;
+  if (pc) memcpy(pc, crf->host.pc.data(), crf->host.pc.size() * 8);
+  return HHG_OK;
+}
+
+// Host only: the per-column tail of hhg_query_context_pseudocounts on caller-supplied context scores
+// (score[L*K], what k_crf_scores produces), for inspection and CPU-side tests.
+int hhg_crf_tail_host(const hhg_crf* crf, int32_t L, double* score, const float* f, const float* neff_m, const hhg_admix* admix,
+                      float* p) {
+  if (!crf || L < 1 || !score || !f || !neff_m || !admix || !p) return fail(HHG_EINVAL, "hhg_crf_tail_host: bad argument");
+  const int K = crf->host.K;
+  for (int i = 0; i < L; ++i) {
+    double cnt[20];
+    for (int a = 0; a < 20; ++a) cnt[a] = f[(size_t)(i + 1) * 20 + a] * neff_m[i + 1];
+    crf_column_tail(K, score + (size_t)i * K, crf->host.pc.data(), cnt, (double)neff_m[i + 1], admix->kind, admix->pca, admix->pcb,
+                    admix->pcc, p + (size_t)(i + 1) * 20);
+  }
+  return HHG_OK;
+}
+
+// Host only: parse without a device (no upload); for CPU-side tests of the parser and the tail.
+int hhg_crf_parse_host(const char* text, int64_t len, hhg_crf** out) {
+  if (!text || len <= 0 || !out) return fail(HHG_EINVAL, "hhg_crf_parse_host: bad argument");
+  std::unique_ptr<hhg_crf> c(new hhg_crf());
+  const std::string msg = crf_parse(text, len, &c->host);
+  if (!msg.empty()) return fail(HHG_EINVAL, "hhg_crf_parse_host: %s", msg.c_str());
+  *out = c.release();
+  return HHG_OK;
+}
+
+// Host only: weights of one state, w[window*20] (row-major window x amino acid) and its bias.
+int hhg_crf_state(const hhg_crf* crf, int32_t k, double* w, double* bias) {
+  if (!crf || k < 0 || k >= crf->host.K || !w || !bias) return fail(HHG_EINVAL, "hhg_crf_state: bad argument");
+  for (int j = 0; j < crf->host.W; ++j)
+    for (int a = 0; a < 20; ++a) w[j * 20 + a] = crf->host.w[((size_t)j * 20 + a) * crf->host.K + k];
+  *bias = crf->host.bias[k];
+  return HHG_OK;
+}
+
+int hhg_query_context_pseudocounts(hhg_ctx* ctx, const hhg_crf* crf, int32_t L, const float* f, const float* neff_m,
+                                   float neff_hmm, const float* pb, const hhg_admix* admix, float* p, float* pav) {
+  if (!ctx || !crf || L < 1 || !f || !neff_m || !admix || !p) return fail(HHG_EINVAL, "hhg_query_context_pseudocounts: bad argument");
+  if (admix->kind < 0 || admix->kind > 2) return fail(HHG_EINVAL, "hhg_query_context_pseudocounts: admixture kind %d (0 constant, 1 CS-BLAST, 2 HHsearch)", admix->kind);
+  if (pav && !pb) return fail(HHG_EINVAL, "hhg_query_context_pseudocounts: pav needs the background pb");
+  CK(cudaSetDevice(ctx->device));
+  const int K = crf->host.K, W = crf->host.W;
+  // HMM::fillCountProfile (src/hhhmm.cpp:1843-1849): counts = f * Neff_M (float product), neff = Neff_M
+  std::vector<double> counts((size_t)L * 20), neff(L);
+  for (int i = 0; i < L; ++i) {
+    neff[i] = neff_m[i + 1];
+    for (int a = 0; a < 20; ++a) counts[(size_t)i * 20 + a] = f[(size_t)(i + 1) * 20 + a] * neff_m[i + 1];
+  }
+  DevBuf<double> d_counts, d_score;
+  CK(d_counts.alloc(counts.size())); CK(d_score.alloc((size_t)L * K));
+  CK(cudaMemcpyAsync(d_counts.p, counts.data(), counts.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  k_crf_scores<<<dim3((K + 255) / 256, L), 256, 0, ctx->stream>>>(L, K, W, crf->d_w.p, crf->d_bias.p, d_counts.p, d_score.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  std::vector<double> score((size_t)L * K);
+  CK(cudaMemcpyAsync(score.data(), d_score.p, score.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  auto work = [&](unsigned w) {
+    for (int i = (int)w; i < L; i += (int)hw)
+      crf_column_tail(K, score.data() + (size_t)i * K, crf->host.pc.data(), counts.data() + (size_t)i * 20, neff[i],
+                      admix->kind, admix->pca, admix->pcb, admix->pcc, p + (size_t)(i + 1) * 20);
+  };
+  std::vector<std::thread> pool;
+  for (unsigned w = 1; w < hw; ++w) pool.emplace_back(work, w);
+  work(0);
+  for (auto& th : pool) th.join();
+  if (pav) {                               // HMM::CalculateAminoAcidBackground (src/hhhmm.cpp:1854-1868)
+    float pv[20];
+    for (int a = 0; a < 20; ++a) pv[a] = pb[a] * 100.0f / neff_hmm;
+    for (int i = 1; i <= L; ++i) for (int a = 0; a < 20; ++a) pv[a] += p[(size_t)i * 20 + a];
+    float sum = 0.0f;
+    for (int a = 0; a < 20; ++a) sum += pv[a];
+    if (sum != 0.0f) { const float fac = 1.0 / sum; for (int a = 0; a < 20; ++a) pv[a] *= fac; }
+    memcpy(pav, pv, 80);
+    memcpy(p, pv, 80); memcpy(p + (size_t)(L + 1) * 20, pv, 80);
+  }
   return HHG_OK;
 }
 

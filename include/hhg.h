@@ -211,6 +211,31 @@ int hhg_query_from_a3m(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_msa
 int hhg_db_create_a3m(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
                       const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
                       const float* R, hhg_db** out);
+/* ---- context-specific pseudocounts of the query (the DEFAULT branch of PrepareQueryHMM) ------------
+ * Replaces HMM::AddContextSpecificPseudocounts (src/hhhmm.cpp:1820-1849) = cs::Pseudocounts::AddTo(count profile, admix)
+ * with the CRF engine (src/cs/crf_pseudocounts-inl.h:74-110, src/cs/pseudocounts-inl.h:41-73), used twice per query by
+ * hhblits: for the query HMM (par.pc_hhm_context_engine: HHsearch admixture 0.9 / 4.0 / 1.0) and for the prefilter
+ * profile (par.pc_prefilter_context_engine: CS-BLAST admixture 0.8 / 2.0).  hhg_crf_create parses the text of a `.crf`
+ * file (HH-suite ships data/context_data.crf: 4000 states, window 13; the file itself is not part of this repository)
+ * and keeps the weights on the device.  The context scores of all states at all columns are computed in a CUDA kernel
+ * (ordered double sums); the log-sum-exp over the states calls exp() / log() of the host's C library, as the reference
+ * does, so it runs on the library's host threads: every output equals the reference's, bit for bit.
+ *   f[(L+2)*20] frequencies without pseudocounts (HMM::f, e.g. from hhg_msa_to_hmm), neff_m[L+1] (Neff_M),
+ *   p[(L+2)*20] out: rows 1..L; with pav != NULL also CalculateAminoAcidBackground (pb, neff_hmm): pav and rows 0, L+1.
+ * Target-Neff admixture (par...target_neff >= 1) is not built (default 0). */
+typedef struct hhg_crf hhg_crf;
+typedef struct hhg_admix { int32_t kind; double pca, pcb, pcc; } hhg_admix;   /* kind 0 constant, 1 CS-BLAST, 2 HHsearch */
+int hhg_crf_create(hhg_ctx* ctx, const char* text, int64_t len, hhg_crf** out);
+int hhg_crf_destroy(hhg_crf* crf);
+int hhg_crf_info(const hhg_crf* crf, int32_t* n_states, int32_t* window, double* pc);
+int hhg_query_context_pseudocounts(hhg_ctx* ctx, const hhg_crf* crf, int32_t L, const float* f, const float* neff_m,
+                                   float neff_hmm, const float* pb, const hhg_admix* admix, float* p, float* pav);
+/* Host only (inspection / CPU-side tests): parse without a device; weights of one state (w[window*20], bias); the
+ * per-column tail on caller-supplied context scores score[L*n_states] (overwritten with the state posteriors). */
+int hhg_crf_parse_host(const char* text, int64_t len, hhg_crf** out);
+int hhg_crf_state(const hhg_crf* crf, int32_t k, double* w, double* bias);
+int hhg_crf_tail_host(const hhg_crf* crf, int32_t L, double* score, const float* f, const float* neff_m, const hhg_admix* admix,
+                      float* p);
 /* Host only: LENG and whether the record carries an ss_pred sequence (no numbers are parsed). */
 int hhg_hhm_scan(const char* rec, int64_t len, int32_t* L, int32_t* has_ss);
 /* Host only: the tokeniser hhg_db_create_hhm runs per record, exposed for inspection and CPU-side tests.

@@ -380,6 +380,30 @@ class RefShim:
             raise IOError(path)
         return dict(L=L, p_raw=p_raw[:L + 2].copy(), p=p_prep[:L + 2].copy(), tr=tr[:L + 1].copy(), pav=pav)
 
+    def crf_text(self):
+        """The context_data.crf bytes embedded in the reference build (what InitializePseudocountsEngine reads)."""
+        n = C.c_longlong()
+        self.lib.hhref_crf_text.restype = C.c_void_p
+        self.lib.hhref_crf_text.argtypes = [C.POINTER(C.c_longlong)]
+        ptr = self.lib.hhref_crf_text(C.byref(n))
+        return C.string_at(ptr, n.value)
+
+    def crf_state(self, k):
+        pc = np.zeros(20, np.float64); w = np.zeros(13 * 20, np.float64); b = C.c_double()
+        self.lib.hhref_crf_state.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
+        n = self.lib.hhref_crf_state(k, pc.ctypes.data, C.byref(b), w.ctypes.data)
+        return n, pc, b.value, w.reshape(13, 20)
+
+    def context_pc(self, f, neff_m, neff_hmm, engine=0):
+        """HMM::AddContextSpecificPseudocounts + CalculateAminoAcidBackground by the compiled reference.
+        engine 0: query HMM (HHsearch admixture), 1: prefilter profile (CS-BLAST admixture)."""
+        f = np.ascontiguousarray(f, np.float32); neff_m = np.ascontiguousarray(neff_m, np.float32)
+        L = f.shape[0] - 2
+        p = np.zeros((L + 2, 20), np.float32); pav = np.zeros(20, np.float32)
+        self.lib.hhref_context_pc.argtypes = [C.c_int, c_f32p, c_f32p, C.c_float, C.c_int, c_f32p, c_f32p]
+        self.lib.hhref_context_pc(L, _p(f, c_f32p), _p(neff_m, c_f32p), float(neff_hmm), engine, _p(p, c_f32p), _p(pav, c_f32p))
+        return p, pav
+
     def set_mac_exclstr(self, q="", t=""):
         """par.exclstr / par.template_exclstr (-excl / -template_excl) for the following mac_realign calls."""
         self.lib.hhref_set_mac_exclstr.argtypes = [C.c_char_p, C.c_char_p]

@@ -58,6 +58,7 @@ extern "C" {
 #include "ffindex.h"
 }
 #include "cs219.lib.h"
+#include "context_data.crf.h"
 #undef private
 #undef protected
 
@@ -779,4 +780,51 @@ extern "C" void hhref_rcp_table(int n, float* out) {
     simdf32_store(res, simdf32_rcp(simdf32_load(in)));
     for (int v = 0; v < VECSIZE_FLOAT && m + v < n; ++v) out[m + v] = res[v];
   }
+}
+
+
+// ---------------------------------------------------------------- context-specific pseudocounts (row a12)
+// The CRF engine of the reference (InitializePseudocountsEngine, src/hhfunc.cpp:204-244) on demand, independent of the
+// nocontxt flag the shim was initialised with.
+static void ensure_context() {
+  if (g->pc_hhm_context_engine) return;
+  InitializePseudocountsEngine(*g->par, g->context_lib, g->crf, g->pc_hhm_context_engine, g->pc_hhm_context_mode,
+                               g->pc_prefilter_context_engine, g->pc_prefilter_context_mode);
+}
+
+// state k of the embedded context_data.crf: pc[20], bias, w[13*20]
+extern "C" int hhref_crf_state(int k, double* pc, double* bias, double* w) {
+  ensure_context();
+  if (!g->crf || k < 0 || k >= (int)g->crf->size()) return -1;
+  const cs::CrfState<cs::AA>& s = (*g->crf)[k];
+  for (int a = 0; a < 20; ++a) pc[a] = s.pc[a];
+  *bias = s.bias_weight;
+  for (size_t j = 0; j < s.context_weights.length(); ++j)
+    for (int a = 0; a < 20; ++a) w[j * 20 + a] = s.context_weights[j][a];
+  return (int)g->crf->size();
+}
+
+// HMM::AddContextSpecificPseudocounts (src/hhhmm.cpp:1820) + CalculateAminoAcidBackground on an HMM with the given raw
+// frequencies f[(L+2)*20] and Neff_M[L+1]; engine 0 = query HMM (par.pc_hhm_context_engine), 1 = prefilter profile.
+extern "C" int hhref_context_pc(int L, const float* f, const float* neff_m, float neff_hmm, int engine, float* p, float* pav) {
+  ensure_context();
+  HMM* h = new HMM(MAXSEQDIS, g->maxres);
+  h->L = L;
+  h->has_pseudocounts = false;
+  h->Neff_HMM = neff_hmm;
+  for (int i = 0; i <= L + 1; ++i) for (int a = 0; a < 20; ++a) h->f[i][a] = f[(size_t)i * 20 + a];
+  for (int i = 0; i <= L; ++i) h->Neff_M[i] = neff_m[i];
+  if (engine == 0) h->AddContextSpecificPseudocounts(g->pc_hhm_context_engine, g->pc_hhm_context_mode);
+  else h->AddContextSpecificPseudocounts(g->pc_prefilter_context_engine, g->pc_prefilter_context_mode);
+  h->CalculateAminoAcidBackground(g->pb);
+  for (int i = 0; i <= L + 1; ++i) for (int a = 0; a < 20; ++a) p[(size_t)i * 20 + a] = h->p[i][a];
+  for (int a = 0; a < 20; ++a) pav[a] = h->pav[a];
+  delete h;
+  return L;
+}
+
+// the embedded context_data.crf text, so tests can hand it to the product without reading /root/reference
+extern "C" const unsigned char* hhref_crf_text(long long* len) {
+  *len = (long long)context_data_crf_len;
+  return context_data_crf;
 }

@@ -88,7 +88,14 @@ using std::max;
 using std::min;
 
 template <typename Kernel, typename... Args>
-void emul_launch(unsigned grid, unsigned threads, Kernel k, Args... args) {
+void emul_launch2(unsigned grid, unsigned grid_y, unsigned threads, Kernel k, Args... args);
+
+template <typename Kernel, typename... Args>
+void emul_launch(unsigned grid, unsigned threads, Kernel k, Args... args) { emul_launch2(grid, 1u, threads, k, args...); }
+
+template <typename Kernel, typename... Args>
+void emul_launch2(unsigned grid, unsigned grid_y, unsigned threads, Kernel k, Args... args) {
+  for (unsigned by = 0; by < grid_y; ++by)
   for (unsigned bx = 0; bx < grid; ++bx) {
     EmulBlock blk;
     blk.bar.reset(new std::barrier<>((std::ptrdiff_t)threads));
@@ -99,7 +106,7 @@ void emul_launch(unsigned grid, unsigned threads, Kernel k, Args... args) {
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < threads; ++t)
       pool.emplace_back([=]() {
-        threadIdx = emul_dim3(t); blockIdx = emul_dim3(bx); blockDim = emul_dim3(threads); gridDim = emul_dim3(grid);
+        threadIdx = emul_dim3(t); blockIdx = emul_dim3(bx, by); blockDim = emul_dim3(threads); gridDim = emul_dim3(grid, grid_y);
         k(args...);
       });
     for (auto& th : pool) th.join();

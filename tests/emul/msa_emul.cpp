@@ -10,6 +10,7 @@
 #include <cstdlib>
 
 #include "../../hh-suite_b200/csrc/hhg_msa.cuh"
+#include "../../hh-suite_b200/csrc/hhg_crf.cuh"
 
 using namespace hhg;
 
@@ -76,4 +77,10 @@ extern "C" int emul_msa_to_hmm(const char* rec, long long len, const int* ip /*m
   memcpy(neff + 2 * (L + 1), nd.data(), (size_t)(L + 1) * 4);
   *neff_hmm = nh;
   return 0;
+}
+
+
+// k_crf_scores (hh-suite_b200/csrc/hhg_crf.cuh) on host memory: w[W*20*K] ([window][aa][state]), bias[K], counts[L*20]
+extern "C" void emul_crf_scores(int L, int K, int W, const double* w, const double* bias, const double* counts, double* score) {
+  emul_launch2((unsigned)((K + 255) / 256), (unsigned)L, 256, k_crf_scores, L, K, W, w, bias, counts, score);
 }

@@ -20,7 +20,8 @@ LIB = os.path.join(EMUL_DIR, "libmsaemul.so")
 @pytest.fixture(scope="module")
 def emul():
     srcs = [os.path.join(EMUL_DIR, "msa_emul.cpp"), os.path.join(EMUL_DIR, "cuda_emul_mw.h"),
-            os.path.join(ROOT, "hh-suite_b200", "csrc", "hhg_msa.cuh"), os.path.join(ROOT, "hh-suite_b200", "csrc", "hhg_math.cuh")]
+            os.path.join(ROOT, "hh-suite_b200", "csrc", "hhg_msa.cuh"), os.path.join(ROOT, "hh-suite_b200", "csrc", "hhg_math.cuh"),
+            os.path.join(ROOT, "hh-suite_b200", "csrc", "hhg_crf.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["g++", "-O1", "-std=c++20", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-DHHG_EMUL",
                                "-o", LIB, srcs[0]])
@@ -84,3 +85,27 @@ def test_emulated_filter_options_and_global_weights(emul, refshim, tmp_path, fil
         path = tmp_path / "m.a3m"
         path.write_bytes(t)
         _cmp(_run(emul, refshim, t, filt=filt, wg=wg), refshim.msa_to_hmm(str(path), filt=filt, wg=wg), f"case {case} {filt} wg={wg}")
+
+
+def test_emulated_context_score_kernel(emul, refshim):
+    """k_crf_scores on the CPU emulator + the library's host tail == the compiled reference's CRF pseudocounts."""
+    from hhsuite_b200 import capi
+    crf = capi.Crf(None, refshim.crf_text())
+    K, W = crf.n_states, crf.window
+    Wt = np.zeros((W, 20, K)); bias = np.zeros(K)
+    for k in range(K):
+        w, b = crf.state(k)
+        Wt[:, :, k] = w; bias[k] = b
+    rng = np.random.default_rng(9)
+    L = 9
+    f = rng.dirichlet(np.full(20, 0.4), L + 2).astype(np.float32)
+    neff_m = np.concatenate([[99.999], rng.uniform(1.0, 8.0, L)]).astype(np.float32)
+    counts = np.ascontiguousarray((f[1:L + 1] * neff_m[1:L + 1, None]).astype(np.float32).astype(np.float64))
+    score = np.zeros((L, K))
+    wt = np.ascontiguousarray(Wt)
+    emul.emul_crf_scores.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
+    emul.emul_crf_scores(L, K, W, wt.ctypes.data, bias.ctypes.data, counts.ctypes.data, score.ctypes.data)
+    got = crf.tail_host(score, f, neff_m, capi.Admix.hhm())
+    ref, _ = refshim.context_pc(f, neff_m, 3.0, engine=0)
+    assert np.array_equal(bits(got[1:L + 1]), bits(ref[1:L + 1]))
+    crf.close()
