@@ -771,6 +771,9 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
   // pass 1: parse everything (host threads); the parsed alignments of one chunk are kept, the rest re-parsed later
   // would double the work, so all are kept: 1 byte per residue
   std::vector<MsaHost> all((size_t)n);
+  const bool timing = getenv("HHG_TIMING") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  double ms_kernels = 0.0;
   {
     const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<std::string> errs(hw);
@@ -789,6 +792,7 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
     for (unsigned w = 0; w < hw; ++w)
       if (err_rec[w] >= 0) return fail(HHG_EINVAL, "record %d: %s", err_rec[w], errs[w].c_str());
   }
+  const auto t_parsed = std::chrono::steady_clock::now();
   std::unique_ptr<hhg_db> holder(new hhg_db());
   hhg_db* db = holder.get();
   db->device = ctx->device;
@@ -838,8 +842,10 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
     const int m = t1 - t0;
     C.host.clear();
     for (int k = t0; k < t1; ++k) C.host.push_back(std::move(all[k]));
+    const auto t_c0 = std::chrono::steady_clock::now();
     rc = msa_chunk_run(ctx, C, *mp, S, pb, t0);
     if (rc != HHG_OK) return rc;
+    ms_kernels += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
     std::vector<long long> rec_off(m);
     long long cols = 0;
     for (int k = 0; k < m; ++k) { rec_off[k] = cols; cols += C.host[k].L; }
@@ -875,6 +881,12 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
   }
   CK(cudaMemcpyAsync(db->cols.p, db->cols_raw.p, db->cols.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (timing) {
+    const double ms_parse = std::chrono::duration<double, std::milli>(t_parsed - t_begin).count();
+    const double ms_all = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    fprintf(stderr, "[hhg] alignment loader: %d records, host scan %.1f ms, staging + filter/weights/M-state/finish kernels %.1f ms, "
+                    "rest (pseudocounts, pav, copies) %.1f ms\n", n, ms_parse, ms_kernels, ms_all - ms_parse - ms_kernels);
+  }
   db->raw = true;
   db->prepared = false;
   *out = holder.release();
