@@ -89,6 +89,9 @@ int strip_rows() {
 
 struct hhg_ctx {
   int device = 0;
+  std::shared_ptr<void> msa_cache;     // MsaChunk reused by the single-alignment calls (hhg_msa_to_hmm, hhg_query_from_a3m)
+  std::shared_ptr<void> crf_cache;     // device + pinned host staging of hhg_query_context_pseudocounts
+  std::shared_ptr<void> msa_rcp;       // DevBuf<float>: the host's RCPPS table (hhg_msa.cuh), uploaded once per context
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = 0;
@@ -474,12 +477,12 @@ struct MsaChunk {
   DevBuf<int> first, last, nres, ksort, in_, inkk, seqid_prev, acc, Ncnt, Nmaxv, idw, ins_k, nfil, status, ni, counter, cnt;
   DevBuf<uint16_t> ins_cnt;
   DevBuf<uint32_t> ins_off;
-  DevBuf<float> wg, f, tr, nm, ni_f, nd, nseg, nhmm, wc, wi, pb, rcp;
+  DevBuf<float> wg, f, tr, nm, ni_f, nd, nseg, nhmm, wc, wi, pb;
   DevBuf<long long> item_off;
   MsaArrays A{};
 };
 
-const float* msa_rcp_table(hhg_ctx* ctx, MsaChunk& C) {
+const float* msa_rcp_table(hhg_ctx* ctx) {
   // RCPPS of this host for every integer argument the weighting can produce (src/hhalignment.cpp:2531)
   static std::vector<float> table;
   static std::once_flag once;
@@ -490,11 +493,13 @@ const float* msa_rcp_table(hhg_ctx* ctx, MsaChunk& C) {
       _mm_storeu_ps(&table[m], _mm_rcp_ps(v));
     }
   });
-  if (C.rcp.n != (size_t)MSA_RCP_N) {
-    if (C.rcp.alloc(MSA_RCP_N) != cudaSuccess) return nullptr;
-    if (cudaMemcpyAsync(C.rcp.p, table.data(), (size_t)MSA_RCP_N * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return nullptr;
+  if (!ctx->msa_rcp) {
+    auto buf = std::make_shared<DevBuf<float>>();
+    if (buf->alloc(MSA_RCP_N) != cudaSuccess) return nullptr;
+    if (cudaMemcpyAsync(buf->p, table.data(), (size_t)MSA_RCP_N * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return nullptr;
+    ctx->msa_rcp = buf;
   }
-  return C.rcp.p;
+  return std::static_pointer_cast<DevBuf<float>>(ctx->msa_rcp)->p;
 }
 
 #define MSA_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(HHG_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
@@ -567,7 +572,7 @@ int msa_chunk_run(hhg_ctx* ctx, MsaChunk& C, const hhg_msa_params& mp, const flo
   MSA_CK(cudaMemsetAsync(C.counter.p, 0, 4, ctx->stream));
   MSA_CK(cudaMemsetAsync(C.nseg.p, 0, nc * 4, ctx->stream));
   MSA_CK(cudaMemsetAsync(C.tr.p, 0, nc * 7 * 4, ctx->stream));
-  const float* rcp = msa_rcp_table(ctx, C);
+  const float* rcp = msa_rcp_table(ctx);
   if (!rcp) return fail(HHG_ECUDA, "reciprocal table upload failed");
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -587,13 +592,29 @@ int msa_chunk_run(hhg_ctx* ctx, MsaChunk& C, const hhg_msa_params& mp, const flo
   MsaFilterParams FP;
   FP.max_seqid = mp.max_seqid; FP.coverage = mp.coverage; FP.qid = mp.qid; FP.Ndiff = mp.Ndiff; FP.qsc = mp.qsc;
   if (S) memcpy(FP.S, S, sizeof(FP.S)); else memset(FP.S, 0, sizeof(FP.S));
+  const bool timing = getenv("HHG_TIMING") != nullptr;
+  cudaEvent_t ev[5] = {};
+  if (timing) for (auto& e : ev) cudaEventCreate(&e);
+  if (timing) cudaEventRecord(ev[0], ctx->stream);
   k_msa_filter<<<m, 256, 0, ctx->stream>>>(A, FP);
+  if (timing) cudaEventRecord(ev[1], ctx->stream);
   k_msa_weights<<<m, 256, 0, ctx->stream>>>(A, C.ni.p);
+  if (timing) cudaEventRecord(ev[2], ctx->stream);
   k_msa_mstate<<<nblk, 256, 0, ctx->stream>>>(A, m, C.item_off.p, items, C.counter.p, C.cnt.p, C.wc.p, C.wi.p, C.member.p,
                                               C.Lmax, C.Nmax, rcp, C.pb.p, mp.wg ? 1 : 0, ctx->lg2.p, ctx->diff.p);
+  if (timing) cudaEventRecord(ev[3], ctx->stream);
   k_msa_finish<<<m, 256, 0, ctx->stream>>>(A, C.pb.p, mp.wg ? 1 : 0, ctx->lg2.p, ctx->diff.p);
+  if (timing) cudaEventRecord(ev[4], ctx->stream);
   ctx->launches += 4;
   MSA_CK(cudaGetLastError());
+  if (timing) {
+    cudaEventSynchronize(ev[4]);
+    float t[4];
+    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], ev[k], ev[k + 1]);
+    fprintf(stderr, "[hhg] alignment kernels (%d alignments, %lld columns): filter %.2f ms, weights %.2f ms, M state %.2f ms, finish %.2f ms\n",
+            m, items, t[0], t[1], t[2], t[3]);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   std::vector<int> status(m);
   MSA_CK(cudaMemcpyAsync(status.data(), C.status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
   MSA_CK(cudaStreamSynchronize(ctx->stream));
@@ -705,7 +726,9 @@ static int msa_to_hmm_impl(hhg_ctx* ctx, const char* rec, int64_t len, const hhg
   if ((rc = seqdb_check(sq)) != HHG_OK) return rc;
   if (mp->qsc > -10.f && !S) return fail(HHG_EINVAL, "hhg_msa_to_hmm: the qsc filter needs the substitution matrix S");
   CK(cudaSetDevice(ctx->device));
-  MsaChunk C;
+  if (!ctx->msa_cache) ctx->msa_cache = std::make_shared<MsaChunk>();      // device buffers persist between calls
+  MsaChunk& C = *std::static_pointer_cast<MsaChunk>(ctx->msa_cache);
+  C.host.clear();
   C.host.resize(1);
   const std::string msg = msa_parse_any(rec, len, sq, mp, &C.host[0]);
   if (!msg.empty()) return fail(HHG_EINVAL, "hhg_msa_to_hmm: %s", msg.c_str());
@@ -1219,19 +1242,32 @@ int hhg_query_context_pseudocounts(hhg_ctx* ctx, const hhg_crf* crf, int32_t L, 
     neff[i] = neff_m[i + 1];
     for (int a = 0; a < 20; ++a) counts[(size_t)i * 20 + a] = f[(size_t)(i + 1) * 20 + a] * neff_m[i + 1];
   }
-  DevBuf<double> d_counts, d_score;
-  CK(d_counts.alloc(counts.size())); CK(d_score.alloc((size_t)L * K));
-  CK(cudaMemcpyAsync(d_counts.p, counts.data(), counts.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  k_crf_scores<<<dim3((K + 255) / 256, L), 256, 0, ctx->stream>>>(L, K, W, crf->d_w.p, crf->d_bias.p, d_counts.p, d_score.p);
+  struct CrfStage {
+    DevBuf<double> counts, score;
+    double* h_score = nullptr; size_t h_n = 0;
+    ~CrfStage() { if (h_score) cudaFreeHost(h_score); }
+  };
+  if (!ctx->crf_cache) ctx->crf_cache = std::make_shared<CrfStage>();
+  CrfStage& st = *std::static_pointer_cast<CrfStage>(ctx->crf_cache);
+  const size_t ns = (size_t)L * K;
+  CK(st.counts.ensure(counts.size())); CK(st.score.ensure(ns));
+  if (st.h_n < ns) {
+    if (st.h_score) cudaFreeHost(st.h_score);
+    st.h_score = nullptr; st.h_n = 0;
+    CK(cudaHostAlloc((void**)&st.h_score, ns * 8, cudaHostAllocDefault));
+    st.h_n = ns;
+  }
+  CK(cudaMemcpyAsync(st.counts.p, counts.data(), counts.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  k_crf_scores<<<dim3((K + 255) / 256, L), 256, 0, ctx->stream>>>(L, K, W, crf->d_w.p, crf->d_bias.p, st.counts.p, st.score.p);
   ctx->launches++;
   CK(cudaGetLastError());
-  std::vector<double> score((size_t)L * K);
-  CK(cudaMemcpyAsync(score.data(), d_score.p, score.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  double* score = st.h_score;
+  CK(cudaMemcpyAsync(score, st.score.p, ns * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   auto work = [&](unsigned w) {
     for (int i = (int)w; i < L; i += (int)hw)
-      crf_column_tail(K, score.data() + (size_t)i * K, crf->host.pc.data(), counts.data() + (size_t)i * 20, neff[i],
+      crf_column_tail(K, score + (size_t)i * K, crf->host.pc.data(), counts.data() + (size_t)i * 20, neff[i],
                       admix->kind, admix->pca, admix->pcb, admix->pcc, p + (size_t)(i + 1) * 20);
   };
   std::vector<std::thread> pool;
