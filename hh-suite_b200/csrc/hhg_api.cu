@@ -853,6 +853,8 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
   A.pcm = pp->pcm; A.pca = pp->pca; A.pcb = pp->pcb; A.pcc = pp->pcc;
 
   const long long kChunkBytes = 256ll << 20;
+  int max_records = 8192;
+  { const char* e = getenv("HHG_MSA_CHUNK_RECORDS"); if (e && atoi(e) > 0) max_records = atoi(e); }   // test knob: many small chunks
   MsaChunk C;
   DevBuf<long long> d_rec_off;
   DevBuf<uint8_t> d_ss;
@@ -861,7 +863,7 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
   while (t0 < n) {
     int t1 = t0;
     long long bytes = 0;
-    while (t1 < n && t1 - t0 < 8192 && (bytes == 0 || bytes + (long long)all[t1].X.size() <= kChunkBytes)) bytes += (long long)all[t1++].X.size();
+    while (t1 < n && t1 - t0 < max_records && (bytes == 0 || bytes + (long long)all[t1].X.size() <= kChunkBytes)) bytes += (long long)all[t1++].X.size();
     const int m = t1 - t0;
     C.host.clear();
     for (int k = t0; k < t1; ++k) C.host.push_back(std::move(all[k]));

@@ -205,7 +205,8 @@ AA = "ARNDCQEGHILKMFPSTWYV"
 
 
 def a3m_text(L: int, nseq: int, seed: int, name: str = "msa", with_ss: bool = False, with_comment: bool = False,
-             consensus_first: bool = False, ident: float = 0.5, dup_frac: float = 0.3, x_frac: float = 0.01) -> str:
+             consensus_first: bool = False, ident: float = 0.5, dup_frac: float = 0.3, x_frac: float = 0.01,
+             ss_conf: bool = True) -> str:
     """A synthetic A3M alignment with L match columns (upper case / '-') and `nseq` sequences after the master:
     point mutations at rate 1-ident, a fraction of near-duplicates (> 90 % identical: removed by the filter), runs
     of deletions, lower-case insert runs, N-/C-terminal truncation (end gaps), a few 'X', optional >ss_pred / >ss_conf
@@ -218,8 +219,10 @@ def a3m_text(L: int, nseq: int, seed: int, name: str = "msa", with_ss: bool = Fa
     if with_ss:
         out.append(">ss_pred PSIPRED predicted secondary structure")
         out.append("".join("CHE"[int(v)] for v in rng.integers(0, 3, L)))
-        out.append(">ss_conf PSIPRED confidence values")
-        out.append("".join(str(int(v)) for v in rng.integers(0, 10, L)))
+        conf = "".join(str(int(v)) for v in rng.integers(0, 10, L))
+        if ss_conf:
+            out.append(">ss_conf PSIPRED confidence values")
+            out.append(conf)
     mseq = "".join(AA[a] for a in master)
     out.append(f">{name}_consensus" if consensus_first else f">{name} master")
     out.append(mseq)

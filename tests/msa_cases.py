@@ -13,6 +13,7 @@ CASES = [  # (match columns, sequences after the master, seed, generator options
     (60, 1, 9, {}),
     (431, 58, 10, dict(ident=0.3)),
     (700, 90, 11, dict(ident=0.6, with_ss=True)),
+    (90, 25, 12, dict(with_ss=True, ss_conf=False)),  # ss_pred without ss_conf: confidence 5 everywhere
 ]
 
 

@@ -78,9 +78,12 @@ def _pack(texts):
 
 
 @pytest.mark.parametrize("pc", [(2, 1.0, 1.5, 1.0), (2, 0.9, 4.0, 0.7), (3, 1.0, 10.0, 0.5), (0, 1.0, 1.5, 1.0)])
-def test_shard_from_a3m_equals_reference_prepared(hhg, gpu_ctx, refshim, tmp_path, pc):
-    """hhg_db_create_a3m: column records and pav == the reference's alignment branch + PrepareTemplateHMM steps."""
+def test_shard_from_a3m_equals_reference_prepared(hhg, gpu_ctx, refshim, tmp_path, pc, monkeypatch):
+    """hhg_db_create_a3m: column records and pav == the reference's alignment branch + PrepareTemplateHMM steps.
+    The second and fourth parameter set load the records in chunks of three (the loader's multi-chunk path)."""
     from tests.test_hhm_db_gpu import _expected_records
+    if pc[0] in (0, 3) or pc[1] != 1.0:
+        monkeypatch.setenv("HHG_MSA_CHUNK_RECORDS", "3")
     texts = msa_cases.texts()
     data, off, ln = _pack(texts)
     pp = refshim.prep_params()
