@@ -576,7 +576,9 @@ int msa_chunk_run(hhg_ctx* ctx, MsaChunk& C, const hhg_msa_params& mp, const flo
   if (!rcp) return fail(HHG_ECUDA, "reciprocal table upload failed");
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  const int nblk = (int)std::min<long long>((long long)sms * 3, std::max<long long>(items, 1));
+  // k_msa_mstate is latency bound inside a block (ordered sums, barriers): 6 blocks per SM = its register / shared-memory
+  // residency (40 registers, 33 KB), every block pulls (alignment, column) items until the queue is empty
+  const int nblk = (int)std::min<long long>((long long)sms * 6, std::max<long long>(items, 1));
   MSA_CK(C.cnt.ensure((size_t)nblk * (C.Lmax + 2) * 24)); MSA_CK(C.wc.ensure((size_t)nblk * (C.Lmax + 2) * 24));
   MSA_CK(C.wi.ensure((size_t)nblk * C.Nmax)); MSA_CK(C.member.ensure((size_t)nblk * C.Nmax));
 
