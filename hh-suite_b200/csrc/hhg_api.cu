@@ -11,7 +11,9 @@
 #include "hhg_hitlist.h"
 
 #include <dlfcn.h>
-#include <xmmintrin.h>
+#if defined(__SSE__)
+#include <xmmintrin.h>     // RCPPS: the alignment weights of the reference go through it (hhg_msa.cuh)
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -488,10 +490,16 @@ const float* msa_rcp_table(hhg_ctx* ctx) {
   static std::once_flag once;
   std::call_once(once, [] {
     table.resize(MSA_RCP_N);
+#if defined(__SSE__)
     for (int m = 0; m < MSA_RCP_N; m += 4) {
       const __m128 v = _mm_set_ps((float)(m + 3), (float)(m + 2), (float)(m + 1), (float)m);
       _mm_storeu_ps(&table[m], _mm_rcp_ps(v));
     }
+#else
+    // no RCPPS on this host: the reference is built through SIMDe there, whose reciprocal estimate differs again;
+    // the exact quotient keeps the result well defined (it will not be bit-identical to such a reference build)
+    for (int m = 0; m < MSA_RCP_N; ++m) table[m] = 1.0f / (float)m;
+#endif
   });
   if (!ctx->msa_rcp) {
     auto buf = std::make_shared<DevBuf<float>>();
@@ -782,8 +790,9 @@ int hhg_ca3m_scan(const char* rec, int64_t len, const hhg_seqdb* seqs, const hhg
 }
 
 static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64_t* off, const int64_t* len,
-                              const hhg_seqdb* sq, const hhg_msa_params* mp, const float* S, const float* pb, const hhg_prep_params* pp,
-                              const float* R, hhg_db** out, float* d_tr_full, float* neff_hmm_out) {
+                              const hhg_seqdb* sq, const hhg_msa_params* mp, const float* S, const float* pb,
+                              const hhg_prep_params* pp, const float* R, hhg_db** out, float* d_tr_full,
+                              float* neff_hmm_out) {
   if (!ctx || !out || n <= 0 || !data || !off || !len || !pp || !R || !pb)
     return fail(HHG_EINVAL, "hhg_db_create_a3m: bad argument");
   int rc = msa_params_check(mp);
@@ -793,55 +802,9 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
   if (pp->pcm < 0 || pp->pcm > 3) return fail(HHG_EINVAL, "hhg_db_create_a3m: pseudocount mode %d does not exist", pp->pcm);
   const bool tau_on_host = pp->pcm == 2 && pp->pcc != 1.0f;
   CK(cudaSetDevice(ctx->device));
-  // pass 1: parse everything (host threads); the parsed alignments of one chunk are kept, the rest re-parsed later
-  // would double the work, so all are kept: 1 byte per residue
-  std::vector<MsaHost> all((size_t)n);
   const bool timing = getenv("HHG_TIMING") != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
-  double ms_kernels = 0.0;
-  {
-    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::vector<std::string> errs(hw);
-    std::vector<int> err_rec(hw, -1);
-    auto work = [&](unsigned w) {
-      for (int k = (int)w; k < n; k += (int)hw) {
-        if (len[k] <= 0) { if (err_rec[w] < 0) { errs[w] = "empty record"; err_rec[w] = k; } continue; }
-        std::string msg = msa_parse_any(data + off[k], len[k], sq, mp, &all[k]);
-        if (!msg.empty() && err_rec[w] < 0) { errs[w] = msg; err_rec[w] = k; }
-      }
-    };
-    std::vector<std::thread> pool;
-    for (unsigned w = 1; w < hw; ++w) pool.emplace_back(work, w);
-    work(0);
-    for (auto& th : pool) th.join();
-    for (unsigned w = 0; w < hw; ++w)
-      if (err_rec[w] >= 0) return fail(HHG_EINVAL, "record %d: %s", err_rec[w], errs[w].c_str());
-  }
-  const auto t_parsed = std::chrono::steady_clock::now();
-  std::unique_ptr<hhg_db> holder(new hhg_db());
-  hhg_db* db = holder.get();
-  db->device = ctx->device;
-  db->n = n;
-  db->L.resize(n);
-  db->col_off.resize(n);
-  long long tot = 0;
-  bool any_ss = false;
-  for (int k = 0; k < n; ++k) {
-    if (all[k].L > 32767) return fail(HHG_EINVAL, "record %d: length %d out of [1,32767]", k, all[k].L);
-    db->L[k] = all[k].L;
-    db->col_off[k] = tot;
-    tot += all[k].L;
-    any_ss |= all[k].kss_pred >= 0;
-  }
-  db->total_cols = tot;
-  db->has_ss = any_ss;
-  cudaError_t e;
-  if ((e = db->cols.alloc((size_t)tot * 7)) != cudaSuccess || (e = db->cols_raw.alloc((size_t)tot * 7)) != cudaSuccess ||
-      (e = db->dL.alloc(n)) != cudaSuccess || (e = db->dcol_off.alloc(n)) != cudaSuccess ||
-      (e = db->pav.alloc((size_t)n * 20)) != cudaSuccess)
-    return fail(HHG_ENOMEM, "hhg_db_create_a3m: %s", cudaGetErrorString(e));
-  CK(cudaMemcpyAsync(db->dL.p, db->L.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(db->dcol_off.p, db->col_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  double ms_scan = 0.0, ms_kernels = 0.0;
 
   HhmPrepArgs A;
   memcpy(A.R, R, sizeof(A.R));
@@ -854,33 +817,76 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
   A.pD2M = 1 - A.pD2D;
   A.pcm = pp->pcm; A.pca = pp->pca; A.pcb = pp->pcb; A.pcc = pp->pcc;
 
-  const long long kChunkBytes = 256ll << 20;
+  // The records go through in groups: host scan of a group (threads) -> kernels -> column records of the group in a
+  // device piece; the shard is assembled from the pieces at the end.  Host memory holds one group of parsed
+  // alignments at a time (a database of alignments is far larger than the shard it turns into).
+  struct Piece { DevBuf<float4> cols; DevBuf<float> pav; int first = 0, n = 0; long long ncols = 0; };
+  std::vector<std::unique_ptr<Piece>> pieces;
+  std::unique_ptr<hhg_db> holder(new hhg_db());
+  hhg_db* db = holder.get();
+  db->device = ctx->device;
+  db->n = n;
+  db->L.resize(n);
+  db->col_off.resize(n);
+  long long tot = 0;
+  bool any_ss = false;
+
+  const long long kGroupText = 256ll << 20;           // bytes of input text per group
   int max_records = 8192;
-  { const char* e = getenv("HHG_MSA_CHUNK_RECORDS"); if (e && atoi(e) > 0) max_records = atoi(e); }   // test knob: many small chunks
+  { const char* e = getenv("HHG_MSA_CHUNK_RECORDS"); if (e && atoi(e) > 0) max_records = atoi(e); }   // test knob: many small groups
   MsaChunk C;
   DevBuf<long long> d_rec_off;
   DevBuf<uint8_t> d_ss;
   DevBuf<float> d_tau;
+  DevBuf<int> d_L;
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   int t0 = 0;
   while (t0 < n) {
     int t1 = t0;
     long long bytes = 0;
-    while (t1 < n && t1 - t0 < max_records && (bytes == 0 || bytes + (long long)all[t1].X.size() <= kChunkBytes)) bytes += (long long)all[t1++].X.size();
+    while (t1 < n && t1 - t0 < max_records && (bytes == 0 || bytes + len[t1] <= kGroupText)) bytes += len[t1++];
     const int m = t1 - t0;
+    const auto t_s0 = std::chrono::steady_clock::now();
     C.host.clear();
-    for (int k = t0; k < t1; ++k) C.host.push_back(std::move(all[k]));
+    C.host.resize(m);
+    {
+      std::vector<std::string> errs(hw);
+      std::vector<int> err_rec(hw, -1);
+      auto work = [&](unsigned w) {
+        for (int k = (int)w; k < m; k += (int)hw) {
+          if (len[t0 + k] <= 0) { if (err_rec[w] < 0) { errs[w] = "empty record"; err_rec[w] = t0 + k; } continue; }
+          std::string msg = msa_parse_any(data + off[t0 + k], len[t0 + k], sq, mp, &C.host[k]);
+          if (!msg.empty() && err_rec[w] < 0) { errs[w] = msg; err_rec[w] = t0 + k; }
+        }
+      };
+      std::vector<std::thread> pool;
+      for (unsigned w = 1; w < hw; ++w) pool.emplace_back(work, w);
+      work(0);
+      for (auto& th : pool) th.join();
+      for (unsigned w = 0; w < hw; ++w)
+        if (err_rec[w] >= 0) return fail(HHG_EINVAL, "record %d: %s", err_rec[w], errs[w].c_str());
+    }
+    std::vector<long long> rec_off(m);
+    std::vector<int> Lg(m);
+    long long cols = 0;
+    for (int k = 0; k < m; ++k) {
+      const int L = C.host[k].L;
+      if (L > 32767) return fail(HHG_EINVAL, "record %d: length %d out of [1,32767]", t0 + k, L);
+      db->L[t0 + k] = L; db->col_off[t0 + k] = tot + cols;
+      rec_off[k] = cols; Lg[k] = L; cols += L;
+      any_ss |= C.host[k].kss_pred >= 0;
+    }
+    ms_scan += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_s0).count();
     const auto t_c0 = std::chrono::steady_clock::now();
     rc = msa_chunk_run(ctx, C, *mp, S, pb, t0);
     if (rc != HHG_OK) return rc;
     ms_kernels += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
-    std::vector<long long> rec_off(m);
-    long long cols = 0;
-    for (int k = 0; k < m; ++k) { rec_off[k] = cols; cols += C.host[k].L; }
     std::vector<uint8_t> ssb((size_t)cols, 0);
-    if (any_ss) for (int k = 0; k < m; ++k) msa_ss_bytes(C.host[k], ssb.data() + rec_off[k]);
-    CK(d_rec_off.ensure(m)); CK(d_ss.ensure((size_t)cols));
+    for (int k = 0; k < m; ++k) msa_ss_bytes(C.host[k], ssb.data() + rec_off[k]);
+    CK(d_rec_off.ensure(m)); CK(d_ss.ensure((size_t)cols)); CK(d_L.ensure(m));
     CK(cudaMemcpyAsync(d_rec_off.p, rec_off.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_ss.p, ssb.data(), (size_t)cols, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_L.p, Lg.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<float> tau_h;
     if (tau_on_host) {
       std::vector<float> nm((size_t)C.col_total);
@@ -893,26 +899,48 @@ static int db_create_a3m_impl(hhg_ctx* ctx, int n, const char* data, const int64
       CK(d_tau.ensure((size_t)cols));
       CK(cudaMemcpyAsync(d_tau.p, tau_h.data(), (size_t)cols * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
-    ColRec* dst = reinterpret_cast<ColRec*>(db->cols_raw.p) + db->col_off[t0];
+    pieces.emplace_back(new Piece());
+    Piece& P = *pieces.back();
+    P.first = t0; P.n = m; P.ncols = cols;
+    cudaError_t e;
+    if ((e = P.cols.alloc((size_t)cols * 7)) != cudaSuccess || (e = P.pav.alloc((size_t)m * 20)) != cudaSuccess)
+      return fail(HHG_ENOMEM, "hhg_db_create_a3m: %s", cudaGetErrorString(e));
+    ColRec* dst = reinterpret_cast<ColRec*>(P.cols.p);
     const int threads = 128;
     k_msa_prepare<<<(unsigned)((cols + threads - 1) / threads), threads, 0, ctx->stream>>>(
-        m, C.d_desc.p, d_rec_off.p, C.A, any_ss ? d_ss.p : nullptr, A, ctx->lg2.p, ctx->diff.p, dst, cols, d_tr_full,
+        m, C.d_desc.p, d_rec_off.p, C.A, d_ss.p, A, ctx->lg2.p, ctx->diff.p, dst, cols, d_tr_full,
         tau_on_host ? d_tau.p : nullptr);
     k_hhm_pav<<<(unsigned)(((long long)m * 32 + threads - 1) / threads), threads, 0, ctx->stream>>>(
-        m, db->dL.p + t0, d_rec_off.p, dst, nullptr, C.nhmm.p, A, db->pav.p + (size_t)t0 * 20, C.pb.p);
+        m, d_L.p, d_rec_off.p, dst, nullptr, C.nhmm.p, A, P.pav.p, C.pb.p);
     ctx->launches += 2;
     CK(cudaGetLastError());
     if (neff_hmm_out) CK(cudaMemcpyAsync(neff_hmm_out + t0, C.nhmm.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));     // host staging of the group is reused by the next one
+    tot += cols;
     t0 = t1;
+  }
+  db->total_cols = tot;
+  db->has_ss = any_ss;
+  cudaError_t e;
+  if ((e = db->cols.alloc((size_t)tot * 7)) != cudaSuccess || (e = db->cols_raw.alloc((size_t)tot * 7)) != cudaSuccess ||
+      (e = db->dL.alloc(n)) != cudaSuccess || (e = db->dcol_off.alloc(n)) != cudaSuccess ||
+      (e = db->pav.alloc((size_t)n * 20)) != cudaSuccess)
+    return fail(HHG_ENOMEM, "hhg_db_create_a3m: %s", cudaGetErrorString(e));
+  CK(cudaMemcpyAsync(db->dL.p, db->L.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(db->dcol_off.p, db->col_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  long long at = 0;
+  for (auto& pc : pieces) {
+    CK(cudaMemcpyAsync(db->cols_raw.p + (size_t)at * 7, pc->cols.p, (size_t)pc->ncols * 7 * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(db->pav.p + (size_t)pc->first * 20, pc->pav.p, (size_t)pc->n * 80, cudaMemcpyDeviceToDevice, ctx->stream));
+    at += pc->ncols;
   }
   CK(cudaMemcpyAsync(db->cols.p, db->cols_raw.p, db->cols.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  pieces.clear();
   if (timing) {
-    const double ms_parse = std::chrono::duration<double, std::milli>(t_parsed - t_begin).count();
     const double ms_all = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     fprintf(stderr, "[hhg] alignment loader: %d records, host scan %.1f ms, staging + filter/weights/M-state/finish kernels %.1f ms, "
-                    "rest (pseudocounts, pav, copies) %.1f ms\n", n, ms_parse, ms_kernels, ms_all - ms_parse - ms_kernels);
+                    "rest (pseudocounts, pav, copies) %.1f ms\n", n, ms_scan, ms_kernels, ms_all - ms_scan - ms_kernels);
   }
   db->raw = true;
   db->prepared = false;
