@@ -584,9 +584,9 @@ int msa_chunk_run(hhg_ctx* ctx, MsaChunk& C, const hhg_msa_params& mp, const flo
   if (!rcp) return fail(HHG_ECUDA, "reciprocal table upload failed");
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  // k_msa_mstate is latency bound inside a block (ordered sums, barriers): 6 blocks per SM = its register / shared-memory
-  // residency (40 registers, 33 KB), every block pulls (alignment, column) items until the queue is empty
-  const int nblk = (int)std::min<long long>((long long)sms * 6, std::max<long long>(items, 1));
+  // k_msa_mstate is latency bound inside a block (ordered sums, barriers): 12 blocks of 128 threads per SM = its register /
+  // shared-memory residency (40 registers, 16 KB), every block pulls (alignment, column) items until the queue is empty
+  const int nblk = (int)std::min<long long>((long long)sms * 12, std::max<long long>(items, 1));
   MSA_CK(C.cnt.ensure((size_t)nblk * (C.Lmax + 2) * 24)); MSA_CK(C.wc.ensure((size_t)nblk * (C.Lmax + 2) * 24));
   MSA_CK(C.wi.ensure((size_t)nblk * C.Nmax)); MSA_CK(C.member.ensure((size_t)nblk * C.Nmax));
 
@@ -610,7 +610,7 @@ int msa_chunk_run(hhg_ctx* ctx, MsaChunk& C, const hhg_msa_params& mp, const flo
   if (timing) cudaEventRecord(ev[1], ctx->stream);
   k_msa_weights<<<m, 256, 0, ctx->stream>>>(A, C.ni.p);
   if (timing) cudaEventRecord(ev[2], ctx->stream);
-  k_msa_mstate<<<nblk, 256, 0, ctx->stream>>>(A, m, C.item_off.p, items, C.counter.p, C.cnt.p, C.wc.p, C.wi.p, C.member.p,
+  k_msa_mstate<<<nblk, MSA_MSTATE_THREADS, 0, ctx->stream>>>(A, m, C.item_off.p, items, C.counter.p, C.cnt.p, C.wc.p, C.wi.p, C.member.p,
                                               C.Lmax, C.Nmax, rcp, C.pb.p, mp.wg ? 1 : 0, ctx->lg2.p, ctx->diff.p);
   if (timing) cudaEventRecord(ev[3], ctx->stream);
   k_msa_finish<<<m, 256, 0, ctx->stream>>>(A, C.pb.p, mp.wg ? 1 : 0, ctx->lg2.p, ctx->diff.p);

@@ -35,6 +35,7 @@ namespace hhg {
 
 constexpr int MSA_ANY = 20, MSA_GAP = 21, MSA_ENDGAP = 22;   // src/hhdecl.h:52-56
 constexpr int MSA_RCP_N = 1 << 21;                            // > 65535 * 20
+constexpr int MSA_MSTATE_THREADS = 128;                       // block size of k_msa_mstate (see the kernel)
 
 // ------------------------------------------------------------------------------------------ host: scanner
 struct MsaHost {
@@ -689,7 +690,10 @@ k_msa_weights(MsaArrays A, int* __restrict__ ni_all) {
 // Persistent blocks pull (alignment, column) items; the block of a column at which the set of sequences with a
 // residue changes owns the whole run of columns up to the next change: it builds the sub-alignment counts n[j][a],
 // the weights wi[k], Neff of the run, and then the emission frequencies and M->x transitions of every column of the run.
-__global__ void __launch_bounds__(256)
+// Block size: most of a block's time is ordered (single-thread or thread-per-row) work between barriers, so many small
+// blocks beat few large ones: 128 threads, 16 KB of shared memory, 40 registers -> 12 resident blocks per SM (ncu of the
+// 256-thread version: 28 % issue-active, barrier = the top stall).
+__global__ void __launch_bounds__(MSA_MSTATE_THREADS)
 k_msa_mstate(MsaArrays A, int n_msa, const long long* __restrict__ item_off, long long n_items, int* __restrict__ counter,
              int* __restrict__ cnt_all, float* __restrict__ wc_all, float* __restrict__ wi_all, uint8_t* __restrict__ mem_all,
              int Lmax, int Nmax_, const float* __restrict__ rcp, const float* __restrict__ pb, int use_global_weights,
@@ -699,8 +703,8 @@ k_msa_mstate(MsaArrays A, int n_msa, const long long* __restrict__ item_off, lon
   float* wc = wc_all + (size_t)blockIdx.x * (Lmax + 2) * 24;
   float* wi = wi_all + (size_t)blockIdx.x * Nmax_;
   uint8_t* member = mem_all + (size_t)blockIdx.x * Nmax_;
-  __shared__ unsigned short s_cnt[23][256];
-  __shared__ float s_f[20][256];
+  __shared__ unsigned short s_cnt[23][MSA_MSTATE_THREADS];
+  __shared__ float s_f[20][MSA_MSTATE_THREADS];
   __shared__ int s_item, s_any, s_nseq, s_jmin, s_jmax;
   __shared__ float s_neff;
 
