@@ -283,6 +283,38 @@ class MsaScanner {
     std::vector<std::vector<uint8_t>> X(N);
     std::vector<std::vector<uint16_t>> I(N);
     int L = maxres - 2, unequal = 0;
+    // "Too few match states" (:861-880): a file with ONE sequence whose upper-case letters + '-' number fewer than 6
+    // is read as if -M first had been given: every letter of that sequence is a match state, '-' columns are not
+    bool by_first = false;
+    if (N - A.N_ss <= 1) {
+      int ms = 0;
+      for (char c : seq[A.kfirst]) ms += (c >= 'A' && c <= 'Z') || c == '-';
+      by_first = ms < 6;
+    }
+    if (by_first) {                                         // Compress, case M == 3 (:1178-1262)
+      const size_t raw = seq[0].size();
+      for (int q = 1; q < N; ++q) if (seq[q].size() != raw) return "sequences do not all have the same number of columns (sequence " + std::to_string(q) + ")";
+      const std::string& fs = seq[A.kfirst];
+      for (int q = 0; q < N; ++q) { X[q].assign(1, MSA_ANY); I[q].assign(1, 0); }
+      int i = 0;
+      for (size_t l = 0; l < raw; ++l) {
+        if (isalpha((unsigned char)fs[l])) {
+          if (i >= maxres - 2) break;
+          ++i;
+          for (int q = 0; q < N; ++q) {
+            const char c = seq[q][l];
+            if (A.keep[q]) { X[q].push_back((uint8_t)aa_code(c)); I[q].push_back(0); }
+            else if (q == A.kss_dssp || q == A.kss_pred) X[q].push_back((uint8_t)ss_code(c));
+            else if (q == A.ksa_dssp) X[q].push_back((uint8_t)sa_code(c));
+            else if (q == A.kss_conf) X[q].push_back((uint8_t)cf_code(c));
+            else X[q].push_back((uint8_t)MSA_GAP);         // rows the reference leaves at their initial GAP
+          }
+        } else {
+          for (int q = 0; q < N; ++q) if (A.keep[q] && aa_code(seq[q][l]) < MSA_GAP) ++I[q].back();
+        }
+      }
+      L = i;
+    } else
     for (int q = 0; q < N; ++q) {
       const std::string& s = seq[q];
       std::vector<uint8_t>& x = X[q];

@@ -17,6 +17,12 @@ CASES = [  # (match columns, sequences after the master, seed, generator options
 ]
 
 
+# hand-written corner cases (CPU tests): a single sequence with fewer than six match states falls back to "-M first"
+# (src/hhalignment.cpp:861-880): lower-case letters become match states, '-' columns do not
+TINY = [b">master\nZ-iwHkv\n", b"#NAME some description\n>master\nlKV\n", b">ss_pred\nHHEC-\n>ss_conf\n12345\n>m\nAc-dE\n",
+        b">m\r\nACDEFGHIKL\r\n>s1 x\r\nAC-EFGHIKL\r\n>s2\r\n.ACDEFGaaHIKL\r\n"]
+
+
 def texts():
     from hhsuite_b200 import synth
     out = [synth.a3m_text(L, n, seed, **kw).encode() for (L, n, seed, kw) in CASES]

@@ -9,7 +9,7 @@ from tests import msa_cases
 
 def test_scanner_equals_reference(refshim, tmp_path):
     from hhsuite_b200 import capi
-    for k, t in enumerate(msa_cases.texts()):
+    for k, t in enumerate(msa_cases.texts() + msa_cases.TINY):
         path = tmp_path / f"m{k}.a3m"
         path.write_bytes(t)
         ref = refshim.msa_to_hmm(str(path))

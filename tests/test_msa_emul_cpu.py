@@ -109,3 +109,11 @@ def test_emulated_context_score_kernel(emul, refshim):
     ref, _ = refshim.context_pc(f, neff_m, 3.0, engine=0)
     assert np.array_equal(bits(got[1:L + 1]), bits(ref[1:L + 1]))
     crf.close()
+
+
+def test_emulated_kernels_on_corner_cases(emul, refshim, tmp_path):
+    for k, t in enumerate(msa_cases.TINY):
+        path = tmp_path / f"t{k}.a3m"
+        path.write_bytes(t)
+        for wg in (0, 1):
+            _cmp(_run(emul, refshim, t, wg=wg), refshim.msa_to_hmm(str(path), wg=wg), f"tiny {k} wg={wg}")
