@@ -64,10 +64,11 @@ class PrepParams(C.Structure):
 
 class MsaParams(C.Structure):
     """hhg_msa_params: the Parameters the A3M branch of HHEntry::getTemplateHMM reads (src/hhdatabase.cpp:441-449;
-    defaults src/hhdecl.cpp:10-14,45,117-135)."""
+    defaults src/hhdecl.cpp:10-14,35-46,131-135).  M: 1 A2M/A3M (upper case = match), 2 gap percentage (Mgaps), 3 first
+    sequence; wg: 0 position-specific weights, 1 global weights."""
     _fields_ = [("maxseq", C.c_int32), ("maxcol", C.c_int32), ("maxres", C.c_int32), ("M", C.c_int32), ("mark", C.c_int32),
                 ("max_seqid", C.c_int32), ("coverage", C.c_int32), ("qid", C.c_int32), ("Ndiff", C.c_int32),
-                ("qsc", C.c_float), ("wg", C.c_int32)]
+                ("qsc", C.c_float), ("wg", C.c_int32), ("Mgaps", C.c_int32)]
 
     @classmethod
     def defaults(cls, **kw):

@@ -641,7 +641,8 @@ int msa_params_check(const hhg_msa_params* mp) {
   if (!mp) return fail(HHG_EINVAL, "alignment parameters are NULL");
   if (mp->maxseq < 2 || mp->maxseq > 65535) return fail(HHG_EINVAL, "maxseq %d outside [2, 65535]", mp->maxseq);
   if (mp->maxres < 8 || mp->maxcol < mp->maxres) return fail(HHG_EINVAL, "maxres %d / maxcol %d", mp->maxres, mp->maxcol);
-  if (mp->M != 1) return fail(HHG_EINVAL, "match-state assignment %d: only 1 (A2M/A3M, upper case = match; par.M_template) is built", mp->M);
+  if (mp->M < 1 || mp->M > 3) return fail(HHG_EINVAL, "match-state assignment %d: 1 (A2M/A3M: upper case = match), 2 (gap percentage, Mgaps) or 3 (first sequence)", mp->M);
+  if (mp->M == 2 && (mp->Mgaps < 0 || mp->Mgaps > 100)) return fail(HHG_EINVAL, "Mgaps %d outside [0, 100]", mp->Mgaps);
   if (mp->mark != 0) return fail(HHG_EINVAL, "the -mark option is not built");
   return HHG_OK;
 }
@@ -664,6 +665,7 @@ void hhg_msa_params_default(hhg_msa_params* mp) {
   mp->M = 1; mp->mark = 0;
   mp->max_seqid = 90; mp->coverage = 0; mp->qid = 0; mp->Ndiff = 100; mp->qsc = -20.0f;   // :35-39, :131-135
   mp->wg = 0;
+  mp->Mgaps = 50;                                                    // :46
 }
 
 int hhg_a3m_scan(const char* rec, int64_t len, const hhg_msa_params* mp, int32_t* L, int32_t* N_in, int32_t* has_ss) {
@@ -671,7 +673,7 @@ int hhg_a3m_scan(const char* rec, int64_t len, const hhg_msa_params* mp, int32_t
   int rc = msa_params_check(mp);
   if (rc != HHG_OK) return rc;
   MsaHost H;
-  const std::string msg = MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, &H);
+  const std::string msg = MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, &H, mp->M, mp->Mgaps);
   if (!msg.empty()) return fail(HHG_EINVAL, "hhg_a3m_scan: %s", msg.c_str());
   *L = H.L; *N_in = H.N_in;
   if (has_ss) *has_ss = H.kss_pred >= 0;
@@ -685,9 +687,9 @@ static int seqdb_check(const hhg_seqdb* sq) {
 }
 
 static std::string msa_parse_any(const char* rec, int64_t len, const hhg_seqdb* sq, const hhg_msa_params* mp, MsaHost* H) {
-  if (!sq) return MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, H);
+  if (!sq) return MsaScanner::parse(rec, len, mp->maxseq, mp->maxcol, mp->maxres, H, mp->M, mp->Mgaps);
   const MsaScanner::SeqDb db{sq->n, sq->data, sq->off, sq->len};
-  return MsaScanner::parse_ca3m(rec, len, db, mp->maxseq, mp->maxcol, mp->maxres, H);
+  return MsaScanner::parse_ca3m(rec, len, db, mp->maxseq, mp->maxcol, mp->maxres, H, mp->M, mp->Mgaps);
 }
 
 static int msa_parse_impl(const char* rec, int64_t len, const hhg_seqdb* sq, const hhg_msa_params* mp, int32_t L_cap,

@@ -101,11 +101,12 @@ class MsaScanner {
 
   // Alignment::Read with mark == 0, then Compress with M == 1.  Returns "" or an error description (the cases in
   // which the reference exits).  maxseq / maxcol / maxres: Parameters of the same names (src/hhdecl.cpp:10-14).
-  static std::string parse(const char* rec, int64_t len, int maxseq, int maxcol, int maxres, MsaHost* out) {
+  static std::string parse(const char* rec, int64_t len, int maxseq, int maxcol, int maxres, MsaHost* out, int M = 1,
+                           int Mgaps = 50) {
     std::vector<std::string> seq;
     std::string msg = read_a3m(rec, len, maxseq, maxcol, out, &seq);
     if (!msg.empty()) return msg;
-    return compress(seq, maxres, out);
+    return compress(seq, maxres, out, M, Mgaps);
   }
 
   // The sequence database of a compressed alignment database (`<db>_sequence.ffdata` + the offset / length columns of
@@ -113,11 +114,12 @@ class MsaScanner {
   struct SeqDb { int64_t n; const char* data; const int64_t* off; const int64_t* len; };
 
   // Alignment::ReadCompressed (src/hhalignment.cpp:546-815) with mark == 0, then Compress with M == 1.
-  static std::string parse_ca3m(const char* rec, int64_t len, const SeqDb& db, int maxseq, int maxcol, int maxres, MsaHost* out) {
+  static std::string parse_ca3m(const char* rec, int64_t len, const SeqDb& db, int maxseq, int maxcol, int maxres, MsaHost* out,
+                                int M = 1, int Mgaps = 50) {
     std::vector<std::string> seq;
     std::string msg = read_ca3m(rec, len, db, maxseq, maxcol, out, &seq);
     if (!msg.empty()) return msg;
-    return compress(seq, maxres, out);
+    return compress(seq, maxres, out, M, Mgaps);
   }
 
  private:
@@ -275,7 +277,7 @@ class MsaScanner {
     return "";
   }
 
-  static std::string compress(const std::vector<std::string>& seq, int maxres, MsaHost* out) {
+  static std::string compress(const std::vector<std::string>& seq, int maxres, MsaHost* out, int M = 1, int Mgaps = 50) {
     MsaHost& A = *out;
 
     // ---- Compress, case M == 1 (:889-990)
@@ -283,15 +285,75 @@ class MsaScanner {
     std::vector<std::vector<uint8_t>> X(N);
     std::vector<std::vector<uint16_t>> I(N);
     int L = maxres - 2, unequal = 0;
+    std::vector<int> raw_nres;                              // see the M == 2 branch
     // "Too few match states" (:861-880): a file with ONE sequence whose upper-case letters + '-' number fewer than 6
     // is read as if -M first had been given: every letter of that sequence is a match state, '-' columns are not
-    bool by_first = false;
-    if (N - A.N_ss <= 1) {
+    bool by_first = M == 3;
+    if (M == 1 && N - A.N_ss <= 1) {
       int ms = 0;
       for (char c : seq[A.kfirst]) ms += (c >= 'A' && c <= 'Z') || c == '-';
       by_first = ms < 6;
     }
-    if (by_first) {                                         // Compress, case M == 3 (:1178-1262)
+    if (M == 2) {                                           // Compress, case M == 2 (:994-1175): gap-percentage rule
+      const size_t raw = seq[A.kfirst].size();
+      for (int q = 0; q < N; ++q)
+        if ((A.keep[q] || q == A.kss_dssp || q == A.kss_pred || q == A.ksa_dssp || q == A.kss_conf) && seq[q].size() != raw)
+          return "sequences do not all have the same number of columns (sequence " + std::to_string(q) + ")";
+      // residue codes of all columns, residues per row, quick sequence weights (:1012-1051)
+      std::vector<std::vector<uint8_t>> C(N);
+      std::vector<int> nr(N, 0);
+      std::vector<float> wq(N, 0.f);
+      for (int q = 0; q < N; ++q) {
+        if (!A.keep[q]) continue;
+        C[q].resize(raw);
+        for (size_t l = 0; l < raw; ++l) { C[q][l] = (uint8_t)aa_code(seq[q][l]); nr[q] += C[q][l] < 20; }
+      }
+      for (size_t l = 0; l < raw; ++l) {
+        int nl[23] = {0};
+        for (int q = 0; q < N; ++q) if (A.keep[q]) ++nl[C[q][l]];
+        int naa = 0;
+        for (int a = 0; a < 20; ++a) naa += nl[a] != 0;
+        if (!naa) naa = 1;
+        for (int q = 0; q < N; ++q)
+          if (A.keep[q] && C[q][l] < 20) wq[q] += 1.0 / float(nl[C[q][l]] * naa * (nr[q] + 30.0));
+      }
+      for (int q = 0; q < N; ++q) {                         // end gaps over the raw columns (:1054-1062)
+        if (!A.keep[q]) continue;
+        for (size_t l = 0; l < raw && C[q][l] == MSA_GAP; ++l) C[q][l] = MSA_ENDGAP;
+        for (size_t l = raw; l-- > 0 && C[q][l] == MSA_GAP;) C[q][l] = MSA_ENDGAP;
+      }
+      for (int q = 0; q < N; ++q) { X[q].assign(1, MSA_ANY); I[q].assign(1, 0); }
+      int i = 0, kfirst = A.kfirst;
+      for (size_t l = 0; l < raw; ++l) {
+        float res = 0, gap = 0;
+        for (int q = 0; q < N; ++q) {
+          if (!A.keep[q]) continue;
+          if (C[q][l] < MSA_GAP) res += wq[q];
+          else if (C[q][l] != MSA_ENDGAP) gap += wq[q];
+        }
+        const float pg = 100. * gap / (res + gap);
+        if (pg <= float(Mgaps)) {
+          if (i >= maxres - 2) break;
+          ++i;
+          for (int q = 0; q < N; ++q) {
+            const char c = seq[q].size() > l ? seq[q][l] : '-';
+            if (A.keep[q]) { X[q].push_back(C[q][l]); I[q].push_back(0); if (kfirst == -1) kfirst = q; }
+            else if (q == A.kss_dssp || q == A.kss_pred) X[q].push_back((uint8_t)ss_code(c));
+            else if (q == A.ksa_dssp) X[q].push_back((uint8_t)sa_code(c));
+            else if (q == A.kss_conf) X[q].push_back((uint8_t)cf_code(c));
+            else { X[q].push_back((uint8_t)MSA_GAP); if (q == kfirst) kfirst = -1; }   // a consensus master row drops out (:1131-1133)
+          }
+        } else {
+          for (int q = 0; q < N; ++q) if (A.keep[q] && C[q][l] < MSA_GAP) ++I[q].back();
+        }
+      }
+      if (kfirst < 0) return "the alignment contains no master sequence";
+      A.kfirst = kfirst;
+      L = i;
+      // Compress fills nres[] with the residues over ALL input columns here, and Filter2 recomputes it over the match
+      // columns only `if (nres == NULL || sizeof(nres) < N_in * sizeof(int))` (:1660), i.e. only when N_in > 2
+      if (N <= 2) raw_nres = nr;
+    } else if (by_first) {                                  // Compress, case M == 3 (:1178-1262)
       const size_t raw = seq[0].size();
       for (int q = 1; q < N; ++q) if (seq[q].size() != raw) return "sequences do not all have the same number of columns (sequence " + std::to_string(q) + ")";
       const std::string& fs = seq[A.kfirst];
@@ -353,7 +415,7 @@ class MsaScanner {
       const std::vector<uint8_t>& x = X[q];
       for (int i = 0; i < (int)x.size() && i <= L + 1; ++i) row[i] = x[i];
       row[0] = MSA_ANY;
-      if (A.keep[q]) {                                      // end gaps (:969-977)
+      if (A.keep[q] && M != 2) {                            // end gaps (:969-977; with M == 2 they were marked on the raw columns)
         for (int i = 1; i <= L && row[i] == MSA_GAP; ++i) row[i] = MSA_ENDGAP;
         for (int i = L; i >= 1 && row[i] == MSA_GAP; --i) row[i] = MSA_ENDGAP;
       }
@@ -373,6 +435,7 @@ class MsaScanner {
       A.last[q] = i;
       int nr = 0;
       for (i = A.first[q]; i <= A.last[q]; ++i) if (row[i] < 20) ++nr;
+      if (!raw_nres.empty()) { A.nres[q] = A.keep[q] ? raw_nres[q] : 0; A.ksort[q] = q; continue; }
       A.nres[q] = nr;
       if (nr == 0) A.keep[q] = 0;
       A.ksort[q] = q;

@@ -155,15 +155,17 @@ int hhg_query_from_hhm(hhg_ctx* ctx, const char* rec, int64_t len, const hhg_pre
  * (:2531), whose bits differ between CPU vendors.  The library samples the host's RCPPS for every possible integer
  * argument once and the kernel looks the values up: the HMM equals the one the reference computes ON THE SAME HOST,
  * bit for bit.
- * Not built: match-state assignment other than by case (-M first / -M <percent>), the -mark option. */
+ * Not built: the -mark option. */
 typedef struct hhg_msa_params {
   int32_t maxseq, maxcol, maxres;   /* par.maxseq 65535, par.maxcol 32765, par.maxres 20001 (src/hhdecl.cpp:10-14)       */
-  int32_t M, mark;                  /* par.M_template 1, par.mark 0: the only values built                              */
+  int32_t M, mark;                  /* par.M / par.M_template: 1 A2M/A3M (match = upper case), 2 gap rule (Mgaps), 3 first  */
+                                    /* sequence (-M a2m | <percent> | first); par.mark 0 is the only value built          */
   int32_t max_seqid, coverage, qid, Ndiff;   /* par.max_seqid_db 90, coverage_db 0, qid_db 0, Ndiff_db 100 (Filter)      */
   float qsc;                        /* par.qsc_db -20 (off); > -10 needs the substitution matrix S                      */
   int32_t wg;                       /* 0: position-specific weights (par.wg; what the realignment stage reads templates   */
                                     /* with), 1: global weights -- ViterbiRunner::alignment reads alignment templates    */
                                     /* with wg = 1 "for performance" (src/hhviterbirunner.cpp:143): use 1 for its shard   */
+  int32_t Mgaps;                    /* par.Mgaps 50: with M = 2, columns with a larger weighted gap percentage are inserts */
 } hhg_msa_params;
 void hhg_msa_params_default(hhg_msa_params* mp);
 /* Host only: number of match columns and of sequences of one A3M record, and whether it carries >ss_pred. */

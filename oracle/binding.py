@@ -591,6 +591,11 @@ class RefShim:
         Alignment::ReadCompressed with <prefix>_sequence.ff* / <prefix>_header.ff*."""
         return self._msa_call(self.lib.hhref_ca3m_to_hmm, [prefix, entry_name], filt, wg, prep, capL, capN)
 
+    def set_M(self, M=1, Mgaps=50):
+        """par.M_template / par.Mgaps (-M a2m | <percent> | first) for the following msa_to_hmm calls."""
+        self.lib.hhref_set_M.argtypes = [C.c_int, C.c_int]
+        self.lib.hhref_set_M(M, Mgaps)
+
     def rcp_table(self, n):
         out = np.zeros(n, np.float32)
         self.lib.hhref_rcp_table.argtypes = [C.c_int, c_f32p]

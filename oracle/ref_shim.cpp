@@ -771,6 +771,9 @@ extern "C" int hhref_ca3m_to_hmm(const char* prefix, const char* entry_name, con
   return rc;
 }
 
+// par.M_template / par.Mgaps (-M a2m | first | <percent>) for the following hhref_msa_to_hmm calls
+extern "C" void hhref_set_M(int M, int Mgaps) { g->par->M_template = M; g->par->Mgaps = Mgaps; }
+
 // _mm_rcp_ps of this host (Alignment::Amino_acid_frequencies_and_transitions_from_M_state uses simdf32_rcp,
 // src/hhalignment.cpp:2531): lets a test compare the product's own sampled table with the reference build's view.
 extern "C" void hhref_rcp_table(int n, float* out) {

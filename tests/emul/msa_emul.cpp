@@ -16,12 +16,12 @@ using namespace hhg;
 
 // One A3M record -> raw HMM, the steps of msa_chunk_run (hhg_api.cu) with host memory.  threads: block size of the
 // emulated launches (a multiple of 32).  lg2 / dif: the fast_log2 tables (1025 floats each).
-extern "C" int emul_msa_to_hmm(const char* rec, long long len, const int* ip /*maxseq,maxcol,maxres,max_seqid,coverage,qid,Ndiff,wg*/,
+extern "C" int emul_msa_to_hmm(const char* rec, long long len, const int* ip /*maxseq,maxcol,maxres,max_seqid,coverage,qid,Ndiff,wg,M,Mgaps*/,
                                float qsc, const float* S, const float* pb, const float* lg2, const float* dif, int threads,
                                int* dims, signed char* keep_out, float* wg_out, float* f, float* tr, float* neff,
                                float* neff_hmm) {
   MsaHost H;
-  const std::string msg = MsaScanner::parse(rec, len, ip[0], ip[1], ip[2], &H);
+  const std::string msg = MsaScanner::parse(rec, len, ip[0], ip[1], ip[2], &H, ip[8], ip[9]);
   if (!msg.empty()) return -1;
   const int N = H.N_in, L = H.L;
   MsaDesc d{N, L, H.stride, H.kfirst, 0, 0, 0, 0};

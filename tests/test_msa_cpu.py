@@ -31,7 +31,7 @@ def test_scanner_errors_and_limits():
     with pytest.raises(capi.HhgError):
         capi.a3m_parse(b">a\n>b\nACDE\n")                                   # a sequence without residues
     with pytest.raises(capi.HhgError):
-        capi.a3m_parse(b">a\nACDEFGHIKL\n", capi.MsaParams.defaults(M=2))   # only match states by case are built
+        capi.a3m_parse(b">a\nACDEFGHIKL\n", capi.MsaParams.defaults(M=4))   # 1 (case), 2 (gap rule), 3 (first sequence)
     # maxseq: rows beyond the limit are ignored like the reference does (with a warning)
     t = b">m\nACDEFGHIKL\n" + b"".join(b">s%d\nACDEFGHIKL\n" % i for i in range(10))
     assert capi.a3m_parse(t, capi.MsaParams.defaults(maxseq=4))["N_in"] == 4

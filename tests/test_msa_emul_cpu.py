@@ -41,9 +41,9 @@ def _tables():
     return lg2, dif
 
 
-def _run(L, refshim, t, filt=(90, 0, 0, -20.0, 100), wg=0, threads=64):
+def _run(L, refshim, t, filt=(90, 0, 0, -20.0, 100), wg=0, threads=64, M=1, Mgaps=50):
     lg2, dif = _tables()
-    ip = np.array([65535, 32765, 20001, filt[0], filt[1], filt[2], filt[4], wg], np.int32)
+    ip = np.array([65535, 32765, 20001, filt[0], filt[1], filt[2], filt[4], wg, M, Mgaps], np.int32)
     Lc, Nc = 1000, 1000
     dims = np.zeros(4, np.int32); keep = np.zeros(Nc, np.int8); wgv = np.zeros(Nc, np.float32)
     f = np.zeros((Lc + 2) * 20, np.float32); tr = np.zeros((Lc + 1) * 7, np.float32)
@@ -117,3 +117,21 @@ def test_emulated_kernels_on_corner_cases(emul, refshim, tmp_path):
         path.write_bytes(t)
         for wg in (0, 1):
             _cmp(_run(emul, refshim, t, wg=wg), refshim.msa_to_hmm(str(path), wg=wg), f"tiny {k} wg={wg}")
+
+
+FASTA = (b">ss_pred\nHHHEEECCCHHH\n>m\nACDEFGHIKLMN\n>s1\nAC-EFGHI-LMN\n>s2\n--DEFaHIKLM-\n>s3\nACDE.GHIKL--\n>s4\n-CDEFGHIKLMN\n",
+         b">m\nMKV-LAAGIV\n>s1\nMRV-LSAGLV\n")
+
+
+@pytest.mark.parametrize("M,Mgaps", [(2, 50), (2, 20), (3, 50)])
+def test_emulated_kernels_with_other_match_state_rules(emul, refshim, tmp_path, M, Mgaps):
+    """-M <percent> / -M first (Compress cases 2 and 3) for alignments that are not A3M; incl. the two-sequence case in
+    which the reference keeps the residue counts of ALL input columns."""
+    try:
+        refshim.set_M(M, Mgaps)
+        for k, t in enumerate(FASTA):
+            path = tmp_path / f"f{k}.fas"
+            path.write_bytes(t)
+            _cmp(_run(emul, refshim, t, M=M, Mgaps=Mgaps), refshim.msa_to_hmm(str(path)), f"fasta {k} M={M}/{Mgaps}")
+    finally:
+        refshim.set_M(1, 50)
